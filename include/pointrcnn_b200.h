@@ -1,0 +1,162 @@
+/*
+ * pointrcnn_b200.h -- C ABI of libpointrcnn_b200.so: B200 (sm_100a) kernels for PointRCNN's
+ * per-scene point-cloud operator path.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain device pointers, sizes and a
+ * CUDA stream (as void*; NULL = legacy default stream); no torch types.  Each one replaces
+ * one native entry point of the reference's three extension modules (paths relative to the
+ * reference tree); the extension-module shims in pointrcnn_b200/ext/{pointnet2_cuda,
+ * iou3d_cuda,roipool3d_cuda}.py bind them under the reference's exact Python names.
+ *
+ * Conventions
+ *   - all tensors contiguous; float = fp32, int = int32, long long = int64
+ *   - the CALLER allocates every output (and zero-/1e10-fills where the reference's Python
+ *     wrappers do: ball-query idx, grad buffers, pooled/empty, FPS temp)
+ *   - scratch memory is caller-provided too (prb_*_workspace_bytes tells how much); nothing
+ *     in this library calls cudaMalloc/cudaFree or synchronises the device, except
+ *     prb_nms*_host which must fill a host buffer before returning (the reference signature)
+ *   - return value: 0 on success, otherwise a cudaError_t (or -1 for bad arguments);
+ *     prb_last_error() gives the message.  Nothing exit()s the process.
+ *   - kernels launch on the given stream, on the current device (callers set the device).
+ */
+#ifndef POINTRCNN_B200_H_
+#define POINTRCNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRB_ABI_VERSION 1
+#if defined(__GNUC__)
+#define PRB_API __attribute__((visibility("default")))
+#else
+#define PRB_API
+#endif
+
+PRB_API int prb_abi_version(void);
+PRB_API const char *prb_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+PRB_API unsigned long long prb_launch_count(void);
+
+/* ------------------------------------------------------------------ pointnet2_cuda ------
+ * replaces pointnet2_lib/pointnet2/src/pointnet2_api.cpp:10-23 */
+
+/* furthest_point_sampling_wrapper, sampling.cpp:36-46 -> sampling_gpu.cu:93-253.
+ * xyz (b,n,3); temp (b,n) in/out running min distance (caller prefills 1e10); idx (b,m) int32.
+ * Index-exact with the reference incl. its tie rule.  new_xyz (b,m,3) may be NULL; when given,
+ * the sampled coordinates are emitted too (replaces the gather_operation that follows FPS in
+ * pointnet2_modules.py:32-35). */
+PRB_API int prb_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                float *new_xyz, void *stream);
+
+/* gather_points_wrapper_fast / gather_points_grad_wrapper_fast, sampling.cpp:11-33 */
+PRB_API int prb_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx,
+                      float *out, void *stream);
+PRB_API int prb_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx,
+                           float *grad_points, void *stream);
+
+/* ball_query_wrapper_fast, ball_query.cpp:14-25 -> ball_query_gpu.cu:9-67.
+ * argument order is the reference's positional order (b,n,m,radius,nsample,new_xyz,xyz,idx). */
+PRB_API int prb_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                   const float *xyz, int *idx, void *stream);
+/* two radii over the same centres in one scan (the MSG case, pointnet2_modules.py:37-38);
+ * each idx_k has the semantics of prb_ball_query(radius_k, nsample_k) */
+PRB_API int prb_ball_query_msg2(int b, int n, int m, float radius0, int nsample0, float radius1, int nsample1,
+                        const float *new_xyz, const float *xyz, int *idx0, int *idx1, void *stream);
+
+/* group_points_wrapper_fast / group_points_grad_wrapper_fast, group_points.cpp:11-36 */
+PRB_API int prb_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                     const int *idx, float *out, void *stream);
+PRB_API int prb_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                          const int *idx, float *grad_points, void *stream);
+
+/* three_nn_wrapper_fast, interpolate.cpp:14-23 (n unknown, m known; outputs d^2 and idx).
+ * weight (b,n,3) may be NULL; when given, the inverse-distance weights of
+ * pointnet2_modules.py:140-142 are emitted as well. */
+PRB_API int prb_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
+                 int *idx, float *weight, void *stream);
+
+/* three_interpolate_wrapper_fast (b,c,m,n) / three_interpolate_grad_wrapper_fast (b,c,n,m),
+ * interpolate.cpp:26-54 -- note the different n/m order of the two, kept as in the reference */
+PRB_API int prb_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                          const float *weight, float *out, void *stream);
+PRB_API int prb_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                               const float *weight, float *grad_points, void *stream);
+
+/* (B,C,N) <-> (B,N,C) layout change used in front of the fused kernels */
+PRB_API int prb_transpose_bcn_to_bnc(int b, int c, int n, const float *in, float *out, void *stream);
+
+/* ------------------------------------------------------------------ fused SA / FP -------
+ * New natives behind PointnetSAModuleMSG.forward / PointnetFPModule.forward
+ * (pointnet2_modules.py:19-55, 127-156).  Eval-mode BatchNorm is folded by the host into a
+ * per-channel (scale, shift); every layer is y = relu(scale * (W x) + shift).
+ * Weights are passed pre-packed by prb_mlp_pack_weights (tile images in the tcgen05 shared-
+ * memory operand layout), so the kernel stages them with plain bulk copies. */
+
+typedef struct prb_mlp_desc {
+    int num_layers;          /* 1..3 */
+    int c_in;                /* input channels of layer 0 (incl. the 3 xyz channels for SA) */
+    int c_out[3];            /* output channels per layer */
+    const float *packed_w;   /* device, from prb_mlp_pack_weights */
+    const float *scale;      /* device; layer after layer, each layer zero-padded to round_up(c_out,32) floats */
+    const float *shift;      /* device; same layout */
+} prb_mlp_desc;
+
+/* bytes of the packed image for one MLP */
+PRB_API size_t prb_mlp_packed_bytes(int num_layers, int c_in, const int *c_out);
+/* host-side packing: w[l] is the (c_out[l], c_in_l) row-major conv weight; dst is HOST memory of
+ * prb_mlp_packed_bytes() bytes which the caller then uploads */
+PRB_API int prb_mlp_pack_weights(int num_layers, int c_in, const int *c_out, const float *const *w, void *dst);
+
+/* grouped MLP + max-pool: for every centre p and every sample s, row = [xyz[idx]-new_xyz[p],
+ * feats_pm[idx]] -> MLP -> max over s.  feats_pm is POINT-major (b,n,c_feat) (NULL if c_feat==0);
+ * out is channel-major (b, out_stride_c, npoint) written at channel offset out_c_off. */
+PRB_API int prb_sa_group_mlp_max(int b, int n, int npoint, int nsample, int c_feat, const float *xyz,
+                         const float *new_xyz, const float *feats_pm, const int *idx,
+                         const prb_mlp_desc *mlp, float *out, int out_stride_c, int out_c_off,
+                         void *stream);
+
+/* feature propagation: row(u) = [sum_k w[u,k]*known_pm[idx[u,k]], skip[:,u]] -> MLP.
+ * known_pm point-major (b,m,c_known); skip channel-major (b,c_skip,n) or NULL; out (b,c_last,n) */
+PRB_API int prb_fp_interp_mlp(int b, int n, int m, int c_known, int c_skip, const float *known_pm,
+                      const int *idx, const float *weight, const float *skip,
+                      const prb_mlp_desc *mlp, float *out, void *stream);
+
+/* ------------------------------------------------------------------ roipool3d_cuda ------
+ * replaces lib/utils/roipool3d/src/roipool3d.cpp:48-79 (forward) -> roipool3d_kernel.cu:209-237.
+ * xyz (B,N,3), boxes3d (B,M,7) ALREADY enlarged, pts_feature (B,N,C) -> pooled (B,M,S,3+C),
+ * empty_flag (B,M) int32; both outputs zero-filled by the caller (rows of empty boxes stay 0).
+ * rois_canonical: NULL, or (B,M,7) original RoIs -> the canonical transform of
+ * lib/net/rcnn_net.py:146-152 is applied to the xyz columns while they are written. */
+PRB_API int prb_roipool3d(int B, int N, int M, int C, int S, const float *xyz, const float *boxes3d,
+                  const float *pts_feature, float *pooled, int *empty_flag,
+                  const float *rois_canonical, void *stream);
+
+/* ------------------------------------------------------------------ iou3d_cuda ----------
+ * replaces lib/utils/iou3d/src/iou3d.cpp:31-71 (matrices) and :73-170 (NMS) */
+PRB_API int prb_boxes_overlap_bev(int num_a, const float *boxes_a, int num_b, const float *boxes_b,
+                          float *ans_overlap, void *stream);
+PRB_API int prb_boxes_iou_bev(int num_a, const float *boxes_a, int num_b, const float *boxes_b,
+                      float *ans_iou, void *stream);
+
+/* scratch for one NMS call over n boxes */
+PRB_API size_t prb_nms_workspace_bytes(int n);
+/* device-resident NMS: boxes (n,5) score-sorted; keep_dev (n) int64 kept positions in order;
+ * num_dev (1) int32.  normal != 0 selects the axis-aligned IoU (nms_normal_gpu). No host sync. */
+PRB_API int prb_nms_device(const float *boxes, int n, float thresh, int normal, long long *keep_dev,
+                   int *num_dev, void *workspace, void *stream);
+/* reference signature (keep on the HOST, count returned): runs prb_nms_device, then one small
+ * D2H of (count + kept indices) and a stream synchronise.  *num_out = number kept. */
+PRB_API int prb_nms_host(const float *boxes, int n, float thresh, int normal, long long *keep_host,
+                 int *num_out, void *workspace, void *stream);
+/* suppression bitmask only (n, ceil(n/64)) uint64, upper-triangle tiles; lower tiles zero */
+PRB_API int prb_nms_mask(const float *boxes, int n, float thresh, int normal, unsigned long long *mask,
+                 void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POINTRCNN_B200_H_ */

@@ -1,0 +1,68 @@
+"""The RPN PointNet++ backbone wiring (mirror of lib/net/pointnet2_msg.py:6-70) parameterised by a plain
+dict instead of the reference's global EasyDict, so benches and GPU tests can build it without the
+reference tree.  Module / parameter names are the reference's (`SA_modules.k.mlps.i.layer{j}...`,
+`FP_modules.k.mlp.layer{j}...`), so a reference checkpoint's backbone keys load as they are.
+"""
+import copy
+
+import torch
+import torch.nn as nn
+
+from .pointnet2.pointnet2_modules import PointnetFPModule, PointnetSAModuleMSG
+
+# tools/cfgs/default.yaml:38-51
+RPN_DEFAULT = dict(
+    USE_BN=True,
+    NPOINTS=[4096, 1024, 256, 64],
+    RADIUS=[[0.1, 0.5], [0.5, 1.0], [1.0, 2.0], [2.0, 4.0]],
+    NSAMPLE=[[16, 32], [16, 32], [16, 32], [16, 32]],
+    MLPS=[[[16, 16, 32], [32, 32, 64]], [[64, 64, 128], [64, 96, 128]], [[128, 196, 256], [128, 196, 256]],
+          [[256, 256, 512], [256, 384, 512]]],
+    FP_MLPS=[[128, 128], [256, 256], [512, 512], [512, 512]],
+)
+
+
+class Pointnet2MSG(nn.Module):
+    def __init__(self, input_channels=0, use_xyz=True, cfg=None):
+        super().__init__()
+        cfg = copy.deepcopy(cfg or RPN_DEFAULT)
+        self.SA_modules = nn.ModuleList()
+        channel_in = input_channels
+        skip_channel_list = [input_channels]
+        channel_out = channel_in
+        for k in range(len(cfg["NPOINTS"])):
+            mlps = [list(m) for m in cfg["MLPS"][k]]
+            channel_out = 0
+            for i in range(len(mlps)):
+                mlps[i] = [channel_in] + mlps[i]
+                channel_out += mlps[i][-1]
+            self.SA_modules.append(PointnetSAModuleMSG(npoint=cfg["NPOINTS"][k], radii=cfg["RADIUS"][k],
+                                                       nsamples=cfg["NSAMPLE"][k], mlps=mlps, use_xyz=use_xyz, bn=cfg["USE_BN"]))
+            skip_channel_list.append(channel_out)
+            channel_in = channel_out
+        self.FP_modules = nn.ModuleList()
+        fp = cfg["FP_MLPS"]
+        for k in range(len(fp)):
+            pre_channel = fp[k + 1][-1] if k + 1 < len(fp) else channel_out
+            self.FP_modules.append(PointnetFPModule(mlp=[pre_channel + skip_channel_list[k]] + list(fp[k])))
+
+    @staticmethod
+    def _break_up_pc(pc):
+        xyz = pc[..., 0:3].contiguous()
+        features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
+        return xyz, features
+
+    def forward(self, pointcloud: torch.Tensor):
+        xyz, features = self._break_up_pc(pointcloud)
+        l_xyz, l_features = [xyz], [features]
+        for sa in self.SA_modules:
+            li_xyz, li_features = sa(l_xyz[-1], l_features[-1])
+            l_xyz.append(li_xyz)
+            l_features.append(li_features)
+        for i in range(-1, -(len(self.FP_modules) + 1), -1):
+            l_features[i - 1] = self.FP_modules[i](l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i])
+        return l_xyz[0], l_features[0]
+
+
+def get_model(input_channels=0, use_xyz=True, cfg=None):
+    return Pointnet2MSG(input_channels=input_channels, use_xyz=use_xyz, cfg=cfg)

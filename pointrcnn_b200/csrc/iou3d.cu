@@ -1,0 +1,320 @@
+// iou3d.cu -- rotated BEV overlap / IoU matrices and bitmask NMS with an on-device greedy scan.
+//
+// Replaces boxes_overlap_bev_gpu / boxes_iou_bev_gpu / nms_gpu / nms_normal_gpu
+// (lib/utils/iou3d/src/iou3d.cpp:31-170 -> iou3d_kernel.cu:223-387).
+//
+// The overlap arithmetic IS the spec (keep masks are compared bit-exactly): corners rotated about the
+// box centre, 4x4 edge intersections (bbox reject, straddle test, line solve with an EPS fallback),
+// corners of one box inside the other (MARGIN 1e-5), centroid, bubble sort by atan2f, fan area / 2.0
+// (iou3d_kernel.cu:34-212).  What changes is everything around it:
+//   * NMS computes only the upper-triangle 64x64 tiles (the scan never reads the others),
+//   * the suppression mask never leaves the device: one CTA runs the greedy scan 64 boxes at a time
+//     (serial resolve on the diagonal word, then a parallel OR of the kept rows into the remaining
+//     columns) and emits the kept indices + count; no cudaMalloc, no 5 MB D2H, no host loop,
+//   * everything runs on the caller's stream.
+#include "common.cuh"
+
+namespace prb {
+
+struct P2 {
+    float x, y;
+};
+__device__ __forceinline__ P2 mk(float x, float y) { P2 p; p.x = x; p.y = y; return p; }
+
+__device__ __forceinline__ float cross2(const P2 &a, const P2 &b) { return a.x * b.y - a.y * b.x; }
+__device__ __forceinline__ float cross3(const P2 &p1, const P2 &p2, const P2 &p0) {
+    return (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
+}
+__device__ __forceinline__ int rect_cross(const P2 &p1, const P2 &p2, const P2 &q1, const P2 &q2) {
+    return min(p1.x, p2.x) <= max(q1.x, q2.x) && min(q1.x, q2.x) <= max(p1.x, p2.x) &&
+           min(p1.y, p2.y) <= max(q1.y, q2.y) && min(q1.y, q2.y) <= max(p1.y, p2.y);
+}
+__device__ __forceinline__ int in_box2d(const float *box, const P2 &p) {
+    const float MARGIN = 1e-5;
+    float center_x = (box[0] + box[2]) / 2;
+    float center_y = (box[1] + box[3]) / 2;
+    float angle_cos = cos(-box[4]), angle_sin = sin(-box[4]);
+    float rot_x = (p.x - center_x) * angle_cos + (p.y - center_y) * angle_sin + center_x;
+    float rot_y = -(p.x - center_x) * angle_sin + (p.y - center_y) * angle_cos + center_y;
+    return (rot_x > box[0] - MARGIN && rot_x < box[2] + MARGIN && rot_y > box[1] - MARGIN && rot_y < box[3] + MARGIN);
+}
+__device__ __forceinline__ int seg_intersection(const P2 &p1, const P2 &p0, const P2 &q1, const P2 &q0, P2 &ans) {
+    const float EPS = 1e-8;
+    if (rect_cross(p0, p1, q0, q1) == 0) return 0;
+    float s1 = cross3(q0, p1, p0);
+    float s2 = cross3(p1, q1, p0);
+    float s3 = cross3(p0, q1, q0);
+    float s4 = cross3(q1, p1, q0);
+    if (!(s1 * s2 > 0 && s3 * s4 > 0)) return 0;
+    float s5 = cross3(q1, p1, p0);
+    if (fabs(s5 - s1) > EPS) {
+        ans.x = (s5 * q0.x - s1 * q1.x) / (s5 - s1);
+        ans.y = (s5 * q0.y - s1 * q1.y) / (s5 - s1);
+    } else {
+        float a0 = p0.y - p1.y, b0 = p1.x - p0.x, c0 = p0.x * p1.y - p1.x * p0.y;
+        float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = q0.x * q1.y - q1.x * q0.y;
+        float D = a0 * b1 - a1 * b0;
+        ans.x = (b0 * c1 - b1 * c0) / D;
+        ans.y = (a1 * c0 - a0 * c1) / D;
+    }
+    return 1;
+}
+__device__ __forceinline__ void rot_center(const P2 &c, const float angle_cos, const float angle_sin, P2 &p) {
+    float new_x = (p.x - c.x) * angle_cos + (p.y - c.y) * angle_sin + c.x;
+    float new_y = -(p.x - c.x) * angle_sin + (p.y - c.y) * angle_cos + c.y;
+    p.x = new_x;
+    p.y = new_y;
+}
+__device__ __forceinline__ int angle_gt(const P2 &a, const P2 &b, const P2 &c) {
+    return atan2(a.y - c.y, a.x - c.x) > atan2(b.y - c.y, b.x - c.x);
+}
+
+// rotated-rectangle intersection area of two [x1,y1,x2,y2,ry] boxes
+__device__ inline float box_overlap(const float *box_a, const float *box_b) {
+    float a_x1 = box_a[0], a_y1 = box_a[1], a_x2 = box_a[2], a_y2 = box_a[3], a_angle = box_a[4];
+    float b_x1 = box_b[0], b_y1 = box_b[1], b_x2 = box_b[2], b_y2 = box_b[3], b_angle = box_b[4];
+    P2 center_a = mk((a_x1 + a_x2) / 2, (a_y1 + a_y2) / 2);
+    P2 center_b = mk((b_x1 + b_x2) / 2, (b_y1 + b_y2) / 2);
+    P2 ca[5], cb[5];
+    ca[0] = mk(a_x1, a_y1); ca[1] = mk(a_x2, a_y1); ca[2] = mk(a_x2, a_y2); ca[3] = mk(a_x1, a_y2);
+    cb[0] = mk(b_x1, b_y1); cb[1] = mk(b_x2, b_y1); cb[2] = mk(b_x2, b_y2); cb[3] = mk(b_x1, b_y2);
+    float a_angle_cos = cos(a_angle), a_angle_sin = sin(a_angle);
+    float b_angle_cos = cos(b_angle), b_angle_sin = sin(b_angle);
+    for (int k = 0; k < 4; k++) {
+        rot_center(center_a, a_angle_cos, a_angle_sin, ca[k]);
+        rot_center(center_b, b_angle_cos, b_angle_sin, cb[k]);
+    }
+    ca[4] = ca[0];
+    cb[4] = cb[0];
+
+    P2 cp[16];
+    P2 poly_center = mk(0, 0);
+    int cnt = 0;
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++)
+            if (seg_intersection(ca[i + 1], ca[i], cb[j + 1], cb[j], cp[cnt])) {
+                poly_center = mk(poly_center.x + cp[cnt].x, poly_center.y + cp[cnt].y);
+                cnt++;
+            }
+    for (int k = 0; k < 4; k++) {
+        if (in_box2d(box_a, cb[k])) {
+            poly_center = mk(poly_center.x + cb[k].x, poly_center.y + cb[k].y);
+            cp[cnt] = cb[k];
+            cnt++;
+        }
+        if (in_box2d(box_b, ca[k])) {
+            poly_center = mk(poly_center.x + ca[k].x, poly_center.y + ca[k].y);
+            cp[cnt] = ca[k];
+            cnt++;
+        }
+    }
+    poly_center.x /= cnt;
+    poly_center.y /= cnt;
+
+    P2 t;
+    for (int j = 0; j < cnt - 1; j++)
+        for (int i = 0; i < cnt - j - 1; i++)
+            if (angle_gt(cp[i], cp[i + 1], poly_center)) {
+                t = cp[i];
+                cp[i] = cp[i + 1];
+                cp[i + 1] = t;
+            }
+
+    float area = 0;
+    for (int k = 0; k < cnt - 1; k++)
+        area += cross2(mk(cp[k].x - cp[0].x, cp[k].y - cp[0].y), mk(cp[k + 1].x - cp[0].x, cp[k + 1].y - cp[0].y));
+    return fabs(area) / 2.0;
+}
+
+__device__ __forceinline__ float iou_bev(const float *box_a, const float *box_b) {
+    const float EPS = 1e-8;
+    float sa = (box_a[2] - box_a[0]) * (box_a[3] - box_a[1]);
+    float sb = (box_b[2] - box_b[0]) * (box_b[3] - box_b[1]);
+    float s_overlap = box_overlap(box_a, box_b);
+    return s_overlap / fmaxf(sa + sb - s_overlap, EPS);
+}
+
+__device__ __forceinline__ float iou_normal(const float *a, const float *b) {
+    const float EPS = 1e-8;
+    float left = fmaxf(a[0], b[0]), right = fminf(a[2], b[2]);
+    float top = fmaxf(a[1], b[1]), bottom = fminf(a[3], b[3]);
+    float width = fmaxf(right - left, 0.f), height = fmaxf(bottom - top, 0.f);
+    float interS = width * height;
+    float Sa = (a[2] - a[0]) * (a[3] - a[1]);
+    float Sb = (b[2] - b[0]) * (b[3] - b[1]);
+    return interS / fmaxf(Sa + Sb - interS, EPS);
+}
+
+// ---------------------------------------------------------------- pairwise matrices
+constexpr int PM_T = 16;
+template <bool IOU>
+__global__ void __launch_bounds__(PM_T * PM_T) pair_matrix_kernel(int num_a, const float *__restrict__ boxes_a, int num_b,
+                                                                  const float *__restrict__ boxes_b, float *__restrict__ out) {
+    __shared__ float sa[PM_T * 5], sb[PM_T * 5];
+    const int a0 = blockIdx.y * PM_T, b0 = blockIdx.x * PM_T;
+    const int t = threadIdx.y * PM_T + threadIdx.x;
+    if (t < PM_T * 5) {
+        int i = a0 * 5 + t;
+        sa[t] = i < num_a * 5 ? boxes_a[i] : 0.f;
+    } else if (t < 2 * PM_T * 5) {
+        int i = b0 * 5 + (t - PM_T * 5);
+        sb[t - PM_T * 5] = i < num_b * 5 ? boxes_b[i] : 0.f;
+    }
+    __syncthreads();
+    const int ai = a0 + threadIdx.y, bi = b0 + threadIdx.x;
+    if (ai >= num_a || bi >= num_b) return;
+    const float *A = sa + threadIdx.y * 5, *Bx = sb + threadIdx.x * 5;
+    out[(size_t)ai * num_b + bi] = IOU ? iou_bev(A, Bx) : box_overlap(A, Bx);
+}
+
+// ---------------------------------------------------------------- NMS mask (upper-triangle tiles)
+template <bool NORMAL>
+__global__ void __launch_bounds__(64) nms_mask_kernel(int n, float thresh, const float *__restrict__ boxes,
+                                                      unsigned long long *__restrict__ mask) {
+    const int row_blk = blockIdx.y, col_blk = blockIdx.x;
+    const int col_blocks = ceil_div(n, 64);
+    const int row_size = min(n - row_blk * 64, 64), col_size = min(n - col_blk * 64, 64);
+    if (row_blk > col_blk) {  // never read by the scan; keep the buffer defined
+        if ((int)threadIdx.x < row_size) mask[(size_t)(row_blk * 64 + threadIdx.x) * col_blocks + col_blk] = 0ull;
+        return;
+    }
+    __shared__ float cbx[64 * 5], rbx[64 * 5];
+    for (int i = threadIdx.x; i < col_size * 5; i += 64) cbx[i] = boxes[(size_t)col_blk * 64 * 5 + i];
+    for (int i = threadIdx.x; i < row_size * 5; i += 64) rbx[i] = boxes[(size_t)row_blk * 64 * 5 + i];
+    __syncthreads();
+    if ((int)threadIdx.x < row_size) {
+        const float *cur = rbx + threadIdx.x * 5;
+        unsigned long long t = 0;
+        const int start = (row_blk == col_blk) ? threadIdx.x + 1 : 0;
+        for (int i = start; i < col_size; i++) {
+            const float v = NORMAL ? iou_normal(cur, cbx + i * 5) : iou_bev(cur, cbx + i * 5);
+            if (v > thresh) t |= 1ULL << i;
+        }
+        mask[(size_t)(row_blk * 64 + threadIdx.x) * col_blocks + col_blk] = t;
+    }
+}
+
+// ---------------------------------------------------------------- greedy scan on the device
+// Same recurrence as the host loop of iou3d.cpp:100-116: box i is kept iff bit i of remv is clear;
+// a kept box ORs its mask row into remv (columns >= its own block).
+constexpr int SCAN_THREADS = 256;
+__global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(int n, const unsigned long long *__restrict__ mask,
+                                                                long long *__restrict__ keep, int *__restrict__ num_out) {
+    extern __shared__ unsigned long long s_remv[];  // col_blocks words
+    __shared__ unsigned long long s_diag[2][64];
+    __shared__ unsigned long long s_kept;
+    __shared__ int s_num;
+    const int tid = threadIdx.x;
+    const int cb = ceil_div(n, 64);
+    for (int j = tid; j < cb; j += SCAN_THREADS) s_remv[j] = 0ull;
+    if (tid == 0) s_num = 0;
+    if (tid < 64 && cb > 0) s_diag[0][tid] = tid < n ? mask[(size_t)tid * cb] : 0ull;
+    __syncthreads();
+    for (int bi = 0; bi < cb; ++bi) {
+        const int par = bi & 1;
+        // prefetch the next block's diagonal words (independent of the scan state)
+        if (tid >= 64 && tid < 128 && bi + 1 < cb) {
+            const int i = (bi + 1) * 64 + (tid - 64);
+            s_diag[par ^ 1][tid - 64] = i < n ? mask[(size_t)i * cb + bi + 1] : 0ull;
+        }
+        if (tid == 0) {
+            unsigned long long cur = s_remv[bi], kept = 0ull;
+            const int lim = min(64, n - bi * 64);
+            int num = s_num;
+            for (int t = 0; t < lim; ++t) {
+                if (!((cur >> t) & 1ull)) {
+                    kept |= 1ull << t;
+                    keep[num++] = (long long)bi * 64 + t;
+                    cur |= s_diag[par][t];
+                }
+            }
+            s_num = num;
+            s_kept = kept;
+        }
+        __syncthreads();
+        const unsigned long long kept = s_kept;
+        for (int j = bi + 1 + tid; j < cb; j += SCAN_THREADS) {
+            unsigned long long acc = s_remv[j], kk = kept;
+            while (kk) {
+                const int t = __ffsll((long long)kk) - 1;
+                kk &= kk - 1;
+                acc |= mask[(size_t)(bi * 64 + t) * cb + j];
+            }
+            s_remv[j] = acc;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) *num_out = s_num;
+}
+
+}  // namespace prb
+
+using namespace prb;
+
+static int pair_matrix(bool iou, int na, const float *a, int nb, const float *b, float *out, void *stream) {
+    PRB_REQUIRE(na >= 0 && nb >= 0 && a && b && out, "boxes matrix: bad arguments");
+    if (na == 0 || nb == 0) return 0;
+    dim3 grid(ceil_div(nb, PM_T), ceil_div(na, PM_T)), block(PM_T, PM_T);
+    if (iou) pair_matrix_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(na, a, nb, b, out);
+    else pair_matrix_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(na, a, nb, b, out);
+    return check_launch("pair_matrix_kernel");
+}
+
+extern "C" int prb_boxes_overlap_bev(int na, const float *a, int nb, const float *b, float *out, void *stream) {
+    return pair_matrix(false, na, a, nb, b, out, stream);
+}
+extern "C" int prb_boxes_iou_bev(int na, const float *a, int nb, const float *b, float *out, void *stream) {
+    return pair_matrix(true, na, a, nb, b, out, stream);
+}
+
+extern "C" int prb_nms_mask(const float *boxes, int n, float thresh, int normal, unsigned long long *mask, void *stream) {
+    PRB_REQUIRE(n >= 0 && boxes && mask, "nms_mask: bad arguments");
+    if (n == 0) return 0;
+    const int cb = ceil_div(n, 64);
+    dim3 grid(cb, cb);
+    if (normal) nms_mask_kernel<true><<<grid, 64, 0, (cudaStream_t)stream>>>(n, thresh, boxes, mask);
+    else nms_mask_kernel<false><<<grid, 64, 0, (cudaStream_t)stream>>>(n, thresh, boxes, mask);
+    return check_launch("nms_mask_kernel");
+}
+
+extern "C" size_t prb_nms_workspace_bytes(int n) {
+    if (n <= 0) return 256;
+    const size_t cb = (size_t)ceil_div(n, 64);
+    return (size_t)n * cb * 8 + (size_t)n * 8 + 256;
+}
+
+extern "C" int prb_nms_device(const float *boxes, int n, float thresh, int normal, long long *keep_dev, int *num_dev,
+                              void *workspace, void *stream) {
+    PRB_REQUIRE(n >= 0 && keep_dev && num_dev && workspace && (n == 0 || boxes), "nms: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) {
+        PRB_CUDA(cudaMemsetAsync(num_dev, 0, sizeof(int), st));
+        return 0;
+    }
+    unsigned long long *mask = (unsigned long long *)workspace;
+    int rc = prb_nms_mask(boxes, n, thresh, normal, mask, stream);
+    if (rc) return rc;
+    const size_t smem = (size_t)ceil_div(n, 64) * 8;
+    PRB_REQUIRE(smem <= 200 * 1024, "nms: %d boxes exceed the single-CTA scan capacity", n);
+    if (smem > 48 * 1024) PRB_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_scan_kernel<<<1, SCAN_THREADS, smem, st>>>(n, mask, keep_dev, num_dev);
+    return check_launch("nms_scan_kernel");
+}
+
+extern "C" int prb_nms_host(const float *boxes, int n, float thresh, int normal, long long *keep_host, int *num_out,
+                            void *workspace, void *stream) {
+    PRB_REQUIRE(n >= 0 && keep_host && num_out && workspace, "nms: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    *num_out = 0;
+    if (n == 0) return 0;
+    const size_t cb = (size_t)ceil_div(n, 64);
+    char *ws = (char *)workspace;
+    long long *keep_dev = (long long *)(ws + (size_t)n * cb * 8);
+    int *num_dev = (int *)(ws + (size_t)n * cb * 8 + (size_t)n * 8);
+    int rc = prb_nms_device(boxes, n, thresh, normal, keep_dev, num_dev, workspace, stream);
+    if (rc) return rc;
+    PRB_CUDA(cudaMemcpyAsync(num_out, num_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PRB_CUDA(cudaMemcpyAsync(keep_host, keep_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    PRB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}

@@ -1,0 +1,138 @@
+// roipool3d.cu -- RoI point pooling (+ optional canonical transform) in one pass per box.
+//
+// Replaces roipool3d_gpu (lib/utils/roipool3d/src/roipool3d.cpp:48-79) -> roipool3dLauncher
+// (roipool3d_kernel.cu:209-237: assign_pts_to_box3d, get_pooled_idx, roipool3d_forward, two
+// cudaMalloc/cudaFree and a (B,N,M) int scratch per call) and, when asked, the canonical transform the
+// caller applies right after (lib/net/rcnn_net.py:146-152, lib/utils/kitti_utils.py:45-63).
+//
+// Semantics (the spec): a point is inside a box iff pt_in_box3d (roipool3d_kernel.cu:14-28) says so;
+// per box the first S inside points in point-index order are copied as rows [x,y,z,features...];
+// 0 < cnt < S pads slot k with slot k % cnt; cnt == 0 sets empty_flag and leaves the rows untouched.
+//
+// Here: one CTA per (scene, box).  Per-box constants (cy, cos, sin, half sizes) are computed once; the
+// CTA streams the scene's xyz 256 points at a time, compacts hits in index order with ballot + a
+// warp-count prefix, stops at S hits, then copies the S rows as one flat, fully coalesced stream.
+// The predicate keeps the reference's arithmetic: double for cy / the h,l,w half sizes and their
+// compares, fp32 FMA shape of the rotation as in the reference's SASS
+//   x_rot = fma(dx, cosa, -(dz*sina)),  z_rot = fma(dz, cosa, dx*sina).
+#include "common.cuh"
+
+namespace prb {
+
+constexpr int RP_THREADS = 256;
+constexpr int RP_WARPS = RP_THREADS / 32;
+
+struct BoxConst {
+    float cx, cy, cz, cosa, sina;
+    double half_h, half_l, half_w;
+};
+
+__device__ __forceinline__ BoxConst make_box(const float *bx) {
+    BoxConst c;
+    const float h = bx[3], w = bx[4], l = bx[5], angle = bx[6];
+    c.cx = bx[0];
+    c.cz = bx[2];
+    c.half_h = (double)h / 2.0;
+    c.half_l = (double)l / 2.0;
+    c.half_w = (double)w / 2.0;
+    c.cy = (float)((double)bx[1] - c.half_h);  // cy = bottom_y - h / 2.0, double then stored to float
+    c.cosa = cosf(angle);
+    c.sina = sinf(angle);
+    return c;
+}
+
+__device__ __forceinline__ bool pt_in_box(const BoxConst &c, float x, float y, float z) {
+    const float dx = x - c.cx, dz = z - c.cz;
+    if (fabsf(dx) > 10.0f || (double)fabsf(y - c.cy) > c.half_h || fabsf(dz) > 10.0f) return false;
+    const float x_rot = __fmaf_rn(dx, c.cosa, -__fmul_rn(dz, c.sina));
+    const float z_rot = __fmaf_rn(dz, c.cosa, __fmul_rn(dx, c.sina));
+    return ((double)x_rot >= -c.half_l) & ((double)x_rot <= c.half_l) & ((double)z_rot >= -c.half_w) &
+           ((double)z_rot <= c.half_w);
+}
+
+__global__ void __launch_bounds__(RP_THREADS) roipool3d_kernel(int N, int M, int C, int S, const float *__restrict__ xyz,
+                                                               const float *__restrict__ boxes3d,
+                                                               const float *__restrict__ pts_feature,
+                                                               float *__restrict__ pooled, int *__restrict__ empty_flag,
+                                                               const float *__restrict__ rois) {
+    extern __shared__ int s_idx[];  // S selected point indices
+    __shared__ int s_wcnt[RP_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int box = blockIdx.x, scene = blockIdx.y;
+    const BoxConst bc = make_box(boxes3d + ((size_t)scene * M + box) * 7);
+    const float *pts = xyz + (size_t)scene * N * 3;
+
+    int cnt = 0;  // uniform across the CTA
+    for (int k0 = 0; k0 < N && cnt < S; k0 += RP_THREADS) {
+        const int k = k0 + tid;
+        bool in = false;
+        if (k < N) in = pt_in_box(bc, pts[(size_t)k * 3], pts[(size_t)k * 3 + 1], pts[(size_t)k * 3 + 2]);
+        const unsigned hits = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) s_wcnt[warp] = __popc(hits);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < RP_WARPS; ++w) {
+            const int c = s_wcnt[w];
+            before += w < warp ? c : 0;
+            total += c;
+        }
+        const int pos = cnt + before + __popc(hits & ((1u << lane) - 1));
+        if (in && pos < S) s_idx[pos] = k;
+        cnt = min(S, cnt + total);
+        __syncthreads();
+    }
+    if (cnt == 0) {
+        if (tid == 0) empty_flag[(size_t)scene * M + box] = 1;
+        return;
+    }
+
+    // canonical transform constants (rcnn_net.py:146-152): xyz -= roi centre, rotate (x,z) by roi ry
+    float rcx = 0.f, rcy = 0.f, rcz = 0.f, rcos = 1.f, rsin = 0.f;
+    if (rois) {
+        const float *r = rois + ((size_t)scene * M + box) * 7;
+        rcx = r[0]; rcy = r[1]; rcz = r[2];
+        rcos = cosf(r[6]); rsin = sinf(r[6]);
+    }
+    const int W = 3 + C;
+    const float *feat = pts_feature + (size_t)scene * N * C;
+    float *dst = pooled + ((size_t)scene * M + box) * (size_t)S * W;
+    // warp per row, lanes along the row: both the feature read and the pooled write are coalesced
+    for (int row = warp; row < S; row += RP_WARPS) {
+        const int k = s_idx[row < cnt ? row : row % cnt];
+        float *o = dst + (size_t)row * W;
+        if (lane < 3) {
+            float v;
+            if (rois) {
+                const float x = pts[(size_t)k * 3] - rcx, y = pts[(size_t)k * 3 + 1] - rcy, z = pts[(size_t)k * 3 + 2] - rcz;
+                // [x z] @ [[cos,-sin],[sin,cos]]^T : x' = x*cos - z*sin, z' = x*sin + z*cos
+                v = lane == 0 ? __fmaf_rn(x, rcos, -__fmul_rn(z, rsin)) : (lane == 1 ? y : __fmaf_rn(x, rsin, __fmul_rn(z, rcos)));
+            } else {
+                v = pts[(size_t)k * 3 + lane];
+            }
+            o[lane] = v;
+        }
+        const float *f = feat + (size_t)k * C;
+        for (int j = lane; j < C; j += 32) o[3 + j] = __ldg(f + j);
+    }
+}
+
+}  // namespace prb
+
+using namespace prb;
+
+extern "C" int prb_roipool3d(int B, int N, int M, int C, int S, const float *xyz, const float *boxes3d,
+                             const float *pts_feature, float *pooled, int *empty_flag, const float *rois_canonical,
+                             void *stream) {
+    PRB_REQUIRE(B >= 0 && N >= 0 && M >= 0 && C >= 0 && S > 0 && xyz && boxes3d && pooled && empty_flag && (C == 0 || pts_feature),
+                "roipool3d: bad arguments");
+    if (B == 0 || M == 0) return 0;
+    PRB_REQUIRE((size_t)S * sizeof(int) <= 200 * 1024, "roipool3d: sampled_pts_num %d too large", S);
+    size_t smem = (size_t)S * sizeof(int);
+    if (smem > 48 * 1024)
+        PRB_CUDA(cudaFuncSetAttribute(roipool3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(M, B);
+    roipool3d_kernel<<<grid, RP_THREADS, smem, (cudaStream_t)stream>>>(N, M, C, S, xyz, boxes3d, pts_feature, pooled,
+                                                                      empty_flag, rois_canonical);
+    return check_launch("roipool3d_kernel");
+}

@@ -1,0 +1,326 @@
+"""Mirror of pointnet2_lib/pointnet2/pointnet2_modules.py (reference :10-160): PointnetSAModuleMSG,
+PointnetSAModule, PointnetFPModule -- same constructor arguments, sub-module names (`groupers`, `mlps`,
+`mlp`) and forward signatures, so checkpoints and lib/net/*.py work unchanged.
+
+Two execution paths per module, chosen per call:
+  fused    (no autograd graph needed, BatchNorm in eval mode or absent, max-pool, power-of-two nsample):
+           FPS(+new_xyz) -> [one ball-query scan for both radii] -> per scale ONE tensor-core kernel that
+           gathers the neighbourhood, runs the whole SharedMLP and max-pools (csrc/mlp_tc.cu).  FP modules:
+           three_nn(+weights) -> ONE kernel that interpolates, concatenates the skip features and runs the MLP.
+  unfused  (training / anything else): the reference's op-by-op sequence on the B200 natives with
+           torch.nn convolutions, full autograd support.
+Set PRB_DISABLE_FUSED=1 to force the unfused path (used by tests to cross-check the two).
+"""
+import ctypes
+import os
+from typing import List
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _cabi as C
+from . import pointnet2_utils
+from . import pytorch_utils as pt_utils
+
+
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+class _FusedMLP:
+    """Device-side image of one SharedMLP for the tensor-core chain: packed weights + folded BN scale/shift.
+    Rebuilt whenever a parameter / buffer version changes (optimizer step, load_state_dict, .to())."""
+
+    def __init__(self):
+        self.key = None
+        self.desc = None
+        self.tensors = None
+        self.c_out = None
+
+    @staticmethod
+    def supported(mlp: nn.Sequential):
+        layers = list(mlp.children())
+        if not 1 <= len(layers) <= 3:
+            return False
+        for layer in layers:
+            names = [k for k, _ in layer.named_children()]
+            if names not in (["conv", "bn", "activation"], ["conv", "activation"]):
+                return False
+            if not isinstance(layer.activation, nn.ReLU):
+                return False
+            conv = layer.conv
+            if tuple(conv.kernel_size) not in ((1, 1), (1,)) or conv.out_channels > 512:
+                return False
+            if "bn" in names and layer.bn.bn.training:
+                return False
+        return True
+
+    def get(self, mlp: nn.Sequential, kind: int, split: int, device):
+        layers = list(mlp.children())
+        tensors = []
+        for layer in layers:
+            tensors += [layer.conv.weight, layer.conv.bias]
+            if hasattr(layer, "bn"):
+                bn = layer.bn.bn
+                tensors += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        key = (kind, split, str(device)) + tuple((id(t), t._version) if t is not None else None for t in tensors)
+        if key == self.key:
+            return self.desc
+        L = len(layers)
+        c_in = layers[0].conv.in_channels
+        c_out = [layer.conv.out_channels for layer in layers]
+        ws, scales, shifts = [], [], []
+        with torch.no_grad():
+            for layer in layers:
+                conv = layer.conv
+                W = conv.weight.detach().reshape(conv.out_channels, -1).float().cpu().contiguous()
+                co = conv.out_channels
+                if hasattr(layer, "bn"):
+                    bn = layer.bn.bn
+                    inv = (bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)).cpu()
+                    sh = (bn.bias.detach().float().cpu() - bn.running_mean.detach().float().cpu() * inv)
+                    if conv.bias is not None:
+                        sh = sh + inv * conv.bias.detach().float().cpu()
+                else:
+                    inv = torch.ones(co)
+                    sh = conv.bias.detach().float().cpu() if conv.bias is not None else torch.zeros(co)
+                pad = _round_up(co, 32) - co
+                ws.append(W)
+                scales.append(F.pad(inv, (0, pad)))
+                shifts.append(F.pad(sh, (0, pad)))
+        lib = C.lib()
+        co_arr = (ctypes.c_int * 3)(*(c_out + [0] * (3 - L)))
+        nbytes = lib.prb_mlp_packed_bytes_ex(kind, split, L, c_in, co_arr)
+        host = np.zeros(nbytes // 4, dtype=np.float32)
+        wp = (ctypes.c_void_p * L)(*[w.data_ptr() for w in ws])
+        C.check(lib.prb_mlp_pack_weights_ex(kind, split, L, c_in, co_arr, wp, host.ctypes.data_as(ctypes.c_void_p)), "mlp_pack")
+        packed = torch.from_numpy(host).to(device)
+        scale = torch.cat(scales).contiguous().to(device)
+        shift = torch.cat(shifts).contiguous().to(device)
+        desc = C.MlpDesc()
+        desc.num_layers, desc.c_in = L, c_in
+        for i in range(3):
+            desc.c_out[i] = c_out[i] if i < L else 0
+        desc.packed_w, desc.scale, desc.shift = packed.data_ptr(), scale.data_ptr(), shift.data_ptr()
+        self.key, self.desc, self.tensors, self.c_out = key, desc, (packed, scale, shift), c_out
+        return desc
+
+
+def _fused_enabled():
+    return os.environ.get("PRB_DISABLE_FUSED", "0") != "1"
+
+
+def _needs_graph(module, *tensors):
+    if not torch.is_grad_enabled():
+        return False
+    if any(t is not None and t.requires_grad for t in tensors):
+        return True
+    return any(p.requires_grad for p in module.parameters())
+
+
+class _PointnetSAModuleBase(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.npoint = None
+        self.groupers = None
+        self.mlps = None
+        self.pool_method = 'max_pool'
+        self._fused = None
+
+    # ------------------------------------------------------------------ fused (tensor-core) path
+    def _can_fuse(self, xyz, features, new_xyz):
+        if not _fused_enabled() or not xyz.is_cuda or self.pool_method != 'max_pool':
+            return False
+        if _needs_graph(self, xyz, features, new_xyz):
+            return False
+        if xyz.dtype != torch.float32 or (features is not None and features.dtype != torch.float32):
+            return False
+        for g, mlp in zip(self.groupers, self.mlps):
+            if not _FusedMLP.supported(mlp):
+                return False
+            if isinstance(g, pointnet2_utils.QueryAndGroup):
+                ns = g.nsample
+                if not g.use_xyz or ns < 4 or ns > 128 or (ns & (ns - 1)):
+                    return False
+            elif isinstance(g, pointnet2_utils.GroupAll):
+                n = xyz.size(1)
+                if not g.use_xyz or n < 4 or n > 128 or (n & (n - 1)):
+                    return False
+            else:
+                return False
+        return True
+
+    def _forward_fused(self, xyz, features, new_xyz):
+        lib = C.lib()
+        B, N, _ = xyz.shape
+        dev = xyz.device
+        xyz = xyz.contiguous()
+        group_all = self.npoint is None
+        if group_all:
+            npoint = 1
+            centres = torch.zeros((B, 1, 3), dtype=torch.float32, device=dev)   # GroupAll: no centre subtraction
+            ret_xyz = None
+        else:
+            if new_xyz is None:
+                _, new_xyz = pointnet2_utils.furthest_point_sample_xyz(xyz, self.npoint)
+            centres = new_xyz.contiguous()
+            npoint = centres.size(1)
+            ret_xyz = new_xyz
+        c_feat = 0 if features is None else features.size(1)
+        feats_pm = pointnet2_utils.transpose_bcn_to_bnc(features.contiguous()) if features is not None else None
+        if self._fused is None or len(self._fused) != len(self.mlps):
+            self._fused = [_FusedMLP() for _ in self.mlps]
+        descs = [f.get(mlp, 0, c_feat, dev) for f, mlp in zip(self._fused, self.mlps)]
+        c_outs = [f.c_out[-1] for f in self._fused]
+        out = torch.empty((B, sum(c_outs), npoint), dtype=torch.float32, device=dev)
+        # neighbour lists
+        if group_all:
+            ar = torch.arange(N, dtype=torch.int32, device=dev).view(1, 1, N).expand(B, 1, N).contiguous()
+            idxs = [ar for _ in self.groupers]
+            nss = [N for _ in self.groupers]
+        elif len(self.groupers) == 2:
+            g0, g1 = self.groupers
+            idxs = pointnet2_utils.ball_query_msg2((g0.radius, g1.radius), (g0.nsample, g1.nsample), xyz, centres)
+            nss = [g0.nsample, g1.nsample]
+        else:
+            idxs = [pointnet2_utils.ball_query(g.radius, g.nsample, xyz, centres) for g in self.groupers]
+            nss = [g.nsample for g in self.groupers]
+        off = 0
+        with torch.cuda.device(dev):
+            for desc, fused, idx, ns in zip(descs, self._fused, idxs, nss):
+                co_arr = (ctypes.c_int * 3)(*(fused.c_out + [0] * (3 - len(fused.c_out))))
+                wsb = lib.prb_sa_workspace_bytes(B, npoint, ns, c_feat, desc.num_layers, co_arr)
+                ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+                C.check(lib.prb_sa_group_mlp_max_ws(B, N, npoint, ns, c_feat, C.ptr(xyz), C.ptr(centres), C.ptr(feats_pm),
+                                                    C.ptr(idx), ctypes.byref(desc), C.ptr(out), out.size(1), off,
+                                                    C.ptr(ws), C.c_size_t(wsb), C.stream()), "sa_group_mlp_max")
+                off += fused.c_out[-1]
+        return ret_xyz, out
+
+    # ------------------------------------------------------------------ reference-shaped path
+    def forward(self, xyz: torch.Tensor, features: torch.Tensor = None, new_xyz=None) -> (torch.Tensor, torch.Tensor):
+        """
+        :param xyz: (B, N, 3) coordinates
+        :param features: (B, C, N) descriptors (channel-major) or None
+        :param new_xyz: optional externally chosen centres (B, npoint, 3)
+        :return: new_xyz (B, npoint, 3), new_features (B, sum_k mlps[k][-1], npoint)
+        """
+        if self._can_fuse(xyz, features, new_xyz):
+            return self._forward_fused(xyz, features, new_xyz)
+
+        new_features_list = []
+        if new_xyz is None and self.npoint is not None:
+            xyz_flipped = xyz.transpose(1, 2).contiguous()
+            new_xyz = pointnet2_utils.gather_operation(
+                xyz_flipped, pointnet2_utils.furthest_point_sample(xyz, self.npoint)).transpose(1, 2).contiguous()
+        for i in range(len(self.groupers)):
+            new_features = self.groupers[i](xyz, new_xyz, features)      # (B, C, npoint, nsample)
+            new_features = self.mlps[i](new_features)                    # (B, mlp[-1], npoint, nsample)
+            if self.pool_method == 'max_pool':
+                new_features = F.max_pool2d(new_features, kernel_size=[1, new_features.size(3)])
+            elif self.pool_method == 'avg_pool':
+                new_features = F.avg_pool2d(new_features, kernel_size=[1, new_features.size(3)])
+            else:
+                raise NotImplementedError
+            new_features_list.append(new_features.squeeze(-1))           # (B, mlp[-1], npoint)
+        return new_xyz, torch.cat(new_features_list, dim=1)
+
+
+class PointnetSAModuleMSG(_PointnetSAModuleBase):
+    """Pointnet set abstraction layer with multiscale grouping"""
+
+    def __init__(self, *, npoint: int, radii: List[float], nsamples: List[int], mlps: List[List[int]], bn: bool = True,
+                 use_xyz: bool = True, pool_method='max_pool', instance_norm=False):
+        super().__init__()
+        assert len(radii) == len(nsamples) == len(mlps)
+        self.npoint = npoint
+        self.groupers = nn.ModuleList()
+        self.mlps = nn.ModuleList()
+        for i in range(len(radii)):
+            self.groupers.append(pointnet2_utils.QueryAndGroup(radii[i], nsamples[i], use_xyz=use_xyz)
+                                 if npoint is not None else pointnet2_utils.GroupAll(use_xyz))
+            mlp_spec = mlps[i]
+            if use_xyz:
+                mlp_spec[0] += 3   # in place, like the reference (pointnet2_modules.py:88-89): callers rely on it
+            self.mlps.append(pt_utils.SharedMLP(mlp_spec, bn=bn, instance_norm=instance_norm))
+        self.pool_method = pool_method
+
+
+class PointnetSAModule(PointnetSAModuleMSG):
+    """Pointnet set abstraction layer"""
+
+    def __init__(self, *, mlp: List[int], npoint: int = None, radius: float = None, nsample: int = None, bn: bool = True,
+                 use_xyz: bool = True, pool_method='max_pool', instance_norm=False):
+        super().__init__(mlps=[mlp], npoint=npoint, radii=[radius], nsamples=[nsample], bn=bn, use_xyz=use_xyz,
+                         pool_method=pool_method, instance_norm=instance_norm)
+
+
+class PointnetFPModule(nn.Module):
+    r"""Propagates the features of one set to another"""
+
+    def __init__(self, *, mlp: List[int], bn: bool = True):
+        super().__init__()
+        self.mlp = pt_utils.SharedMLP(mlp, bn=bn)
+        self._fused = None
+
+    def _can_fuse(self, unknown, known, unknow_feats, known_feats):
+        if not _fused_enabled() or known is None or not unknown.is_cuda:
+            return False
+        if _needs_graph(self, unknown, known, unknow_feats, known_feats):
+            return False
+        if known_feats.dtype != torch.float32 or (unknow_feats is not None and unknow_feats.dtype != torch.float32):
+            return False
+        return _FusedMLP.supported(self.mlp)
+
+    def _forward_fused(self, unknown, known, unknow_feats, known_feats):
+        lib = C.lib()
+        dev = unknown.device
+        B, n, _ = unknown.shape
+        m = known.size(1)
+        c_known = known_feats.size(1)
+        c_skip = 0 if unknow_feats is None else unknow_feats.size(1)
+        _, idx, weight = pointnet2_utils.three_nn_weights(unknown.contiguous(), known.contiguous())
+        known_pm = pointnet2_utils.transpose_bcn_to_bnc(known_feats.contiguous())
+        skip = unknow_feats.contiguous() if unknow_feats is not None else None
+        if self._fused is None:
+            self._fused = _FusedMLP()
+        desc = self._fused.get(self.mlp, 1, c_known, dev)
+        c_out = self._fused.c_out
+        out = torch.empty((B, c_out[-1], n), dtype=torch.float32, device=dev)
+        co_arr = (ctypes.c_int * 3)(*(c_out + [0] * (3 - len(c_out))))
+        with torch.cuda.device(dev):
+            wsb = lib.prb_fp_workspace_bytes(B, n, c_known, c_skip, desc.num_layers, co_arr)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            C.check(lib.prb_fp_interp_mlp_ws(B, n, m, c_known, c_skip, C.ptr(known_pm), C.ptr(idx), C.ptr(weight), C.ptr(skip),
+                                             ctypes.byref(desc), C.ptr(out), C.ptr(ws), C.c_size_t(wsb), C.stream()),
+                    "fp_interp_mlp")
+        return out
+
+    def forward(self, unknown: torch.Tensor, known: torch.Tensor, unknow_feats: torch.Tensor,
+                known_feats: torch.Tensor) -> torch.Tensor:
+        """
+        :param unknown: (B, n, 3) positions to propagate to
+        :param known: (B, m, 3) positions to propagate from (None: broadcast known_feats)
+        :param unknow_feats: (B, C1, n) skip features or None
+        :param known_feats: (B, C2, m)
+        :return: (B, mlp[-1], n)
+        """
+        if self._can_fuse(unknown, known, unknow_feats, known_feats):
+            return self._forward_fused(unknown, known, unknow_feats, known_feats)
+
+        if known is not None:
+            dist, idx = pointnet2_utils.three_nn(unknown, known)
+            dist_recip = 1.0 / (dist + 1e-8)
+            norm = torch.sum(dist_recip, dim=2, keepdim=True)
+            weight = dist_recip / norm
+            interpolated_feats = pointnet2_utils.three_interpolate(known_feats, idx, weight)
+        else:
+            interpolated_feats = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
+        if unknow_feats is not None:
+            new_features = torch.cat([interpolated_feats, unknow_feats], dim=1)   # (B, C2 + C1, n)
+        else:
+            new_features = interpolated_feats
+        new_features = self.mlp(new_features.unsqueeze(-1))
+        return new_features.squeeze(-1)
