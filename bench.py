@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- scenes/s of the RPN PointNet++ backbone forward (4 SA-MSG + 4 FP, tools/cfgs/default.yaml)
+on synthetic 16384x4 clouds, batch 16 per GPU (BASELINE.json configs[1]).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU restatement of the same path on the host cores
+
+One JSON line on rank 0.  `value` = device-resident throughput (CUDA events, max over ranks, L2 flushed between
+steps); `e2e` = same metric through the public module API with pinned host input, H2D and a D2H metric read in the
+timed region; `roofline` = dominant kernel family (CUDA events on the launching stream inside the timed region);
+`cpu_baseline` = oracle port on the host cores over a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+POINTS, CHANNELS, BATCH = 16384, 4, 16
+CONFIG_SEED = 2000  # seed = 1000*config + scene index
+
+
+def make_scenes(first, count):
+    import synth
+    return np.concatenate([synth.u_kitti(1, POINTS, CONFIG_SEED + first + i, channels=CHANNELS) for i in range(count)], 0)
+
+
+def build_model(device):
+    import torch
+    from pointrcnn_b200.backbone import Pointnet2MSG
+    torch.manual_seed(0)
+    net = Pointnet2MSG(input_channels=CHANNELS - 3).eval()
+    g = torch.Generator().manual_seed(1)
+    for m in net.modules():   # non-trivial eval-mode BN
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+    return net.to(device)
+
+
+def mlp_flops_per_scene(net):
+    """2*MAC of every SA / FP SharedMLP per scene (algorithmic FLOPs of the tensor-core kernels)"""
+    sa = fp = 0
+    n = POINTS
+    for mod in net.SA_modules:
+        for grouper, mlp in zip(mod.groupers, mod.mlps):
+            rows = mod.npoint * grouper.nsample
+            sa += 2 * rows * sum(l.conv.in_channels * l.conv.out_channels for l in mlp.children())
+    npts = [POINTS] + [m.npoint for m in net.SA_modules]
+    for k, mod in enumerate(net.FP_modules):
+        fp += 2 * npts[k] * sum(l.conv.in_channels * l.conv.out_channels for l in mod.mlp.children())
+    del n
+    return sa, fp
+
+
+def folded_specs(net):
+    from oracle import oracle as O
+
+    def fold(mlp):
+        out = []
+        for layer in mlp.children():
+            b = layer.bn.bn
+            bn = dict(weight=b.weight.detach().cpu().numpy(), bias=b.bias.detach().cpu().numpy(),
+                      running_mean=b.running_mean.cpu().numpy(), running_var=b.running_var.cpu().numpy(), eps=b.eps)
+            out.append(O.fold_bn(layer.conv.weight.detach().cpu().numpy(), None, bn))
+        return out
+    sa = [dict(npoint=m.npoint, radii=[g.radius for g in m.groupers], nsamples=[g.nsample for g in m.groupers],
+               mlps=[fold(x) for x in m.mlps]) for m in net.SA_modules]
+    fp = [fold(m.mlp) for m in net.FP_modules]
+    return sa, fp
+
+
+def cpu_backbone(pc, sa, fp):
+    """the CPU restatement of lib/net/pointnet2_msg.py:56-70 on top of the oracle ops"""
+    from oracle import oracle as O
+    xyz = np.ascontiguousarray(pc[..., :3])
+    feats = np.ascontiguousarray(np.transpose(pc[..., 3:], (0, 2, 1))) if pc.shape[-1] > 3 else None
+    l_xyz, l_f = [xyz], [feats]
+    for s in sa:
+        nx, nf, _ = O.sa_module_msg(l_xyz[-1], l_f[-1], s["npoint"], s["radii"], s["nsamples"], s["mlps"])
+        l_xyz.append(nx)
+        l_f.append(nf)
+    for i in range(-1, -(len(fp) + 1), -1):
+        l_f[i - 1] = O.fp_module(l_xyz[i - 1], l_xyz[i], l_f[i - 1], l_f[i], fp[i])
+    return l_f[0]
+
+
+def time_cpu(net_cpu_specs, scenes, steps=1, warmup=0):
+    sa, fp = net_cpu_specs
+    pc = make_scenes(0, scenes)
+    for _ in range(warmup):
+        cpu_backbone(pc, sa, fp)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_backbone(pc, sa, fp)
+    dt = (time.perf_counter() - t0) / steps
+    return scenes / dt, dt
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained"), src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference has no CPU implementation of this path; the arm times the CPU restatement
+    (oracle port) with all host threads on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import oracle as O
+    net = build_model("cpu")
+    specs = folded_specs(net)
+    scenes = args.cpu_scenes
+    val, dt = time_cpu(specs, scenes, steps=max(1, args.steps), warmup=min(1, args.warmup))
+    cores = O.num_threads()
+    line = {"impl": "reference", "metric": "scenes/sec RPN backbone fwd (16384 pts)", "value": val, "unit": "scenes/s",
+            "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": min(1, args.warmup), "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "RPN PointNet++ backbone fwd, 4 SA-MSG + 4 FP, 16384x4 pts (BASELINE configs[1])",
+                       "per_step": "%d scenes (bounded sample)" % scenes},
+            "cpu_baseline": {"value": val, "unit": "scenes/s", "cores": cores, "kind": "port",
+                             "sample": "%d scenes per step, oracle/pointops_oracle.c (OpenMP) + numpy fp32 MLP" % scenes},
+            "e2e": {"value": val, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    del torch
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-scenes", type=int, default=2, help="scenes per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-kernel-family table as JSON here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from pointrcnn_b200 import _cabi, prof
+    from pointrcnn_b200.parallel_utils import max_over_ranks
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, K = max(3, args.warmup), max(1, args.steps)
+
+    net = build_model(dev)
+    host_np = make_scenes(rank * BATCH, BATCH)                      # this rank's 16 scenes (weak scaling)
+    host = torch.from_numpy(host_np).pin_memory()
+    pc = host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    with torch.no_grad():
+        for _ in range(W):
+            net(pc)
+        torch.cuda.synchronize()
+
+        # ---------------- device-resident throughput
+        sampler = ClockSampler(local) if rank == 0 else None
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        launches0 = _cabi.launch_count()
+        prof.enable()
+        barrier(); torch.cuda.synchronize()
+        for a, b in ev:
+            flush.fill_(1.0)          # L2 flush between timed iterations (not timed)
+            a.record()
+            xyz, feats = net(pc)
+            b.record()
+        torch.cuda.synchronize(); barrier()
+        prof.disable()
+        launches = (_cabi.launch_count() - launches0) // K
+        fam = prof.collect()
+        clocks = sampler.stop() if sampler else None
+        ms = sum(a.elapsed_time(b) for a, b in ev) / K
+        ms = max_over_ranks(ms, device=dev)
+
+        # ---------------- end to end: pinned host input -> H2D -> backbone -> metric -> D2H
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        barrier(); torch.cuda.synchronize()
+        for a, b in ev2:
+            flush.fill_(1.0)
+            a.record()
+            x = host.to(dev, non_blocking=True)
+            _, f = net(x)
+            metric = f.mean(dim=(1, 2)).cpu()                       # per-scene feature mean: the step's result
+            b.record()
+        torch.cuda.synchronize(); barrier()
+        ms_e2e = sum(a.elapsed_time(b) for a, b in ev2) / K
+        ms_e2e = max_over_ranks(ms_e2e, device=dev)
+        d2h_bytes = metric.numel() * 4
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    pk = peaks()
+    sa_flops, fp_flops = mlp_flops_per_scene(net)
+    tf32_peak = pk["bf16"] / 2.0          # tcgen05 kind::tf32 runs at half the bf16 rate; bf16 figure is the measured one
+    fam_ms = {k: v[0] / K for k, v in fam.items()}
+    kernels = []
+    if "sa_mlp" in fam_ms:
+        kernels.append({"name": "mlp_chain_kernel (SA: gather + SharedMLP + max-pool)", "ms_per_step": fam_ms["sa_mlp"],
+                        "bound": "tensor", "achieved": sa_flops * BATCH / (fam_ms["sa_mlp"] * 1e-3) / 1e12, "peak": tf32_peak,
+                        "unit": "TFLOP/s"})
+    if "fp_mlp" in fam_ms:
+        kernels.append({"name": "mlp_chain_kernel (FP: interpolate + SharedMLP)", "ms_per_step": fam_ms["fp_mlp"],
+                        "bound": "tensor", "achieved": fp_flops * BATCH / (fam_ms["fp_mlp"] * 1e-3) / 1e12, "peak": tf32_peak,
+                        "unit": "TFLOP/s"})
+    if "fps" in fam_ms:
+        rounds = sum(m.npoint - 1 for m in net.SA_modules)
+        npts = [POINTS] + [m.npoint for m in net.SA_modules]
+        fps_bytes = sum(npts[i] * 12 + npts[i + 1] * 16 for i in range(len(net.SA_modules))) * BATCH
+        kernels.append({"name": "fps_rank_kernel (dependency chain: %d serial rounds/scene)" % rounds, "ms_per_step": fam_ms["fps"],
+                        "bound": "hbm", "achieved": fps_bytes / (fam_ms["fps"] * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                        "us_per_round": fam_ms["fps"] * 1e3 / rounds})
+    for name in ("ball_query", "three_nn", "transpose"):
+        if name in fam_ms:
+            kernels.append({"name": name, "ms_per_step": fam_ms[name]})
+    for k in kernels:
+        if "achieved" in k:
+            k["frac"] = k["achieved"] / k["peak"]
+        k["share"] = k["ms_per_step"] / ms
+    dom = max((k for k in kernels if "achieved" in k), key=lambda k: k["ms_per_step"], default=None)
+    roofline = None
+    if dom:
+        roofline = {"kernel": dom["name"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
+                    "frac": dom["frac"], "traffic": None, "peak_source": pk["src"] + (" bf16/2" if dom["bound"] == "tensor" else " copy"),
+                    "share_of_step": dom["share"]}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        cval, cdt = time_cpu(folded_specs(net.cpu()), args.cpu_scenes)
+        cpu = {"value": cval, "unit": "scenes/s", "cores": O.num_threads(), "kind": "port",
+               "sample": "%d scenes of the same workload, %.1f s (oracle C/OpenMP ops + numpy fp32 MLP)" % (args.cpu_scenes, cdt)}
+
+    scenes = BATCH * world
+    line = {"metric": "scenes/sec RPN backbone fwd (16384 pts)", "value": scenes / (ms * 1e-3), "unit": "scenes/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (tf32 tensor-core MLP, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": "RPN PointNet++ backbone fwd: 4 SA-MSG + 4 FP (tools/cfgs/default.yaml), 16384x4 uniform KITTI-scope "
+                                   "points, eval-mode BN (BASELINE configs[1])", "batch_per_gpu": BATCH, "global_batch": scenes,
+                       "parallelism": "dp%d (scene sharding, no data-path collective)" % world, "l2": "256 MB flush write between timed steps"},
+            "e2e": {"value": scenes / (ms_e2e * 1e-3), "unit": "scenes/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
+    if args.profile_out:
+        json.dump(line, open(args.profile_out, "w"), indent=1)
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

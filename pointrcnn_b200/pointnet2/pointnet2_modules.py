@@ -21,6 +21,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _cabi as C
+from .. import prof
 from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
 
@@ -193,9 +194,10 @@ class _PointnetSAModuleBase(nn.Module):
                 co_arr = (ctypes.c_int * 3)(*(fused.c_out + [0] * (3 - len(fused.c_out))))
                 wsb = lib.prb_sa_workspace_bytes(B, npoint, ns, c_feat, desc.num_layers, co_arr)
                 ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-                C.check(lib.prb_sa_group_mlp_max_ws(B, N, npoint, ns, c_feat, C.ptr(xyz), C.ptr(centres), C.ptr(feats_pm),
-                                                    C.ptr(idx), ctypes.byref(desc), C.ptr(out), out.size(1), off,
-                                                    C.ptr(ws), C.c_size_t(wsb), C.stream()), "sa_group_mlp_max")
+                with prof.region("sa_mlp"):
+                    C.check(lib.prb_sa_group_mlp_max_ws(B, N, npoint, ns, c_feat, C.ptr(xyz), C.ptr(centres), C.ptr(feats_pm),
+                                                        C.ptr(idx), ctypes.byref(desc), C.ptr(out), out.size(1), off,
+                                                        C.ptr(ws), C.c_size_t(wsb), C.stream()), "sa_group_mlp_max")
                 off += fused.c_out[-1]
         return ret_xyz, out
 
@@ -293,9 +295,10 @@ class PointnetFPModule(nn.Module):
         with torch.cuda.device(dev):
             wsb = lib.prb_fp_workspace_bytes(B, n, c_known, c_skip, desc.num_layers, co_arr)
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-            C.check(lib.prb_fp_interp_mlp_ws(B, n, m, c_known, c_skip, C.ptr(known_pm), C.ptr(idx), C.ptr(weight), C.ptr(skip),
-                                             ctypes.byref(desc), C.ptr(out), C.ptr(ws), C.c_size_t(wsb), C.stream()),
-                    "fp_interp_mlp")
+            with prof.region("fp_mlp"):
+                C.check(lib.prb_fp_interp_mlp_ws(B, n, m, c_known, c_skip, C.ptr(known_pm), C.ptr(idx), C.ptr(weight), C.ptr(skip),
+                                                 ctypes.byref(desc), C.ptr(out), C.ptr(ws), C.c_size_t(wsb), C.stream()),
+                        "fp_interp_mlp")
         return out
 
     def forward(self, unknown: torch.Tensor, known: torch.Tensor, unknow_feats: torch.Tensor,

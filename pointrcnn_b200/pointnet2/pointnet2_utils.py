@@ -13,6 +13,7 @@ import torch.nn as nn
 from torch.autograd import Function
 
 from .. import _cabi as C
+from .. import prof
 from ..ext import pointnet2_cuda as pointnet2
 
 
@@ -47,7 +48,7 @@ def furthest_point_sample_xyz(xyz: torch.Tensor, npoint: int):
     idx = _cuda_empty((B, npoint), torch.int32, xyz)
     new_xyz = _cuda_empty((B, npoint, 3), torch.float32, xyz)
     temp = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device)
-    with torch.cuda.device(xyz.device):
+    with torch.cuda.device(xyz.device), prof.region("fps"):
         C.check(C.lib().prb_furthest_point_sampling(B, N, int(npoint), C.ptr(xyz), C.ptr(temp), C.ptr(idx), C.ptr(new_xyz),
                                                     C.stream()), "furthest_point_sampling")
     return idx, new_xyz
@@ -109,7 +110,7 @@ def three_nn_weights(unknown: torch.Tensor, known: torch.Tensor):
     dist2 = _cuda_empty((B, N, 3), torch.float32, unknown)
     idx = _cuda_empty((B, N, 3), torch.int32, unknown)
     weight = _cuda_empty((B, N, 3), torch.float32, unknown)
-    with torch.cuda.device(unknown.device):
+    with torch.cuda.device(unknown.device), prof.region("three_nn"):
         C.check(C.lib().prb_three_nn(B, N, int(m), C.ptr(unknown), C.ptr(known), C.ptr(dist2), C.ptr(idx), C.ptr(weight),
                                      C.stream()), "three_nn")
     return dist2, idx, weight
@@ -194,7 +195,7 @@ def ball_query_msg2(radii, nsamples, xyz: torch.Tensor, new_xyz: torch.Tensor):
     npoint = new_xyz.size(1)
     idx0 = torch.zeros((B, npoint, nsamples[0]), dtype=torch.int32, device=xyz.device)
     idx1 = torch.zeros((B, npoint, nsamples[1]), dtype=torch.int32, device=xyz.device)
-    with torch.cuda.device(xyz.device):
+    with torch.cuda.device(xyz.device), prof.region("ball_query"):
         C.check(C.lib().prb_ball_query_msg2(B, N, npoint, C.c_float(radii[0]), int(nsamples[0]), C.c_float(radii[1]),
                                             int(nsamples[1]), C.ptr(new_xyz), C.ptr(xyz), C.ptr(idx0), C.ptr(idx1), C.stream()),
                 "ball_query_msg2")
@@ -206,7 +207,7 @@ def transpose_bcn_to_bnc(t: torch.Tensor) -> torch.Tensor:
     assert t.is_contiguous()
     B, Cc, N = t.size()
     out = _cuda_empty((B, N, Cc), torch.float32, t)
-    with torch.cuda.device(t.device):
+    with torch.cuda.device(t.device), prof.region("transpose"):
         C.check(C.lib().prb_transpose_bcn_to_bnc(B, Cc, N, C.ptr(t), C.ptr(out), C.stream()), "transpose")
     return out
 

@@ -1,0 +1,260 @@
+"""GPU tests of the tcgen05 MLP chain and of the fused SA / FP module paths.
+
+Tolerances.  The reference's MLP is torch.nn.Conv2d (cuDNN, TF32 allowed by torch's default) and is not
+pinned by any reference test.  Two checks:
+  tight : against an fp32 numpy evaluation whose OPERANDS are rounded to TF32 exactly as the kernel does
+          (weights at pack time, activations per layer) -- only the fp32 accumulation order differs, so any
+          layout / descriptor / pipeline bug shows up as a gross error.  |err| <= 2e-4 * (1 + |ref|).
+  loose : against the plain fp32 oracle: |err| <= 1e-2 * max|ref| (three chained TF32 layers).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+from pointrcnn_b200 import _cabi as C  # noqa: E402
+from pointrcnn_b200.backbone import Pointnet2MSG  # noqa: E402
+from pointrcnn_b200.pointnet2 import pointnet2_modules as pm  # noqa: E402
+
+
+def tf32(x):
+    """cvt.rna.tf32.f32 on a numpy array"""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).copy()
+    finite = (u & 0x7F800000) != 0x7F800000
+    u[finite] += 0x1000
+    u &= 0xFFFFE000
+    return u.view(np.float32)
+
+
+def mlp_tf32_ref(x, layers):
+    h = x.astype(np.float32)
+    for W, sc, sh in layers:
+        h = tf32(h) @ tf32(W).T
+        h = np.maximum(h * sc[None] + sh[None], 0).astype(np.float32)
+    return h
+
+
+def _rand_layers(rng, dims):
+    layers = []
+    for ci, co in zip(dims[:-1], dims[1:]):
+        W = (rng.standard_normal((co, ci)) * np.sqrt(2.0 / ci)).astype(np.float32)
+        sc = rng.uniform(0.5, 1.5, co).astype(np.float32)
+        sh = rng.normal(0, 0.2, co).astype(np.float32)
+        layers.append((W, sc, sh))
+    return layers
+
+
+def _desc(layers, kind, split, dev):
+    L = len(layers)
+    c_in = layers[0][0].shape[1]
+    c_out = [l[0].shape[0] for l in layers]
+    lib = C.lib()
+    co = (ctypes.c_int * 3)(*(c_out + [0] * (3 - L)))
+    nbytes = lib.prb_mlp_packed_bytes_ex(kind, split, L, c_in, co)
+    host = np.zeros(nbytes // 4, dtype=np.float32)
+    ws = [np.ascontiguousarray(l[0]) for l in layers]
+    wp = (ctypes.c_void_p * L)(*[w.ctypes.data for w in ws])
+    C.check(lib.prb_mlp_pack_weights_ex(kind, split, L, c_in, co, wp, host.ctypes.data_as(ctypes.c_void_p)), "pack")
+    pad = lambda v: np.pad(v, (0, (-len(v)) % 32))
+    keep = [torch.from_numpy(host).to(dev),
+            torch.from_numpy(np.concatenate([pad(l[1]) for l in layers])).to(dev),
+            torch.from_numpy(np.concatenate([pad(l[2]) for l in layers])).to(dev)]
+    d = C.MlpDesc()
+    d.num_layers, d.c_in = L, c_in
+    for i in range(3):
+        d.c_out[i] = c_out[i] if i < L else 0
+    d.packed_w, d.scale, d.shift = keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr()
+    return d, keep, co
+
+
+ROW_CASES = [
+    (128, [32, 32]),                 # one tile, one chunk, one K-step group: the smallest possible UMMA
+    (128, [64, 64]),
+    (1000, [40, 48]),                # K and N not multiples of 32, tail tile
+    (4096, [99, 64, 64, 128]),       # SA2 scale 0 shape
+    (3000, [259, 128, 196, 256]),    # SA3: N padded 196 -> 224
+    (2000, [515, 256, 256, 512]),    # SA4 s0: split after two layers (N=512 needs the whole TMEM)
+    (1500, [515, 256, 384, 512]),    # SA4 s1: every layer its own launch
+    (20000, [257, 128, 128]),        # FP0, many tiles per CTA (ring wrap-around, phase bits)
+    (700, [1536, 512, 512]),         # FP3: two N halves per K chunk
+]
+
+
+@pytest.mark.parametrize("rows,dims", ROW_CASES)
+def test_mlp_rows_tcgen05(cuda, rows, dims):
+    rng = np.random.default_rng(rows + len(dims))
+    layers = _rand_layers(rng, dims)
+    x = rng.standard_normal((rows, dims[0])).astype(np.float32)
+    d, keep, co = _desc(layers, 2, 0, cuda)
+    lib = C.lib()
+    np_last = (dims[-1] + 31) // 32 * 32
+    out = torch.full((rows, np_last), float("nan"), device=cuda)
+    wsb = lib.prb_rows_workspace_bytes(C.c_long(rows), dims[0], len(layers), co)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=cuda)
+    xt = torch.from_numpy(x).to(cuda)
+    C.check(lib.prb_mlp_rows(C.c_long(rows), dims[0], C.ptr(xt), ctypes.byref(d), C.ptr(out), np_last, C.ptr(ws),
+                             C.c_size_t(wsb), C.stream()), "mlp_rows")
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()[:, :dims[-1]]
+    assert np.isfinite(got).all()
+    tight = mlp_tf32_ref(x, layers)
+    err = np.abs(got - tight)
+    assert (err <= 2e-4 * (1 + np.abs(tight))).all(), "tight check failed: max err %g" % err.max()
+    loose = O.shared_mlp(x, layers)
+    assert np.abs(got - loose).max() <= 1e-2 * np.abs(loose).max()
+    if np_last > dims[-1]:
+        assert np.count_nonzero(out.cpu().numpy()[:, dims[-1]:]) == 0, "padding channels must be exactly zero"
+
+
+# ------------------------------------------------------------------------------------------------ modules
+def _randomise_bn(module, seed):
+    g = torch.Generator().manual_seed(seed)
+    for m in module.modules():
+        if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d)):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+
+
+def _folded(mlp):
+    layers = []
+    for layer in mlp.children():
+        conv = layer.conv
+        bn = None
+        if hasattr(layer, "bn"):
+            b = layer.bn.bn
+            bn = dict(weight=b.weight.detach().cpu().numpy(), bias=b.bias.detach().cpu().numpy(),
+                      running_mean=b.running_mean.cpu().numpy(), running_var=b.running_var.cpu().numpy(), eps=b.eps)
+        layers.append(O.fold_bn(conv.weight.detach().cpu().numpy(), None if conv.bias is None else conv.bias.detach().cpu().numpy(), bn))
+    return layers
+
+
+def _unfused(fn):
+    import os
+    os.environ["PRB_DISABLE_FUSED"] = "1"
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        return fn()
+    finally:
+        os.environ["PRB_DISABLE_FUSED"] = "0"
+        torch.backends.cudnn.allow_tf32 = old
+
+
+SA_CASES = [
+    # npoint, radii, nsamples, mlps, c_feat, N, cloud
+    (256, [0.1, 0.2], [16, 32], [[16, 16, 32], [32, 32, 64]], 0, 2048, "cube"),      # SA1-like, no features
+    (512, [0.1], [32], [[16, 32]], 1, 4096, "cube"),                                 # BASELINE config 1 shape (C0=1)
+    (128, [0.2, 0.4], [16, 32], [[64, 64, 128], [64, 96, 128]], 96, 1024, "cube"),   # SA2
+    (64, [0.3, 0.5], [16, 32], [[128, 196, 256], [128, 196, 256]], 256, 256, "cube"),  # SA3
+    (16, [0.5, 0.9], [16, 32], [[256, 256, 512], [256, 384, 512]], 512, 64, "cube"),   # SA4 (split launches)
+    (32, [0.4], [64], [[128, 128, 256]], 128, 128, "cube"),                          # RCNN SA2 (nsample 64)
+]
+
+
+@pytest.mark.parametrize("npoint,radii,nsamples,mlps,c_feat,N,kind", SA_CASES)
+def test_sa_module_fused_vs_unfused_vs_oracle(cuda, npoint, radii, nsamples, mlps, c_feat, N, kind):
+    torch.manual_seed(0)
+    B = 2
+    spec = [[c_feat] + list(m) for m in mlps]
+    mod = pm.PointnetSAModuleMSG(npoint=npoint, radii=list(radii), nsamples=list(nsamples), mlps=spec, bn=True).to(cuda).eval()
+    _randomise_bn(mod, 1)
+    xyz = synth.u_cube(B, N, 5 + N)
+    feats = np.random.default_rng(2).standard_normal((B, c_feat, N)).astype(np.float32) if c_feat else None
+    x = torch.from_numpy(xyz).to(cuda)
+    f = torch.from_numpy(feats).to(cuda) if c_feat else None
+    with torch.no_grad():
+        new_xyz, out = mod(x, f)
+        ref_xyz, ref_out = _unfused(lambda: mod(x, f))
+    assert torch.equal(new_xyz, ref_xyz)
+    assert out.shape == ref_out.shape == (B, sum(m[-1] for m in mlps), npoint)
+    scale = ref_out.abs().max().item()
+    assert (out - ref_out).abs().max().item() <= 1e-2 * scale, "fused SA differs from the op-by-op fp32 path"
+    # CPU oracle (fp32) of the whole module
+    o_xyz, o_out, _ = O.sa_module_msg(xyz, feats, npoint, radii, nsamples, [_folded(m) for m in mod.mlps])
+    assert np.array_equal(new_xyz.cpu().numpy(), o_xyz)
+    assert np.abs(out.cpu().numpy() - o_out).max() <= 1e-2 * np.abs(o_out).max()
+
+
+def test_sa_module_group_all_and_no_bn(cuda):
+    torch.manual_seed(1)
+    B, N, c_feat = 6, 32, 256
+    mod = pm.PointnetSAModule(mlp=[c_feat, 256, 256, 512], npoint=None, radius=None, nsample=None, bn=False).to(cuda).eval()
+    for p in mod.parameters():
+        if p.dim() == 1:
+            p.data.normal_(0, 0.1)   # non-zero conv biases
+    xyz = torch.from_numpy(synth.u_cube(B, N, 3)).to(cuda)
+    f = torch.randn(B, c_feat, N, device=cuda)
+    with torch.no_grad():
+        nx, out = mod(xyz, f)
+        rx, ref = _unfused(lambda: mod(xyz, f))
+    assert nx is None and rx is None
+    assert out.shape == ref.shape == (B, 512, 1)
+    assert (out - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+
+
+FP_CASES = [
+    (256, 64, 1024, 512, [512, 512]),     # FP3 (split: N=512 twice)
+    (1024, 256, 512, 256, [512, 512]),    # FP2
+    (4096, 1024, 512, 96, [256, 256]),    # FP1
+    (2048, 512, 256, 1, [128, 128]),      # FP0 with intensity
+    (2048, 512, 256, 0, [128, 128]),      # FP0 without skip features
+    (200, 50, 64, 3, [64]),               # n not a multiple of 128 -> tiles straddle scenes
+]
+
+
+@pytest.mark.parametrize("n,m,c_known,c_skip,mlp", FP_CASES)
+def test_fp_module_fused_vs_unfused_vs_oracle(cuda, n, m, c_known, c_skip, mlp):
+    torch.manual_seed(2)
+    B = 2
+    mod = pm.PointnetFPModule(mlp=[c_known + c_skip] + list(mlp)).to(cuda).eval()
+    _randomise_bn(mod, 3)
+    unknown = synth.u_cube(B, n, 7 + n)
+    known = np.ascontiguousarray(unknown[:, ::n // m][:, :m])
+    rng = np.random.default_rng(4)
+    kf = rng.standard_normal((B, c_known, m)).astype(np.float32)
+    sf = rng.standard_normal((B, c_skip, n)).astype(np.float32) if c_skip else None
+    tu, tk, tkf = torch.from_numpy(unknown).to(cuda), torch.from_numpy(known).to(cuda), torch.from_numpy(kf).to(cuda)
+    tsf = torch.from_numpy(sf).to(cuda) if c_skip else None
+    with torch.no_grad():
+        out = mod(tu, tk, tsf, tkf)
+        ref = _unfused(lambda: mod(tu, tk, tsf, tkf))
+    assert out.shape == ref.shape == (B, mlp[-1], n)
+    assert (out - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    o = O.fp_module(unknown, known, sf, kf, _folded(mod.mlp))
+    assert np.abs(out.cpu().numpy() - o).max() <= 1e-2 * np.abs(o).max()
+
+
+def test_backbone_fused_vs_unfused(cuda):
+    torch.manual_seed(3)
+    net = Pointnet2MSG(input_channels=1).to(cuda).eval()
+    _randomise_bn(net, 5)
+    pc = torch.from_numpy(synth.u_kitti(2, 16384, 99, channels=4)).to(cuda)
+    with torch.no_grad():
+        xyz, feats = net(pc)
+        rxyz, rfeats = _unfused(lambda: net(pc))
+    assert feats.shape == (2, 128, 16384)
+    assert torch.equal(xyz, rxyz)
+    rel = (feats - rfeats).abs().max().item() / rfeats.abs().max().item()
+    assert rel <= 2e-2, "backbone output differs: %g" % rel
+
+
+def test_training_path_autograd(cuda):
+    """grad-enabled calls take the op-by-op path and back-propagate through the B200 scatter kernels"""
+    torch.manual_seed(4)
+    sa = pm.PointnetSAModuleMSG(npoint=64, radii=[0.3], nsamples=[16], mlps=[[8, 16, 32]], bn=True).to(cuda).train()
+    fp = pm.PointnetFPModule(mlp=[32 + 8, 16]).to(cuda).train()
+    xyz = torch.from_numpy(synth.u_cube(2, 512, 1)).to(cuda)
+    f = torch.randn(2, 8, 512, device=cuda, requires_grad=True)
+    nx, nf = sa(xyz, f)
+    up = fp(xyz, nx, f, nf)
+    up.sum().backward()
+    assert f.grad is not None and torch.isfinite(f.grad).all() and f.grad.abs().sum() > 0
+    assert all(p.grad is not None for p in sa.parameters())

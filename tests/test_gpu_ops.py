@@ -1,0 +1,307 @@
+"""GPU parity tests (run with -m gpu on the B200 box): every native of the C ABI against
+  (1) the CPU oracle (oracle/pointops_oracle.c, bit-exact for index work), and
+  (2) the reference's own CUDA kernels rebuilt for sm_100a (oracle/_ref) when that library is present.
+Calls go through the reference-named extension modules / Python wrappers, i.e. through the C ABI.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import oracle as O
+from oracle import refgpu as R
+
+pytestmark = pytest.mark.gpu
+
+from pointrcnn_b200.ext import iou3d_cuda, roipool3d_cuda  # noqa: E402
+from pointrcnn_b200.iou3d import iou3d_utils  # noqa: E402
+from pointrcnn_b200.pointnet2 import pointnet2_utils as pu  # noqa: E402
+from pointrcnn_b200.roipool3d import roipool3d_utils  # noqa: E402
+
+HAVE_REF = R.available()
+
+
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+# ------------------------------------------------------------------------------------------------ FPS
+FPS_CASES = [
+    # (B, N, M, cloud)            what it exercises
+    (2, 16384, 4096, "kitti"),    # cluster of 8 CTAs, 4095 rounds (RPN SA1 shape)
+    (3, 4096, 1024, "kitti"),     # single CTA 512x8
+    (3, 1024, 256, "cube"),
+    (5, 256, 64, "kitti"),
+    (7, 512, 128, "dup"),         # RCNN SA1 shape, duplicate-heavy (tie rule)
+    (7, 128, 32, "dup"),
+    (2, 300, 50, "kitti"),        # n not a power of two: S=256, Q=2, holes in the rank space
+    (2, 1500, 100, "dup"),        # S=1024, Q=2
+    (1, 20000, 64, "kitti"),      # rank copy does not fit shared memory
+    (2, 16384, 300, "dup"),       # cluster + ties
+    (1, 70, 70, "cube"),          # m == n, tiny
+]
+
+
+def _cloud(kind, B, N, seed):
+    return {"kitti": synth.u_kitti, "cube": synth.u_cube, "dup": synth.dup_cloud}[kind](B, N, seed)
+
+
+@pytest.mark.parametrize("B,N,M,kind", FPS_CASES)
+def test_fps_index_exact(cuda, B, N, M, kind):
+    xyz = _cloud(kind, B, N, 11 + N)
+    want, want_temp = O.fps(xyz, M, return_temp=True)
+    x = T(xyz, cuda)
+    got = pu.furthest_point_sample(x, M)
+    assert got.dtype == torch.int32 and tuple(got.shape) == (B, M)
+    assert np.array_equal(got.cpu().numpy(), want), "FPS indices differ from the oracle"
+    idx2, new_xyz = pu.furthest_point_sample_xyz(x, M)
+    assert np.array_equal(idx2.cpu().numpy(), want)
+    exp_xyz = np.stack([xyz[b][want[b]] for b in range(B)])
+    assert np.array_equal(new_xyz.cpu().numpy(), exp_xyz), "emitted new_xyz != xyz[idx]"
+    if HAVE_REF:
+        ref, ref_temp = R.fps(x, M, return_temp=True)
+        assert torch.equal(got, ref), "FPS indices differ from the reference kernel"
+        assert np.array_equal(ref_temp.cpu().numpy(), want_temp), "oracle temp != reference temp"
+
+
+@pytest.mark.parametrize("env", [{"PRB_FPS_CS": "1"}, {"PRB_FPS_CS": "2"}, {"PRB_FPS_CS": "4"}, {"PRB_FPS_GENERIC": "1"},
+                                 {"PRB_FPS_CS": "1", "PRB_FPS_THREADS": "1024"}])
+def test_fps_all_kernel_variants_agree(cuda, env):
+    xyz = synth.dup_cloud(2, 8192, 5, unique=3000)
+    want = O.fps(xyz, 512)
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        got = pu.furthest_point_sample(T(xyz, cuda), 512)
+    finally:
+        for k, v in old.items():
+            os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_fps_temp_writeback_and_m_edge(cuda):
+    from pointrcnn_b200.ext import pointnet2_cuda
+    xyz = synth.u_kitti(2, 2048, 3)
+    x = T(xyz, cuda)
+    temp = torch.full((2, 2048), 1e10, device=cuda)
+    idx = torch.empty((2, 100), dtype=torch.int32, device=cuda)
+    pointnet2_cuda.furthest_point_sampling_wrapper(2, 2048, 100, x, temp, idx)
+    _, want_temp = O.fps(xyz, 100, return_temp=True)
+    assert np.array_equal(temp.cpu().numpy(), want_temp)
+    one = pu.furthest_point_sample(x, 1)
+    assert torch.count_nonzero(one) == 0
+
+
+# ------------------------------------------------------------------------------------------------ ball query / grouping
+@pytest.mark.parametrize("kind,N,M,r,ns", [("cube", 16384, 4096, 0.1, 32), ("kitti", 16384, 4096, 0.5, 32),
+                                           ("kitti", 4096, 1024, 1.0, 16), ("cube", 1000, 77, 0.3, 64),
+                                           ("dup", 512, 128, 0.2, 64), ("kitti", 256, 64, 4.0, 32)])
+def test_ball_query_exact(cuda, kind, N, M, r, ns):
+    xyz = _cloud(kind, 2, N, 21 + N)
+    fidx = O.fps(xyz, M)
+    new_xyz = np.stack([xyz[b][fidx[b]] for b in range(2)])
+    want = O.ball_query(r, ns, xyz, new_xyz)
+    x, c = T(xyz, cuda), T(new_xyz, cuda)
+    got = pu.ball_query(r, ns, x, c)
+    assert np.array_equal(got.cpu().numpy(), want)
+    if HAVE_REF:
+        assert torch.equal(got, R.ball_query(r, ns, x, c))
+
+
+def test_ball_query_no_hit_rows_stay_zero_and_msg2(cuda):
+    xyz = synth.u_kitti(2, 4096, 9)
+    centres = xyz[:, :128].copy()
+    centres[:, ::2] += 500.0   # every other centre is far from everything
+    x, c = T(xyz, cuda), T(centres, cuda)
+    a = pu.ball_query(0.5, 16, x, c)
+    assert torch.count_nonzero(a[:, ::2]) == 0
+    assert np.array_equal(a.cpu().numpy(), O.ball_query(0.5, 16, xyz, centres))
+    i0, i1 = pu.ball_query_msg2((0.5, 1.0), (16, 32), x, c)
+    assert torch.equal(i0, a)
+    assert torch.equal(i1, pu.ball_query(1.0, 32, x, c))
+
+
+def test_group_gather_and_grads(cuda):
+    rng = np.random.default_rng(0)
+    B, C, N, M, S = 2, 19, 777, 60, 16
+    feats = rng.standard_normal((B, C, N)).astype(np.float32)
+    idx = rng.integers(0, N, (B, M, S)).astype(np.int32)
+    f, i = T(feats, cuda), T(idx, cuda)
+    got = pu.grouping_operation(f, i)
+    assert np.array_equal(got.cpu().numpy(), O.group(feats, idx))
+    gidx = idx[:, :, 0].copy()
+    g2 = pu.gather_operation(f, T(gidx, cuda))
+    assert np.array_equal(g2.cpu().numpy(), O.gather(feats, gidx))
+    # backward: scatter-add (atomic order differs -> tolerance)
+    fr = f.clone().requires_grad_(True)
+    go = rng.standard_normal((B, C, M, S)).astype(np.float32)
+    pu.grouping_operation(fr, i).backward(T(go, cuda))
+    np.testing.assert_allclose(fr.grad.cpu().numpy(), O.group_grad(go, idx, N), rtol=1e-5, atol=1e-5)
+    fr2 = f.clone().requires_grad_(True)
+    go2 = rng.standard_normal((B, C, M)).astype(np.float32)
+    pu.gather_operation(fr2, T(gidx, cuda)).backward(T(go2, cuda))
+    np.testing.assert_allclose(fr2.grad.cpu().numpy(), O.gather_grad(go2, gidx, N), rtol=1e-5, atol=1e-5)
+    if HAVE_REF:
+        assert torch.equal(got, R.group(f, i))
+
+
+# ------------------------------------------------------------------------------------------------ three_nn / interpolate
+@pytest.mark.parametrize("n,m,kind", [(16384, 4096, "kitti"), (1024, 256, "cube"), (256, 64, "dup"), (100, 2, "kitti"), (33, 3, "cube")])
+def test_three_nn_exact(cuda, n, m, kind):
+    unknown = _cloud(kind, 2, n, 31 + n)
+    known = np.ascontiguousarray(unknown[:, ::max(1, n // m)][:, :m])
+    d2, idx = O.three_nn(unknown, known)
+    u, k = T(unknown, cuda), T(known, cuda)
+    dist, gi = pu.three_nn(u, k)
+    assert np.array_equal(gi.cpu().numpy(), idx)
+    got_d2, _, w = pu.three_nn_weights(u, k)
+    assert np.array_equal(got_d2.cpu().numpy(), d2)
+    np.testing.assert_allclose(dist.cpu().numpy(), np.sqrt(d2), rtol=1e-6)
+    if m >= 3:
+        np.testing.assert_allclose(w.cpu().numpy(), O.interp_weights(d2), rtol=2e-6, atol=1e-7)
+    if HAVE_REF:
+        rd2, ridx = R.three_nn(u, k)
+        assert torch.equal(gi, ridx) and torch.equal(got_d2, rd2)
+
+
+def test_three_interpolate_and_grad(cuda):
+    rng = np.random.default_rng(1)
+    B, C, M, N = 2, 37, 300, 1000
+    feats = rng.standard_normal((B, C, M)).astype(np.float32)
+    idx = rng.integers(0, M, (B, N, 3)).astype(np.int32)
+    w = rng.random((B, N, 3)).astype(np.float32)
+    w /= w.sum(axis=2, keepdims=True)
+    f, i, ww = T(feats, cuda), T(idx, cuda), T(w, cuda)
+    got = pu.three_interpolate(f, i, ww)
+    want = O.three_interpolate(feats, idx, w)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-6)   # north_star: 1e-5 rel
+    assert np.array_equal(got.cpu().numpy(), want), "same FMA order as the reference SASS -> expected bit-exact"
+    fr = f.clone().requires_grad_(True)
+    go = rng.standard_normal((B, C, N)).astype(np.float32)
+    pu.three_interpolate(fr, i, ww).backward(T(go, cuda))
+    np.testing.assert_allclose(fr.grad.cpu().numpy(), O.three_interpolate_grad(go, idx, w, M), rtol=1e-4, atol=1e-4)
+    if HAVE_REF:
+        assert torch.equal(got, R.three_interpolate(f, i, ww))
+
+
+# ------------------------------------------------------------------------------------------------ roipool3d
+def _roi_scene(B, N, M, C, seed):
+    rng = np.random.default_rng(seed)
+    xyz = synth.u_kitti(B, N, seed)
+    boxes = np.stack([synth.boxes3d(M, seed + b)[0] for b in range(B)])
+    # make boxes land on points: move a third of them onto random points, blow some up to saturate 512
+    for b in range(B):
+        pick = rng.integers(0, N, M // 3)
+        boxes[b, : M // 3, 0] = xyz[b, pick, 0]
+        boxes[b, : M // 3, 2] = xyz[b, pick, 2]
+        boxes[b, : M // 3, 1] = xyz[b, pick, 1] + 0.8
+        boxes[b, : M // 8, 3:6] *= 6.0
+    feat = rng.standard_normal((B, N, C)).astype(np.float32)
+    return xyz, boxes.astype(np.float32), feat
+
+
+@pytest.mark.parametrize("B,N,M,C,S", [(2, 16384, 64, 130, 512), (1, 4096, 33, 5, 128), (2, 2000, 16, 0, 64)])
+def test_roipool3d_vs_reference_and_oracle(cuda, B, N, M, C, S):
+    xyz, boxes, feat = _roi_scene(B, N, M, C, 41 + N)
+    x, bx, f = T(xyz, cuda), T(boxes, cuda), T(feat, cuda)
+    pooled = torch.zeros((B, M, S, 3 + C), device=cuda)
+    empty = torch.zeros((B, M), dtype=torch.int32, device=cuda)
+    roipool3d_cuda.forward(x, bx, f, pooled, empty)
+    if HAVE_REF and C > 0:
+        rp, re = R.roipool3d(x, f, bx, S)
+        assert torch.equal(empty, re), "empty flags differ from the reference kernel"
+        assert torch.equal(pooled, rp), "pooled rows differ from the reference kernel"
+    # CPU oracle uses host libm for cos/sin: flags may differ only for points within 1e-4 m of a box face
+    op, oe = O.roipool3d(xyz, feat, boxes, S)
+    gp, ge = pooled.cpu().numpy(), empty.cpu().numpy()
+    same = np.all(gp.reshape(B, M, -1) == op.reshape(B, M, -1), axis=2) & (ge == oe)
+    assert same.mean() > 0.97, "too many boxes disagree with the CPU oracle: %f" % same.mean()
+    assert ge.sum() > 0 and (1 - ge).sum() > 0, "test should cover empty and non-empty boxes"
+    for b, m in zip(*np.nonzero(~same)):
+        mg = O.pts_in_boxes3d_margin(xyz[b], boxes[b, m:m + 1])[0]
+        assert mg.min() < 1e-4, "non-borderline roipool3d mismatch at scene %d box %d" % (b, m)
+
+
+def test_roipool3d_utils_and_canonical(cuda):
+    xyz, boxes, feat = _roi_scene(2, 8192, 48, 6, 77)
+    x, bx, f = T(xyz, cuda), T(boxes, cuda), T(feat, cuda)
+    pooled, empty = roipool3d_utils.roipool3d_gpu(x, f, bx, 1.0, sampled_pt_num=256)
+    large = O.enlarge_box3d(boxes, 1.0)
+    op, oe = O.roipool3d(xyz, feat, large, 256)
+    ok = np.all(pooled.cpu().numpy().reshape(2, 48, -1) == op.reshape(2, 48, -1), axis=2)
+    assert ok.mean() > 0.95
+    pc, ec = roipool3d_utils.roipool3d_gpu(x, f, bx, 1.0, sampled_pt_num=256, canonical_rois=bx)
+    assert torch.equal(ec, empty)
+    want = O.canonical_transform(pooled.cpu().numpy(), boxes)
+    nz = (empty.cpu().numpy() == 0)
+    np.testing.assert_allclose(pc.cpu().numpy()[nz], want[nz], rtol=1e-5, atol=2e-5)
+    assert torch.count_nonzero(pc[empty.bool()]) == 0
+
+
+# ------------------------------------------------------------------------------------------------ iou3d
+def test_overlap_and_iou_matrices(cuda):
+    a = synth.sorted_bev(300, 5)
+    b = synth.sorted_bev(217, 6)
+    b[:100] = a[50:150] + np.float32(0.01)      # heavy overlaps
+    b[100] = a[0]                               # identical boxes
+    ta, tb = T(a, cuda), T(b, cuda)
+    ov = torch.zeros((300, 217), device=cuda)
+    iou = torch.zeros((300, 217), device=cuda)
+    iou3d_cuda.boxes_overlap_bev_gpu(ta, tb, ov)
+    iou3d_cuda.boxes_iou_bev_gpu(ta, tb, iou)
+    want_ov, want_iou = O.boxes_overlap_bev(a, b), O.boxes_iou_bev(a, b)
+    # north_star: IoU within 1e-5 rel of the reference; the CPU oracle differs by libm ulps in sin/cos/atan2
+    np.testing.assert_allclose(ov.cpu().numpy(), want_ov, rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(iou.cpu().numpy(), want_iou, rtol=2e-4, atol=2e-5)
+    assert (want_iou > 0.5).sum() > 50
+    if HAVE_REF:
+        assert torch.equal(ov, R.boxes_overlap_bev(ta, tb)), "overlap matrix not bit-identical to the reference kernel"
+        assert torch.equal(iou, R.boxes_iou_bev(ta, tb)), "IoU matrix not bit-identical to the reference kernel"
+
+
+@pytest.mark.parametrize("n,thresh,normal", [(100, 0.1, False), (1000, 0.3, False), (2700, 0.8, True), (6300, 0.8, True),
+                                             (6300, 0.85, True), (65, 0.5, False), (64, 0.5, True), (1, 0.5, False)])
+def test_nms_keep_exact(cuda, n, thresh, normal):
+    boxes = synth.sorted_bev(n, 100 + n)
+    tb = T(boxes, cuda)
+    keep = torch.zeros(n, dtype=torch.int64)
+    num = (iou3d_cuda.nms_normal_gpu if normal else iou3d_cuda.nms_gpu)(tb, keep, thresh)
+    got = keep[:num].numpy()
+    if HAVE_REF:
+        want = R.nms(tb, thresh, normal).numpy()
+        assert np.array_equal(got, want), "keep list differs from the reference nms"
+        rm = R.nms_mask(tb, thresh, normal).cpu().numpy().view(np.uint64)
+        from pointrcnn_b200 import _cabi as C
+        mask = torch.zeros((n, (n + 63) // 64), dtype=torch.int64, device=cuda)
+        C.check(C.lib().prb_nms_mask(C.ptr(tb), n, C.c_float(thresh), int(normal), C.ptr(mask), C.stream()), "nms_mask")
+        mm = mask.cpu().numpy().view(np.uint64)
+        rows = np.arange(n)[:, None] // 64
+        cols = np.arange(mm.shape[1])[None, :]
+        upper = cols >= rows
+        assert np.array_equal(mm[upper], rm[upper]), "upper-triangle mask differs from the reference kernel"
+        assert not mm[~upper].any()
+    if normal:  # no transcendental in the axis-aligned IoU -> the CPU oracle is bit-exact too
+        assert np.array_equal(got, O.nms(boxes, thresh, normal=True))
+    else:
+        want = O.nms(boxes, thresh, normal=False)
+        agree = len(set(got.tolist()) & set(want.tolist())) / max(1, len(want))
+        assert agree > 0.98
+
+
+def test_iou3d_utils_api(cuda):
+    b3, scores = synth.boxes3d(500, 9)
+    tb, ts = T(b3, cuda), T(scores, cuda)
+    iou = iou3d_utils.boxes_iou3d_gpu(tb[:200], tb[200:])
+    np.testing.assert_allclose(iou.cpu().numpy(), O.boxes_iou3d(b3[:200], b3[200:]), rtol=3e-4, atol=3e-5)
+    bev = T(synth.to_bev(b3), cuda)
+    keep = iou3d_utils.nms_normal_gpu(bev, ts, 0.7)
+    order = np.argsort(-scores, kind="stable")
+    want = order[O.nms(synth.to_bev(b3)[order], 0.7, normal=True)]
+    assert keep.dtype == torch.int64 and keep.is_cuda
+    assert np.array_equal(keep.cpu().numpy(), want)
+    keep_r = iou3d_utils.nms_gpu(bev, ts, 0.1)
+    assert 0 < keep_r.numel() < 500
+    bi = iou3d_utils.boxes_iou_bev(bev[:10], bev[:10])
+    assert torch.allclose(torch.diagonal(bi), torch.ones(10, device=cuda), atol=1e-4)
