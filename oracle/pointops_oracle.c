@@ -207,7 +207,7 @@ ORC_API void orc_three_nn(int b, int n, int m, const float *unknown, const float
         }
 }
 
-/* out = w0*p0 + w1*p1 + w2*p2 ; reference SASS: FMUL(w0,p0) -> FFMA(w1,p1,.) -> FFMA(w2,p2,.) */
+/* out = w0*p0 + w1*p1 + w2*p2 ; reference SASS (sm_100a, nvcc 12.9 -O2): FMUL(w1,p1) -> FFMA(w0,p0,.) -> FFMA(w2,p2,.) */
 ORC_API void orc_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
                                    const float *weight, float *out) {
 #pragma omp parallel for collapse(2)
@@ -218,8 +218,8 @@ ORC_API void orc_three_interpolate(int b, int c, int m, int n, const float *poin
             for (int j = 0; j < n; ++j) {
                 const int *ix = idx + ((size_t)bi * n + j) * 3;
                 const float *w = weight + ((size_t)bi * n + j) * 3;
-                float t = w[0] * src[ix[0]];
-                t = fmaf(w[1], src[ix[1]], t);
+                float t = w[1] * src[ix[1]];
+                t = fmaf(w[0], src[ix[0]], t);
                 dst[j] = fmaf(w[2], src[ix[2]], t);
             }
         }

@@ -271,7 +271,8 @@ __global__ void __launch_bounds__(1024, 1) fps_generic_kernel(const FpsParams p)
 template <int THREADS, int PPT, int CS>
 static int launch_rank(const FpsParams &p, size_t smem, cudaStream_t stream) {
     auto kern = fps_rank_kernel<THREADS, PPT, CS>;
-    if (smem > 48 * 1024) PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // static shared memory counts against the 48 KB default too
+    if (smem + 2048 > 48 * 1024) PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.b * CS);
     cfg.blockDim = dim3(THREADS);

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(NN_THREADS) three_nn_kernel(int n, int m, cons
 }
 
 // out[b,c,j] = w0*p[c,i0] + w1*p[c,i1] + w2*p[c,i2]; one CTA owns a block of channels of one scene
-// (rows stay L1-resident); reference contraction: FMUL(w0,p0) -> FFMA(w1,p1,.) -> FFMA(w2,p2,.)
+// (rows stay L1-resident); reference contraction (its sm_100a SASS): FMUL(w1,p1) -> FFMA(w0,p0,.) -> FFMA(w2,p2,.)
 constexpr int TI_THREADS = 256;
 constexpr int TI_CH = 8;
 
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(TI_THREADS) three_interpolate_kernel(int c, in
             if (ch < nch) {
                 const float *row = src + (size_t)ch * m;
                 dst[(size_t)ch * n + j] =
-                    __fmaf_rn(w2, __ldg(row + k2), __fmaf_rn(w1, __ldg(row + k1), __fmul_rn(w0, __ldg(row + k0))));
+                    __fmaf_rn(w2, __ldg(row + k2), __fmaf_rn(w0, __ldg(row + k0), __fmul_rn(w1, __ldg(row + k1))));
             }
     }
 }

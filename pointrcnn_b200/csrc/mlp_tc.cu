@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const Chain
                                 float o[4];
 #pragma unroll
                                 for (int q = 0; q < 4; ++q)  // same contraction as three_interpolate (interpolate_gpu.cu:96)
-                                    o[q] = __fmaf_rn(w2, a2[q], __fmaf_rn(w1, a1[q], __fmul_rn(w0, a0[q])));
+                                    o[q] = __fmaf_rn(w2, a2[q], __fmaf_rn(w0, a0[q], __fmul_rn(w1, a1[q])));
                                 v = make_float4(o[0], o[1], o[2], o[3]);
                             } else {
                                 const float *src;

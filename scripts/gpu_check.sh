@@ -10,6 +10,7 @@ echo "== golden";      timeout 300 python oracle/make_golden.py gpurun_out/golde
 echo "== mlp tests";   timeout 900 python -m pytest tests/test_gpu_mlp.py -m gpu -q -rf --no-header -p no:cacheprovider > gpurun_out/pytest_mlp.log 2>&1; echo "mlp rc=$?"
 tail -5 gpurun_out/pytest_mlp.log
 echo "== smoke";       timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
+echo "== ref cuda"; timeout 600 python oracle/bench_ref_cuda.py > gpurun_out/bench_ref_cuda.log 2>&1; echo "refcuda rc=$?"; tail -1 gpurun_out/bench_ref_cuda.log | cut -c1-800
 echo "== bench";       timeout 600 python bench.py --steps 10 --warmup 3 --profile-out gpurun_out/bench_profile.json > gpurun_out/bench.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench.log | cut -c1-1500
 if [ "$1" == "ncu" ]; then
   echo "== ncu launch list"

