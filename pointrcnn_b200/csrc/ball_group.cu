@@ -69,18 +69,31 @@ __global__ void __launch_bounds__(BQ_THREADS) ball_query_kernel(const BqParams<N
         }
         __syncthreads();
         if (!warp_busy) continue;  // uniform per warp; the CTA-level barriers stay matched
+        float rmax = p.r2[0];
+#pragma unroll
+        for (int r = 1; r < NR; ++r) rmax = fmaxf(rmax, p.r2[r]);
         for (int i0 = 0; i0 < tn; i0 += 32) {
             const int i = i0 + lane;
             const bool in = i < tn;
             const float x = in ? sx[i] : 0.f, y = in ? sy[i] : 0.f, z = in ? sz[i] : 0.f;
+            // pass 1: distances to the warp's live centres, ONE vote for "anything inside the largest ball?"
+            // (LiDAR-like scenes: almost every 32-point step has no hit at all)
+            float d2[BQ_CPW];
+            bool any_hit = false;
+#pragma unroll
+            for (int c = 0; c < BQ_CPW; ++c) {
+                // reference: d2 = (new_x-x)^2 + (new_y-y)^2 + (new_z-z)^2 in its SASS contraction order
+                d2[c] = dist2_ref(cx[c] - x, cy[c] - y, cz[c] - z);
+                any_hit |= live[c] && d2[c] < rmax;
+            }
+            if (!__any_sync(0xffffffffu, in && any_hit)) continue;
+            // pass 2: ordered compaction of the hits
 #pragma unroll
             for (int c = 0; c < BQ_CPW; ++c) {
                 if (!live[c]) continue;
-                // reference: d2 = (new_x-x)^2 + (new_y-y)^2 + (new_z-z)^2 in its SASS contraction order
-                const float d2 = dist2_ref(cx[c] - x, cy[c] - y, cz[c] - z);
 #pragma unroll
                 for (int r = 0; r < NR; ++r) {
-                    const unsigned hits = __ballot_sync(0xffffffffu, in && d2 < p.r2[r]);
+                    const unsigned hits = __ballot_sync(0xffffffffu, in && d2[c] < p.r2[r]);
                     if (hits == 0 || cnt[c][r] >= p.ns[r]) continue;
                     if (cnt[c][r] == 0) first[c][r] = t0 + i0 + __ffs(hits) - 1;
                     const int pos = cnt[c][r] + __popc(hits & ((1u << lane) - 1));

@@ -15,9 +15,9 @@
 // xyz and the running min-distance in registers, so "lowest position wins" IS the tie rule at every
 // level: strict '>' inside a thread, lowest lane inside a warp (redux.max + ballot + ffs), lowest
 // warp inside a CTA, lowest CTA inside a cluster.  One __syncthreads per round.  A scene is spread
-// over a thread-block cluster of CS CTAs (CS*THREADS*PPT >= n): the per-CTA winners are exchanged
-// with st.async into every peer's shared memory + mbarrier complete_tx (no cluster barrier in the
-// loop).  Every CTA keeps a rank-ordered copy of the scene's xyz in shared memory, so the winner's
+// over a thread-block cluster of CS CTAs (CS*THREADS*PPT >= n): every warp pushes its winner with ONE
+// relaxed 64-bit remote store (dist | round tag | rank) into every CTA's slot array and every warp
+// polls its local copy -- no block barrier, no cluster barrier, no mbarrier inside the loop.  Every CTA keeps a rank-ordered copy of the scene's xyz in shared memory, so the winner's
 // coordinates are one broadcast LDS away.  new_xyz is emitted on the fly.
 #include <limits.h>
 
@@ -62,27 +62,15 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
     return r;
 }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+// 8-byte relaxed store into a peer CTA's shared memory / relaxed poll of the local copy (cluster scope):
+// key and round tag travel in ONE 64-bit word, so no separate flag or barrier is needed
+__device__ __forceinline__ void st_cluster_b64(uint32_t remote_addr, uint64_t v) {
+    asm volatile("st.relaxed.cluster.shared::cluster.b64 [%0], %1;" ::"r"(remote_addr), "l"(v) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-// 8-byte store into a peer CTA's shared memory that completes 8 tx-bytes on the peer's mbarrier
-__device__ __forceinline__ void st_async_b64(uint32_t remote_addr, uint64_t v, uint32_t remote_bar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
-                 "l"(v), "r"(remote_bar)
-                 : "memory");
+__device__ __forceinline__ uint64_t ld_cluster_b64(uint32_t local_addr) {
+    uint64_t v;
+    asm volatile("ld.relaxed.cluster.shared::cta.b64 %0, [%1];" : "=l"(v) : "r"(local_addr) : "memory");
+    return v;
 }
 
 constexpr int kMaxWarps = 32;
@@ -93,8 +81,9 @@ __global__ void __launch_bounds__(THREADS, 1) fps_rank_kernel(const FpsParams p)
     constexpr int W = THREADS / 32;
     extern __shared__ __align__(16) float s_pts[];  // rank-ordered xyz (3 floats per rank), optional
     __shared__ int2 s_wkey[2][kMaxWarps];           // per-warp (dist bits, rank), double buffered
-    __shared__ __align__(8) uint64_t s_slot[2][kMaxCluster];  // per-CTA winners (cluster exchange)
-    __shared__ __align__(8) uint64_t s_bar[2];
+    // cluster exchange: every warp of every CTA pushes its winner straight into every CTA's slot array;
+    // word = dist bits (32) | round tag (12) | rank (20); double buffered by round parity
+    __shared__ __align__(8) uint64_t s_slot[2][kMaxCluster * (THREADS / 32)];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
@@ -105,13 +94,8 @@ __global__ void __launch_bounds__(THREADS, 1) fps_rank_kernel(const FpsParams p)
     int *idx = p.idx + (size_t)scene * m;
     float *new_xyz = p.new_xyz ? p.new_xyz + (size_t)scene * m * 3 : nullptr;
 
-    if (CS > 1) {
-        if (tid == 0) {
-            mbar_init(smem_u32(&s_bar[0]), 1);
-            mbar_init(smem_u32(&s_bar[1]), 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-    }
+    if (CS > 1)
+        for (int i = tid; i < 2 * CS * W; i += THREADS) (&s_slot[0][0])[i] = 0ull;   // tag 0 is never waited for first
 
     // rank-ordered copy of the scene (coalesced global reads, scattered shared stores)
     if (p.use_smem_xyz) {
@@ -149,12 +133,9 @@ __global__ void __launch_bounds__(THREADS, 1) fps_rank_kernel(const FpsParams p)
         idx[0] = 0;  // holds RANKS until the fix-up pass below
         if (new_xyz) { new_xyz[0] = cx; new_xyz[1] = cy; new_xyz[2] = cz; }
     }
-    uint32_t phase0 = 0, phase1 = 0;
 
     for (int j = 1; j < m; ++j) {
         const int par = j & 1;
-        if (CS > 1 && tid == 0) mbar_arrive_expect_tx(smem_u32(&s_bar[par]), CS * 8);
-
         float best = -1.f;
         int bslot = 0;
 #pragma unroll
@@ -169,36 +150,38 @@ __global__ void __launch_bounds__(THREADS, 1) fps_rank_kernel(const FpsParams p)
         int wm = __reduce_max_sync(0xffffffffu, vb);
         unsigned bal = __ballot_sync(0xffffffffu, vb == wm);
         int wr = __shfl_sync(0xffffffffu, g * PPT + bslot, __ffs(bal) - 1);
-        if (lane == 0) s_wkey[par][warp] = make_int2(wm, wr);
-        __syncthreads();
 
         int r;  // winning rank, uniform
         if (CS == 1) {
+            if (lane == 0) s_wkey[par][warp] = make_int2(wm, wr);
+            __syncthreads();
             int2 kv = lane < W ? s_wkey[par][lane] : make_int2(INT_MIN, 0);
             int cm = __reduce_max_sync(0xffffffffu, kv.x);
             unsigned b2 = __ballot_sync(0xffffffffu, kv.x == cm);
             r = __shfl_sync(0xffffffffu, kv.y, __ffs(b2) - 1);
         } else {
-            if (warp == 0) {
-                int2 kv = lane < W ? s_wkey[par][lane] : make_int2(INT_MIN, 0);
-                int cm = __reduce_max_sync(0xffffffffu, kv.x);
-                unsigned b2 = __ballot_sync(0xffffffffu, kv.x == cm);
-                int cr = __shfl_sync(0xffffffffu, kv.y, __ffs(b2) - 1);
-                if (lane < CS) {
-                    uint64_t key = ((uint64_t)(uint32_t)cm << 32) | (uint32_t)cr;
-                    uint32_t dst = map_to_cta(smem_u32(&s_slot[par][crank]), lane);
-                    uint32_t bar = map_to_cta(smem_u32(&s_bar[par]), lane);
-                    st_async_b64(dst, key, bar);
+            constexpr int NSLOT = CS * W;                 // one slot per (CTA, warp), ordered by rank range
+            const uint32_t tag = (uint32_t)j & 0xFFFu;
+            if (lane < CS) {
+                const uint64_t key = ((uint64_t)(uint32_t)wm << 32) | ((uint64_t)tag << 20) | (uint32_t)wr;
+                st_cluster_b64(map_to_cta(smem_u32(&s_slot[par][crank * W + warp]), lane), key);
+            }
+            // poll until all NSLOT winners of this round have landed, keep the best (max dist, then lowest slot)
+            int bv = INT_MIN, bs = NSLOT, br = 0;
+#pragma unroll
+            for (int q = 0; q < (NSLOT + 31) / 32; ++q) {
+                const int sl = lane + 32 * q;
+                if (sl < NSLOT) {
+                    uint64_t key;
+                    do { key = ld_cluster_b64(smem_u32(&s_slot[par][sl])); } while ((((uint32_t)key >> 20) & 0xFFFu) != tag);
+                    const int v = (int)(uint32_t)(key >> 32);
+                    if (v > bv) { bv = v; bs = sl; br = (int)((uint32_t)key & 0xFFFFFu); }
                 }
             }
-            uint32_t ph = par ? phase1 : phase0;
-            mbar_wait_cluster(smem_u32(&s_bar[par]), ph);
-            if (par) phase1 ^= 1; else phase0 ^= 1;
-            uint64_t key = lane < CS ? s_slot[par][lane] : 0ull;
-            int kx = lane < CS ? (int)(uint32_t)(key >> 32) : INT_MIN;
-            int cm = __reduce_max_sync(0xffffffffu, kx);
-            unsigned b2 = __ballot_sync(0xffffffffu, kx == cm);
-            r = __shfl_sync(0xffffffffu, (int)(uint32_t)key, __ffs(b2) - 1);
+            const int cm = __reduce_max_sync(0xffffffffu, bv);
+            const unsigned smin = __reduce_min_sync(0xffffffffu, bv == cm ? (unsigned)bs : 0xffffffffu);
+            const unsigned b2 = __ballot_sync(0xffffffffu, bv == cm && (unsigned)bs == smin);
+            r = __shfl_sync(0xffffffffu, br, __ffs(b2) - 1);
         }
 
         if (p.use_smem_xyz) {

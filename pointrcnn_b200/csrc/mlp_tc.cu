@@ -34,8 +34,7 @@ constexpr int TM = 128;              // rows per tile (= TMEM lanes, UMMA M)
 constexpr int KC = 32;               // K columns per chunk (128 bytes of fp32/tf32)
 constexpr int A_STAGE_BYTES = TM * KC * 4;        // 16 KB
 constexpr int B_TILE_ROWS = 256;                  // max N per MMA / per weight tile
-constexpr int B_STAGE_BYTES = B_TILE_ROWS * KC * 4;  // 32 KB
-constexpr int NA = 4, NB = 4;        // ring depths
+constexpr int MAX_STAGES = 4;        // ring depth upper bound (runtime depth in ChainParams)
 constexpr int ROW_THREADS = 128;
 constexpr int CHAIN_THREADS = 192;   // 4 row warps + producer warp + MMA warp
 constexpr int MAX_LAYERS = 3;
@@ -52,6 +51,10 @@ struct ChainParams {
     const float *w[MAX_LAYERS];      // packed weight images
     const float *scale[MAX_LAYERS];  // np floats (zero padded)
     const float *shift[MAX_LAYERS];
+    // resources (sized per launch so that small layers run several CTAs per SM)
+    int na, nb;                // ring depths
+    int b_stage_bytes;         // weight stage size = min(256, max np) * 128
+    int tmem_cols;             // power of two >= 32
     // layer-0 K segments (each padded to a multiple of KC)
     int nseg, seg_chunks[2], seg_width[2];
     long total_rows;
@@ -103,7 +106,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {   // ncols: power of two >= 32
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
@@ -123,15 +126,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives lane (base+i)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+// 32 lanes x 16 consecutive fp32 columns: thread i of the warp receives lane (base+i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -160,6 +160,22 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 // byte offset of (row r, 16-byte unit j) inside a K-major SWIZZLE_128B stage
 __device__ __forceinline__ uint32_t swz(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
+// Shared memory is carved at run time (ring depths and the weight-stage size depend on the chain), so that
+// narrow layers (SA1/SA2) fit 2-3 CTAs per SM and overlap their latency-bound gathers.
+struct SmemFixed {
+    int row_src[TM][3];      // SA: global point row (slot 0); FP: 3 known rows
+    float row_aux[TM][3];    // SA: centre xyz; FP: 3 weights
+    int row_valid[TM];
+    float red[32][33];       // [channel][partial group] staging of the max-pool epilogue
+    uint64_t a_full[MAX_STAGES], a_empty[MAX_STAGES], b_full[MAX_STAGES], b_empty[MAX_STAGES], d_full[MAX_LAYERS];
+    uint32_t tmem_base;
+};
+
+__host__ __device__ inline size_t chain_smem_bytes(int na, int nb, int b_stage_bytes, int np_total) {
+    return 1024 /*alignment slack*/ + (size_t)na * A_STAGE_BYTES + (size_t)nb * b_stage_bytes + (size_t)2 * np_total * sizeof(float) +
+           sizeof(SmemFixed) + 64;
+}
+
 struct RingPos {
     uint32_t stage, phase;
     __device__ void advance(int depth) {
@@ -167,27 +183,20 @@ struct RingPos {
     }
 };
 
-struct Smem {
-    // 1024-byte aligned stages first
-    uint8_t a[NA][A_STAGE_BYTES];
-    uint8_t b[NB][B_STAGE_BYTES];
-    float scale[MAX_LAYERS][MAX_NP];
-    float shift[MAX_LAYERS][MAX_NP];
-    // per-tile row metadata
-    int row_src[TM][3];      // SA: global point row (slot 0); FP: 3 known rows
-    float row_aux[TM][3];    // SA: centre xyz; FP: 3 weights
-    int row_valid[TM];
-    float red[32][33];       // [channel][partial group] staging of the max-pool epilogue
-    uint64_t a_full[NA], a_empty[NA], b_full[NB], b_empty[NB], d_full[MAX_LAYERS];
-    uint32_t tmem_base;
-};
-
 // ------------------------------------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const ChainParams p) {
+__global__ void __launch_bounds__(CHAIN_THREADS, 2) mlp_chain_kernel(const ChainParams p) {
     extern __shared__ uint8_t smem_raw[];
-    Smem &S = *reinterpret_cast<Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int L = p.num_layers;
+    int np_total = 0, sc_off[MAX_LAYERS];
+    for (int l = 0; l < L; ++l) { sc_off[l] = np_total; np_total += p.np[l]; }
+    uint8_t *sA = base;
+    uint8_t *sB = sA + (size_t)p.na * A_STAGE_BYTES;
+    float *s_scale = reinterpret_cast<float *>(sB + (size_t)p.nb * p.b_stage_bytes);
+    float *s_shift = s_scale + np_total;
+    SmemFixed &S = *reinterpret_cast<SmemFixed *>((reinterpret_cast<uintptr_t>(s_shift + np_total) + 15) & ~(uintptr_t)15);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NA = p.na, NB = p.nb;
 
     if (tid == 0) {
         for (int i = 0; i < NA; ++i) { mbar_init(s2u(&S.a_full[i]), ROW_THREADS); mbar_init(s2u(&S.a_empty[i]), 1); }
@@ -195,9 +204,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const Chain
         for (int i = 0; i < MAX_LAYERS; ++i) mbar_init(s2u(&S.d_full[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) tmem_alloc(s2u(&S.tmem_base), 512);
+    if (warp == 5) tmem_alloc(s2u(&S.tmem_base), (uint32_t)p.tmem_cols);
     for (int l = 0; l < L; ++l)
-        for (int i = tid; i < p.np[l]; i += CHAIN_THREADS) { S.scale[l][i] = p.scale[l][i]; S.shift[l][i] = p.shift[l][i]; }
+        for (int i = tid; i < p.np[l]; i += CHAIN_THREADS) { s_scale[sc_off[l] + i] = p.scale[l][i]; s_shift[sc_off[l] + i] = p.shift[l][i]; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -217,7 +226,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const Chain
                             mbar_wait(s2u(&S.b_empty[rb.stage]), rb.phase ^ 1);
                             mbar_expect_tx(s2u(&S.b_full[rb.stage]), bytes);
                             const float *src = p.w[l] + ((size_t)kc * p.np[l] + (size_t)h * B_TILE_ROWS) * KC;
-                            bulk_g2s(s2u(S.b[rb.stage]), src, bytes, s2u(&S.b_full[rb.stage]));
+                            bulk_g2s(s2u(sB + (size_t)rb.stage * p.b_stage_bytes), src, bytes, s2u(&S.b_full[rb.stage]));
                             rb.advance(NB);
                         }
                 }
@@ -240,12 +249,12 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const Chain
                         }
                         const int ksteps = (valid + 7) >> 3;
                         mbar_wait(s2u(&S.a_full[ra.stage]), ra.phase);
-                        const uint64_t adesc = make_desc(s2u(S.a[ra.stage]));
+                        const uint64_t adesc = make_desc(s2u(sA + (size_t)ra.stage * A_STAGE_BYTES));
                         for (int h = 0; h < halves; ++h) {
                             const int rows = min(B_TILE_ROWS, p.np[l] - h * B_TILE_ROWS);
                             mbar_wait(s2u(&S.b_full[rb.stage]), rb.phase);
                             tc_fence_after();
-                            const uint64_t bdesc = make_desc(s2u(S.b[rb.stage]));
+                            const uint64_t bdesc = make_desc(s2u(sB + (size_t)rb.stage * p.b_stage_bytes));
                             const uint32_t idesc = make_idesc(rows);
                             const uint32_t d = tmem + (uint32_t)(p.dcol[l] + h * B_TILE_ROWS);
                             for (int ks = 0; ks < ksteps; ++ks)  // +32 bytes (= 2 x 16 B) per K=8 step inside the swizzle row
@@ -266,29 +275,42 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const Chain
         uint32_t dphase = 0;
         const int r = tid;  // my row inside the tile / my TMEM lane
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int j8 = lane & 7;            // my 16-byte unit inside a 128-byte row (gathers)
+        const int rsub = lane >> 3;         // which of the 4 rows a warp-wide gather step covers
+
+        // tile metadata is fetched one tile ahead (global loads of idx / centres / weights overlap the MMAs)
+        int m_src[3] = {0, 0, 0};
+        float m_aux[3] = {0.f, 0.f, 0.f};
+        bool m_valid = false;
+        auto fetch_meta = [&](int tile) {
             const long R = (long)tile * TM + r;
-            const bool valid = R < p.total_rows;
-            // ---- tile metadata
-            named_bar_rows();  // previous tile's readers of S.row_* are done
-            S.row_valid[r] = valid;
+            m_valid = tile < p.num_tiles && R < p.total_rows;
             if (p.mode_in == IN_SA) {
-                long pr = valid ? R / p.ns : 0;                 // global centre index
-                int scene = (int)(pr / p.npoint);
-                int k = valid ? p.idx[R] : 0;
-                S.row_src[r][0] = scene * p.n + k;
-                S.row_aux[r][0] = p.new_xyz[pr * 3 + 0];
-                S.row_aux[r][1] = p.new_xyz[pr * 3 + 1];
-                S.row_aux[r][2] = p.new_xyz[pr * 3 + 2];
+                const long pr = m_valid ? R / p.ns : 0;                 // global centre index
+                const int scene = (int)(pr / p.npoint);
+                m_src[0] = scene * p.n + (m_valid ? __ldg(p.idx + R) : 0);
+                m_aux[0] = __ldg(p.new_xyz + pr * 3 + 0);
+                m_aux[1] = __ldg(p.new_xyz + pr * 3 + 1);
+                m_aux[2] = __ldg(p.new_xyz + pr * 3 + 2);
             } else if (p.mode_in == IN_FP) {
-                long rr = valid ? R : 0;
-                int scene = (int)(rr / p.n);
+                const long rr = m_valid ? R : 0;
+                const int scene = (int)(rr / p.n);
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
-                    S.row_src[r][q] = scene * p.m + p.idx[rr * 3 + q];
-                    S.row_aux[r][q] = p.weight[rr * 3 + q];
+                    m_src[q] = scene * p.m + __ldg(p.idx + rr * 3 + q);
+                    m_aux[q] = __ldg(p.weight + rr * 3 + q);
                 }
             }
+        };
+        fetch_meta(blockIdx.x);
+
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const long R = (long)tile * TM + r;
+            const bool valid = m_valid;
+            named_bar_rows();  // previous tile's readers of S.row_* are done
+            S.row_valid[r] = valid;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { S.row_src[r][q] = m_src[q]; S.row_aux[r][q] = m_aux[q]; }
             named_bar_rows();
 
             // ---- layer 0: build A chunks from global memory
@@ -297,108 +319,145 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const Chain
                 if (p.nseg > 1 && c >= p.seg_chunks[0]) { c -= p.seg_chunks[0]; seg = 1; }
                 const int k0 = c * KC;                       // first column of this chunk inside its segment
                 const int width = p.seg_width[seg];
-                mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
-                uint8_t *A = S.a[ra.stage];
+                uint8_t *A = sA + (size_t)ra.stage * A_STAGE_BYTES;
                 const bool rows_seg = (p.mode_in == IN_DIRECT) || (p.mode_in == IN_SA && seg == 0 && p.c_feat > 0) ||
                                       (p.mode_in == IN_FP && seg == 0);
                 if (rows_seg) {
-                    // point-major sources: 8 lanes cover one row's 128 bytes, a warp covers 4 rows per step
-                    const int j = lane & 7;
-                    const int kk = k0 + 4 * j;
-                    for (int rr = warp * 32 + (lane >> 3); rr < warp * 32 + 32; rr += 4) {
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (S.row_valid[rr] && kk < width) {
-                            if (p.mode_in == IN_FP) {
-                                const int C = p.c_known;
-                                const float w0 = S.row_aux[rr][0], w1 = S.row_aux[rr][1], w2 = S.row_aux[rr][2];
-                                const float *s0 = p.known_pm + (size_t)S.row_src[rr][0] * C + kk;
-                                const float *s1 = p.known_pm + (size_t)S.row_src[rr][1] * C + kk;
-                                const float *s2 = p.known_pm + (size_t)S.row_src[rr][2] * C + kk;
-                                float a0[4], a1[4], a2[4];
-                                if ((C & 3) == 0) {
-                                    const float4 t0 = __ldg((const float4 *)s0), t1 = __ldg((const float4 *)s1), t2 = __ldg((const float4 *)s2);
-                                    a0[0] = t0.x; a0[1] = t0.y; a0[2] = t0.z; a0[3] = t0.w;
-                                    a1[0] = t1.x; a1[1] = t1.y; a1[2] = t1.z; a1[3] = t1.w;
-                                    a2[0] = t2.x; a2[1] = t2.y; a2[2] = t2.z; a2[3] = t2.w;
-                                } else {
+                    // point-major sources: 8 lanes cover one row's 128 bytes, a warp covers 4 rows per step, 8 steps.
+                    // All loads of the chunk are issued before the first use (memory-level parallelism).
+                    const int kk = k0 + 4 * j8;
+                    if (p.mode_in == IN_FP) {
+                        const int C = p.c_known;
+                        const bool vec = (C & 3) == 0;
 #pragma unroll
-                                    for (int q = 0; q < 4; ++q) {
-                                        const bool in = kk + q < width;
-                                        a0[q] = in ? __ldg(s0 + q) : 0.f; a1[q] = in ? __ldg(s1 + q) : 0.f; a2[q] = in ? __ldg(s2 + q) : 0.f;
+                        for (int half = 0; half < 2; ++half) {
+                            float4 t0[4], t1[4], t2[4];
+                            float w0[4], w1[4], w2[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int rr = warp * 32 + rsub + 4 * (half * 4 + i);
+                                t0[i] = t1[i] = t2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                w0[i] = S.row_aux[rr][0]; w1[i] = S.row_aux[rr][1]; w2[i] = S.row_aux[rr][2];
+                                if (S.row_valid[rr] && kk < width) {
+                                    const float *s0 = p.known_pm + (size_t)S.row_src[rr][0] * C + kk;
+                                    const float *s1 = p.known_pm + (size_t)S.row_src[rr][1] * C + kk;
+                                    const float *s2 = p.known_pm + (size_t)S.row_src[rr][2] * C + kk;
+                                    if (vec) {
+                                        t0[i] = __ldg((const float4 *)s0); t1[i] = __ldg((const float4 *)s1); t2[i] = __ldg((const float4 *)s2);
+                                    } else {
+                                        float a0[4], a1[4], a2[4];
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q) {
+                                            const bool in = kk + q < width;
+                                            a0[q] = in ? __ldg(s0 + q) : 0.f; a1[q] = in ? __ldg(s1 + q) : 0.f; a2[q] = in ? __ldg(s2 + q) : 0.f;
+                                        }
+                                        t0[i] = make_float4(a0[0], a0[1], a0[2], a0[3]);
+                                        t1[i] = make_float4(a1[0], a1[1], a1[2], a1[3]);
+                                        t2[i] = make_float4(a2[0], a2[1], a2[2], a2[3]);
                                     }
                                 }
-                                float o[4];
+                            }
+                            if (half == 0) mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
 #pragma unroll
-                                for (int q = 0; q < 4; ++q)  // same contraction as three_interpolate (interpolate_gpu.cu:96)
-                                    o[q] = __fmaf_rn(w2, a2[q], __fmaf_rn(w0, a0[q], __fmul_rn(w1, a1[q])));
-                                v = make_float4(o[0], o[1], o[2], o[3]);
-                            } else {
-                                const float *src;
-                                int pitch;
-                                if (p.mode_in == IN_DIRECT) { pitch = p.x_pitch; src = p.x_rows + ((size_t)tile * TM + rr) * pitch + kk; }
-                                else { pitch = p.c_feat; src = p.feats_pm + (size_t)S.row_src[rr][0] * pitch + kk; }
-                                if ((pitch & 3) == 0 && kk + 3 < width) {
-                                    v = __ldg((const float4 *)src);
+                            for (int i = 0; i < 4; ++i) {
+                                const int rr = warp * 32 + rsub + 4 * (half * 4 + i);
+                                // same contraction as three_interpolate (reference SASS): fma(w2,p2, fma(w0,p0, w1*p1))
+                                float4 v;
+                                v.x = to_tf32(__fmaf_rn(w2[i], t2[i].x, __fmaf_rn(w0[i], t0[i].x, __fmul_rn(w1[i], t1[i].x))));
+                                v.y = to_tf32(__fmaf_rn(w2[i], t2[i].y, __fmaf_rn(w0[i], t0[i].y, __fmul_rn(w1[i], t1[i].y))));
+                                v.z = to_tf32(__fmaf_rn(w2[i], t2[i].z, __fmaf_rn(w0[i], t0[i].z, __fmul_rn(w1[i], t1[i].z))));
+                                v.w = to_tf32(__fmaf_rn(w2[i], t2[i].w, __fmaf_rn(w0[i], t0[i].w, __fmul_rn(w1[i], t1[i].w))));
+                                *reinterpret_cast<float4 *>(A + swz(rr, j8)) = v;
+                            }
+                        }
+                    } else {
+                        const int pitch = p.mode_in == IN_DIRECT ? p.x_pitch : p.c_feat;
+                        const bool vec = (pitch & 3) == 0 && kk + 3 < width;
+                        float4 t[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = warp * 32 + rsub + 4 * i;
+                            t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (S.row_valid[rr] && kk < width) {
+                                const float *src = p.mode_in == IN_DIRECT ? p.x_rows + ((size_t)tile * TM + rr) * pitch + kk
+                                                                          : p.feats_pm + (size_t)S.row_src[rr][0] * pitch + kk;
+                                if (vec) {
+                                    t[i] = __ldg((const float4 *)src);
                                 } else {
                                     float o[4];
 #pragma unroll
                                     for (int q = 0; q < 4; ++q) o[q] = (kk + q < width) ? __ldg(src + q) : 0.f;
-                                    v = make_float4(o[0], o[1], o[2], o[3]);
+                                    t[i] = make_float4(o[0], o[1], o[2], o[3]);
                                 }
                             }
                         }
-                        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-                        *reinterpret_cast<float4 *>(A + swz(rr, j)) = v;
+                        mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = warp * 32 + rsub + 4 * i;
+                            float4 v = t[i];
+                            v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                            *reinterpret_cast<float4 *>(A + swz(rr, j8)) = v;
+                        }
                     }
                 } else if (p.mode_in == IN_SA) {
                     // relative xyz segment: [x - cx, y - cy, z - cz, 0 ...]; one K=8 step is consumed
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (valid) {
-                        const float *q = p.xyz + (size_t)S.row_src[r][0] * 3;
-                        v.x = to_tf32(q[0] - S.row_aux[r][0]);
-                        v.y = to_tf32(q[1] - S.row_aux[r][1]);
-                        v.z = to_tf32(q[2] - S.row_aux[r][2]);
+                        const float *q = p.xyz + (size_t)m_src[0] * 3;
+                        v.x = to_tf32(__ldg(q + 0) - m_aux[0]);
+                        v.y = to_tf32(__ldg(q + 1) - m_aux[1]);
+                        v.z = to_tf32(__ldg(q + 2) - m_aux[2]);
                     }
+                    mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
                     *reinterpret_cast<float4 *>(A + swz(r, 0)) = v;
                     *reinterpret_cast<float4 *>(A + swz(r, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
                 } else {
                     // FP skip segment: channel-major (b, c_skip, n); lanes run along consecutive points
                     const long rr0 = valid ? R : 0;
                     const int scene = (int)(rr0 / p.n), u = (int)(rr0 - (long)scene * p.n);
-                    const float *base = p.skip + (size_t)scene * p.c_skip * p.n + u;
+                    const float *bsrc = p.skip + (size_t)scene * p.c_skip * p.n + u;
+                    float o[32];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float o[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int ch = k0 + 4 * j + q;
-                            o[q] = (valid && ch < width) ? to_tf32(__ldg(base + (size_t)ch * p.n)) : 0.f;
-                        }
-                        *reinterpret_cast<float4 *>(A + swz(r, j)) = make_float4(o[0], o[1], o[2], o[3]);
+                    for (int q = 0; q < 32; ++q) {
+                        const int ch = k0 + q;
+                        o[q] = (valid && ch < width) ? __ldg(bsrc + (size_t)ch * p.n) : 0.f;
                     }
+                    mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4 *>(A + swz(r, j)) =
+                            make_float4(to_tf32(o[4 * j]), to_tf32(o[4 * j + 1]), to_tf32(o[4 * j + 2]), to_tf32(o[4 * j + 3]));
                 }
                 fence_async_smem();
                 mbar_arrive(s2u(&S.a_full[ra.stage]));
                 ra.advance(NA);
             }
 
+            // next tile's metadata: issue the loads now, consume them at the top of the next iteration
+            fetch_meta(tile + gridDim.x);
+
             // ---- layers 1..L-1: previous accumulator -> scale/shift/ReLU -> next A operand
             for (int l = 1; l < L; ++l) {
                 mbar_wait(s2u(&S.d_full[l - 1]), dphase);
                 tc_fence_after();
                 for (int kc = 0; kc < p.nchunks[l]; ++kc) {
-                    uint32_t acc[32];
-                    tmem_ld32(tmem + lane_base + (uint32_t)(p.dcol[l - 1] + kc * KC), acc);
                     mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
-                    uint8_t *A = S.a[ra.stage];
-                    const float *sc = &S.scale[l - 1][kc * KC], *sh = &S.shift[l - 1][kc * KC];
+                    uint8_t *A = sA + (size_t)ra.stage * A_STAGE_BYTES;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float o[4];
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t acc[16];
+                        tmem_ld16(tmem + lane_base + (uint32_t)(p.dcol[l - 1] + kc * KC + hh * 16), acc);
+                        const float *sc = s_scale + sc_off[l - 1] + kc * KC + hh * 16;
+                        const float *sh = s_shift + sc_off[l - 1] + kc * KC + hh * 16;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            o[q] = to_tf32(fmaxf(fmaf(__uint_as_float(acc[4 * j + q]), sc[4 * j + q], sh[4 * j + q]), 0.f));
-                        *reinterpret_cast<float4 *>(A + swz(r, j)) = make_float4(o[0], o[1], o[2], o[3]);
+                        for (int j = 0; j < 4; ++j) {
+                            float o[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                o[q] = to_tf32(fmaxf(fmaf(__uint_as_float(acc[4 * j + q]), sc[4 * j + q], sh[4 * j + q]), 0.f));
+                            *reinterpret_cast<float4 *>(A + swz(r, hh * 4 + j)) = make_float4(o[0], o[1], o[2], o[3]);
+                        }
                     }
                     tc_fence_before();
                     fence_async_smem();
@@ -411,18 +470,18 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const Chain
             mbar_wait(s2u(&S.d_full[L - 1]), dphase);
             tc_fence_after();
             const int Cl = p.c_last;
-            for (int c0 = 0; c0 < Cl; c0 += 32) {
-                uint32_t acc[32];
-                tmem_ld32(tmem + lane_base + (uint32_t)(p.dcol[L - 1] + c0), acc);
-                float v[32];
+            const float *sc = s_scale + sc_off[L - 1], *sh = s_shift + sc_off[L - 1];
+            for (int c0 = 0; c0 < Cl; c0 += 16) {
+                uint32_t acc[16];
+                tmem_ld16(tmem + lane_base + (uint32_t)(p.dcol[L - 1] + c0), acc);
+                float v[16];
 #pragma unroll
-                for (int q = 0; q < 32; ++q)
-                    v[q] = fmaxf(fmaf(__uint_as_float(acc[q]), S.scale[L - 1][c0 + q], S.shift[L - 1][c0 + q]), 0.f);
+                for (int q = 0; q < 16; ++q) v[q] = fmaxf(fmaf(__uint_as_float(acc[q]), sc[c0 + q], sh[c0 + q]), 0.f);
                 if (p.mode_out == OUT_ROWS) {
                     if (valid) {
                         float *o = p.out + (size_t)R * p.out_pitch + c0;
 #pragma unroll
-                        for (int q = 0; q < 32; q += 4)
+                        for (int q = 0; q < 16; q += 4)
                             *reinterpret_cast<float4 *>(o + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
                     }
                 } else if (p.mode_out == OUT_FP) {
@@ -430,7 +489,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const Chain
                         const int scene = (int)(R / p.n), u = (int)(R - (long)scene * p.n);
                         float *o = p.out + ((size_t)scene * p.out_stride_c + p.out_c_off + c0) * p.n + u;
 #pragma unroll
-                        for (int q = 0; q < 32; ++q)
+                        for (int q = 0; q < 16; ++q)
                             if (c0 + q < Cl) o[(size_t)q * p.n] = v[q];
                     }
                 } else {
@@ -439,7 +498,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const Chain
                     const int ns = p.ns;
                     const int w = ns < 32 ? ns : 32;
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) {
+                    for (int q = 0; q < 16; ++q) {
                         float x = v[q];
                         for (int off = 1; off < w; off <<= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, off));
                         v[q] = x;
@@ -451,10 +510,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const Chain
                     if ((lane % w) == 0) {
                         const int pg = warp * gpw + lane / w;
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) S.red[q][pg] = v[q];
+                        for (int q = 0; q < 16; ++q) S.red[q][pg] = v[q];
                     }
                     named_bar_rows();
-                    for (int e = r; e < 32 * G; e += ROW_THREADS) {
+                    for (int e = r; e < 16 * G; e += ROW_THREADS) {
                         const int q = e / G, g = e - q * G;
                         float x = S.red[q][g * ppc];
                         for (int t = 1; t < ppc; ++t) x = fmaxf(x, S.red[q][g * ppc + t]);
@@ -474,7 +533,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const Chain
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem, 512);
+    if (warp == 5) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -598,17 +657,48 @@ int prb_mlp_pack_weights(int num_layers, int c_in, const int *c_out, const float
 
 namespace prb {
 
-// launch one fused segment [l0, l1) of the chain
+// launch one fused segment of the chain: size rings / TMEM to the segment, pick the CTAs-per-SM it allows
 static int launch_chain(ChainParams &p, cudaStream_t st) {
-    static bool attr_set = false;
-    const size_t smem = sizeof(Smem) + 1024;
-    if (!attr_set) {
-        PRB_CUDA(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+    static int max_optin = 0;
+    if (!max_optin) {
+        int dev = 0;
+        PRB_CUDA(cudaGetDevice(&dev));
+        PRB_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     }
     p.num_tiles = (int)((p.total_rows + TM - 1) / TM);
     if (p.num_tiles == 0) return 0;
-    int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    const int L = p.num_layers;
+    int np_total = 0, np_max = 0;
+    for (int l = 0; l < L; ++l) { np_total += p.np[l]; np_max = p.np[l] > np_max ? p.np[l] : np_max; }
+    p.b_stage_bytes = (np_max < B_TILE_ROWS ? np_max : B_TILE_ROWS) * KC * 4;
+    int need = p.np[0];
+    if (L >= 2) need = p.np[0] + p.np[1];
+    if (L >= 3 && p.np[1] + p.np[2] > need) need = p.np[1] + p.np[2];
+    int cols = 32;
+    while (cols < need) cols <<= 1;
+    p.tmem_cols = cols;
+    p.dcol[0] = 0;
+    if (L >= 2) p.dcol[1] = cols - p.np[1];
+    if (L >= 3) p.dcol[2] = 0;
+    // occupancy: as many CTAs per SM as TMEM, shared memory and the register bound (2) allow
+    const int sm_smem = 227 * 1024;
+    int occ = 512 / cols;
+    if (occ > 2) occ = 2;
+    const char *e = getenv("PRB_MLP_OCC");
+    if (e && atoi(e) > 0 && atoi(e) < occ) occ = atoi(e);
+    size_t smem = 0;
+    for (;; --occ) {
+        int depth = occ >= 2 ? 3 : 4;
+        for (; depth >= 2; --depth) {
+            smem = chain_smem_bytes(depth, depth, p.b_stage_bytes, np_total);
+            if (smem * occ <= (size_t)sm_smem - 1024 * occ && smem <= (size_t)max_optin) { p.na = p.nb = depth; break; }
+        }
+        if (depth >= 2 || occ == 1) break;
+    }
+    PRB_REQUIRE(smem <= (size_t)max_optin, "mlp: %zu bytes of shared memory needed, %d available", smem, max_optin);
+    PRB_CUDA(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = num_sms() * occ;
+    if (grid > p.num_tiles) grid = p.num_tiles;
     mlp_chain_kernel<<<grid, CHAIN_THREADS, smem, st>>>(p);
     return check_launch("mlp_chain_kernel");
 }
@@ -672,9 +762,6 @@ static int run_chain(const ChainIO &io, const prb_mlp_desc *mlp, void *workspace
             p.scale[i] = mlp->scale + soff[l];
             p.shift[i] = mlp->shift + soff[l];
         }
-        p.dcol[0] = 0;
-        if (p.num_layers >= 2) p.dcol[1] = 512 - p.np[1];
-        if (p.num_layers >= 3) p.dcol[2] = 0;
         if (l0 > 0) {  // continue from materialised rows
             p.mode_in = IN_DIRECT;
             p.x_rows = cur_rows;
