@@ -62,21 +62,48 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
     return r;
 }
-// 8-byte relaxed store into a peer CTA's shared memory / relaxed poll of the local copy (cluster scope):
-// key and round tag travel in ONE 64-bit word, so no separate flag or barrier is needed
-__device__ __forceinline__ void st_cluster_b64(uint32_t remote_addr, uint64_t v) {
-    asm volatile("st.relaxed.cluster.shared::cluster.b64 [%0], %1;" ::"r"(remote_addr), "l"(v) : "memory");
+// ---- cluster exchange primitives (variants are selected at compile time; see XCHG below)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ uint64_t ld_cluster_b64(uint32_t local_addr) {
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// 8-byte store into a peer CTA's shared memory that completes 8 tx-bytes on the peer's mbarrier
+__device__ __forceinline__ void st_async_b64(uint32_t remote_addr, uint64_t v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "l"(v), "r"(remote_bar)
+                 : "memory");
+}
+// plain 8-byte store into a peer CTA's shared memory / volatile poll of the local copy: key and round tag travel
+// in ONE 64-bit word, so no separate flag is needed
+__device__ __forceinline__ void st_cluster_b64(uint32_t remote_addr, uint64_t v) {
+    asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(remote_addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_poll_b64(uint32_t local_addr) {
     uint64_t v;
-    asm volatile("ld.relaxed.cluster.shared::cta.b64 %0, [%1];" : "=l"(v) : "r"(local_addr) : "memory");
+    asm volatile("ld.volatile.shared::cta.b64 %0, [%1];" : "=l"(v) : "r"(local_addr) : "memory");
     return v;
 }
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
+// exchange variants: 0 = st.async + mbarrier complete_tx; 1 = per-CTA winner, plain remote store + tag polling;
+// 2 = per-CTA winner, plain remote store + cluster barrier; 3 = per-warp winners pushed to every CTA + tag polling
 constexpr int kMaxWarps = 32;
 constexpr int kMaxCluster = 8;
 
-template <int THREADS, int PPT, int CS>
+template <int THREADS, int PPT, int CS, int XCHG>
 __global__ void __launch_bounds__(THREADS, 1) fps_rank_kernel(const FpsParams p) {
     constexpr int W = THREADS / 32;
     extern __shared__ __align__(16) float s_pts[];  // rank-ordered xyz (3 floats per rank), optional
@@ -84,6 +111,7 @@ __global__ void __launch_bounds__(THREADS, 1) fps_rank_kernel(const FpsParams p)
     // cluster exchange: every warp of every CTA pushes its winner straight into every CTA's slot array;
     // word = dist bits (32) | round tag (12) | rank (20); double buffered by round parity
     __shared__ __align__(8) uint64_t s_slot[2][kMaxCluster * (THREADS / 32)];
+    __shared__ __align__(8) uint64_t s_bar[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
@@ -94,8 +122,14 @@ __global__ void __launch_bounds__(THREADS, 1) fps_rank_kernel(const FpsParams p)
     int *idx = p.idx + (size_t)scene * m;
     float *new_xyz = p.new_xyz ? p.new_xyz + (size_t)scene * m * 3 : nullptr;
 
-    if (CS > 1)
+    if (CS > 1) {
         for (int i = tid; i < 2 * CS * W; i += THREADS) (&s_slot[0][0])[i] = 0ull;   // tag 0 is never waited for first
+        if (XCHG == 0 && tid == 0) {
+            mbar_init(smem_u32(&s_bar[0]), 1);
+            mbar_init(smem_u32(&s_bar[1]), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
 
     // rank-ordered copy of the scene (coalesced global reads, scattered shared stores)
     if (p.use_smem_xyz) {
@@ -134,8 +168,10 @@ __global__ void __launch_bounds__(THREADS, 1) fps_rank_kernel(const FpsParams p)
         if (new_xyz) { new_xyz[0] = cx; new_xyz[1] = cy; new_xyz[2] = cz; }
     }
 
+    uint32_t phase0 = 0, phase1 = 0;
     for (int j = 1; j < m; ++j) {
         const int par = j & 1;
+        if (CS > 1 && XCHG == 0 && tid == 0) mbar_arrive_expect_tx(smem_u32(&s_bar[par]), CS * 8);
         float best = -1.f;
         int bslot = 0;
 #pragma unroll
@@ -152,13 +188,39 @@ __global__ void __launch_bounds__(THREADS, 1) fps_rank_kernel(const FpsParams p)
         int wr = __shfl_sync(0xffffffffu, g * PPT + bslot, __ffs(bal) - 1);
 
         int r;  // winning rank, uniform
-        if (CS == 1) {
+        if (CS == 1 || XCHG != 3) {
+            // CTA-level winner (lowest warp wins ties)
             if (lane == 0) s_wkey[par][warp] = make_int2(wm, wr);
             __syncthreads();
             int2 kv = lane < W ? s_wkey[par][lane] : make_int2(INT_MIN, 0);
             int cm = __reduce_max_sync(0xffffffffu, kv.x);
             unsigned b2 = __ballot_sync(0xffffffffu, kv.x == cm);
             r = __shfl_sync(0xffffffffu, kv.y, __ffs(b2) - 1);
+            if (CS > 1) {
+                const uint32_t tag = (uint32_t)j & 0xFFFu;
+                const uint64_t key = ((uint64_t)(uint32_t)cm << 32) | ((uint64_t)tag << 20) | (uint32_t)r;
+                uint64_t got = 0;
+                if (XCHG == 0) {
+                    if (warp == 0 && lane < CS)
+                        st_async_b64(map_to_cta(smem_u32(&s_slot[par][crank]), lane), key, map_to_cta(smem_u32(&s_bar[par]), lane));
+                    mbar_wait_cluster(smem_u32(&s_bar[par]), par ? phase1 : phase0);
+                    if (par) phase1 ^= 1; else phase0 ^= 1;
+                    if (lane < CS) got = s_slot[par][lane];
+                } else if (XCHG == 1) {
+                    if (warp == 0 && lane < CS) st_cluster_b64(map_to_cta(smem_u32(&s_slot[par][crank]), lane), key);
+                    if (lane < CS)
+                        do { got = ld_poll_b64(smem_u32(&s_slot[par][lane])); } while ((((uint32_t)got >> 20) & 0xFFFu) != tag);
+                } else {
+                    if (warp == 0 && lane < CS) st_cluster_b64(map_to_cta(smem_u32(&s_slot[par][crank]), lane), key);
+                    cluster_arrive_release();
+                    cluster_wait_acquire();
+                    if (lane < CS) got = ld_poll_b64(smem_u32(&s_slot[par][lane]));
+                }
+                const int kx = lane < CS ? (int)(uint32_t)(got >> 32) : INT_MIN;
+                const int gm = __reduce_max_sync(0xffffffffu, kx);
+                const unsigned b3 = __ballot_sync(0xffffffffu, kx == gm);
+                r = __shfl_sync(0xffffffffu, (int)((uint32_t)got & 0xFFFFFu), __ffs(b3) - 1);
+            }
         } else {
             constexpr int NSLOT = CS * W;                 // one slot per (CTA, warp), ordered by rank range
             const uint32_t tag = (uint32_t)j & 0xFFFu;
@@ -173,7 +235,7 @@ __global__ void __launch_bounds__(THREADS, 1) fps_rank_kernel(const FpsParams p)
                 const int sl = lane + 32 * q;
                 if (sl < NSLOT) {
                     uint64_t key;
-                    do { key = ld_cluster_b64(smem_u32(&s_slot[par][sl])); } while ((((uint32_t)key >> 20) & 0xFFFu) != tag);
+                    do { key = ld_poll_b64(smem_u32(&s_slot[par][sl])); } while ((((uint32_t)key >> 20) & 0xFFFu) != tag);
                     const int v = (int)(uint32_t)(key >> 32);
                     if (v > bv) { bv = v; bs = sl; br = (int)((uint32_t)key & 0xFFFFFu); }
                 }
@@ -251,9 +313,9 @@ __global__ void __launch_bounds__(1024, 1) fps_generic_kernel(const FpsParams p)
     }
 }
 
-template <int THREADS, int PPT, int CS>
+template <int THREADS, int PPT, int CS, int XCHG>
 static int launch_rank(const FpsParams &p, size_t smem, cudaStream_t stream) {
-    auto kern = fps_rank_kernel<THREADS, PPT, CS>;
+    auto kern = fps_rank_kernel<THREADS, PPT, CS, XCHG>;
     // static shared memory counts against the 48 KB default too
     if (smem + 2048 > 48 * 1024) PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
@@ -273,13 +335,20 @@ static int launch_rank(const FpsParams &p, size_t smem, cudaStream_t stream) {
 }
 
 template <int CS>
-static int dispatch_cs(const FpsParams &p, int threads, int ppt, size_t smem, cudaStream_t st) {
-#define PRB_FPS_CASE(T, P) \
-    if (threads == T && ppt == P) return launch_rank<T, P, CS>(p, smem, st);
-    PRB_FPS_CASE(128, 1) PRB_FPS_CASE(128, 2) PRB_FPS_CASE(128, 4)
-    PRB_FPS_CASE(256, 4) PRB_FPS_CASE(256, 8)
-    PRB_FPS_CASE(512, 2) PRB_FPS_CASE(512, 4) PRB_FPS_CASE(512, 8) PRB_FPS_CASE(512, 16)
-    PRB_FPS_CASE(1024, 4) PRB_FPS_CASE(1024, 8)
+static int dispatch_cs(const FpsParams &p, int threads, int ppt, int xchg, size_t smem, cudaStream_t st) {
+#define PRB_FPS_CASE(T, P)                                                        \
+    if (threads == T && ppt == P) {                                               \
+        if (CS == 1 || xchg == 2) return launch_rank<T, P, CS, 2>(p, smem, st);   \
+        if (xchg == 0) return launch_rank<T, P, CS, 0>(p, smem, st);              \
+        if (xchg == 1) return launch_rank<T, P, CS, 1>(p, smem, st);              \
+        return launch_rank<T, P, CS, 3>(p, smem, st);                             \
+    }
+    if (CS == 1) {
+        PRB_FPS_CASE(128, 1) PRB_FPS_CASE(128, 2) PRB_FPS_CASE(128, 4)
+        PRB_FPS_CASE(256, 4) PRB_FPS_CASE(256, 8)
+        PRB_FPS_CASE(1024, 4) PRB_FPS_CASE(1024, 8)
+    }
+    PRB_FPS_CASE(256, 4) PRB_FPS_CASE(512, 2) PRB_FPS_CASE(512, 4) PRB_FPS_CASE(512, 8) PRB_FPS_CASE(512, 16)
 #undef PRB_FPS_CASE
     set_error("fps: no kernel instance for threads=%d ppt=%d cs=%d", threads, ppt, CS);
     return -1;
@@ -343,11 +412,12 @@ extern "C" int prb_furthest_point_sampling(int b, int n, int m, const float *xyz
     size_t smem_pts = (size_t)n_pad * 3 * sizeof(float);
     p.use_smem_xyz = smem_pts <= 200 * 1024 ? 1 : 0;
     size_t smem = p.use_smem_xyz ? smem_pts : 0;
+    const int xchg = env_int("PRB_FPS_XCHG", 0);
     switch (cs) {
-        case 1: return dispatch_cs<1>(p, threads, ppt, smem, st);
-        case 2: return dispatch_cs<2>(p, threads, ppt, smem, st);
-        case 4: return dispatch_cs<4>(p, threads, ppt, smem, st);
-        case 8: return dispatch_cs<8>(p, threads, ppt, smem, st);
+        case 1: return dispatch_cs<1>(p, threads, ppt, xchg, smem, st);
+        case 2: return dispatch_cs<2>(p, threads, ppt, xchg, smem, st);
+        case 4: return dispatch_cs<4>(p, threads, ppt, xchg, smem, st);
+        case 8: return dispatch_cs<8>(p, threads, ppt, xchg, smem, st);
     }
     set_error("fps: bad cluster size %d", cs);
     return -1;
