@@ -377,12 +377,18 @@ extern "C" int prb_furthest_point_sampling(int b, int n, int m, const float *xyz
     const int n_pad = p.S * p.Q;
 
     // configuration: cluster size, threads per CTA, points per thread
+    // A cluster of CS CTAs per scene cuts the per-round compute CS-fold, but all b clusters must be co-resident
+    // in ONE wave (each needs CS free SMs inside one GPC).  Measured on B200, n=16384, m=4096 (profiles/
+    // r1_fps_sweep.json): b=2 -> CS=8 2.23 ms, CS=4 2.60 ms; b=16 -> CS=8 4.37 ms (two waves), CS=4 2.61 ms.
     int cs = env_int("PRB_FPS_CS", 0);
     if (cs == 0) {
         cs = 1;
         if (n_pad >= 8192) {
             cs = 8;
-            while (cs > 1 && (long)b * cs > 2L * num_sms()) cs >>= 1;
+            const int cap8 = 12, cap4 = 32, cap2 = 72;   // co-resident clusters (conservative: 148 SMs, 8 GPCs)
+            if (b > cap8) cs = 4;
+            if (b > cap4) cs = 2;
+            if (b > cap2) cs = 1;
         }
     }
     while (cs < 8 && ceil_div(n_pad, cs) > 8192) cs <<= 1;  // keep the register-resident path

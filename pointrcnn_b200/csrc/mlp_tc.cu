@@ -35,8 +35,6 @@ constexpr int KC = 32;               // K columns per chunk (128 bytes of fp32/t
 constexpr int A_STAGE_BYTES = TM * KC * 4;        // 16 KB
 constexpr int B_TILE_ROWS = 256;                  // max N per MMA / per weight tile
 constexpr int MAX_STAGES = 4;        // ring depth upper bound (runtime depth in ChainParams)
-constexpr int ROW_THREADS = 128;
-constexpr int CHAIN_THREADS = 192;   // 4 row warps + producer warp + MMA warp
 constexpr int MAX_LAYERS = 3;
 constexpr int MAX_NP = 512;
 
@@ -97,6 +95,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "D_%=:\n\t}" ::"r"(bar), "r"(parity)
         : "memory");
 }
+// same, with a suspend-time hint: the single producer / MMA-issuer threads should sleep in hardware instead of
+// spinning in the issue slots of the row warps that share their scheduler
+__device__ __forceinline__ void mbar_wait_sleepy(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra D_%=;\n\t"
+        "bra W_%=;\n\t"
+        "D_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(20000u)
+        : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -141,7 +151,6 @@ __device__ __forceinline__ float to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-__device__ __forceinline__ void named_bar_rows() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row atoms of 1024 bytes (SBO), version 1
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
@@ -161,19 +170,19 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 __device__ __forceinline__ uint32_t swz(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
 // Shared memory is carved at run time (ring depths and the weight-stage size depend on the chain), so that
-// narrow layers (SA1/SA2) fit 2-3 CTAs per SM and overlap their latency-bound gathers.
+// narrow layers (SA1/SA2) fit 2 CTAs per SM and overlap their latency-bound gathers.
+constexpr int POOL_STRIDE = 20;      // floats per row of the max-pool staging tile (80 B: conflict-free 128-bit stores)
 struct SmemFixed {
     int row_src[TM][3];      // SA: global point row (slot 0); FP: 3 known rows
     float row_aux[TM][3];    // SA: centre xyz; FP: 3 weights
     int row_valid[TM];
-    float red[32][33];       // [channel][partial group] staging of the max-pool epilogue
     uint64_t a_full[MAX_STAGES], a_empty[MAX_STAGES], b_full[MAX_STAGES], b_empty[MAX_STAGES], d_full[MAX_LAYERS];
     uint32_t tmem_base;
 };
 
-__host__ __device__ inline size_t chain_smem_bytes(int na, int nb, int b_stage_bytes, int np_total) {
+__host__ __device__ inline size_t chain_smem_bytes(int ng, int na, int nb, int b_stage_bytes, int np_total) {
     return 1024 /*alignment slack*/ + (size_t)na * A_STAGE_BYTES + (size_t)nb * b_stage_bytes + (size_t)2 * np_total * sizeof(float) +
-           sizeof(SmemFixed) + 64;
+           (size_t)ng * (TM * POOL_STRIDE + 8 * 16) * sizeof(float) + sizeof(SmemFixed) + 64;
 }
 
 struct RingPos {
@@ -183,8 +192,22 @@ struct RingPos {
     }
 };
 
+// barrier over one row group (128 threads) / over all row threads
+__device__ __forceinline__ void bar_group(int grp) {
+    if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+    else if (grp == 1) asm volatile("bar.sync 3, 128;" ::: "memory");
+    else asm volatile("bar.sync 4, 128;" ::: "memory");
+}
+template <int NG>
+__device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, %0;" ::"n"(128 * NG) : "memory"); }
+
 // ------------------------------------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(CHAIN_THREADS, 2) mlp_chain_kernel(const ChainParams p) {
+// NG row groups of 4 warps each (warp w: TMEM lane quarter w%4, group w/4) + producer warp + MMA warp.
+// The A chunks (and the 16-column epilogue batches) of a tile are dealt round-robin to the groups, so 4*NG warps
+// hide each other's latencies while the stage order seen by the MMA issuer stays sequential.
+template <int NG>
+__global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kernel(const ChainParams p) {
+    constexpr int NTHREADS = 128 * NG + 64;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int L = p.num_layers;
@@ -194,25 +217,26 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) mlp_chain_kernel(const Chain
     uint8_t *sB = sA + (size_t)p.na * A_STAGE_BYTES;
     float *s_scale = reinterpret_cast<float *>(sB + (size_t)p.nb * p.b_stage_bytes);
     float *s_shift = s_scale + np_total;
-    SmemFixed &S = *reinterpret_cast<SmemFixed *>((reinterpret_cast<uintptr_t>(s_shift + np_total) + 15) & ~(uintptr_t)15);
+    float *s_pool = s_shift + np_total;                                  // NG x (TM x POOL_STRIDE + 8 x 16)
+    SmemFixed &S = *reinterpret_cast<SmemFixed *>((reinterpret_cast<uintptr_t>(s_pool + NG * (TM * POOL_STRIDE + 128)) + 15) & ~(uintptr_t)15);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NA = p.na, NB = p.nb;
 
     if (tid == 0) {
-        for (int i = 0; i < NA; ++i) { mbar_init(s2u(&S.a_full[i]), ROW_THREADS); mbar_init(s2u(&S.a_empty[i]), 1); }
+        for (int i = 0; i < NA; ++i) { mbar_init(s2u(&S.a_full[i]), 128); mbar_init(s2u(&S.a_empty[i]), 1); }
         for (int i = 0; i < NB; ++i) { mbar_init(s2u(&S.b_full[i]), 1); mbar_init(s2u(&S.b_empty[i]), 1); }
         for (int i = 0; i < MAX_LAYERS; ++i) mbar_init(s2u(&S.d_full[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) tmem_alloc(s2u(&S.tmem_base), (uint32_t)p.tmem_cols);
+    if (warp == 4 * NG + 1) tmem_alloc(s2u(&S.tmem_base), (uint32_t)p.tmem_cols);
     for (int l = 0; l < L; ++l)
-        for (int i = tid; i < p.np[l]; i += CHAIN_THREADS) { s_scale[sc_off[l] + i] = p.scale[l][i]; s_shift[sc_off[l] + i] = p.shift[l][i]; }
+        for (int i = tid; i < p.np[l]; i += NTHREADS) { s_scale[sc_off[l] + i] = p.scale[l][i]; s_shift[sc_off[l] + i] = p.shift[l][i]; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
 
-    if (warp == 4) {
+    if (warp == 4 * NG) {
         // ===================================================== weight producer
         if (lane == 0) {
             RingPos rb = {0, 0};
@@ -223,7 +247,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) mlp_chain_kernel(const Chain
                         for (int h = 0; h < halves; ++h) {
                             const int rows = min(B_TILE_ROWS, p.np[l] - h * B_TILE_ROWS);
                             const uint32_t bytes = (uint32_t)rows * KC * 4;
-                            mbar_wait(s2u(&S.b_empty[rb.stage]), rb.phase ^ 1);
+                            mbar_wait_sleepy(s2u(&S.b_empty[rb.stage]), rb.phase ^ 1);
                             mbar_expect_tx(s2u(&S.b_full[rb.stage]), bytes);
                             const float *src = p.w[l] + ((size_t)kc * p.np[l] + (size_t)h * B_TILE_ROWS) * KC;
                             bulk_g2s(s2u(sB + (size_t)rb.stage * p.b_stage_bytes), src, bytes, s2u(&S.b_full[rb.stage]));
@@ -232,7 +256,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) mlp_chain_kernel(const Chain
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 4 * NG + 1) {
         // ===================================================== MMA issuer
         if (lane == 0) {
             RingPos ra = {0, 0}, rb = {0, 0};
@@ -248,11 +272,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) mlp_chain_kernel(const Chain
                             valid = min(KC, p.seg_width[s] - c * KC);
                         }
                         const int ksteps = (valid + 7) >> 3;
-                        mbar_wait(s2u(&S.a_full[ra.stage]), ra.phase);
+                        mbar_wait_sleepy(s2u(&S.a_full[ra.stage]), ra.phase);
                         const uint64_t adesc = make_desc(s2u(sA + (size_t)ra.stage * A_STAGE_BYTES));
                         for (int h = 0; h < halves; ++h) {
                             const int rows = min(B_TILE_ROWS, p.np[l] - h * B_TILE_ROWS);
-                            mbar_wait(s2u(&S.b_full[rb.stage]), rb.phase);
+                            mbar_wait_sleepy(s2u(&S.b_full[rb.stage]), rb.phase);
                             tc_fence_after();
                             const uint64_t bdesc = make_desc(s2u(sB + (size_t)rb.stage * p.b_stage_bytes));
                             const uint32_t idesc = make_idesc(rows);
@@ -270,13 +294,17 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) mlp_chain_kernel(const Chain
             }
         }
     } else {
-        // ===================================================== row threads (warps 0-3)
+        // ===================================================== row threads (warps 0 .. 4*NG-1)
         RingPos ra = {0, 0};
         uint32_t dphase = 0;
-        const int r = tid;  // my row inside the tile / my TMEM lane
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        const int wq = warp & 3, grp = warp >> 2;
+        const int r = wq * 32 + lane;       // my row inside the tile / my TMEM lane
+        const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
         const int j8 = lane & 7;            // my 16-byte unit inside a 128-byte row (gathers)
         const int rsub = lane >> 3;         // which of the 4 rows a warp-wide gather step covers
+        uint32_t cc = 0;                    // chunk counter: chunk cc belongs to group cc % NG
+        float *pool = s_pool + grp * (TM * POOL_STRIDE + 128);
+        float *pool2 = pool + TM * POOL_STRIDE;   // 8 x 16 partial maxima (nsample > 32)
 
         // tile metadata is fetched one tile ahead (global loads of idx / centres / weights overlap the MMAs)
         int m_src[3] = {0, 0, 0};
@@ -307,14 +335,17 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) mlp_chain_kernel(const Chain
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const long R = (long)tile * TM + r;
             const bool valid = m_valid;
-            named_bar_rows();  // previous tile's readers of S.row_* are done
-            S.row_valid[r] = valid;
+            bar_rows<NG>();  // previous tile's readers of S.row_* are done
+            if (grp == 0) {
+                S.row_valid[r] = valid;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) { S.row_src[r][q] = m_src[q]; S.row_aux[r][q] = m_aux[q]; }
-            named_bar_rows();
+                for (int q = 0; q < 3; ++q) { S.row_src[r][q] = m_src[q]; S.row_aux[r][q] = m_aux[q]; }
+            }
+            bar_rows<NG>();
 
             // ---- layer 0: build A chunks from global memory
-            for (int kc = 0; kc < p.nchunks[0]; ++kc) {
+            for (int kc = 0; kc < p.nchunks[0]; ++kc, ++cc, ra.advance(NA)) {
+                if ((int)(cc % NG) != grp) continue;
                 int c = kc, seg = 0;
                 if (p.nseg > 1 && c >= p.seg_chunks[0]) { c -= p.seg_chunks[0]; seg = 1; }
                 const int k0 = c * KC;                       // first column of this chunk inside its segment
@@ -335,7 +366,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) mlp_chain_kernel(const Chain
                             float w0[4], w1[4], w2[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const int rr = warp * 32 + rsub + 4 * (half * 4 + i);
+                                const int rr = wq * 32 + rsub + 4 * (half * 4 + i);
                                 t0[i] = t1[i] = t2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                                 w0[i] = S.row_aux[rr][0]; w1[i] = S.row_aux[rr][1]; w2[i] = S.row_aux[rr][2];
                                 if (S.row_valid[rr] && kk < width) {
@@ -360,7 +391,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) mlp_chain_kernel(const Chain
                             if (half == 0) mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const int rr = warp * 32 + rsub + 4 * (half * 4 + i);
+                                const int rr = wq * 32 + rsub + 4 * (half * 4 + i);
                                 // same contraction as three_interpolate (reference SASS): fma(w2,p2, fma(w0,p0, w1*p1))
                                 float4 v;
                                 v.x = to_tf32(__fmaf_rn(w2[i], t2[i].x, __fmaf_rn(w0[i], t0[i].x, __fmul_rn(w1[i], t1[i].x))));
@@ -376,7 +407,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) mlp_chain_kernel(const Chain
                         float4 t[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const int rr = warp * 32 + rsub + 4 * i;
+                            const int rr = wq * 32 + rsub + 4 * i;
                             t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (S.row_valid[rr] && kk < width) {
                                 const float *src = p.mode_in == IN_DIRECT ? p.x_rows + ((size_t)tile * TM + rr) * pitch + kk
@@ -394,7 +425,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) mlp_chain_kernel(const Chain
                         mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const int rr = warp * 32 + rsub + 4 * i;
+                            const int rr = wq * 32 + rsub + 4 * i;
                             float4 v = t[i];
                             v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
                             *reinterpret_cast<float4 *>(A + swz(rr, j8)) = v;
@@ -431,7 +462,6 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) mlp_chain_kernel(const Chain
                 }
                 fence_async_smem();
                 mbar_arrive(s2u(&S.a_full[ra.stage]));
-                ra.advance(NA);
             }
 
             // next tile's metadata: issue the loads now, consume them at the top of the next iteration
@@ -441,7 +471,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) mlp_chain_kernel(const Chain
             for (int l = 1; l < L; ++l) {
                 mbar_wait(s2u(&S.d_full[l - 1]), dphase);
                 tc_fence_after();
-                for (int kc = 0; kc < p.nchunks[l]; ++kc) {
+                for (int kc = 0; kc < p.nchunks[l]; ++kc, ++cc, ra.advance(NA)) {
+                    if ((int)(cc % NG) != grp) continue;
                     mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
                     uint8_t *A = sA + (size_t)ra.stage * A_STAGE_BYTES;
 #pragma unroll
@@ -462,16 +493,15 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) mlp_chain_kernel(const Chain
                     tc_fence_before();
                     fence_async_smem();
                     mbar_arrive(s2u(&S.a_full[ra.stage]));
-                    ra.advance(NA);
                 }
             }
 
-            // ---- final epilogue
+            // ---- final epilogue: 16-column batches dealt round-robin to the row groups
             mbar_wait(s2u(&S.d_full[L - 1]), dphase);
             tc_fence_after();
             const int Cl = p.c_last;
             const float *sc = s_scale + sc_off[L - 1], *sh = s_shift + sc_off[L - 1];
-            for (int c0 = 0; c0 < Cl; c0 += 16) {
+            for (int c0 = grp * 16; c0 < Cl; c0 += 16 * NG) {
                 uint32_t acc[16];
                 tmem_ld16(tmem + lane_base + (uint32_t)(p.dcol[L - 1] + c0), acc);
                 float v[16];
@@ -493,35 +523,52 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) mlp_chain_kernel(const Chain
                             if (c0 + q < Cl) o[(size_t)q * p.n] = v[q];
                     }
                 } else {
-                    // max over the nsample consecutive rows of each centre.  Groups are whole (total_rows is a
-                    // multiple of nsample), so rows of the tail tile past total_rows form groups that are skipped.
+                    // max over the nsample consecutive rows of each centre, through a shared staging tile:
+                    // thread (seg, q) reduces the <=16 rows of one segment for channel c0+q; segments of a centre
+                    // with nsample > 16 are combined with one shuffle (32) or a second tiny tile (64, 128).
+                    // Groups are whole (total_rows is a multiple of nsample): tail groups past total_rows are skipped.
                     const int ns = p.ns;
-                    const int w = ns < 32 ? ns : 32;
+                    const int g16 = r >> 4, q = r & 15;          // (segment of 16 rows, channel) handled by this thread
+                    bar_group(grp);                              // previous readers of the staging tile are done
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        float x = v[q];
-                        for (int off = 1; off < w; off <<= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, off));
-                        v[q] = x;
-                    }
-                    const int gpw = 32 / w;                   // partial groups per warp
-                    const int ppc = ns > 32 ? ns / 32 : 1;    // partials per centre
-                    const int G = TM / ns;                    // centres per tile
-                    named_bar_rows();                         // previous readers of S.red are done
-                    if ((lane % w) == 0) {
-                        const int pg = warp * gpw + lane / w;
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<float4 *>(pool + r * POOL_STRIDE + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    bar_group(grp);
+                    if (ns >= 16) {
+                        float x = pool[(g16 * 16) * POOL_STRIDE + q];
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) S.red[q][pg] = v[q];
-                    }
-                    named_bar_rows();
-                    for (int e = r; e < 16 * G; e += ROW_THREADS) {
-                        const int q = e / G, g = e - q * G;
-                        float x = S.red[q][g * ppc];
-                        for (int t = 1; t < ppc; ++t) x = fmaxf(x, S.red[q][g * ppc + t]);
-                        const long Rg = (long)tile * TM + (long)g * ns;
-                        if (Rg < p.total_rows && c0 + q < Cl) {
-                            const long pr = Rg / ns;
-                            const int scene = (int)(pr / p.npoint), pp = (int)(pr - (long)scene * p.npoint);
-                            p.out[((size_t)scene * p.out_stride_c + p.out_c_off + c0 + q) * p.npoint + pp] = x;
+                        for (int s = 1; s < 16; ++s) x = fmaxf(x, pool[(g16 * 16 + s) * POOL_STRIDE + q]);
+                        if (ns == 32) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 16));
+                        if (ns > 32) {
+                            pool2[g16 * 16 + q] = x;
+                            bar_group(grp);
+                            const int per = ns >> 4;
+                            if ((g16 % per) == 0) {
+                                for (int s = 1; s < per; ++s) x = fmaxf(x, pool2[(g16 + s) * 16 + q]);
+                            }
+                        }
+                        const int per = ns >> 4;                 // 16-row segments per centre
+                        if ((g16 % per) == 0) {
+                            const long Rg = (long)tile * TM + (long)g16 * 16;
+                            if (Rg < p.total_rows && c0 + q < Cl) {
+                                const long pr = Rg / ns;
+                                const int scene = (int)(pr / p.npoint), pp = (int)(pr - (long)scene * p.npoint);
+                                p.out[((size_t)scene * p.out_stride_c + p.out_c_off + c0 + q) * p.npoint + pp] = x;
+                            }
+                        }
+                    } else {
+                        // nsample 4 or 8: 128/ns centres per tile, 16 channels each -> (16/ns) items per thread
+                        const int per16 = 16 / ns;
+                        for (int t = 0; t < per16; ++t) {
+                            const int row0 = g16 * 16 + t * ns;
+                            float x = pool[row0 * POOL_STRIDE + q];
+                            for (int s = 1; s < ns; ++s) x = fmaxf(x, pool[(row0 + s) * POOL_STRIDE + q]);
+                            const long Rg = (long)tile * TM + row0;
+                            if (Rg < p.total_rows && c0 + q < Cl) {
+                                const long pr = Rg / ns;
+                                const int scene = (int)(pr / p.npoint), pp = (int)(pr - (long)scene * p.npoint);
+                                p.out[((size_t)scene * p.out_stride_c + p.out_c_off + c0 + q) * p.npoint + pp] = x;
+                            }
                         }
                     }
                 }
@@ -533,7 +580,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 2) mlp_chain_kernel(const Chain
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+    if (warp == 4 * NG + 1) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -680,26 +727,37 @@ static int launch_chain(ChainParams &p, cudaStream_t st) {
     p.dcol[0] = 0;
     if (L >= 2) p.dcol[1] = cols - p.np[1];
     if (L >= 3) p.dcol[2] = 0;
-    // occupancy: as many CTAs per SM as TMEM, shared memory and the register bound (2) allow
+    // Row-thread parallelism: NG groups of 4 row warps in one CTA (chunks dealt round-robin), or -- when TMEM and
+    // shared memory allow two CTAs per SM -- NG=1 with two independent CTAs.
     const int sm_smem = 227 * 1024;
-    int occ = 512 / cols;
-    if (occ > 2) occ = 2;
-    const char *e = getenv("PRB_MLP_OCC");
-    if (e && atoi(e) > 0 && atoi(e) < occ) occ = atoi(e);
+    int ng = 0;
+    if (const char *e = getenv("PRB_MLP_NG")) ng = atoi(e);
+    int occ = 1;
+    if (ng == 0) ng = (cols <= 256) ? 1 : 2;
+    if (ng == 1 && cols <= 256) occ = 2;
+    if (const char *e = getenv("PRB_MLP_OCC")) { int o = atoi(e); if (o >= 1 && o < occ) occ = o; }
     size_t smem = 0;
     for (;; --occ) {
         int depth = occ >= 2 ? 3 : 4;
         for (; depth >= 2; --depth) {
-            smem = chain_smem_bytes(depth, depth, p.b_stage_bytes, np_total);
+            smem = chain_smem_bytes(ng, depth, depth, p.b_stage_bytes, np_total);
             if (smem * occ <= (size_t)sm_smem - 1024 * occ && smem <= (size_t)max_optin) { p.na = p.nb = depth; break; }
         }
         if (depth >= 2 || occ == 1) break;
     }
     PRB_REQUIRE(smem <= (size_t)max_optin, "mlp: %zu bytes of shared memory needed, %d available", smem, max_optin);
-    PRB_CUDA(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = num_sms() * occ;
     if (grid > p.num_tiles) grid = p.num_tiles;
-    mlp_chain_kernel<<<grid, CHAIN_THREADS, smem, st>>>(p);
+    if (ng == 1) {
+        PRB_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mlp_chain_kernel<1><<<grid, 128 + 64, smem, st>>>(p);
+    } else if (ng == 2) {
+        PRB_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mlp_chain_kernel<2><<<grid, 256 + 64, smem, st>>>(p);
+    } else {
+        PRB_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mlp_chain_kernel<3><<<grid, 384 + 64, smem, st>>>(p);
+    }
     return check_launch("mlp_chain_kernel");
 }
 
