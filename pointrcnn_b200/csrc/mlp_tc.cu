@@ -843,7 +843,8 @@ static int run_chain(const ChainIO &io, const prb_mlp_desc *mlp, void *workspace
             cur_pitch = g[l1 - 1].np;
             pingpong ^= 1;
         } else {
-            p.c_last = mlp->c_out[L - 1];
+            // row-major output: write the padded width so the padding channels are defined (zero)
+            p.c_last = p.mode_out == OUT_ROWS ? g[L - 1].np : mlp->c_out[L - 1];
             int rc = launch_chain(p, st);
             if (rc) return rc;
         }
