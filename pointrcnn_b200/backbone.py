@@ -54,6 +54,8 @@ class Pointnet2MSG(nn.Module):
 
     def forward(self, pointcloud: torch.Tensor):
         xyz, features = self._break_up_pc(pointcloud)
+        if self._plannable(xyz, features):
+            return self._forward_planned(xyz, features)
         l_xyz, l_features = [xyz], [features]
         for sa in self.SA_modules:
             li_xyz, li_features = sa(l_xyz[-1], l_features[-1])
@@ -61,6 +63,69 @@ class Pointnet2MSG(nn.Module):
             l_features.append(li_features)
         for i in range(-1, -(len(self.FP_modules) + 1), -1):
             l_features[i - 1] = self.FP_modules[i](l_xyz[i - 1], l_xyz[i], l_features[i - 1], l_features[i])
+        return l_xyz[0], l_features[0]
+
+    # ------------------------------------------------------------------ stream-planned forward (eval / no_grad)
+    # Everything geometric -- the four FPS levels, the ball queries, the 3-NN searches -- depends on the input
+    # coordinates only.  The planned forward runs that chain on side streams and lets the feature MLPs (main stream)
+    # follow it level by level: the FPS of level k+1 and all neighbour searches overlap the MLP of level k.
+    # Same kernels, same results as the level-by-level loop.
+    def _plannable(self, xyz, features):
+        import os
+        if os.environ.get("PRB_DISABLE_PLAN", "0") == "1" or not xyz.is_cuda:
+            return False
+        if not all(m._can_fuse(xyz, features, None) for m in self.SA_modules):
+            return False
+        probe = torch.empty(0, device=xyz.device)
+        return all(m._can_fuse(xyz, xyz, None, probe) for m in self.FP_modules)
+
+    def _forward_planned(self, xyz, features):
+        dev = xyz.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_streams", None) is None or self._streams[0].device != dev:
+            self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_fps, s_nbr = self._streams
+        start = torch.cuda.Event()
+        start.record(main)
+        nlev = len(self.SA_modules)
+        l_xyz = [xyz]
+        ev_fps, ev_bq, geo = [], [], []
+        # FPS chain on its own stream
+        with torch.cuda.stream(s_fps):
+            s_fps.wait_event(start)
+            from .pointnet2 import pointnet2_utils as pu
+            for sa in self.SA_modules:
+                _, nx = pu.furthest_point_sample_xyz(l_xyz[-1], sa.npoint)
+                nx.record_stream(main); nx.record_stream(s_nbr)
+                e = torch.cuda.Event(); e.record(s_fps)
+                l_xyz.append(nx); ev_fps.append(e)
+        # neighbour searches on a second stream, each as soon as its centres exist
+        with torch.cuda.stream(s_nbr):
+            s_nbr.wait_event(start)
+            for k, sa in enumerate(self.SA_modules):
+                s_nbr.wait_event(ev_fps[k])
+                _, centres, idxs, nss = sa.fused_geometry(l_xyz[k], l_xyz[k + 1])
+                for t in idxs:
+                    t.record_stream(main)
+                e = torch.cuda.Event(); e.record(s_nbr)
+                geo.append((centres, idxs, nss)); ev_bq.append(e)
+            nn, ev_nn = {}, {}
+            for i in range(-1, -(len(self.FP_modules) + 1), -1):
+                lvl = nlev + i          # unknown level index (i=-1 -> nlev-1)
+                idx, w = self.FP_modules[i].fused_geometry(l_xyz[lvl], l_xyz[lvl + 1])
+                idx.record_stream(main); w.record_stream(main)
+                e = torch.cuda.Event(); e.record(s_nbr)
+                nn[i], ev_nn[i] = (idx, w), e
+        # feature MLPs on the caller's stream
+        l_features = [features]
+        for k, sa in enumerate(self.SA_modules):
+            main.wait_event(ev_bq[k])
+            centres, idxs, nss = geo[k]
+            l_features.append(sa.fused_mlp(l_xyz[k], l_features[k], centres, idxs, nss))
+        for i in range(-1, -(len(self.FP_modules) + 1), -1):
+            main.wait_event(ev_nn[i])
+            idx, w = nn[i]
+            l_features[i - 1] = self.FP_modules[i].fused_mlp(l_xyz[i - 1].size(1), idx, w, l_features[i - 1], l_features[i])
         return l_xyz[0], l_features[0]
 
 

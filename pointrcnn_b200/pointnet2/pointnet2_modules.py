@@ -153,41 +153,37 @@ class _PointnetSAModuleBase(nn.Module):
                 return False
         return True
 
-    def _forward_fused(self, xyz, features, new_xyz):
+    def fused_geometry(self, xyz, new_xyz=None):
+        """sampling + neighbour search of the fused path (depends on coordinates only, so a caller may run it on a side
+        stream, ahead of the feature MLPs): returns (ret_xyz, centres (B,npoint,3), [idx per scale], [nsample per scale])"""
+        B, N, _ = xyz.shape
+        dev = xyz.device
+        if self.npoint is None:
+            centres = torch.zeros((B, 1, 3), dtype=torch.float32, device=dev)   # GroupAll: no centre subtraction
+            ar = torch.arange(N, dtype=torch.int32, device=dev).view(1, 1, N).expand(B, 1, N).contiguous()
+            return None, centres, [ar for _ in self.groupers], [N for _ in self.groupers]
+        if new_xyz is None:
+            _, new_xyz = pointnet2_utils.furthest_point_sample_xyz(xyz, self.npoint)
+        centres = new_xyz.contiguous()
+        if len(self.groupers) == 2:
+            g0, g1 = self.groupers
+            idxs = list(pointnet2_utils.ball_query_msg2((g0.radius, g1.radius), (g0.nsample, g1.nsample), xyz, centres))
+        else:
+            idxs = [pointnet2_utils.ball_query(g.radius, g.nsample, xyz, centres) for g in self.groupers]
+        return new_xyz, centres, idxs, [g.nsample for g in self.groupers]
+
+    def fused_mlp(self, xyz, features, centres, idxs, nss):
+        """gather + SharedMLP + max-pool of every scale (one tensor-core kernel per scale) -> (B, sum C_out, npoint)"""
         lib = C.lib()
         B, N, _ = xyz.shape
         dev = xyz.device
-        xyz = xyz.contiguous()
-        group_all = self.npoint is None
-        if group_all:
-            npoint = 1
-            centres = torch.zeros((B, 1, 3), dtype=torch.float32, device=dev)   # GroupAll: no centre subtraction
-            ret_xyz = None
-        else:
-            if new_xyz is None:
-                _, new_xyz = pointnet2_utils.furthest_point_sample_xyz(xyz, self.npoint)
-            centres = new_xyz.contiguous()
-            npoint = centres.size(1)
-            ret_xyz = new_xyz
+        npoint = centres.size(1)
         c_feat = 0 if features is None else features.size(1)
         feats_pm = pointnet2_utils.transpose_bcn_to_bnc(features.contiguous()) if features is not None else None
         if self._fused is None or len(self._fused) != len(self.mlps):
             self._fused = [_FusedMLP() for _ in self.mlps]
         descs = [f.get(mlp, 0, c_feat, dev) for f, mlp in zip(self._fused, self.mlps)]
-        c_outs = [f.c_out[-1] for f in self._fused]
-        out = torch.empty((B, sum(c_outs), npoint), dtype=torch.float32, device=dev)
-        # neighbour lists
-        if group_all:
-            ar = torch.arange(N, dtype=torch.int32, device=dev).view(1, 1, N).expand(B, 1, N).contiguous()
-            idxs = [ar for _ in self.groupers]
-            nss = [N for _ in self.groupers]
-        elif len(self.groupers) == 2:
-            g0, g1 = self.groupers
-            idxs = pointnet2_utils.ball_query_msg2((g0.radius, g1.radius), (g0.nsample, g1.nsample), xyz, centres)
-            nss = [g0.nsample, g1.nsample]
-        else:
-            idxs = [pointnet2_utils.ball_query(g.radius, g.nsample, xyz, centres) for g in self.groupers]
-            nss = [g.nsample for g in self.groupers]
+        out = torch.empty((B, sum(f.c_out[-1] for f in self._fused), npoint), dtype=torch.float32, device=dev)
         off = 0
         with torch.cuda.device(dev):
             for desc, fused, idx, ns in zip(descs, self._fused, idxs, nss):
@@ -199,7 +195,12 @@ class _PointnetSAModuleBase(nn.Module):
                                                         C.ptr(idx), ctypes.byref(desc), C.ptr(out), out.size(1), off,
                                                         C.ptr(ws), C.c_size_t(wsb), C.stream()), "sa_group_mlp_max")
                 off += fused.c_out[-1]
-        return ret_xyz, out
+        return out
+
+    def _forward_fused(self, xyz, features, new_xyz):
+        xyz = xyz.contiguous()
+        ret_xyz, centres, idxs, nss = self.fused_geometry(xyz, new_xyz)
+        return ret_xyz, self.fused_mlp(xyz, features, centres, idxs, nss)
 
     # ------------------------------------------------------------------ reference-shaped path
     def forward(self, xyz: torch.Tensor, features: torch.Tensor = None, new_xyz=None) -> (torch.Tensor, torch.Tensor):
@@ -276,14 +277,16 @@ class PointnetFPModule(nn.Module):
             return False
         return _FusedMLP.supported(self.mlp)
 
-    def _forward_fused(self, unknown, known, unknow_feats, known_feats):
-        lib = C.lib()
-        dev = unknown.device
-        B, n, _ = unknown.shape
-        m = known.size(1)
-        c_known = known_feats.size(1)
-        c_skip = 0 if unknow_feats is None else unknow_feats.size(1)
+    def fused_geometry(self, unknown, known):
+        """3-NN search + inverse-distance weights (coordinates only) -> (idx (B,n,3) int32, weight (B,n,3))"""
         _, idx, weight = pointnet2_utils.three_nn_weights(unknown.contiguous(), known.contiguous())
+        return idx, weight
+
+    def fused_mlp(self, n, idx, weight, unknow_feats, known_feats):
+        lib = C.lib()
+        dev = known_feats.device
+        B, c_known, m = known_feats.shape
+        c_skip = 0 if unknow_feats is None else unknow_feats.size(1)
         known_pm = pointnet2_utils.transpose_bcn_to_bnc(known_feats.contiguous())
         skip = unknow_feats.contiguous() if unknow_feats is not None else None
         if self._fused is None:
@@ -300,6 +303,10 @@ class PointnetFPModule(nn.Module):
                                                  ctypes.byref(desc), C.ptr(out), C.ptr(ws), C.c_size_t(wsb), C.stream()),
                         "fp_interp_mlp")
         return out
+
+    def _forward_fused(self, unknown, known, unknow_feats, known_feats):
+        idx, weight = self.fused_geometry(unknown, known)
+        return self.fused_mlp(unknown.size(1), idx, weight, unknow_feats, known_feats)
 
     def forward(self, unknown: torch.Tensor, known: torch.Tensor, unknow_feats: torch.Tensor,
                 known_feats: torch.Tensor) -> torch.Tensor:
