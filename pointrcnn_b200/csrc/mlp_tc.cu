@@ -58,7 +58,7 @@ struct ChainParams {
     long total_rows;
     int num_tiles;
     // SA
-    int n, npoint, ns, c_feat;
+    int n, npoint, ns, log_ns, c_feat;
     const float *xyz, *new_xyz, *feats_pm;
     const int *idx;
     // FP
@@ -209,7 +209,9 @@ template <int NG>
 __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kernel(const ChainParams p) {
     constexpr int NTHREADS = 128 * NG + 64;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ SmemFixed S;
+    // keep the pointer arithmetic on the __shared__ symbol itself so the compiler emits LDS/STS, not generic accesses
+    uint8_t *base = smem_raw + ((1024u - (s2u(smem_raw) & 1023u)) & 1023u);
     const int L = p.num_layers;
     int np_total = 0, sc_off[MAX_LAYERS];
     for (int l = 0; l < L; ++l) { sc_off[l] = np_total; np_total += p.np[l]; }
@@ -218,7 +220,6 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
     float *s_scale = reinterpret_cast<float *>(sB + (size_t)p.nb * p.b_stage_bytes);
     float *s_shift = s_scale + np_total;
     float *s_pool = s_shift + np_total;                                  // NG x (TM x POOL_STRIDE + 8 x 16)
-    SmemFixed &S = *reinterpret_cast<SmemFixed *>((reinterpret_cast<uintptr_t>(s_pool + NG * (TM * POOL_STRIDE + 128)) + 15) & ~(uintptr_t)15);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NA = p.na, NB = p.nb;
 
@@ -310,23 +311,27 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
         int m_src[3] = {0, 0, 0};
         float m_aux[3] = {0.f, 0.f, 0.f};
         bool m_valid = false;
+        int m_scene = 0, m_u = 0;            // FP: scene / point index of my row
         auto fetch_meta = [&](int tile) {
-            const long R = (long)tile * TM + r;
-            m_valid = tile < p.num_tiles && R < p.total_rows;
+            const unsigned R = (unsigned)tile * TM + r;          // total_rows < 2^31 (checked on the host)
+            m_valid = tile < p.num_tiles && (long)R < p.total_rows;
             if (p.mode_in == IN_SA) {
-                const long pr = m_valid ? R / p.ns : 0;                 // global centre index
-                const int scene = (int)(pr / p.npoint);
-                m_src[0] = scene * p.n + (m_valid ? __ldg(p.idx + R) : 0);
-                m_aux[0] = __ldg(p.new_xyz + pr * 3 + 0);
-                m_aux[1] = __ldg(p.new_xyz + pr * 3 + 1);
-                m_aux[2] = __ldg(p.new_xyz + pr * 3 + 2);
-            } else if (p.mode_in == IN_FP) {
-                const long rr = m_valid ? R : 0;
-                const int scene = (int)(rr / p.n);
+                const unsigned pr = m_valid ? (R >> p.log_ns) : 0u;     // global centre index (nsample is a power of two)
+                const unsigned scene = pr / (unsigned)p.npoint;
+                m_src[0] = (int)scene * p.n + (m_valid ? __ldg(p.idx + R) : 0);
+                m_aux[0] = __ldg(p.new_xyz + (size_t)pr * 3 + 0);
+                m_aux[1] = __ldg(p.new_xyz + (size_t)pr * 3 + 1);
+                m_aux[2] = __ldg(p.new_xyz + (size_t)pr * 3 + 2);
+            } else if (p.mode_in == IN_FP || p.mode_out == OUT_FP) {
+                const unsigned rr = m_valid ? R : 0u;
+                const unsigned scene = rr / (unsigned)p.n;
+                m_scene = (int)scene; m_u = (int)(rr - scene * (unsigned)p.n);
+                if (p.mode_in == IN_FP) {
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    m_src[q] = scene * p.m + __ldg(p.idx + rr * 3 + q);
-                    m_aux[q] = __ldg(p.weight + rr * 3 + q);
+                    for (int q = 0; q < 3; ++q) {
+                        m_src[q] = (int)scene * p.m + __ldg(p.idx + (size_t)rr * 3 + q);
+                        m_aux[q] = __ldg(p.weight + (size_t)rr * 3 + q);
+                    }
                 }
             }
         };
@@ -335,6 +340,7 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const long R = (long)tile * TM + r;
             const bool valid = m_valid;
+            const int my_scene = m_scene, my_u = m_u;
             bar_rows<NG>();  // previous tile's readers of S.row_* are done
             if (grp == 0) {
                 S.row_valid[r] = valid;
@@ -445,9 +451,7 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
                     *reinterpret_cast<float4 *>(A + swz(r, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
                 } else {
                     // FP skip segment: channel-major (b, c_skip, n); lanes run along consecutive points
-                    const long rr0 = valid ? R : 0;
-                    const int scene = (int)(rr0 / p.n), u = (int)(rr0 - (long)scene * p.n);
-                    const float *bsrc = p.skip + (size_t)scene * p.c_skip * p.n + u;
+                    const float *bsrc = p.skip + (size_t)my_scene * p.c_skip * p.n + my_u;
                     float o[32];
 #pragma unroll
                     for (int q = 0; q < 32; ++q) {
@@ -501,6 +505,15 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
             tc_fence_after();
             const int Cl = p.c_last;
             const float *sc = s_scale + sc_off[L - 1], *sh = s_shift + sc_off[L - 1];
+            // SA max-pool: thread (g16, q) owns 16-row segment g16 and channel q of every batch
+            size_t e_off = 0;
+            bool e_ok = false;
+            if (p.mode_out == OUT_SA_MAX && p.ns >= 16) {
+                const unsigned Rg = (unsigned)tile * TM + (unsigned)(r >> 4) * 16u;
+                e_ok = (long)Rg < p.total_rows && (((r >> 4) & ((p.ns >> 4) - 1)) == 0);
+                const unsigned pr = Rg >> p.log_ns, scene = pr / (unsigned)p.npoint, pp = pr - scene * (unsigned)p.npoint;
+                e_off = ((size_t)scene * p.out_stride_c + p.out_c_off + (r & 15)) * p.npoint + pp;
+            }
             for (int c0 = grp * 16; c0 < Cl; c0 += 16 * NG) {
                 uint32_t acc[16];
                 tmem_ld16(tmem + lane_base + (uint32_t)(p.dcol[L - 1] + c0), acc);
@@ -516,8 +529,7 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
                     }
                 } else if (p.mode_out == OUT_FP) {
                     if (valid) {
-                        const int scene = (int)(R / p.n), u = (int)(R - (long)scene * p.n);
-                        float *o = p.out + ((size_t)scene * p.out_stride_c + p.out_c_off + c0) * p.n + u;
+                        float *o = p.out + ((size_t)my_scene * p.out_stride_c + p.out_c_off + c0) * p.n + my_u;
 #pragma unroll
                         for (int q = 0; q < 16; ++q)
                             if (c0 + q < Cl) o[(size_t)q * p.n] = v[q];
@@ -547,15 +559,7 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
                                 for (int s = 1; s < per; ++s) x = fmaxf(x, pool2[(g16 + s) * 16 + q]);
                             }
                         }
-                        const int per = ns >> 4;                 // 16-row segments per centre
-                        if ((g16 % per) == 0) {
-                            const long Rg = (long)tile * TM + (long)g16 * 16;
-                            if (Rg < p.total_rows && c0 + q < Cl) {
-                                const long pr = Rg / ns;
-                                const int scene = (int)(pr / p.npoint), pp = (int)(pr - (long)scene * p.npoint);
-                                p.out[((size_t)scene * p.out_stride_c + p.out_c_off + c0 + q) * p.npoint + pp] = x;
-                            }
-                        }
+                        if (e_ok && c0 + q < Cl) p.out[e_off + (size_t)c0 * p.npoint] = x;
                     } else {
                         // nsample 4 or 8: 128/ns centres per tile, 16 channels each -> (16/ns) items per thread
                         const int per16 = 16 / ns;
@@ -563,10 +567,9 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
                             const int row0 = g16 * 16 + t * ns;
                             float x = pool[row0 * POOL_STRIDE + q];
                             for (int s = 1; s < ns; ++s) x = fmaxf(x, pool[(row0 + s) * POOL_STRIDE + q]);
-                            const long Rg = (long)tile * TM + row0;
-                            if (Rg < p.total_rows && c0 + q < Cl) {
-                                const long pr = Rg / ns;
-                                const int scene = (int)(pr / p.npoint), pp = (int)(pr - (long)scene * p.npoint);
+                            const unsigned Rg = (unsigned)tile * TM + (unsigned)row0;
+                            if ((long)Rg < p.total_rows && c0 + q < Cl) {
+                                const unsigned pr = Rg >> p.log_ns, scene = pr / (unsigned)p.npoint, pp = pr - scene * (unsigned)p.npoint;
                                 p.out[((size_t)scene * p.out_stride_c + p.out_c_off + c0 + q) * p.npoint + pp] = x;
                             }
                         }
@@ -791,6 +794,7 @@ static size_t chain_workspace_bytes(long rows, int L, int kind, int c_in, int sp
 // run the whole chain, splitting where TMEM cannot hold two consecutive accumulators
 static int run_chain(const ChainIO &io, const prb_mlp_desc *mlp, void *workspace, size_t workspace_bytes, cudaStream_t st) {
     const int L = mlp->num_layers;
+    PRB_REQUIRE(io.rows < 0x7fffff00L, "mlp: %ld rows exceed the 2^31 row limit", io.rows);
     PRB_REQUIRE(L >= 1 && L <= MAX_LAYERS, "mlp: num_layers %d unsupported", L);
     PackSegs ps;
     default_segs(io.kind, mlp->c_in, io.split, &ps);
@@ -881,6 +885,8 @@ PRB_API int prb_sa_group_mlp_max_ws(int b, int n, int npoint, int nsample, int c
     io.rows = (long)b * npoint * nsample;
     io.base.mode_in = IN_SA; io.base.mode_out = OUT_SA_MAX;
     io.base.n = n; io.base.npoint = npoint; io.base.ns = nsample; io.base.c_feat = c_feat;
+    io.base.log_ns = 0;
+    while ((1 << io.base.log_ns) < nsample) ++io.base.log_ns;
     io.base.xyz = xyz; io.base.new_xyz = new_xyz; io.base.feats_pm = feats_pm; io.base.idx = idx;
     io.base.out = out; io.base.out_stride_c = out_stride_c; io.base.out_c_off = out_c_off;
     return run_chain(io, mlp, workspace, workspace_bytes, (cudaStream_t)stream);
