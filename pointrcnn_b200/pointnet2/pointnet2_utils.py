@@ -21,6 +21,48 @@ def _cuda_empty(shape, dtype, like):
     return torch.empty(shape, dtype=dtype, device=like.device)
 
 
+# Neighbour searches go through the hash grid (csrc/grid.cu) when the searched set is large enough to pay for the
+# build; results are identical to the brute-force kernels either way.  PRB_DISABLE_GRID=1 forces brute force.
+GRID_MIN_POINTS_BQ = 2048
+GRID_MIN_POINTS_NN = 512
+
+
+def _use_grid(n_points, threshold):
+    import os
+    return n_points >= threshold and os.environ.get("PRB_DISABLE_GRID", "0") != "1"
+
+
+def _ball_query_native(B, N, npoint, radii, nsamples, new_xyz, xyz, idxs):
+    import ctypes
+    lib = C.lib()
+    if _use_grid(N, GRID_MIN_POINTS_BQ) and all(r > 0 for r in radii):
+        nr = len(radii)
+        wsb = lib.prb_grid_workspace_bytes(B, N, npoint)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=xyz.device)
+        rad = (ctypes.c_float * nr)(*radii)
+        nsm = (ctypes.c_int * nr)(*[int(x) for x in nsamples])
+        ptrs = (ctypes.c_void_p * nr)(*[t.data_ptr() for t in idxs])
+        C.check(lib.prb_ball_query_grid(B, N, npoint, nr, rad, nsm, C.ptr(new_xyz), C.ptr(xyz), ptrs, C.ptr(ws), C.c_size_t(wsb),
+                                        C.stream()), "ball_query_grid")
+    elif len(radii) == 2:
+        C.check(lib.prb_ball_query_msg2(B, N, npoint, C.c_float(radii[0]), int(nsamples[0]), C.c_float(radii[1]), int(nsamples[1]),
+                                        C.ptr(new_xyz), C.ptr(xyz), C.ptr(idxs[0]), C.ptr(idxs[1]), C.stream()), "ball_query_msg2")
+    else:
+        C.check(lib.prb_ball_query(B, N, npoint, C.c_float(radii[0]), int(nsamples[0]), C.ptr(new_xyz), C.ptr(xyz), C.ptr(idxs[0]),
+                                   C.stream()), "ball_query")
+
+
+def _three_nn_native(B, N, m, unknown, known, dist2, idx, weight):
+    lib = C.lib()
+    if _use_grid(m, GRID_MIN_POINTS_NN):
+        wsb = lib.prb_grid_workspace_bytes(B, m, N)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=unknown.device)
+        C.check(lib.prb_three_nn_grid(B, N, m, C.ptr(unknown), C.ptr(known), C.ptr(dist2), C.ptr(idx), C.ptr(weight), C.ptr(ws),
+                                      C.c_size_t(wsb), C.stream()), "three_nn_grid")
+    else:
+        C.check(lib.prb_three_nn(B, N, m, C.ptr(unknown), C.ptr(known), C.ptr(dist2), C.ptr(idx), C.ptr(weight), C.stream()), "three_nn")
+
+
 class FurthestPointSampling(Function):
     @staticmethod
     def forward(ctx, xyz: torch.Tensor, npoint: int) -> torch.Tensor:
@@ -89,7 +131,9 @@ class ThreeNN(Function):
         m = known.size(1)
         dist2 = _cuda_empty((B, N, 3), torch.float32, unknown)
         idx = _cuda_empty((B, N, 3), torch.int32, unknown)
-        pointnet2.three_nn_wrapper(B, N, m, unknown, known, dist2, idx)
+        C.require_cuda(unknown, known)
+        with torch.cuda.device(unknown.device), prof.region("three_nn"):
+            _three_nn_native(B, N, int(m), unknown, known, dist2, idx, None)
         return torch.sqrt(dist2), idx
 
     @staticmethod
@@ -111,8 +155,7 @@ def three_nn_weights(unknown: torch.Tensor, known: torch.Tensor):
     idx = _cuda_empty((B, N, 3), torch.int32, unknown)
     weight = _cuda_empty((B, N, 3), torch.float32, unknown)
     with torch.cuda.device(unknown.device), prof.region("three_nn"):
-        C.check(C.lib().prb_three_nn(B, N, int(m), C.ptr(unknown), C.ptr(known), C.ptr(dist2), C.ptr(idx), C.ptr(weight),
-                                     C.stream()), "three_nn")
+        _three_nn_native(B, N, int(m), unknown, known, dist2, idx, weight)
     return dist2, idx, weight
 
 
@@ -176,7 +219,9 @@ class BallQuery(Function):
         B, N, _ = xyz.size()
         npoint = new_xyz.size(1)
         idx = torch.zeros((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
-        pointnet2.ball_query_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx)
+        C.require_cuda(xyz, new_xyz)
+        with torch.cuda.device(xyz.device), prof.region("ball_query"):
+            _ball_query_native(B, N, npoint, [float(radius)], [int(nsample)], new_xyz, xyz, [idx])
         return idx
 
     @staticmethod
@@ -196,9 +241,7 @@ def ball_query_msg2(radii, nsamples, xyz: torch.Tensor, new_xyz: torch.Tensor):
     idx0 = torch.zeros((B, npoint, nsamples[0]), dtype=torch.int32, device=xyz.device)
     idx1 = torch.zeros((B, npoint, nsamples[1]), dtype=torch.int32, device=xyz.device)
     with torch.cuda.device(xyz.device), prof.region("ball_query"):
-        C.check(C.lib().prb_ball_query_msg2(B, N, npoint, C.c_float(radii[0]), int(nsamples[0]), C.c_float(radii[1]),
-                                            int(nsamples[1]), C.ptr(new_xyz), C.ptr(xyz), C.ptr(idx0), C.ptr(idx1), C.stream()),
-                "ball_query_msg2")
+        _ball_query_native(B, N, npoint, list(radii), list(nsamples), new_xyz, xyz, [idx0, idx1])
     return idx0, idx1
 
 

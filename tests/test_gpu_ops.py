@@ -306,3 +306,48 @@ def test_iou3d_utils_api(cuda):
     assert 0 < keep_r.numel() < 500
     bi = iou3d_utils.boxes_iou_bev(bev[:10], bev[:10])
     assert torch.allclose(torch.diagonal(bi), torch.ones(10, device=cuda), atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ hash-grid paths
+@pytest.mark.parametrize("kind,N,M,radii,nss", [
+    ("kitti", 8192, 2048, (0.5, 1.0), (16, 32)),     # sparse: everything answered by the grid
+    ("cube", 4096, 512, (0.1, 0.3), (16, 32)),       # dense: >128 candidates per ball -> overflow list -> scan kernel
+    ("dup", 2048, 512, (0.3, 0.6), (8, 64)),         # exact duplicates share cells
+    ("cube", 300, 40, (0.2,), (16,)),                # tiny set through the grid, single radius
+    ("kitti", 5000, 777, (2.0, 4.0), (16, 32)),      # n not a power of two, big balls
+])
+def test_ball_query_grid_path_exact(cuda, kind, N, M, radii, nss):
+    xyz = _cloud(kind, 2, N, 51 + N)
+    fidx = O.fps(xyz, M)
+    new_xyz = np.stack([xyz[b][fidx[b]] for b in range(2)])
+    x, c = T(xyz, cuda), T(new_xyz, cuda)
+    old = pu.GRID_MIN_POINTS_BQ
+    pu.GRID_MIN_POINTS_BQ = 1
+    try:
+        if len(radii) == 2:
+            got = pu.ball_query_msg2(radii, nss, x, c)
+        else:
+            got = [pu.ball_query(radii[0], nss[0], x, c)]
+    finally:
+        pu.GRID_MIN_POINTS_BQ = old
+    for g, r, ns in zip(got, radii, nss):
+        assert np.array_equal(g.cpu().numpy(), O.ball_query(r, ns, xyz, new_xyz)), "grid ball query differs (r=%g)" % r
+
+
+@pytest.mark.parametrize("kind,n,m", [("kitti", 8192, 2048), ("cube", 2000, 500), ("dup", 1024, 256), ("cube", 100, 5),
+                                      ("kitti", 300, 3), ("dup", 4096, 64)])
+def test_three_nn_grid_path_exact(cuda, kind, n, m):
+    unknown = _cloud(kind, 2, n, 61 + n)
+    known = np.ascontiguousarray(unknown[:, ::max(1, n // m)][:, :m])
+    if kind == "kitti":
+        unknown[0, :10] += 300.0         # far-away queries: third neighbour beyond one cell -> brute-force list
+    d2, idx = O.three_nn(unknown, known)
+    old = pu.GRID_MIN_POINTS_NN
+    pu.GRID_MIN_POINTS_NN = 1
+    try:
+        got_d2, got_idx, w = pu.three_nn_weights(T(unknown, cuda), T(known, cuda))
+    finally:
+        pu.GRID_MIN_POINTS_NN = old
+    assert np.array_equal(got_idx.cpu().numpy(), idx)
+    assert np.array_equal(got_d2.cpu().numpy(), d2)
+    np.testing.assert_allclose(w.cpu().numpy(), O.interp_weights(d2), rtol=2e-6, atol=1e-7)
