@@ -285,14 +285,18 @@ __global__ void __launch_bounds__(GR_THREADS) three_nn_grid_kernel(const GridNnP
     int walked = 0;
     bool over = false;
     // a bucket reached twice (hash collision between neighbour cells) is harmless: nn_insert ignores a point that is
-    // already in the list, and a point that was evicted cannot re-enter (everything kept is lexicographically smaller)
-#pragma unroll 1
-    for (int c = 0; c < 27 && !over; ++c) {
-        const unsigned hsh = cell_hash(cx + c % 3 - 1, cy + (c / 3) % 3 - 1, cz + c / 9 - 1, p.g.table_size - 1);
-        for (int j = heads[hsh]; j >= 0; j = next[j]) {
-            const float d = dist2_ref(ux - kn[(size_t)j * 3], uy - kn[(size_t)j * 3 + 1], uz - kn[(size_t)j * 3 + 2]);
+    // already in the list, and a point that was evicted cannot re-enter (everything kept is lexicographically smaller).
+    // All 27 bucket heads are fetched up front (independent loads), then the lists are walked.
+    int hd[27];
+#pragma unroll
+    for (int c = 0; c < 27; ++c)
+        hd[c] = __ldg(heads + cell_hash(cx + c % 3 - 1, cy + (c / 3) % 3 - 1, cz + c / 9 - 1, p.g.table_size - 1));
+#pragma unroll
+    for (int c = 0; c < 27; ++c) {
+        for (int j = hd[c]; j >= 0 && !over; j = __ldg(next + j)) {
+            const float d = dist2_ref(ux - __ldg(kn + (size_t)j * 3), uy - __ldg(kn + (size_t)j * 3 + 1), uz - __ldg(kn + (size_t)j * 3 + 2));
             nn_insert(d, j, b1, b2, b3, i1, i2, i3);
-            if (++walked > 2048) { over = true; break; }
+            if (++walked > 2048) over = true;
         }
     }
     const float hb = p.h[scene] * 0.9999f;
@@ -303,25 +307,45 @@ __global__ void __launch_bounds__(GR_THREADS) three_nn_grid_kernel(const GridNnP
     nn_store(p, ((size_t)scene * p.n + u) * 3, b1, b2, b3, i1, i2, i3);
 }
 
+__device__ __forceinline__ void nn_insert_lex(float d, int k, float &b1, float &b2, float &b3, int &i1, int &i2, int &i3) {
+    if (d < b1 || (d == b1 && k < i1)) {
+        b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k;
+    } else if (d < b2 || (d == b2 && k < i2)) {
+        b3 = b2; i3 = i2; b2 = d; i2 = k;
+    } else if (d < b3 || (d == b3 && k < i3)) {
+        b3 = d; i3 = k;
+    }
+}
+
+// brute force for the queries the grid could not certify: one WARP per query, lanes scan the known points strided,
+// each keeps its lexicographic top-3 and the 32 lists are merged with shuffles (the top-3 of a union does not depend
+// on the visiting order)
 __global__ void __launch_bounds__(GR_THREADS) three_nn_overflow_kernel(const GridNnParams p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int total = p.overflow[0];
-    for (int item = blockIdx.x * GR_THREADS + threadIdx.x; item < total; item += gridDim.x * GR_THREADS) {
+    const int BIG = 0x7fffffff;
+    for (int item = blockIdx.x * GR_WARPS + warp; item < total; item += gridDim.x * GR_WARPS) {
         const int id = p.overflow[1 + item];
         const int scene = id / p.n;
         const float *q = p.unknown + (size_t)id * 3;
         const float ux = q[0], uy = q[1], uz = q[2];
         const float *kn = p.known + (size_t)scene * p.m * 3;
         float b1 = CUDART_INF_F, b2 = CUDART_INF_F, b3 = CUDART_INF_F;
-        int i1 = 0, i2 = 0, i3 = 0;
-        for (int k = 0; k < p.m; ++k) {
+        int i1 = BIG, i2 = BIG, i3 = BIG;
+        for (int k = lane; k < p.m; k += 32) {
             const float d = dist2_ref(ux - kn[(size_t)k * 3], uy - kn[(size_t)k * 3 + 1], uz - kn[(size_t)k * 3 + 2]);
-            if (d < b3) {
-                if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k; }
-                else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = k; }
-                else { b3 = d; i3 = k; }
-            }
+            if (d < CUDART_INF_F || true) nn_insert_lex(d, k, b1, b2, b3, i1, i2, i3);
         }
-        nn_store(p, (size_t)id * 3, b1, b2, b3, i1, i2, i3);
+        for (int o = 16; o; o >>= 1) {
+            const float e1 = __shfl_xor_sync(0xffffffffu, b1, o), e2 = __shfl_xor_sync(0xffffffffu, b2, o), e3 = __shfl_xor_sync(0xffffffffu, b3, o);
+            const int j1 = __shfl_xor_sync(0xffffffffu, i1, o), j2 = __shfl_xor_sync(0xffffffffu, i2, o), j3 = __shfl_xor_sync(0xffffffffu, i3, o);
+            if (j1 != BIG) nn_insert_lex(e1, j1, b1, b2, b3, i1, i2, i3);
+            if (j2 != BIG) nn_insert_lex(e2, j2, b1, b2, b3, i1, i2, i3);
+            if (j3 != BIG) nn_insert_lex(e3, j3, b1, b2, b3, i1, i2, i3);
+        }
+        // fewer than three known points: the reference leaves index 0 / distance 1e40 (-> inf)
+        if (lane == 0)
+            nn_store(p, (size_t)id * 3, b1, b2, b3, i1 == BIG ? 0 : i1, i2 == BIG ? 0 : i2, i3 == BIG ? 0 : i3);
     }
 }
 
