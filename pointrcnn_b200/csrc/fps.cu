@@ -15,10 +15,10 @@
 // xyz and the running min-distance in registers, so "lowest position wins" IS the tie rule at every
 // level: strict '>' inside a thread, lowest lane inside a warp (redux.max + ballot + ffs), lowest
 // warp inside a CTA, lowest CTA inside a cluster.  One __syncthreads per round.  A scene is spread
-// over a thread-block cluster of CS CTAs (CS*THREADS*PPT >= n): every warp pushes its winner with ONE
-// relaxed 64-bit remote store (dist | round tag | rank) into every CTA's slot array and every warp
-// polls its local copy -- no block barrier, no cluster barrier, no mbarrier inside the loop.  Every CTA keeps a rank-ordered copy of the scene's xyz in shared memory, so the winner's
-// coordinates are one broadcast LDS away.  new_xyz is emitted on the fly.
+// over a thread-block cluster of CS CTAs (CS*THREADS*PPT >= n): each CTA's winner -- distance, rank AND
+// coordinates, 32 bytes -- goes to every peer with two st.async stores that complete a transaction count on the
+// peer's mbarrier (no cluster barrier in the loop).  A CTA mirrors only its OWN points in shared memory (<= 48 KB, so several clusters share an
+// SM); the winner's coordinates travel with the message.  new_xyz is emitted on the fly.
 #include <limits.h>
 
 #include "common.cuh"
@@ -62,7 +62,7 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
     return r;
 }
-// ---- cluster exchange primitives (variants are selected at compile time; see XCHG below)
+// ---- cluster exchange primitives
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -79,38 +79,34 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity)
         : "memory");
 }
-// 8-byte store into a peer CTA's shared memory that completes 8 tx-bytes on the peer's mbarrier
-__device__ __forceinline__ void st_async_b64(uint32_t remote_addr, uint64_t v, uint32_t remote_bar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
-                 "l"(v), "r"(remote_bar)
+// 16-byte store into a peer CTA's shared memory that completes 16 tx-bytes on the peer's mbarrier.
+// (Measured alternatives, profiles/r1_fps_sweep.json: plain remote stores + tag polling, cluster barriers and
+//  per-warp direct pushes are all 1.3-5x slower per round than st.async + mbarrier complete_tx.)
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_addr),
+                 "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_bar)
                  : "memory");
 }
-// plain 8-byte store into a peer CTA's shared memory / volatile poll of the local copy: key and round tag travel
-// in ONE 64-bit word, so no separate flag is needed
-__device__ __forceinline__ void st_cluster_b64(uint32_t remote_addr, uint64_t v) {
-    asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(remote_addr), "l"(v) : "memory");
-}
-__device__ __forceinline__ uint64_t ld_poll_b64(uint32_t local_addr) {
-    uint64_t v;
-    asm volatile("ld.volatile.shared::cta.b64 %0, [%1];" : "=l"(v) : "r"(local_addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
-// exchange variants: 0 = st.async + mbarrier complete_tx; 1 = per-CTA winner, plain remote store + tag polling;
-// 2 = per-CTA winner, plain remote store + cluster barrier; 3 = per-warp winners pushed to every CTA + tag polling
 constexpr int kMaxWarps = 32;
 constexpr int kMaxCluster = 8;
 
-template <int THREADS, int PPT, int CS, int XCHG>
+// one exchanged winner: 32 bytes = two 16-byte st.async: {dist bits, rank, x, y} {z, -, -, -}
+struct __align__(16) FpsMsg {
+    int dist_bits;
+    int rank;
+    float x, y;
+    float z;
+    int pad[3];
+};
+
+template <int THREADS, int PPT, int CS>
 __global__ void __launch_bounds__(THREADS, 1) fps_rank_kernel(const FpsParams p) {
     constexpr int W = THREADS / 32;
-    extern __shared__ __align__(16) float s_pts[];  // rank-ordered xyz (3 floats per rank), optional
-    __shared__ int2 s_wkey[2][kMaxWarps];           // per-warp (dist bits, rank), double buffered
-    // cluster exchange: every warp of every CTA pushes its winner straight into every CTA's slot array;
-    // word = dist bits (32) | round tag (12) | rank (20); double buffered by round parity
-    __shared__ __align__(8) uint64_t s_slot[2][kMaxCluster * (THREADS / 32)];
+    constexpr int CAP = THREADS * PPT;               // ranks owned by this CTA
+    extern __shared__ __align__(16) float s_pts[];   // xyz of MY ranks (3 floats per rank), optional for CS == 1
+    __shared__ int2 s_wkey[2][kMaxWarps];            // per-warp (dist bits, rank), double buffered
+    __shared__ FpsMsg s_slot[2][kMaxCluster];        // per-CTA winners (cluster exchange), double buffered
     __shared__ __align__(8) uint64_t s_bar[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -122,26 +118,14 @@ __global__ void __launch_bounds__(THREADS, 1) fps_rank_kernel(const FpsParams p)
     int *idx = p.idx + (size_t)scene * m;
     float *new_xyz = p.new_xyz ? p.new_xyz + (size_t)scene * m * 3 : nullptr;
 
-    if (CS > 1) {
-        for (int i = tid; i < 2 * CS * W; i += THREADS) (&s_slot[0][0])[i] = 0ull;   // tag 0 is never waited for first
-        if (XCHG == 0 && tid == 0) {
-            mbar_init(smem_u32(&s_bar[0]), 1);
-            mbar_init(smem_u32(&s_bar[1]), 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
+    if (CS > 1 && tid == 0) {
+        mbar_init(smem_u32(&s_bar[0]), 1);
+        mbar_init(smem_u32(&s_bar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
-    // rank-ordered copy of the scene (coalesced global reads, scattered shared stores)
-    if (p.use_smem_xyz) {
-        for (int k = tid; k < n; k += THREADS) {
-            int r = k_to_rank(k, S, logS, Q);
-            s_pts[r * 3 + 0] = xyz[k * 3 + 0];
-            s_pts[r * 3 + 1] = xyz[k * 3 + 1];
-            s_pts[r * 3 + 2] = xyz[k * 3 + 2];
-        }
-    }
-
-    // my PPT consecutive ranks
+    // my PPT consecutive ranks: coordinates + running min distance in registers, coordinates mirrored in shared
+    // memory so that the CTA's winner can be looked up by rank
     const int g = crank * THREADS + tid;
     float px[PPT], py[PPT], pz[PPT], pd[PPT];
 #pragma unroll
@@ -156,6 +140,11 @@ __global__ void __launch_bounds__(THREADS, 1) fps_rank_kernel(const FpsParams p)
             px[i] = py[i] = pz[i] = 0.f;
             pd[i] = -1.f;
         }
+        if (p.use_smem_xyz) {
+            s_pts[(tid * PPT + i) * 3 + 0] = px[i];
+            s_pts[(tid * PPT + i) * 3 + 1] = py[i];
+            s_pts[(tid * PPT + i) * 3 + 2] = pz[i];
+        }
     }
     __syncthreads();
     if (CS > 1) cluster_sync_all();
@@ -167,11 +156,11 @@ __global__ void __launch_bounds__(THREADS, 1) fps_rank_kernel(const FpsParams p)
         idx[0] = 0;  // holds RANKS until the fix-up pass below
         if (new_xyz) { new_xyz[0] = cx; new_xyz[1] = cy; new_xyz[2] = cz; }
     }
-
     uint32_t phase0 = 0, phase1 = 0;
+
     for (int j = 1; j < m; ++j) {
         const int par = j & 1;
-        if (CS > 1 && XCHG == 0 && tid == 0) mbar_arrive_expect_tx(smem_u32(&s_bar[par]), CS * 8);
+        if (CS > 1 && tid == 0) mbar_arrive_expect_tx(smem_u32(&s_bar[par]), CS * 32);
         float best = -1.f;
         int bslot = 0;
 #pragma unroll
@@ -186,71 +175,40 @@ __global__ void __launch_bounds__(THREADS, 1) fps_rank_kernel(const FpsParams p)
         int wm = __reduce_max_sync(0xffffffffu, vb);
         unsigned bal = __ballot_sync(0xffffffffu, vb == wm);
         int wr = __shfl_sync(0xffffffffu, g * PPT + bslot, __ffs(bal) - 1);
+        if (lane == 0) s_wkey[par][warp] = make_int2(wm, wr);
+        __syncthreads();
 
-        int r;  // winning rank, uniform
-        if (CS == 1 || XCHG != 3) {
-            // CTA-level winner (lowest warp wins ties)
-            if (lane == 0) s_wkey[par][warp] = make_int2(wm, wr);
-            __syncthreads();
-            int2 kv = lane < W ? s_wkey[par][lane] : make_int2(INT_MIN, 0);
-            int cm = __reduce_max_sync(0xffffffffu, kv.x);
-            unsigned b2 = __ballot_sync(0xffffffffu, kv.x == cm);
-            r = __shfl_sync(0xffffffffu, kv.y, __ffs(b2) - 1);
-            if (CS > 1) {
-                const uint32_t tag = (uint32_t)j & 0xFFFu;
-                const uint64_t key = ((uint64_t)(uint32_t)cm << 32) | ((uint64_t)tag << 20) | (uint32_t)r;
-                uint64_t got = 0;
-                if (XCHG == 0) {
-                    if (warp == 0 && lane < CS)
-                        st_async_b64(map_to_cta(smem_u32(&s_slot[par][crank]), lane), key, map_to_cta(smem_u32(&s_bar[par]), lane));
-                    mbar_wait_cluster(smem_u32(&s_bar[par]), par ? phase1 : phase0);
-                    if (par) phase1 ^= 1; else phase0 ^= 1;
-                    if (lane < CS) got = s_slot[par][lane];
-                } else if (XCHG == 1) {
-                    if (warp == 0 && lane < CS) st_cluster_b64(map_to_cta(smem_u32(&s_slot[par][crank]), lane), key);
-                    if (lane < CS)
-                        do { got = ld_poll_b64(smem_u32(&s_slot[par][lane])); } while ((((uint32_t)got >> 20) & 0xFFFu) != tag);
-                } else {
-                    if (warp == 0 && lane < CS) st_cluster_b64(map_to_cta(smem_u32(&s_slot[par][crank]), lane), key);
-                    cluster_arrive_release();
-                    cluster_wait_acquire();
-                    if (lane < CS) got = ld_poll_b64(smem_u32(&s_slot[par][lane]));
-                }
-                const int kx = lane < CS ? (int)(uint32_t)(got >> 32) : INT_MIN;
-                const int gm = __reduce_max_sync(0xffffffffu, kx);
-                const unsigned b3 = __ballot_sync(0xffffffffu, kx == gm);
-                r = __shfl_sync(0xffffffffu, (int)((uint32_t)got & 0xFFFFFu), __ffs(b3) - 1);
+        // CTA-level winner (lowest warp wins ties)
+        int2 kv = lane < W ? s_wkey[par][lane] : make_int2(INT_MIN, 0);
+        int cm = __reduce_max_sync(0xffffffffu, kv.x);
+        unsigned b2 = __ballot_sync(0xffffffffu, kv.x == cm);
+        int r = __shfl_sync(0xffffffffu, kv.y, __ffs(b2) - 1);   // winning rank, uniform in the CTA
+
+        if (CS == 1) {
+            if (p.use_smem_xyz) {
+                cx = s_pts[r * 3 + 0]; cy = s_pts[r * 3 + 1]; cz = s_pts[r * 3 + 2];
+            } else {
+                int k = rank_to_k(r, S, logS, Q);
+                cx = xyz[k * 3 + 0]; cy = xyz[k * 3 + 1]; cz = xyz[k * 3 + 2];
             }
         } else {
-            constexpr int NSLOT = CS * W;                 // one slot per (CTA, warp), ordered by rank range
-            const uint32_t tag = (uint32_t)j & 0xFFFu;
-            if (lane < CS) {
-                const uint64_t key = ((uint64_t)(uint32_t)wm << 32) | ((uint64_t)tag << 20) | (uint32_t)wr;
-                st_cluster_b64(map_to_cta(smem_u32(&s_slot[par][crank * W + warp]), lane), key);
+            // my CTA's winner (with its coordinates) goes to every CTA of the cluster: two 16-byte st.async per peer
+            if (warp == 0 && lane < CS) {
+                const int lr = r - crank * CAP;
+                const float wx = s_pts[lr * 3 + 0], wy = s_pts[lr * 3 + 1], wz = s_pts[lr * 3 + 2];
+                const uint32_t dst = map_to_cta(smem_u32(&s_slot[par][crank]), lane);
+                const uint32_t bar = map_to_cta(smem_u32(&s_bar[par]), lane);
+                st_async_v4(dst, (uint32_t)cm, (uint32_t)r, __float_as_uint(wx), __float_as_uint(wy), bar);
+                st_async_v4(dst + 16, __float_as_uint(wz), 0u, 0u, 0u, bar);
             }
-            // poll until all NSLOT winners of this round have landed, keep the best (max dist, then lowest slot)
-            int bv = INT_MIN, bs = NSLOT, br = 0;
-#pragma unroll
-            for (int q = 0; q < (NSLOT + 31) / 32; ++q) {
-                const int sl = lane + 32 * q;
-                if (sl < NSLOT) {
-                    uint64_t key;
-                    do { key = ld_poll_b64(smem_u32(&s_slot[par][sl])); } while ((((uint32_t)key >> 20) & 0xFFFu) != tag);
-                    const int v = (int)(uint32_t)(key >> 32);
-                    if (v > bv) { bv = v; bs = sl; br = (int)((uint32_t)key & 0xFFFFFu); }
-                }
-            }
-            const int cm = __reduce_max_sync(0xffffffffu, bv);
-            const unsigned smin = __reduce_min_sync(0xffffffffu, bv == cm ? (unsigned)bs : 0xffffffffu);
-            const unsigned b2 = __ballot_sync(0xffffffffu, bv == cm && (unsigned)bs == smin);
-            r = __shfl_sync(0xffffffffu, br, __ffs(b2) - 1);
-        }
-
-        if (p.use_smem_xyz) {
-            cx = s_pts[r * 3 + 0]; cy = s_pts[r * 3 + 1]; cz = s_pts[r * 3 + 2];
-        } else {
-            int k = rank_to_k(r, S, logS, Q);
-            cx = xyz[k * 3 + 0]; cy = xyz[k * 3 + 1]; cz = xyz[k * 3 + 2];
+            mbar_wait_cluster(smem_u32(&s_bar[par]), par ? phase1 : phase0);
+            if (par) phase1 ^= 1; else phase0 ^= 1;
+            const int kx = lane < CS ? s_slot[par][lane].dist_bits : INT_MIN;
+            const int gm = __reduce_max_sync(0xffffffffu, kx);
+            const unsigned b3 = __ballot_sync(0xffffffffu, kx == gm);
+            const FpsMsg &win = s_slot[par][__ffs(b3) - 1];      // lowest CTA wins ties: broadcast LDS
+            r = win.rank;
+            cx = win.x; cy = win.y; cz = win.z;
         }
         if (writer) {
             idx[j] = r;
@@ -313,9 +271,9 @@ __global__ void __launch_bounds__(1024, 1) fps_generic_kernel(const FpsParams p)
     }
 }
 
-template <int THREADS, int PPT, int CS, int XCHG>
+template <int THREADS, int PPT, int CS>
 static int launch_rank(const FpsParams &p, size_t smem, cudaStream_t stream) {
-    auto kern = fps_rank_kernel<THREADS, PPT, CS, XCHG>;
+    auto kern = fps_rank_kernel<THREADS, PPT, CS>;
     // static shared memory counts against the 48 KB default too
     if (smem + 2048 > 48 * 1024) PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
@@ -335,17 +293,12 @@ static int launch_rank(const FpsParams &p, size_t smem, cudaStream_t stream) {
 }
 
 template <int CS>
-static int dispatch_cs(const FpsParams &p, int threads, int ppt, int xchg, size_t smem, cudaStream_t st) {
-#define PRB_FPS_CASE(T, P)                                                        \
-    if (threads == T && ppt == P) {                                               \
-        if (CS == 1 || xchg == 2) return launch_rank<T, P, CS, 2>(p, smem, st);   \
-        if (xchg == 0) return launch_rank<T, P, CS, 0>(p, smem, st);              \
-        if (xchg == 1) return launch_rank<T, P, CS, 1>(p, smem, st);              \
-        return launch_rank<T, P, CS, 3>(p, smem, st);                             \
-    }
+static int dispatch_cs(const FpsParams &p, int threads, int ppt, size_t smem, cudaStream_t st) {
+#define PRB_FPS_CASE(T, P) \
+    if (threads == T && ppt == P) return launch_rank<T, P, CS>(p, smem, st);
     if (CS == 1) {
         PRB_FPS_CASE(128, 1) PRB_FPS_CASE(128, 2) PRB_FPS_CASE(128, 4)
-        PRB_FPS_CASE(256, 4) PRB_FPS_CASE(256, 8)
+        PRB_FPS_CASE(256, 8)
         PRB_FPS_CASE(1024, 4) PRB_FPS_CASE(1024, 8)
     }
     PRB_FPS_CASE(256, 4) PRB_FPS_CASE(512, 2) PRB_FPS_CASE(512, 4) PRB_FPS_CASE(512, 8) PRB_FPS_CASE(512, 16)
@@ -377,18 +330,14 @@ extern "C" int prb_furthest_point_sampling(int b, int n, int m, const float *xyz
     const int n_pad = p.S * p.Q;
 
     // configuration: cluster size, threads per CTA, points per thread
-    // A cluster of CS CTAs per scene cuts the per-round compute CS-fold, but all b clusters must be co-resident
-    // in ONE wave (each needs CS free SMs inside one GPC).  Measured on B200, n=16384, m=4096 (profiles/
-    // r1_fps_sweep.json): b=2 -> CS=8 2.23 ms, CS=4 2.60 ms; b=16 -> CS=8 4.37 ms (two waves), CS=4 2.61 ms.
+    // A cluster of CS CTAs per scene cuts the per-round compute CS-fold; each CTA keeps only its own slice of the
+    // scene in shared memory (<= 48 KB), so the b clusters share SMs and fit one wave up to b*CS ~ 2 x #SMs.
     int cs = env_int("PRB_FPS_CS", 0);
     if (cs == 0) {
         cs = 1;
         if (n_pad >= 8192) {
             cs = 8;
-            const int cap8 = 12, cap4 = 32, cap2 = 72;   // co-resident clusters (conservative: 148 SMs, 8 GPCs)
-            if (b > cap8) cs = 4;
-            if (b > cap4) cs = 2;
-            if (b > cap2) cs = 1;
+            while (cs > 1 && (long)b * cs > 2L * num_sms()) cs >>= 1;
         }
     }
     while (cs < 8 && ceil_div(n_pad, cs) > 8192) cs <<= 1;  // keep the register-resident path
@@ -415,15 +364,15 @@ extern "C" int prb_furthest_point_sampling(int b, int n, int m, const float *xyz
         fps_generic_kernel<<<b, p.S < 32 ? 32 : p.S, 0, st>>>(p);
         return check_launch("fps_generic_kernel");
     }
-    size_t smem_pts = (size_t)n_pad * 3 * sizeof(float);
-    p.use_smem_xyz = smem_pts <= 200 * 1024 ? 1 : 0;
+    // shared copy of the CTA's own coordinates: whole (padded) scene for a single CTA, one slice in a cluster
+    size_t smem_pts = (size_t)threads * ppt * 3 * sizeof(float);
+    p.use_smem_xyz = (cs > 1 || smem_pts <= 200 * 1024) ? 1 : 0;
     size_t smem = p.use_smem_xyz ? smem_pts : 0;
-    const int xchg = env_int("PRB_FPS_XCHG", 0);
     switch (cs) {
-        case 1: return dispatch_cs<1>(p, threads, ppt, xchg, smem, st);
-        case 2: return dispatch_cs<2>(p, threads, ppt, xchg, smem, st);
-        case 4: return dispatch_cs<4>(p, threads, ppt, xchg, smem, st);
-        case 8: return dispatch_cs<8>(p, threads, ppt, xchg, smem, st);
+        case 1: return dispatch_cs<1>(p, threads, ppt, smem, st);
+        case 2: return dispatch_cs<2>(p, threads, ppt, smem, st);
+        case 4: return dispatch_cs<4>(p, threads, ppt, smem, st);
+        case 8: return dispatch_cs<8>(p, threads, ppt, smem, st);
     }
     set_error("fps: bad cluster size %d", cs);
     return -1;

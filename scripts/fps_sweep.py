@@ -8,11 +8,11 @@ from pointrcnn_b200.pointnet2 import pointnet2_utils as pu
 
 dev = torch.device("cuda:0")
 res = []
-for (B, N, M) in [(16, 16384, 4096), (16, 4096, 1024), (16, 1024, 256), (2, 16384, 4096)]:
+for (B, N, M) in [(16, 16384, 4096), (32, 16384, 4096), (16, 4096, 1024), (2, 16384, 4096)]:
     x = torch.from_numpy(synth.u_kitti(B, N, 5)[..., :3].copy()).to(dev)
     base = None
     for cs in (1, 2, 4, 8):
-        for xchg in ((0,) if cs == 1 else (0, 1, 2, 3)):
+        for xchg in (0,):
             for thr in ((0, 1024) if cs == 1 else (0,)):
                 os.environ["PRB_FPS_CS"] = str(cs); os.environ["PRB_FPS_XCHG"] = str(xchg); os.environ["PRB_FPS_THREADS"] = str(thr)
                 try:

@@ -66,8 +66,8 @@ def test_fps_index_exact(cuda, B, N, M, kind):
         assert np.array_equal(ref_temp.cpu().numpy(), want_temp), "oracle temp != reference temp"
 
 
-@pytest.mark.parametrize("env", [{"PRB_FPS_CS": "1"}, {"PRB_FPS_CS": "2"}, {"PRB_FPS_CS": "4"}, {"PRB_FPS_GENERIC": "1"},
-                                 {"PRB_FPS_CS": "1", "PRB_FPS_THREADS": "1024"}])
+@pytest.mark.parametrize("env", [{"PRB_FPS_CS": "1"}, {"PRB_FPS_CS": "2"}, {"PRB_FPS_CS": "4"}, {"PRB_FPS_CS": "8"},
+                                 {"PRB_FPS_GENERIC": "1"}, {"PRB_FPS_CS": "1", "PRB_FPS_THREADS": "1024"}])
 def test_fps_all_kernel_variants_agree(cuda, env):
     xyz = synth.dup_cloud(2, 8192, 5, unique=3000)
     want = O.fps(xyz, 512)
