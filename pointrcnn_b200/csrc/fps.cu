@@ -330,13 +330,14 @@ extern "C" int prb_furthest_point_sampling(int b, int n, int m, const float *xyz
     const int n_pad = p.S * p.Q;
 
     // configuration: cluster size, threads per CTA, points per thread
-    // A cluster of CS CTAs per scene cuts the per-round compute CS-fold; each CTA keeps only its own slice of the
-    // scene in shared memory (<= 48 KB), so the b clusters share SMs and fit one wave up to b*CS ~ 2 x #SMs.
+    // A cluster of CS CTAs per scene cuts the per-round compute CS-fold; each CTA mirrors only its own slice of the
+    // scene in shared memory (<= 48 KB).  Measured (profiles/r1_fps_sweep.json, n=16384, m=4096, ns per round):
+    // b=2: CS=8 538, CS=4 614, CS=2 803;  b=16: CS=8 691 (CTAs start sharing SMs), CS=4 617;  b=32: CS=4 617.
     int cs = env_int("PRB_FPS_CS", 0);
     if (cs == 0) {
         cs = 1;
         if (n_pad >= 8192) {
-            cs = 8;
+            cs = (long)b * 8 <= num_sms() / 2 ? 8 : 4;
             while (cs > 1 && (long)b * cs > 2L * num_sms()) cs >>= 1;
         }
     }
