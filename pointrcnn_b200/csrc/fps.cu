@@ -334,6 +334,7 @@ extern "C" int prb_furthest_point_sampling(int b, int n, int m, const float *xyz
     // scene in shared memory (<= 48 KB).  Measured (profiles/r1_fps_sweep.json, n=16384, m=4096, ns per round):
     // b=2: CS=8 538, CS=4 614, CS=2 803;  b=16: CS=8 691 (CTAs start sharing SMs), CS=4 617;  b=32: CS=4 617.
     int cs = env_int("PRB_FPS_CS", 0);
+    if (cs != 0 && n_pad < 4096) cs = 1;       // the override is meant for the big levels only
     if (cs == 0) {
         cs = 1;
         if (n_pad >= 8192) {
