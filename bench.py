@@ -6,10 +6,15 @@ on synthetic 16384x4 clouds, batch 16 per GPU (BASELINE.json configs[1]).
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
     python bench.py --impl reference ...      # the CPU restatement of the same path on the host cores
 
-One JSON line on rank 0.  `value` = device-resident throughput (CUDA events, max over ranks, L2 flushed between
-steps); `e2e` = same metric through the public module API with pinned host input, H2D and a D2H metric read in the
-timed region; `roofline` = dominant kernel family (CUDA events on the launching stream inside the timed region);
-`cpu_baseline` = oracle port on the host cores over a bounded sample of the same workload.
+One JSON line on rank 0.
+  value        device-resident throughput: K steps (one batch of 16 scenes each) through pointrcnn_b200.pipeline.
+               BatchPipeline with `--inflight` independent batches in flight, CUDA events around the K steps, max over
+               ranks; inputs rotate through a pool larger than L2.
+  e2e          the same K steps with pinned HOST inputs: H2D of every step's input and a D2H read of every step's
+               per-scene metric inside the timed region.
+  single_batch one batch at a time on one stream with an L2 flush in between (per-batch latency view).
+  roofline / kernels   per-kernel-family device times from CUDA events on the launching stream (sequential pass).
+  cpu_baseline oracle port on the host cores over a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -190,6 +195,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-scenes", type=int, default=2, help="scenes per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=3, help="independent batches in flight (CUDA streams); 1 = sequential")
+    ap.add_argument("--pool", type=int, default=40, help="distinct input batches rotated through (40 x 4.2 MB > 126 MB L2)")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel-family table as JSON here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -211,54 +218,65 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W, K = max(3, args.warmup), max(1, args.steps)
 
+    from pointrcnn_b200.pipeline import BatchPipeline
     net = build_model(dev)
-    host_np = make_scenes(rank * BATCH, BATCH)                      # this rank's 16 scenes (weak scaling)
-    host = torch.from_numpy(host_np).pin_memory()
-    pc = host.to(dev)
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+    # input pool: distinct batches, together larger than the 126 MB L2, rotated through -> no step finds its input in L2
+    P = max(1, args.pool)
+    host_pool = [torch.from_numpy(make_scenes((rank * P + i) * BATCH, BATCH)).pin_memory() for i in range(P)]
+    dev_pool = [h.to(dev) for h in host_pool]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2 (sequential pass)
+    F = max(1, args.inflight)
+    pipe = BatchPipeline(lambda x: net(x)[1], inflight=F, device=dev)
+    pipe_metric = BatchPipeline(lambda x: net(x)[1].mean(dim=(1, 2)), inflight=F, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
 
     with torch.no_grad():
-        for _ in range(W):
-            net(pc)
+        for i in range(W):
+            net(dev_pool[i % P])
+        pipe.run([dev_pool[i % P] for i in range(2 * F)])
         torch.cuda.synchronize()
 
-        # ---------------- device-resident throughput
+        # ---------------- device-resident throughput: K steps, F independent batches in flight
         sampler = ClockSampler(local) if rank == 0 else None
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = _cabi.launch_count()
-        prof.enable()
         barrier(); torch.cuda.synchronize()
-        for a, b in ev:
-            flush.fill_(1.0)          # L2 flush between timed iterations (not timed)
-            a.record()
-            xyz, feats = net(pc)
-            b.record()
+        t0.record()
+        pipe.run([dev_pool[(W + i) % P] for i in range(K)])
+        t1.record()
         torch.cuda.synchronize(); barrier()
-        prof.disable()
         launches = (_cabi.launch_count() - launches0) // K
-        fam = prof.collect()
         clocks = sampler.stop() if sampler else None
-        ms = sum(a.elapsed_time(b) for a, b in ev) / K
-        ms = max_over_ranks(ms, device=dev)
+        ms = max_over_ranks(t0.elapsed_time(t1) / K, device=dev)
 
-        # ---------------- end to end: pinned host input -> H2D -> backbone -> metric -> D2H
-        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        # ---------------- end to end: pinned host input -> H2D -> backbone -> metric -> D2H, same pipeline
         barrier(); torch.cuda.synchronize()
-        for a, b in ev2:
+        t0.record()
+        metrics = pipe_metric.run([host_pool[(W + i) % P] for i in range(K)], to_host=True)
+        t1.record()
+        torch.cuda.synchronize(); barrier()
+        ms_e2e = max_over_ranks(t0.elapsed_time(t1) / K, device=dev)
+        d2h_bytes = metrics[0].numel() * 4
+
+        # ---------------- sequential pass (one batch at a time, L2 flushed in between): per-batch latency and the
+        # per-kernel-family breakdown (CUDA events on the launching stream)
+        KS = min(K, 10)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KS)]
+        prof.enable()
+        torch.cuda.synchronize()
+        for i, (a, b_) in enumerate(ev):
             flush.fill_(1.0)
             a.record()
-            x = host.to(dev, non_blocking=True)
-            _, f = net(x)
-            metric = f.mean(dim=(1, 2)).cpu()                       # per-scene feature mean: the step's result
-            b.record()
-        torch.cuda.synchronize(); barrier()
-        ms_e2e = sum(a.elapsed_time(b) for a, b in ev2) / K
-        ms_e2e = max_over_ranks(ms_e2e, device=dev)
-        d2h_bytes = metric.numel() * 4
+            net(dev_pool[i % P])
+            b_.record()
+        torch.cuda.synchronize()
+        prof.disable()
+        fam = prof.collect()
+        ms_seq = sum(a.elapsed_time(b_) for a, b_ in ev) / KS
+        host = host_pool[0]
 
     if world > 1:
         dist.destroy_process_group()
@@ -268,7 +286,7 @@ def main():
     pk = peaks()
     sa_flops, fp_flops = mlp_flops_per_scene(net)
     tf32_peak = pk["bf16"] / 2.0          # tcgen05 kind::tf32 runs at half the bf16 rate; bf16 figure is the measured one
-    fam_ms = {k: v[0] / K for k, v in fam.items()}
+    fam_ms = {k: v[0] / KS for k, v in fam.items()}
     kernels = []
     if "sa_mlp" in fam_ms:
         kernels.append({"name": "mlp_chain_kernel (SA: gather + SharedMLP + max-pool)", "ms_per_step": fam_ms["sa_mlp"],
@@ -291,7 +309,7 @@ def main():
     for k in kernels:
         if "achieved" in k:
             k["frac"] = k["achieved"] / k["peak"]
-        k["share"] = k["ms_per_step"] / ms
+        k["share"] = k["ms_per_step"] / ms_seq     # share of the sequential (single batch) step
     dom = max((k for k in kernels if "achieved" in k), key=lambda k: k["ms_per_step"], default=None)
     roofline = None
     if dom:
@@ -312,7 +330,10 @@ def main():
             "dtype": "f32 (tf32 tensor-core MLP, fp32 accumulate)", "data": "synthetic",
             "config": {"workload": "RPN PointNet++ backbone fwd: 4 SA-MSG + 4 FP (tools/cfgs/default.yaml), 16384x4 uniform KITTI-scope "
                                    "points, eval-mode BN (BASELINE configs[1])", "batch_per_gpu": BATCH, "global_batch": scenes,
-                       "parallelism": "dp%d (scene sharding, no data-path collective)" % world, "l2": "256 MB flush write between timed steps"},
+                       "parallelism": "dp%d (scene sharding, no data-path collective)" % world,
+                       "batches_in_flight": F, "l2": "inputs rotate through %d distinct batches (%.0f MB > 126 MB L2)" % (P, P * BATCH * POINTS * CHANNELS * 4 / 1e6)},
+            "single_batch": {"ms_per_step": ms_seq, "value": BATCH / (ms_seq * 1e-3), "unit": "scenes/s",
+                             "note": "one batch at a time on one stream, 256 MB L2 flush write between steps"},
             "e2e": {"value": scenes / (ms_e2e * 1e-3), "unit": "scenes/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}

@@ -1,0 +1,49 @@
+"""Batch pipelining: consecutive, independent batches on alternating CUDA streams.
+
+Furthest-point sampling is a dependency chain (4095 serial rounds for the first RPN level) that keeps only
+64 of 148 SMs busy, and nothing else of the SAME batch can run before it ends.  Consecutive batches are
+independent (the reference's eval loop processes them one after another), so batch i+1's sampling chain can
+overlap batch i's neighbour searches and tensor-core MLPs.  Measured on B200 (RPN backbone, 16 scenes of 16384
+points per batch): 5.73 ms per batch back to back on one stream, 3.92 ms with two batches in flight, 3.55 ms with
+three (profiles/r1_notes.md).  Results are identical to the sequential loop -- only the stream assignment differs.
+"""
+import torch
+
+
+class BatchPipeline:
+    def __init__(self, fn, inflight=3, device=None):
+        """fn: callable(batch_on_device) -> tensor or tuple of tensors; inflight: batches in flight (streams)"""
+        self.fn = fn
+        self.device = torch.device(device if device is not None else "cuda", torch.cuda.current_device()) \
+            if not isinstance(device, torch.device) else device
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(max(1, inflight))]
+
+    def run(self, batches, to_host=False):
+        """batches: iterable of tensors (device, or pinned host -> copied inside the pipeline).
+        Returns the list of results; with to_host=True results are pinned host tensors (valid after return)."""
+        caller = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(caller)
+        for s in self.streams:
+            s.wait_event(ready)
+        results = []
+        for i, b in enumerate(batches):
+            s = self.streams[i % len(self.streams)]
+            with torch.cuda.stream(s):
+                x = b if b.is_cuda else b.to(self.device, non_blocking=True)
+                out = self.fn(x)
+                if to_host:
+                    outs = out if isinstance(out, (tuple, list)) else (out,)
+                    host = []
+                    for o in outs:
+                        h = torch.empty(o.shape, dtype=o.dtype, pin_memory=True)
+                        h.copy_(o, non_blocking=True)
+                        host.append(h)
+                    out = host[0] if len(host) == 1 else tuple(host)
+                results.append(out)
+        for s in self.streams:
+            caller.wait_stream(s)
+        if to_host:
+            for s in self.streams:
+                s.synchronize()
+        return results

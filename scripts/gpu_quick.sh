@@ -8,6 +8,6 @@ for plan in 0; do
   python - <<PY
 import json
 d=json.load(open('gpurun_out/bench_plan$plan.json'))
-print(round(d['value'],1),'scenes/s', round(d['ms_per_step'],3),'ms  e2e',round(d['e2e']['value'],1), {k['name'][:24]:round(k['ms_per_step'],3) for k in d['kernels']})
+print(round(d['value'],1),'scenes/s', round(d['ms_per_step'],3),'ms  e2e',round(d['e2e']['value'],1),'single',round(d['single_batch']['ms_per_step'],3), {k['name'][:24]:round(k['ms_per_step'],3) for k in d['kernels']})
 PY
 done
