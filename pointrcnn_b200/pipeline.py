@@ -17,6 +17,7 @@ class BatchPipeline:
         self.device = torch.device(device if device is not None else "cuda", torch.cuda.current_device()) \
             if not isinstance(device, torch.device) else device
         self.streams = [torch.cuda.Stream(self.device) for _ in range(max(1, inflight))]
+        self._host = {}   # (slot, output index, shape, dtype) -> reusable pinned result buffer (cudaHostAlloc is slow)
 
     def run(self, batches, to_host=False):
         """batches: iterable of tensors (device, or pinned host -> copied inside the pipeline).
@@ -35,8 +36,11 @@ class BatchPipeline:
                 if to_host:
                     outs = out if isinstance(out, (tuple, list)) else (out,)
                     host = []
-                    for o in outs:
-                        h = torch.empty(o.shape, dtype=o.dtype, pin_memory=True)
+                    for j, o in enumerate(outs):
+                        key = (i, j, tuple(o.shape), o.dtype)
+                        h = self._host.get(key)
+                        if h is None:
+                            h = self._host[key] = torch.empty(o.shape, dtype=o.dtype, pin_memory=True)
                         h.copy_(o, non_blocking=True)
                         host.append(h)
                     out = host[0] if len(host) == 1 else tuple(host)
