@@ -237,6 +237,7 @@ def main():
         for i in range(W):
             net(dev_pool[i % P])
         pipe.run([dev_pool[i % P] for i in range(2 * F)])
+        pipe_metric.run([host_pool[i % P] for i in range(K)], to_host=True)    # also allocates the pinned result buffers
         torch.cuda.synchronize()
 
         # ---------------- device-resident throughput: K steps, F independent batches in flight
