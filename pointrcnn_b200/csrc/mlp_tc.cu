@@ -112,6 +112,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -350,6 +357,11 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
             bar_rows<NG>();
 
             // ---- layer 0: build A chunks from global memory
+            // Feature rows with a 16-byte aligned pitch are gathered with cp.async straight into the swizzled stage
+            // (no registers, up to two chunks of loads in flight per group); their fp32 bits reach the tensor core
+            // unrounded, which then drops the low 13 mantissa bits itself.
+            uint32_t pend_bar[2];
+            int npend = 0;
             for (int kc = 0; kc < p.nchunks[0]; ++kc, ++cc, ra.advance(NA)) {
                 if ((int)(cc % NG) != grp) continue;
                 int c = kc, seg = 0;
@@ -409,7 +421,28 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
                         }
                     } else {
                         const int pitch = p.mode_in == IN_DIRECT ? p.x_pitch : p.c_feat;
-                        const bool vec = (pitch & 3) == 0 && kk + 3 < width;
+                        if ((pitch & 3) == 0) {
+                            // asynchronous path: width is a multiple of 4 too, so a unit is either all data or all padding
+                            mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int rr = wq * 32 + rsub + 4 * i;
+                                const bool ok = S.row_valid[rr] && kk < width;
+                                const float *src = p.mode_in == IN_DIRECT ? p.x_rows + ((size_t)tile * TM + rr) * pitch + kk
+                                                                          : p.feats_pm + (size_t)S.row_src[rr][0] * pitch + kk;
+                                cp_async16(s2u(A + swz(rr, j8)), ok ? src : (const float *)p.w[0], ok ? 16u : 0u);
+                            }
+                            cp_async_commit();
+                            if (npend == 2) {          // retire the oldest chunk: its copies have landed
+                                cp_async_wait<2>();
+                                fence_async_smem();
+                                mbar_arrive(pend_bar[0]);
+                                pend_bar[0] = pend_bar[1];
+                                npend = 1;
+                            }
+                            pend_bar[npend++] = s2u(&S.a_full[ra.stage]);
+                            continue;                  // (the for-increment advances cc and the ring)
+                        }
                         float4 t[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -418,14 +451,10 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
                             if (S.row_valid[rr] && kk < width) {
                                 const float *src = p.mode_in == IN_DIRECT ? p.x_rows + ((size_t)tile * TM + rr) * pitch + kk
                                                                           : p.feats_pm + (size_t)S.row_src[rr][0] * pitch + kk;
-                                if (vec) {
-                                    t[i] = __ldg((const float4 *)src);
-                                } else {
-                                    float o[4];
+                                float o[4];
 #pragma unroll
-                                    for (int q = 0; q < 4; ++q) o[q] = (kk + q < width) ? __ldg(src + q) : 0.f;
-                                    t[i] = make_float4(o[0], o[1], o[2], o[3]);
-                                }
+                                for (int q = 0; q < 4; ++q) o[q] = (kk + q < width) ? __ldg(src + q) : 0.f;
+                                t[i] = make_float4(o[0], o[1], o[2], o[3]);
                             }
                         }
                         mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
@@ -466,6 +495,19 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
                 }
                 fence_async_smem();
                 mbar_arrive(s2u(&S.a_full[ra.stage]));
+            }
+
+            if (npend == 2) {
+                cp_async_wait<1>();
+                fence_async_smem();
+                mbar_arrive(pend_bar[0]);
+                pend_bar[0] = pend_bar[1];
+                npend = 1;
+            }
+            if (npend == 1) {
+                cp_async_wait<0>();
+                fence_async_smem();
+                mbar_arrive(pend_bar[0]);
             }
 
             // next tile's metadata: issue the loads now, consume them at the top of the next iteration

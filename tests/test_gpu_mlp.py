@@ -35,10 +35,20 @@ def tf32(x):
     return u.view(np.float32)
 
 
+def tf32_trunc(x):
+    """what the tensor core does to raw fp32 operand bits: the low 13 mantissa bits are dropped"""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).copy()
+    u &= 0xFFFFE000
+    return u.view(np.float32)
+
+
 def mlp_tf32_ref(x, layers):
+    """layer-0 rows with a 16-byte aligned pitch are copied to shared memory unrounded (cp.async) and truncated by the
+    tensor core; everything built in registers (other pitches, later layers, weights) is rounded with cvt.rna"""
     h = x.astype(np.float32)
-    for W, sc, sh in layers:
-        h = tf32(h) @ tf32(W).T
+    for li, (W, sc, sh) in enumerate(layers):
+        a = tf32_trunc(h) if (li == 0 and x.shape[1] % 4 == 0) else tf32(h)
+        h = a @ tf32(W).T
         h = np.maximum(h * sc[None] + sh[None], 0).astype(np.float32)
     return h
 
