@@ -107,6 +107,18 @@ __device__ __forceinline__ void mbar_wait_sleepy(uint32_t bar, uint32_t parity) 
         "D_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(20000u)
         : "memory");
 }
+// one non-blocking probe of a phase (true = completed)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -360,8 +372,26 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
             // Feature rows with a 16-byte aligned pitch are gathered with cp.async straight into the swizzled stage
             // (no registers, up to two chunks of loads in flight per group); their fp32 bits reach the tensor core
             // unrounded, which then drops the low 13 mantissa bits itself.
-            uint32_t pend_bar[2];
+            uint32_t pend_bar[2] = {0u, 0u};
             int npend = 0;
+            // publish every chunk whose cp.async copies are still pending (all of them: groups complete in order)
+            auto retire_all = [&]() {
+                if (npend > 0) {
+                    cp_async_wait<0>();
+                    fence_async_smem();
+                    mbar_arrive(pend_bar[0]);
+                    if (npend == 2) mbar_arrive(pend_bar[1]);
+                    npend = 0;
+                }
+            };
+            // claim the next ring stage.  Never block on the consumer while own chunks are unpublished: the stage we
+            // wait for may only be released after one of them has been consumed (deadlock otherwise).
+            auto acquire_stage = [&]() {
+                if (!mbar_test(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1)) {
+                    retire_all();
+                    mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
+                }
+            };
             for (int kc = 0; kc < p.nchunks[0]; ++kc, ++cc, ra.advance(NA)) {
                 if ((int)(cc % NG) != grp) continue;
                 int c = kc, seg = 0;
@@ -406,7 +436,7 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
                                     }
                                 }
                             }
-                            if (half == 0) mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
+                            if (half == 0) acquire_stage();
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const int rr = wq * 32 + rsub + 4 * (half * 4 + i);
@@ -423,7 +453,7 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
                         const int pitch = p.mode_in == IN_DIRECT ? p.x_pitch : p.c_feat;
                         if ((pitch & 3) == 0) {
                             // asynchronous path: width is a multiple of 4 too, so a unit is either all data or all padding
-                            mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
+                            acquire_stage();
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const int rr = wq * 32 + rsub + 4 * i;
@@ -457,7 +487,7 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
                                 t[i] = make_float4(o[0], o[1], o[2], o[3]);
                             }
                         }
-                        mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
+                        acquire_stage();
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int rr = wq * 32 + rsub + 4 * i;
@@ -475,7 +505,7 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
                         v.y = to_tf32(__ldg(q + 1) - m_aux[1]);
                         v.z = to_tf32(__ldg(q + 2) - m_aux[2]);
                     }
-                    mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
+                    acquire_stage();
                     *reinterpret_cast<float4 *>(A + swz(r, 0)) = v;
                     *reinterpret_cast<float4 *>(A + swz(r, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
                 } else {
@@ -487,7 +517,7 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
                         const int ch = k0 + q;
                         o[q] = (valid && ch < width) ? __ldg(bsrc + (size_t)ch * p.n) : 0.f;
                     }
-                    mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
+                    acquire_stage();
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<float4 *>(A + swz(r, j)) =
@@ -497,18 +527,7 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
                 mbar_arrive(s2u(&S.a_full[ra.stage]));
             }
 
-            if (npend == 2) {
-                cp_async_wait<1>();
-                fence_async_smem();
-                mbar_arrive(pend_bar[0]);
-                pend_bar[0] = pend_bar[1];
-                npend = 1;
-            }
-            if (npend == 1) {
-                cp_async_wait<0>();
-                fence_async_smem();
-                mbar_arrive(pend_bar[0]);
-            }
+            retire_all();
 
             // next tile's metadata: issue the loads now, consume them at the top of the next iteration
             fetch_meta(tile + gridDim.x);
