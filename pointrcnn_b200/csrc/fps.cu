@@ -101,7 +101,7 @@ struct __align__(16) FpsMsg {
 };
 
 template <int THREADS, int PPT, int CS>
-__global__ void __launch_bounds__(THREADS, (THREADS * PPT <= 4096 && THREADS <= 512) ? 2 : 1) fps_rank_kernel(const FpsParams p) {
+__global__ void __launch_bounds__(THREADS, 1) fps_rank_kernel(const FpsParams p) {
     constexpr int W = THREADS / 32;
     constexpr int CAP = THREADS * PPT;               // ranks owned by this CTA
     extern __shared__ __align__(16) float s_pts[];   // xyz of MY ranks (3 floats per rank), optional for CS == 1

@@ -53,6 +53,8 @@ struct ChainParams {
     int na, nb;                // ring depths
     int b_stage_bytes;         // weight stage size = min(256, max np) * 128
     int tmem_cols;             // power of two >= 32
+    int gather_mode;           // layer-0 row gather: 0 registers (+cvt.rna), 1 cp.async.cg, 2 cp.async.ca
+    int round_out;             // OUT_ROWS: round to tf32 (intermediate segment of a split chain)
     // layer-0 K segments (each padded to a multiple of KC)
     int nseg, seg_chunks[2], seg_width[2];
     long total_rows;
@@ -127,6 +129,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 // 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void *src, uint32_t src_bytes) {   // also allocates in L1
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -451,7 +456,7 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
                         }
                     } else {
                         const int pitch = p.mode_in == IN_DIRECT ? p.x_pitch : p.c_feat;
-                        if ((pitch & 3) == 0) {
+                        if ((pitch & 3) == 0 && p.gather_mode != 0) {
                             // asynchronous path: width is a multiple of 4 too, so a unit is either all data or all padding
                             acquire_stage();
 #pragma unroll
@@ -460,7 +465,8 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
                                 const bool ok = S.row_valid[rr] && kk < width;
                                 const float *src = p.mode_in == IN_DIRECT ? p.x_rows + ((size_t)tile * TM + rr) * pitch + kk
                                                                           : p.feats_pm + (size_t)S.row_src[rr][0] * pitch + kk;
-                                cp_async16(s2u(A + swz(rr, j8)), ok ? src : (const float *)p.w[0], ok ? 16u : 0u);
+                                if (p.gather_mode == 1) cp_async16(s2u(A + swz(rr, j8)), ok ? src : (const float *)p.w[0], ok ? 16u : 0u);
+                                else cp_async16_ca(s2u(A + swz(rr, j8)), ok ? src : (const float *)p.w[0], ok ? 16u : 0u);
                             }
                             cp_async_commit();
                             if (npend == 2) {          // retire the oldest chunk: its copies have landed
@@ -481,10 +487,14 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
                             if (S.row_valid[rr] && kk < width) {
                                 const float *src = p.mode_in == IN_DIRECT ? p.x_rows + ((size_t)tile * TM + rr) * pitch + kk
                                                                           : p.feats_pm + (size_t)S.row_src[rr][0] * pitch + kk;
-                                float o[4];
+                                if ((pitch & 3) == 0) {
+                                    t[i] = __ldg((const float4 *)src);
+                                } else {
+                                    float o[4];
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) o[q] = (kk + q < width) ? __ldg(src + q) : 0.f;
-                                t[i] = make_float4(o[0], o[1], o[2], o[3]);
+                                    for (int q = 0; q < 4; ++q) o[q] = (kk + q < width) ? __ldg(src + q) : 0.f;
+                                    t[i] = make_float4(o[0], o[1], o[2], o[3]);
+                                }
                             }
                         }
                         acquire_stage();
@@ -584,6 +594,10 @@ __global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kern
                 if (p.mode_out == OUT_ROWS) {
                     if (valid) {
                         float *o = p.out + (size_t)R * p.out_pitch + c0;
+                        if (p.round_out) {   // the next launch of a split chain reads these rows as its A operand
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) v[q] = to_tf32(v[q]);
+                        }
 #pragma unroll
                         for (int q = 0; q < 16; q += 4)
                             *reinterpret_cast<float4 *>(o + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
@@ -778,6 +792,8 @@ static int launch_chain(ChainParams &p, cudaStream_t st) {
     }
     p.num_tiles = (int)((p.total_rows + TM - 1) / TM);
     if (p.num_tiles == 0) return 0;
+    p.gather_mode = 2;
+    if (const char *e = getenv("PRB_MLP_GATHER")) p.gather_mode = atoi(e);
     const int L = p.num_layers;
     int np_total = 0, np_max = 0;
     for (int l = 0; l < L; ++l) { np_total += p.np[l]; np_max = p.np[l] > np_max ? p.np[l] : np_max; }
@@ -899,6 +915,7 @@ static int run_chain(const ChainIO &io, const prb_mlp_desc *mlp, void *workspace
             PRB_REQUIRE(workspace && workspace_bytes >= 2 * buf_bytes, "mlp: workspace too small (%zu < %zu)", workspace_bytes, 2 * buf_bytes);
             float *dst = (float *)((char *)workspace + (pingpong ? workspace_bytes / 2 / 256 * 256 : 0));
             p.mode_out = OUT_ROWS;
+            p.round_out = 1;
             p.out = dst;
             p.out_pitch = g[l1 - 1].np;
             p.c_last = g[l1 - 1].np;
