@@ -792,7 +792,7 @@ static int launch_chain(ChainParams &p, cudaStream_t st) {
     }
     p.num_tiles = (int)((p.total_rows + TM - 1) / TM);
     if (p.num_tiles == 0) return 0;
-    p.gather_mode = 2;
+    p.gather_mode = 0;   // measured (profiles/r1_notes.md): register gather 1.53 ms, cp.async.cg 1.66, cp.async.ca 1.67 per batch of SA chains
     if (const char *e = getenv("PRB_MLP_GATHER")) p.gather_mode = atoi(e);
     const int L = p.num_layers;
     int np_total = 0, np_max = 0;
