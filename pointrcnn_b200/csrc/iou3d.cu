@@ -197,35 +197,52 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(int n, float thresh, const
 // ---------------------------------------------------------------- greedy scan on the device
 // Same recurrence as the host loop of iou3d.cpp:100-116: box i is kept iff bit i of remv is clear;
 // a kept box ORs its mask row into remv (columns >= its own block).
+// One CTA walks the 64-box blocks in order.  The 64 mask rows of the NEXT block are prefetched into shared memory
+// with cp.async while the current block is resolved (serial pass over its diagonal word by one thread, then a
+// parallel OR of the kept rows into the remaining columns, all from shared memory).
 constexpr int SCAN_THREADS = 256;
+__device__ __forceinline__ void scan_cp_async8(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
 __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(int n, const unsigned long long *__restrict__ mask,
                                                                 long long *__restrict__ keep, int *__restrict__ num_out) {
-    extern __shared__ unsigned long long s_remv[];  // col_blocks words
-    __shared__ unsigned long long s_diag[2][64];
+    extern __shared__ unsigned long long s_dyn[];   // remv[cb] then two row tiles of 64 x cb words
     __shared__ unsigned long long s_kept;
     __shared__ int s_num;
     const int tid = threadIdx.x;
     const int cb = ceil_div(n, 64);
+    unsigned long long *s_remv = s_dyn;
+    unsigned long long *s_tile[2] = {s_dyn + cb, s_dyn + cb + (size_t)64 * cb};
     for (int j = tid; j < cb; j += SCAN_THREADS) s_remv[j] = 0ull;
     if (tid == 0) s_num = 0;
-    if (tid < 64 && cb > 0) s_diag[0][tid] = tid < n ? mask[(size_t)tid * cb] : 0ull;
-    __syncthreads();
-    for (int bi = 0; bi < cb; ++bi) {
-        const int par = bi & 1;
-        // prefetch the next block's diagonal words (independent of the scan state)
-        if (tid >= 64 && tid < 128 && bi + 1 < cb) {
-            const int i = (bi + 1) * 64 + (tid - 64);
-            s_diag[par ^ 1][tid - 64] = i < n ? mask[(size_t)i * cb + bi + 1] : 0ull;
+    auto prefetch = [&](int bi, int buf) {   // rows bi*64.., columns bi..cb-1 (the only ones the scan reads)
+        const int rows = min(64, n - bi * 64), cols = cb - bi;
+        for (int e = tid; e < rows * cols; e += SCAN_THREADS) {
+            const int t = e / cols, j = bi + e - t * cols;
+            scan_cp_async8((uint32_t)__cvta_generic_to_shared(s_tile[buf] + (size_t)t * cb + j), mask + (size_t)(bi * 64 + t) * cb + j);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (cb > 0) prefetch(0, 0);
+    for (int bi = 0; bi < cb; ++bi) {
+        const int buf = bi & 1;
+        if (bi + 1 < cb) {
+            prefetch(bi + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const unsigned long long *tile = s_tile[buf];
+        const int lim = min(64, n - bi * 64);
         if (tid == 0) {
             unsigned long long cur = s_remv[bi], kept = 0ull;
-            const int lim = min(64, n - bi * 64);
             int num = s_num;
             for (int t = 0; t < lim; ++t) {
                 if (!((cur >> t) & 1ull)) {
                     kept |= 1ull << t;
                     keep[num++] = (long long)bi * 64 + t;
-                    cur |= s_diag[par][t];
+                    cur |= tile[(size_t)t * cb + bi];
                 }
             }
             s_num = num;
@@ -234,12 +251,49 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(int n, const uns
         __syncthreads();
         const unsigned long long kept = s_kept;
         for (int j = bi + 1 + tid; j < cb; j += SCAN_THREADS) {
-            unsigned long long acc = s_remv[j], kk = kept;
-            while (kk) {
-                const int t = __ffsll((long long)kk) - 1;
-                kk &= kk - 1;
-                acc |= mask[(size_t)(bi * 64 + t) * cb + j];
-            }
+            unsigned long long acc = s_remv[j];
+#pragma unroll 8
+            for (int t = 0; t < 64; ++t)
+                if ((kept >> t) & 1ull) acc |= tile[(size_t)t * cb + j];
+            s_remv[j] = acc;
+        }
+        __syncthreads();   // tile[buf] is overwritten by the prefetch of block bi+2
+    }
+    if (tid == 0) *num_out = s_num;
+}
+
+// fallback for very large n (the prefetched tiles no longer fit shared memory): same recurrence, mask rows read
+// straight from global memory
+__global__ void __launch_bounds__(SCAN_THREADS) nms_scan_global_kernel(int n, const unsigned long long *__restrict__ mask,
+                                                                       long long *__restrict__ keep, int *__restrict__ num_out) {
+    extern __shared__ unsigned long long s_remv[];  // col_blocks words
+    __shared__ unsigned long long s_diag[64];
+    __shared__ unsigned long long s_kept;
+    __shared__ int s_num;
+    const int tid = threadIdx.x;
+    const int cb = ceil_div(n, 64);
+    for (int j = tid; j < cb; j += SCAN_THREADS) s_remv[j] = 0ull;
+    if (tid == 0) s_num = 0;
+    __syncthreads();
+    for (int bi = 0; bi < cb; ++bi) {
+        if (tid < 64) { const int i = bi * 64 + tid; s_diag[tid] = i < n ? mask[(size_t)i * cb + bi] : 0ull; }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long cur = s_remv[bi], kept = 0ull;
+            const int lim = min(64, n - bi * 64);
+            int num = s_num;
+            for (int t = 0; t < lim; ++t)
+                if (!((cur >> t) & 1ull)) { kept |= 1ull << t; keep[num++] = (long long)bi * 64 + t; cur |= s_diag[t]; }
+            s_num = num;
+            s_kept = kept;
+        }
+        __syncthreads();
+        const unsigned long long kept = s_kept;
+        for (int j = bi + 1 + tid; j < cb; j += SCAN_THREADS) {
+            unsigned long long acc = s_remv[j];
+#pragma unroll 8
+            for (int t = 0; t < 64; ++t)
+                if ((kept >> t) & 1ull) acc |= mask[(size_t)(bi * 64 + t) * cb + j];
             s_remv[j] = acc;
         }
         __syncthreads();
@@ -294,8 +348,15 @@ extern "C" int prb_nms_device(const float *boxes, int n, float thresh, int norma
     unsigned long long *mask = (unsigned long long *)workspace;
     int rc = prb_nms_mask(boxes, n, thresh, normal, mask, stream);
     if (rc) return rc;
-    const size_t smem = (size_t)ceil_div(n, 64) * 8;
-    PRB_REQUIRE(smem <= 200 * 1024, "nms: %d boxes exceed the single-CTA scan capacity", n);
+    const size_t cbs = (size_t)ceil_div(n, 64);
+    const size_t smem = (cbs + 2 * 64 * cbs) * 8;   // remv + two prefetched row tiles
+    if (smem > 220 * 1024) {                        // > ~13.6k boxes: rows straight from global memory
+        const size_t smem_g = cbs * 8;
+        PRB_REQUIRE(smem_g <= 200 * 1024, "nms: %d boxes exceed the single-CTA scan capacity", n);
+        if (smem_g > 48 * 1024) PRB_CUDA(cudaFuncSetAttribute(nms_scan_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        nms_scan_global_kernel<<<1, SCAN_THREADS, smem_g, st>>>(n, mask, keep_dev, num_dev);
+        return check_launch("nms_scan_global_kernel");
+    }
     if (smem > 48 * 1024) PRB_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nms_scan_kernel<<<1, SCAN_THREADS, smem, st>>>(n, mask, keep_dev, num_dev);
     return check_launch("nms_scan_kernel");

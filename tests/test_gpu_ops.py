@@ -263,7 +263,8 @@ def test_overlap_and_iou_matrices(cuda):
 
 
 @pytest.mark.parametrize("n,thresh,normal", [(100, 0.1, False), (1000, 0.3, False), (2700, 0.8, True), (6300, 0.8, True),
-                                             (6300, 0.85, True), (65, 0.5, False), (64, 0.5, True), (1, 0.5, False)])
+                                             (6300, 0.85, True), (65, 0.5, False), (64, 0.5, True), (1, 0.5, False),
+                                             (15000, 0.7, True)])
 def test_nms_keep_exact(cuda, n, thresh, normal):
     boxes = synth.sorted_bev(n, 100 + n)
     tb = T(boxes, cuda)
