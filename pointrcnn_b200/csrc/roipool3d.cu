@@ -63,24 +63,12 @@ __global__ void __launch_bounds__(RP_THREADS) roipool3d_kernel(int N, int M, int
     const float *pts = xyz + (size_t)scene * N * 3;
 
     int cnt = 0;  // uniform across the CTA
-    constexpr int PPT = 4;   // points per thread and step: one barrier pair per 1024 points
-    for (int k0 = 0; k0 < N && cnt < S; k0 += RP_THREADS * PPT) {
-        // thread t tests points k0 + 4t .. 4t+3 (consecutive, so index order = (thread, slot) order)
-        unsigned in_bits = 0;
-#pragma unroll
-        for (int i = 0; i < PPT; ++i) {
-            const int k = k0 + tid * PPT + i;
-            if (k < N && pt_in_box(bc, pts[(size_t)k * 3], pts[(size_t)k * 3 + 1], pts[(size_t)k * 3 + 2])) in_bits |= 1u << i;
-        }
-        const int mine = __popc(in_bits);
-        // exclusive prefix of the per-thread counts: warp scan + per-warp totals
-        int incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (lane == 31) s_wcnt[warp] = incl;
+    for (int k0 = 0; k0 < N && cnt < S; k0 += RP_THREADS) {
+        const int k = k0 + tid;
+        bool in = false;
+        if (k < N) in = pt_in_box(bc, pts[(size_t)k * 3], pts[(size_t)k * 3 + 1], pts[(size_t)k * 3 + 2]);
+        const unsigned hits = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) s_wcnt[warp] = __popc(hits);
         __syncthreads();
         int before = 0, total = 0;
 #pragma unroll
@@ -89,13 +77,8 @@ __global__ void __launch_bounds__(RP_THREADS) roipool3d_kernel(int N, int M, int
             before += w < warp ? c : 0;
             total += c;
         }
-        int pos = cnt + before + incl - mine;
-#pragma unroll
-        for (int i = 0; i < PPT; ++i)
-            if ((in_bits >> i) & 1u) {
-                if (pos < S) s_idx[pos] = k0 + tid * PPT + i;
-                ++pos;
-            }
+        const int pos = cnt + before + __popc(hits & ((1u << lane) - 1));
+        if (in && pos < S) s_idx[pos] = k;
         cnt = min(S, cnt + total);
         __syncthreads();
     }
@@ -114,27 +97,23 @@ __global__ void __launch_bounds__(RP_THREADS) roipool3d_kernel(int N, int M, int
     const int W = 3 + C;
     const float *feat = pts_feature + (size_t)scene * N * C;
     float *dst = pooled + ((size_t)scene * M + box) * (size_t)S * W;
-    // the box's S rows are one contiguous block of S*(3+C) floats: a flat loop gives fully coalesced 128-byte stores
-    // (rows are 4-byte aligned only: 3+C is odd for the RCNN's 133-float rows) and contiguous feature reads
-    int row = tid / W, col = tid - row * W;
-    const int drow = RP_THREADS / W, dcol = RP_THREADS - drow * W;
-    for (int e = tid; e < S * W; e += RP_THREADS) {
+    // warp per row, lanes along the row: both the feature read and the pooled write are coalesced
+    for (int row = warp; row < S; row += RP_WARPS) {
         const int k = s_idx[row < cnt ? row : row % cnt];
-        float v;
-        if (col < 3) {
+        float *o = dst + (size_t)row * W;
+        if (lane < 3) {
+            float v;
             if (rois) {
                 const float x = pts[(size_t)k * 3] - rcx, y = pts[(size_t)k * 3 + 1] - rcy, z = pts[(size_t)k * 3 + 2] - rcz;
                 // [x z] @ [[cos,-sin],[sin,cos]]^T : x' = x*cos - z*sin, z' = x*sin + z*cos
-                v = col == 0 ? __fmaf_rn(x, rcos, -__fmul_rn(z, rsin)) : (col == 1 ? y : __fmaf_rn(x, rsin, __fmul_rn(z, rcos)));
+                v = lane == 0 ? __fmaf_rn(x, rcos, -__fmul_rn(z, rsin)) : (lane == 1 ? y : __fmaf_rn(x, rsin, __fmul_rn(z, rcos)));
             } else {
-                v = pts[(size_t)k * 3 + col];
+                v = pts[(size_t)k * 3 + lane];
             }
-        } else {
-            v = __ldg(feat + (size_t)k * C + (col - 3));
+            o[lane] = v;
         }
-        dst[e] = v;
-        row += drow; col += dcol;
-        if (col >= W) { col -= W; ++row; }
+        const float *f = feat + (size_t)k * C;
+        for (int j = lane; j < C; j += 32) o[3 + j] = __ldg(f + j);
     }
 }
 
