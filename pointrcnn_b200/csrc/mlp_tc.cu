@@ -229,8 +229,8 @@ __device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, %0;" ::"n
 // NG row groups of 4 warps each (warp w: TMEM lane quarter w%4, group w/4) + producer warp + MMA warp.
 // The A chunks (and the 16-column epilogue batches) of a tile are dealt round-robin to the groups, so 4*NG warps
 // hide each other's latencies while the stage order seen by the MMA issuer stays sequential.
-template <int NG>
-__global__ void __launch_bounds__(128 * NG + 64, NG == 1 ? 2 : 1) mlp_chain_kernel(const ChainParams p) {
+template <int NG, int MINB>
+__global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const ChainParams p) {
     constexpr int NTHREADS = 128 * NG + 64;
     extern __shared__ uint8_t smem_raw[];
     __shared__ SmemFixed S;
@@ -808,36 +808,37 @@ static int launch_chain(ChainParams &p, cudaStream_t st) {
     if (L >= 2) p.dcol[1] = cols - p.np[1];
     if (L >= 3) p.dcol[2] = 0;
     // Row-thread parallelism: NG groups of 4 row warps in one CTA (chunks dealt round-robin), or -- when TMEM and
-    // shared memory allow two CTAs per SM -- NG=1 with two independent CTAs.
+    // shared memory allow several CTAs per SM -- NG=1 with 2 or 3 independent CTAs (the 3-CTA build is capped at 112
+    // registers per thread).
     const int sm_smem = 227 * 1024;
     int ng = 0;
     if (const char *e = getenv("PRB_MLP_NG")) ng = atoi(e);
     int occ = 1;
     if (ng == 0) ng = (cols <= 256) ? 1 : 2;
-    if (ng == 1 && cols <= 256) occ = 2;
+    if (ng == 1) occ = 512 / cols > 3 ? 3 : 512 / cols;
     if (const char *e = getenv("PRB_MLP_OCC")) { int o = atoi(e); if (o >= 1 && o < occ) occ = o; }
     size_t smem = 0;
     for (;; --occ) {
         int depth = occ >= 2 ? 3 : 4;
         for (; depth >= 2; --depth) {
             smem = chain_smem_bytes(ng, depth, depth, p.b_stage_bytes, np_total);
-            if (smem * occ <= (size_t)sm_smem - 1024 * occ && smem <= (size_t)max_optin) { p.na = p.nb = depth; break; }
+            if ((smem + 1024 + 3744) * occ <= (size_t)sm_smem && smem <= (size_t)max_optin) { p.na = p.nb = depth; break; }
         }
         if (depth >= 2 || occ == 1) break;
     }
     PRB_REQUIRE(smem <= (size_t)max_optin, "mlp: %zu bytes of shared memory needed, %d available", smem, max_optin);
     int grid = num_sms() * occ;
     if (grid > p.num_tiles) grid = p.num_tiles;
-    if (ng == 1) {
-        PRB_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mlp_chain_kernel<1><<<grid, 128 + 64, smem, st>>>(p);
-    } else if (ng == 2) {
-        PRB_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mlp_chain_kernel<2><<<grid, 256 + 64, smem, st>>>(p);
-    } else {
-        PRB_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mlp_chain_kernel<3><<<grid, 384 + 64, smem, st>>>(p);
-    }
+#define PRB_LAUNCH_CHAIN(NGV, MB)                                                                                              \
+    do {                                                                                                                       \
+        PRB_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<NGV, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        mlp_chain_kernel<NGV, MB><<<grid, 128 * NGV + 64, smem, st>>>(p);                                                     \
+    } while (0)
+    if (ng == 1 && occ >= 3) PRB_LAUNCH_CHAIN(1, 3);
+    else if (ng == 1) PRB_LAUNCH_CHAIN(1, 2);
+    else if (ng == 2) PRB_LAUNCH_CHAIN(2, 1);
+    else PRB_LAUNCH_CHAIN(3, 1);
+#undef PRB_LAUNCH_CHAIN
     return check_launch("mlp_chain_kernel");
 }
 
