@@ -43,11 +43,14 @@ def tf32_trunc(x):
 
 
 def mlp_tf32_ref(x, layers):
-    """layer-0 rows with a 16-byte aligned pitch are copied to shared memory unrounded (cp.async) and truncated by the
-    tensor core; everything built in registers (other pitches, later layers, weights) is rounded with cvt.rna"""
+    """every operand built in registers is rounded with cvt.rna (weights at pack time, activations per layer).  With the
+    optional cp.async gather (PRB_MLP_GATHER=1/2) layer-0 rows of 16-byte aligned pitch reach the tensor core unrounded
+    and are truncated there."""
+    import os
+    async_gather = os.environ.get("PRB_MLP_GATHER", "0") in ("1", "2")
     h = x.astype(np.float32)
     for li, (W, sc, sh) in enumerate(layers):
-        a = tf32_trunc(h) if (li == 0 and x.shape[1] % 4 == 0) else tf32(h)
+        a = tf32_trunc(h) if (async_gather and li == 0 and x.shape[1] % 4 == 0) else tf32(h)
         h = a @ tf32(W).T
         h = np.maximum(h * sc[None] + sh[None], 0).astype(np.float32)
     return h
