@@ -170,9 +170,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// relu + round-to-nearest-even to tf32 in ONE instruction (F2FP.RELU.TF32.F32)
+__device__ __forceinline__ float relu_to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rn.relu.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// round-to-nearest-even to tf32: one F2FP instruction (cvt.rna expands to a 4-instruction sequence)
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    asm("cvt.rn.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
 
@@ -561,7 +568,7 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                             float o[4];
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
-                                o[q] = to_tf32(fmaxf(fmaf(__uint_as_float(acc[4 * j + q]), sc[4 * j + q], sh[4 * j + q]), 0.f));
+                                o[q] = relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + q]), sc[4 * j + q], sh[4 * j + q]));
                             *reinterpret_cast<float4 *>(A + swz(r, hh * 4 + j)) = make_float4(o[0], o[1], o[2], o[3]);
                         }
                     }

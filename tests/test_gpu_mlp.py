@@ -35,6 +35,14 @@ def tf32(x):
     return u.view(np.float32)
 
 
+def tf32_rn(x):
+    """cvt.rn.tf32.f32 (round to nearest even), used for the activations between layers (fused with the ReLU)"""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    lsb = (u >> 13) & 1
+    u = (u + 0xFFF + lsb) & 0xFFFFE000
+    return u.astype(np.uint32).view(np.float32)
+
+
 def tf32_trunc(x):
     """what the tensor core does to raw fp32 operand bits: the low 13 mantissa bits are dropped"""
     u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).copy()
@@ -43,14 +51,14 @@ def tf32_trunc(x):
 
 
 def mlp_tf32_ref(x, layers):
-    """every operand built in registers is rounded with cvt.rna (weights at pack time, activations per layer).  With the
+    """weights are rounded at pack time (host, ties away), every A operand built in registers with cvt.rn (ties even).  With the
     optional cp.async gather (PRB_MLP_GATHER=1/2) layer-0 rows of 16-byte aligned pitch reach the tensor core unrounded
     and are truncated there."""
     import os
     async_gather = os.environ.get("PRB_MLP_GATHER", "0") in ("1", "2")
     h = x.astype(np.float32)
     for li, (W, sc, sh) in enumerate(layers):
-        a = tf32_trunc(h) if (async_gather and li == 0 and x.shape[1] % 4 == 0) else tf32(h)
+        a = tf32_trunc(h) if (async_gather and li == 0 and x.shape[1] % 4 == 0) else tf32_rn(h)
         h = a @ tf32(W).T
         h = np.maximum(h * sc[None] + sh[None], 0).astype(np.float32)
     return h
