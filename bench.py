@@ -120,7 +120,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
@@ -233,6 +233,9 @@ def main():
         if world > 1:
             dist.barrier()
 
+    # clock / throttle sampling runs through every timed region; nvidia-smi is started before the warm-up because its
+    # start-up takes the driver lock for a few hundred ms (it once stalled a 70 ms timed region to 430 ms)
+    sampler = ClockSampler(local) if rank == 0 else None
     with torch.no_grad():
         for i in range(W):
             net(dev_pool[i % P])
@@ -241,7 +244,6 @@ def main():
         torch.cuda.synchronize()
 
         # ---------------- device-resident throughput: K steps, F independent batches in flight
-        sampler = ClockSampler(local) if rank == 0 else None
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = _cabi.launch_count()
         barrier(); torch.cuda.synchronize()
@@ -250,7 +252,6 @@ def main():
         t1.record()
         torch.cuda.synchronize(); barrier()
         launches = (_cabi.launch_count() - launches0) // K
-        clocks = sampler.stop() if sampler else None
         ms = max_over_ranks(t0.elapsed_time(t1) / K, device=dev)
 
         # ---------------- end to end: pinned host input -> H2D -> backbone -> metric -> D2H, same pipeline
@@ -278,6 +279,7 @@ def main():
         fam = prof.collect()
         ms_seq = sum(a.elapsed_time(b_) for a, b_ in ev) / KS
         host = host_pool[0]
+    clocks = sampler.stop() if sampler else None
 
     if world > 1:
         dist.destroy_process_group()
