@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                 const int k0 = c * KC;                       // first column of this chunk inside its segment
                 const int width = p.seg_width[seg];
                 uint8_t *A = sA + (size_t)ra.stage * A_STAGE_BYTES;
-                const bool rows_seg = (p.mode_in == IN_DIRECT) || (p.mode_in == IN_SA && seg == 0 && p.c_feat > 0) ||
+                const bool rows_seg = (p.mode_in == IN_DIRECT) || (p.mode_in == IN_SA && seg == 0 && p.c_feat > 5) ||
                                       (p.mode_in == IN_FP && seg == 0);
                 if (rows_seg) {
                     // point-major sources: 8 lanes cover one row's 128 bytes, a warp covers 4 rows per step, 8 steps.
@@ -514,17 +514,25 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                         }
                     }
                 } else if (p.mode_in == IN_SA) {
-                    // relative xyz segment: [x - cx, y - cy, z - cz, 0 ...]; one K=8 step is consumed
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    // relative xyz segment: [x - cx, y - cy, z - cz, (<= 5 feature channels,) 0 ...]; one K=8 step
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), v2 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (valid) {
                         const float *q = p.xyz + (size_t)m_src[0] * 3;
                         v.x = to_tf32(__ldg(q + 0) - m_aux[0]);
                         v.y = to_tf32(__ldg(q + 1) - m_aux[1]);
                         v.z = to_tf32(__ldg(q + 2) - m_aux[2]);
+                        if (p.c_feat > 0 && p.c_feat <= 5) {
+                            const float *f = p.feats_pm + (size_t)m_src[0] * p.c_feat;
+                            v.w = to_tf32(__ldg(f));
+                            if (p.c_feat > 1) v2.x = to_tf32(__ldg(f + 1));
+                            if (p.c_feat > 2) v2.y = to_tf32(__ldg(f + 2));
+                            if (p.c_feat > 3) v2.z = to_tf32(__ldg(f + 3));
+                            if (p.c_feat > 4) v2.w = to_tf32(__ldg(f + 4));
+                        }
                     }
                     acquire_stage();
                     *reinterpret_cast<float4 *>(A + swz(r, 0)) = v;
-                    *reinterpret_cast<float4 *>(A + swz(r, 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4 *>(A + swz(r, 1)) = v2;
                 } else {
                     // FP skip segment: channel-major (b, c_skip, n); lanes run along consecutive points
                     const float *bsrc = p.skip + (size_t)my_scene * p.c_skip * p.n + my_u;
@@ -561,15 +569,17 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                     for (int hh = 0; hh < 2; ++hh) {
                         uint32_t acc[16];
                         tmem_ld16(tmem + lane_base + (uint32_t)(p.dcol[l - 1] + kc * KC + hh * 16), acc);
-                        const float *sc = s_scale + sc_off[l - 1] + kc * KC + hh * 16;
-                        const float *sh = s_shift + sc_off[l - 1] + kc * KC + hh * 16;
+                        const float4 *sc4 = reinterpret_cast<const float4 *>(s_scale + sc_off[l - 1] + kc * KC + hh * 16);
+                        const float4 *sh4 = reinterpret_cast<const float4 *>(s_shift + sc_off[l - 1] + kc * KC + hh * 16);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            float o[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                o[q] = relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + q]), sc[4 * j + q], sh[4 * j + q]));
-                            *reinterpret_cast<float4 *>(A + swz(r, hh * 4 + j)) = make_float4(o[0], o[1], o[2], o[3]);
+                            const float4 a = sc4[j], b = sh4[j];     // broadcast LDS.128
+                            float4 o;
+                            o.x = relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 0]), a.x, b.x));
+                            o.y = relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 1]), a.y, b.y));
+                            o.z = relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 2]), a.z, b.z));
+                            o.w = relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 3]), a.w, b.w));
+                            *reinterpret_cast<float4 *>(A + swz(r, hh * 4 + j)) = o;
                         }
                     }
                     tc_fence_before();
@@ -596,8 +606,17 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                 uint32_t acc[16];
                 tmem_ld16(tmem + lane_base + (uint32_t)(p.dcol[L - 1] + c0), acc);
                 float v[16];
+                {
+                    const float4 *sc4 = reinterpret_cast<const float4 *>(sc + c0), *sh4 = reinterpret_cast<const float4 *>(sh + c0);
 #pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = fmaxf(fmaf(__uint_as_float(acc[q]), sc[c0 + q], sh[c0 + q]), 0.f);
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 a = sc4[j], b = sh4[j];
+                        v[4 * j + 0] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 0]), a.x, b.x), 0.f);
+                        v[4 * j + 1] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 1]), a.y, b.y), 0.f);
+                        v[4 * j + 2] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 2]), a.z, b.z), 0.f);
+                        v[4 * j + 3] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 3]), a.w, b.w), 0.f);
+                    }
+                }
                 if (p.mode_out == OUT_ROWS) {
                     if (valid) {
                         float *o = p.out + (size_t)R * p.out_pitch + c0;
@@ -718,7 +737,9 @@ static void default_segs(int kind, int c_in, int a, PackSegs *ps) {
     // kind 1 (FP): original [interp(a), skip(c_in-a)] kept in order, split in two padded segments
     // kind 2 (DIRECT): one segment
     if (kind == 0) {
-        if (a > 0) { ps->nseg = 2; ps->src_off[0] = 3; ps->width[0] = a; ps->src_off[1] = 0; ps->width[1] = 3; }
+        // a handful of feature channels (e.g. the intensity of the first RPN level) ride in the xyz chunk: [xyz, feats]
+        if (a > 0 && a <= 5) { ps->nseg = 1; ps->src_off[0] = 0; ps->width[0] = 3 + a; }
+        else if (a > 0) { ps->nseg = 2; ps->src_off[0] = 3; ps->width[0] = a; ps->src_off[1] = 0; ps->width[1] = 3; }
         else { ps->nseg = 1; ps->src_off[0] = 0; ps->width[0] = 3; }
     } else if (kind == 1 && c_in - a > 0) {
         ps->nseg = 2; ps->src_off[0] = 0; ps->width[0] = a; ps->src_off[1] = a; ps->width[1] = c_in - a;

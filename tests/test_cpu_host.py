@@ -126,12 +126,12 @@ def test_weight_packing_layout():
     """prb_mlp_pack_weights_ex is host code: check the K-major SWIZZLE_128B tile image element by element"""
     from pointrcnn_b200 import _cabi as C
     rng = np.random.default_rng(0)
-    c_feat, couts = 5, [20, 40]
+    c_feat, couts = 7, [20, 40]
     W0 = rng.standard_normal((20, 3 + c_feat)).astype(np.float32)
     W1 = rng.standard_normal((40, 20)).astype(np.float32)
     co = (ctypes.c_int * 3)(20, 40, 0)
     nbytes = C.lib().prb_mlp_packed_bytes_ex(0, c_feat, 2, 3 + c_feat, co)
-    # layer 0: segments [feat(5)->32][xyz(3)->32] = 2 chunks, np=32 ; layer 1: K=32 -> 1 chunk, np=64
+    # layer 0: segments [feat(7)->32][xyz(3)->32] = 2 chunks, np=32 ; layer 1: K=32 -> 1 chunk, np=64
     assert nbytes == (2 * 32 * 32 + 1 * 64 * 32) * 4
     host = np.zeros(nbytes // 4, np.float32)
     wp = (ctypes.c_void_p * 2)(W0.ctypes.data, W1.ctypes.data)
@@ -157,6 +157,17 @@ def test_weight_packing_layout():
         for kk in range(32):
             want = tf32(W1[n, kk]) if (n < 40 and kk < 20) else 0.0
             assert elem(l1, 64, 0, n, kk) == want
+    # up to five feature channels ride in the xyz chunk, in the reference's own column order [xyz, feats]
+    Wc = rng.standard_normal((16, 4)).astype(np.float32)
+    co1 = (ctypes.c_int * 3)(16, 0, 0)
+    nb = C.lib().prb_mlp_packed_bytes_ex(0, 1, 1, 4, co1)
+    assert nb == 32 * 32 * 4
+    h2 = np.zeros(nb // 4, np.float32)
+    wp1 = (ctypes.c_void_p * 1)(Wc.ctypes.data)
+    assert C.lib().prb_mlp_pack_weights_ex(0, 1, 1, 4, co1, wp1, h2.ctypes.data_as(ctypes.c_void_p)) == 0
+    for n in range(32):
+        for kk in range(32):
+            assert elem(h2, 32, 0, n, kk) == (tf32(Wc[n, kk]) if (n < 16 and kk < 4) else 0.0)
 
 
 # ------------------------------------------------------------------------------------------------ host logic
