@@ -124,6 +124,20 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def wait_started(self, timeout=15.0):
+        """block until nvidia-smi has printed its first sample: its start-up holds the driver lock for a while and
+        must not fall into a timed region"""
+        if self.p is None:
+            return
+        t0 = time.time()
+        while time.time() - t0 < timeout:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    return
+            except OSError:
+                pass
+            time.sleep(0.05)
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
@@ -242,6 +256,8 @@ def main():
         pipe.run([dev_pool[i % P] for i in range(2 * F)])
         pipe_metric.run([host_pool[i % P] for i in range(K)], to_host=True)    # also allocates the pinned result buffers
         torch.cuda.synchronize()
+        if sampler:
+            sampler.wait_started()
 
         # ---------------- device-resident throughput: K steps, F independent batches in flight
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
