@@ -113,57 +113,67 @@ def time_cpu(net_cpu_specs, scenes, steps=1, warmup=0):
 
 
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / throttle-reason samples every 100 ms while the timed regions run.  NVML is queried in-process
+    (what nvidia-smi itself does) from a background thread: spawning nvidia-smi takes the driver lock for hundreds of
+    milliseconds at start-up and occasionally stalled a timed region."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
     def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        import threading
+        self.samples, self.stop_flag, self.h, self.nv = [], False, None, None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
-
-    def wait_started(self, timeout=15.0):
-        """block until nvidia-smi has printed its first sample: its start-up holds the driver lock for a while and
-        must not fall into a timed region"""
-        if self.p is None:
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; map through it when it is set
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+        except Exception:
             return
-        t0 = time.time()
-        while time.time() - t0 < timeout:
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
             try:
-                if os.path.getsize(self.f.name) > 0:
-                    return
-            except OSError:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, mx, rs))
+            except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.1)
+
+    def wait_started(self, timeout=5.0):
+        t0 = time.time()
+        while self.nv is not None and not self.samples and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        """samples taken from here on belong to the timed regions"""
+        self.first = len(self.samples)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "source": "nvml"}
+        if self.nv is None:
+            out["source"] = "unavailable"
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
-        os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
-        for r in rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            out["sm_mhz"] = statistics.median(sm)
-            out["sm_max_mhz"] = max(mx)
-            out["samples"] = len(sm)
-        out["reasons"] = sorted(reasons)
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        rows = self.samples[getattr(self, "first", 0):] or self.samples
+        if rows:
+            out["sm_mhz"] = statistics.median(r[0] for r in rows)
+            out["sm_max_mhz"] = max(r[1] for r in rows)
+            out["samples"] = len(rows)
+            seen = set()
+            for r in rows:
+                for name, bit in self.REASONS.items():
+                    if r[2] & bit:
+                        seen.add(name)
+            out["reasons"] = sorted(seen)
         return out
 
 
@@ -204,12 +214,14 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-scenes", type=int, default=2, help="scenes per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=3, help="independent batches in flight (CUDA streams); 1 = sequential")
+    ap.add_argument("--inflight", type=int, default=4, help="independent batches in flight (CUDA streams); 1 = sequential")
+    ap.add_argument("--fps-cluster", type=int, default=2, help="FPS cluster size while batches are pipelined (0 = the "
+                    "single-batch heuristic); measured: 5190 scenes/s with 4 CTAs per scene, 5650 with 2 (profiles/r1_notes.md)")
     ap.add_argument("--pool", type=int, default=40, help="distinct input batches rotated through (40 x 4.2 MB > 126 MB L2)")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel-family table as JSON here")
     args = ap.parse_args()
@@ -240,8 +252,8 @@ def main():
     dev_pool = [h.to(dev) for h in host_pool]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2 (sequential pass)
     F = max(1, args.inflight)
-    pipe = BatchPipeline(lambda x: net(x)[1], inflight=F, device=dev)
-    pipe_metric = BatchPipeline(lambda x: net(x)[1].mean(dim=(1, 2)), inflight=F, device=dev)
+    pipe = BatchPipeline(lambda x: net(x)[1], inflight=F, device=dev, fps_cluster=args.fps_cluster)
+    pipe_metric = BatchPipeline(lambda x: net(x)[1].mean(dim=(1, 2)), inflight=F, device=dev, fps_cluster=args.fps_cluster)
 
     def barrier():
         if world > 1:
@@ -258,6 +270,7 @@ def main():
         torch.cuda.synchronize()
         if sampler:
             sampler.wait_started()
+            sampler.mark()
 
         # ---------------- device-resident throughput: K steps, F independent batches in flight
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -350,7 +363,7 @@ def main():
             "config": {"workload": "RPN PointNet++ backbone fwd: 4 SA-MSG + 4 FP (tools/cfgs/default.yaml), 16384x4 uniform KITTI-scope "
                                    "points, eval-mode BN (BASELINE configs[1])", "batch_per_gpu": BATCH, "global_batch": scenes,
                        "parallelism": "dp%d (scene sharding, no data-path collective)" % world,
-                       "batches_in_flight": F, "l2": "inputs rotate through %d distinct batches (%.0f MB > 126 MB L2)" % (P, P * BATCH * POINTS * CHANNELS * 4 / 1e6)},
+                       "batches_in_flight": F, "fps_cluster_while_pipelined": args.fps_cluster, "l2": "inputs rotate through %d distinct batches (%.0f MB > 126 MB L2)" % (P, P * BATCH * POINTS * CHANNELS * 4 / 1e6)},
             "single_batch": {"ms_per_step": ms_seq, "value": BATCH / (ms_seq * 1e-3), "unit": "scenes/s",
                              "note": "one batch at a time on one stream, 256 MB L2 flush write between steps"},
             "e2e": {"value": scenes / (ms_e2e * 1e-3), "unit": "scenes/s", "ms_per_step": ms_e2e,
