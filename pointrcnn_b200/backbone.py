@@ -45,6 +45,7 @@ class Pointnet2MSG(nn.Module):
         for k in range(len(fp)):
             pre_channel = fp[k + 1][-1] if k + 1 < len(fp) else channel_out
             self.FP_modules.append(PointnetFPModule(mlp=[pre_channel + skip_channel_list[k]] + list(fp[k])))
+        self.FP_modules[0].emit_point_major = False   # the finest level feeds the heads, nothing gathers from it
 
     @staticmethod
     def _break_up_pc(pc):

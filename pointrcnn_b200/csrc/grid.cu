@@ -29,7 +29,7 @@ constexpr int BQ_CAP = 128;   // candidates per centre handled on the grid path
 struct GridView {
     int table_size;           // power of two
     const int *heads;         // (b, table_size), -1 = empty
-    const int *next;          // (b, n)
+    const float4 *nodes;      // (b, n): {x, y, z, next index as int bits}: ONE 16-byte load per visited candidate
     const double *inv_h;      // (b) 1 / cell edge
 };
 
@@ -89,14 +89,15 @@ __global__ void grid_set_cell_kernel(int b, double h, double *__restrict__ inv_h
 
 __global__ void __launch_bounds__(256) grid_insert_kernel(int n, int table_size, const float *__restrict__ xyz,
                                                           const double *__restrict__ inv_h, int *__restrict__ heads,
-                                                          int *__restrict__ next) {
+                                                          float4 *__restrict__ nodes) {
     const int scene = blockIdx.y;
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const float *p = xyz + ((size_t)scene * n + i) * 3;
     const double ih = inv_h[scene];
     const unsigned hsh = cell_hash(cell_coord(p[0], ih), cell_coord(p[1], ih), cell_coord(p[2], ih), table_size - 1);
-    next[(size_t)scene * n + i] = atomicExch(heads + (size_t)scene * table_size + hsh, i);
+    const int nxt = atomicExch(heads + (size_t)scene * table_size + hsh, i);
+    nodes[(size_t)scene * n + i] = make_float4(p[0], p[1], p[2], __int_as_float(nxt));
 }
 
 // ---------------------------------------------------------------- ball query on the grid
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(GR_THREADS) ball_query_grid_kernel(const GridB
     const float *q = p.new_xyz + ((size_t)scene * p.m + centre) * 3;
     const float cx = q[0], cy = q[1], cz = q[2];
     const float *xyz = p.xyz + (size_t)scene * p.n * 3;
-    const int *next = p.g.next + (size_t)scene * p.n;
+    const float4 *nodes = p.g.nodes + (size_t)scene * p.n;
     const double ih = p.g.inv_h[scene];
     float rmax = p.r2[0];
 #pragma unroll
@@ -141,12 +142,13 @@ __global__ void __launch_bounds__(GR_THREADS) ball_query_grid_kernel(const GridB
     int walked = 0;
     bool over = false;
     while (j >= 0) {
-        const float d2 = dist2_ref(cx - xyz[(size_t)j * 3], cy - xyz[(size_t)j * 3 + 1], cz - xyz[(size_t)j * 3 + 2]);
+        const float4 nd = __ldg(nodes + j);
+        const float d2 = dist2_ref(cx - nd.x, cy - nd.y, cz - nd.z);
         if (d2 < rmax) {
             const int pos = atomicAdd(&s_cnt[warp], 1);
             if (pos < BQ_CAP) s_cand[warp][pos] = j;
         }
-        j = next[j];
+        j = __float_as_int(nd.w);
         if (++walked > 4 * BQ_CAP) { over = true; break; }     // pathological bucket: leave it to the scan kernel
     }
     __syncwarp();
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(GR_THREADS) three_nn_grid_kernel(const GridNnP
     const float *q = p.unknown + ((size_t)scene * p.n + u) * 3;
     const float ux = q[0], uy = q[1], uz = q[2];
     const float *kn = p.known + (size_t)scene * p.m * 3;
-    const int *next = p.g.next + (size_t)scene * p.m;
+    const float4 *nodes = p.g.nodes + (size_t)scene * p.m;
     const int *heads = p.g.heads + (size_t)scene * p.g.table_size;
     const double ih = p.g.inv_h[scene];
     const int cx = cell_coord(ux, ih), cy = cell_coord(uy, ih), cz = cell_coord(uz, ih);
@@ -293,9 +295,11 @@ __global__ void __launch_bounds__(GR_THREADS) three_nn_grid_kernel(const GridNnP
         hd[c] = __ldg(heads + cell_hash(cx + c % 3 - 1, cy + (c / 3) % 3 - 1, cz + c / 9 - 1, p.g.table_size - 1));
 #pragma unroll
     for (int c = 0; c < 27; ++c) {
-        for (int j = hd[c]; j >= 0 && !over; j = __ldg(next + j)) {
-            const float d = dist2_ref(ux - __ldg(kn + (size_t)j * 3), uy - __ldg(kn + (size_t)j * 3 + 1), uz - __ldg(kn + (size_t)j * 3 + 2));
+        for (int j = hd[c]; j >= 0 && !over;) {
+            const float4 nd = __ldg(nodes + j);
+            const float d = dist2_ref(ux - nd.x, uy - nd.y, uz - nd.z);
             nn_insert(d, j, b1, b2, b3, i1, i2, i3);
+            j = __float_as_int(nd.w);
             if (++walked > 2048) over = true;
         }
     }
@@ -357,14 +361,15 @@ static int table_size_for(int n) {
 
 struct GridWs {
     int table;
-    int *heads, *next, *overflow;
+    int *heads, *overflow;
+    float4 *nodes;
     double *inv_h;
     float *h;
 };
 
 static size_t grid_ws_bytes(int b, int n_points, int n_queries) {
     const size_t t = (size_t)table_size_for(n_points);
-    return (size_t)b * t * 4 + (size_t)b * n_points * 4 + ((size_t)b * n_queries + 64) * 4 + (size_t)b * 16 + 1024;
+    return (size_t)b * t * 4 + (size_t)b * n_points * 16 + ((size_t)b * n_queries + 64) * 4 + (size_t)b * 16 + 2048;
 }
 
 static GridWs carve(void *ws, int b, int n_points, int n_queries) {
@@ -373,8 +378,8 @@ static GridWs carve(void *ws, int b, int n_points, int n_queries) {
     char *c = (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     g.inv_h = (double *)c; c += (((size_t)b * 8 + 255) & ~(size_t)255);
     g.h = (float *)c; c += (((size_t)b * 4 + 255) & ~(size_t)255);
+    g.nodes = (float4 *)c; c += (size_t)b * n_points * 16;
     g.heads = (int *)c; c += (size_t)b * g.table * 4;
-    g.next = (int *)c; c += (size_t)b * n_points * 4;
     g.overflow = (int *)c;
     (void)n_queries;
     return g;
@@ -405,14 +410,14 @@ PRB_API int prb_ball_query_grid(int b, int n, int m, int nr, const float *radius
     PRB_CUDA(cudaMemsetAsync(w.overflow, 0, 4, st));
     grid_set_cell_kernel<<<ceil_div(b, 128), 128, 0, st>>>(b, (double)rmax * 1.0001, w.inv_h, w.h);
     if (int rc = check_launch("grid_set_cell_kernel")) return rc;
-    grid_insert_kernel<<<dim3(ceil_div(n, 256), b), 256, 0, st>>>(n, w.table, xyz, w.inv_h, w.heads, w.next);
+    grid_insert_kernel<<<dim3(ceil_div(n, 256), b), 256, 0, st>>>(n, w.table, xyz, w.inv_h, w.heads, w.nodes);
     if (int rc = check_launch("grid_insert_kernel")) return rc;
     const dim3 grid(ceil_div(m, GR_WARPS), b);
     const int ogrid = 2 * num_sms();
     if (nr == 1) {
         GridBqParams<1> p;
         p.b = b; p.n = n; p.m = m; p.r2[0] = radius[0] * radius[0]; p.ns[0] = nsample[0]; p.idx[0] = idx[0];
-        p.new_xyz = new_xyz; p.xyz = xyz; p.g = {w.table, w.heads, w.next, w.inv_h}; p.overflow = w.overflow;
+        p.new_xyz = new_xyz; p.xyz = xyz; p.g = {w.table, w.heads, w.nodes, w.inv_h}; p.overflow = w.overflow;
         ball_query_grid_kernel<1><<<grid, GR_THREADS, 0, st>>>(p);
         if (int rc = check_launch("ball_query_grid_kernel<1>")) return rc;
         ball_query_overflow_kernel<1><<<ogrid, GR_THREADS, 0, st>>>(p);
@@ -421,7 +426,7 @@ PRB_API int prb_ball_query_grid(int b, int n, int m, int nr, const float *radius
     GridBqParams<2> p;
     p.b = b; p.n = n; p.m = m;
     for (int r = 0; r < 2; ++r) { p.r2[r] = radius[r] * radius[r]; p.ns[r] = nsample[r]; p.idx[r] = idx[r]; }
-    p.new_xyz = new_xyz; p.xyz = xyz; p.g = {w.table, w.heads, w.next, w.inv_h}; p.overflow = w.overflow;
+    p.new_xyz = new_xyz; p.xyz = xyz; p.g = {w.table, w.heads, w.nodes, w.inv_h}; p.overflow = w.overflow;
     ball_query_grid_kernel<2><<<grid, GR_THREADS, 0, st>>>(p);
     if (int rc = check_launch("ball_query_grid_kernel<2>")) return rc;
     ball_query_overflow_kernel<2><<<ogrid, GR_THREADS, 0, st>>>(p);
@@ -442,11 +447,11 @@ PRB_API int prb_three_nn_grid(int b, int n, int m, const float *unknown, const f
     PRB_CUDA(cudaMemsetAsync(w.overflow, 0, 4, st));
     grid_cell_from_bbox_kernel<<<b, 256, 0, st>>>(m, known, w.inv_h, w.h);
     if (int rc = check_launch("grid_cell_from_bbox_kernel")) return rc;
-    grid_insert_kernel<<<dim3(ceil_div(m, 256), b), 256, 0, st>>>(m, w.table, known, w.inv_h, w.heads, w.next);
+    grid_insert_kernel<<<dim3(ceil_div(m, 256), b), 256, 0, st>>>(m, w.table, known, w.inv_h, w.heads, w.nodes);
     if (int rc = check_launch("grid_insert_kernel")) return rc;
     GridNnParams p;
     p.b = b; p.n = n; p.m = m; p.unknown = unknown; p.known = known; p.dist2 = dist2; p.weight = weight; p.idx = idx;
-    p.g = {w.table, w.heads, w.next, w.inv_h}; p.h = w.h; p.overflow = w.overflow;
+    p.g = {w.table, w.heads, w.nodes, w.inv_h}; p.h = w.h; p.overflow = w.overflow;
     three_nn_grid_kernel<<<dim3(ceil_div(n, GR_THREADS), b), GR_THREADS, 0, st>>>(p);
     if (int rc = check_launch("three_nn_grid_kernel")) return rc;
     three_nn_overflow_kernel<<<2 * num_sms(), GR_THREADS, 0, st>>>(p);

@@ -71,6 +71,7 @@ struct ChainParams {
     int x_pitch;
     // output
     float *out;
+    float *out_pm;       // optional second copy of the final output in point-major layout (rows x out_stride_c)
     int c_last;          // true channel count of the last layer
     int out_stride_c, out_c_off, out_pitch;
 };
@@ -594,13 +595,14 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
             const int Cl = p.c_last;
             const float *sc = s_scale + sc_off[L - 1], *sh = s_shift + sc_off[L - 1];
             // SA max-pool: thread (g16, q) owns 16-row segment g16 and channel q of every batch
-            size_t e_off = 0;
+            size_t e_off = 0, e_pm = 0;
             bool e_ok = false;
             if (p.mode_out == OUT_SA_MAX && p.ns >= 16) {
                 const unsigned Rg = (unsigned)tile * TM + (unsigned)(r >> 4) * 16u;
                 e_ok = (long)Rg < p.total_rows && (((r >> 4) & ((p.ns >> 4) - 1)) == 0);
                 const unsigned pr = Rg >> p.log_ns, scene = pr / (unsigned)p.npoint, pp = pr - scene * (unsigned)p.npoint;
                 e_off = ((size_t)scene * p.out_stride_c + p.out_c_off + (r & 15)) * p.npoint + pp;
+                e_pm = ((size_t)scene * p.npoint + pp) * p.out_stride_c + p.out_c_off + (r & 15);
             }
             for (int c0 = grp * 16; c0 < Cl; c0 += 16 * NG) {
                 uint32_t acc[16];
@@ -634,6 +636,17 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
 #pragma unroll
                         for (int q = 0; q < 16; ++q)
                             if (c0 + q < Cl) o[(size_t)q * p.n] = v[q];
+                        if (p.out_pm) {   // point-major copy for the next consumer (no transpose kernel)
+                            float *o2 = p.out_pm + (size_t)R * p.out_stride_c + p.out_c_off + c0;
+                            if ((p.out_stride_c & 3) == 0 && c0 + 16 <= Cl) {
+#pragma unroll
+                                for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4 *>(o2 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 16; ++q)
+                                    if (c0 + q < Cl) o2[q] = v[q];
+                            }
+                        }
                     }
                 } else {
                     // max over the nsample consecutive rows of each centre, through a shared staging tile:
@@ -660,7 +673,10 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                                 for (int s = 1; s < per; ++s) x = fmaxf(x, pool2[(g16 + s) * 16 + q]);
                             }
                         }
-                        if (e_ok && c0 + q < Cl) p.out[e_off + (size_t)c0 * p.npoint] = x;
+                        if (e_ok && c0 + q < Cl) {
+                            p.out[e_off + (size_t)c0 * p.npoint] = x;
+                            if (p.out_pm) p.out_pm[e_pm + c0] = x;
+                        }
                     } else {
                         // nsample 4 or 8: 128/ns centres per tile, 16 channels each -> (16/ns) items per thread
                         const int per16 = 16 / ns;
@@ -672,6 +688,7 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                             if ((long)Rg < p.total_rows && c0 + q < Cl) {
                                 const unsigned pr = Rg >> p.log_ns, scene = pr / (unsigned)p.npoint, pp = pr - scene * (unsigned)p.npoint;
                                 p.out[((size_t)scene * p.out_stride_c + p.out_c_off + c0 + q) * p.npoint + pp] = x;
+                                if (p.out_pm) p.out_pm[((size_t)scene * p.npoint + pp) * p.out_stride_c + p.out_c_off + c0 + q] = x;
                             }
                         }
                     }
@@ -945,6 +962,7 @@ static int run_chain(const ChainIO &io, const prb_mlp_desc *mlp, void *workspace
             float *dst = (float *)((char *)workspace + (pingpong ? workspace_bytes / 2 / 256 * 256 : 0));
             p.mode_out = OUT_ROWS;
             p.round_out = 1;
+            p.out_pm = nullptr;
             p.out = dst;
             p.out_pitch = g[l1 - 1].np;
             p.c_last = g[l1 - 1].np;
@@ -979,8 +997,8 @@ PRB_API size_t prb_rows_workspace_bytes(long rows, int c_in, int num_layers, con
 }
 
 PRB_API int prb_sa_group_mlp_max_ws(int b, int n, int npoint, int nsample, int c_feat, const float *xyz, const float *new_xyz,
-                                    const float *feats_pm, const int *idx, const prb_mlp_desc *mlp, float *out, int out_stride_c,
-                                    int out_c_off, void *workspace, size_t workspace_bytes, void *stream) {
+                                    const float *feats_pm, const int *idx, const prb_mlp_desc *mlp, float *out, float *out_pm,
+                                    int out_stride_c, int out_c_off, void *workspace, size_t workspace_bytes, void *stream) {
     PRB_REQUIRE(b >= 0 && n > 0 && npoint > 0 && nsample > 0 && xyz && new_xyz && idx && mlp && out, "sa_group_mlp_max: bad arguments");
     PRB_REQUIRE(mlp->c_in == 3 + c_feat, "sa_group_mlp_max: c_in %d != 3 + c_feat %d", mlp->c_in, c_feat);
     PRB_REQUIRE(c_feat == 0 || feats_pm, "sa_group_mlp_max: features missing");
@@ -995,13 +1013,13 @@ PRB_API int prb_sa_group_mlp_max_ws(int b, int n, int npoint, int nsample, int c
     io.base.log_ns = 0;
     while ((1 << io.base.log_ns) < nsample) ++io.base.log_ns;
     io.base.xyz = xyz; io.base.new_xyz = new_xyz; io.base.feats_pm = feats_pm; io.base.idx = idx;
-    io.base.out = out; io.base.out_stride_c = out_stride_c; io.base.out_c_off = out_c_off;
+    io.base.out = out; io.base.out_pm = out_pm; io.base.out_stride_c = out_stride_c; io.base.out_c_off = out_c_off;
     return run_chain(io, mlp, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 PRB_API int prb_fp_interp_mlp_ws(int b, int n, int m, int c_known, int c_skip, const float *known_pm, const int *idx,
-                                 const float *weight, const float *skip, const prb_mlp_desc *mlp, float *out, void *workspace,
-                                 size_t workspace_bytes, void *stream) {
+                                 const float *weight, const float *skip, const prb_mlp_desc *mlp, float *out, float *out_pm,
+                                 void *workspace, size_t workspace_bytes, void *stream) {
     PRB_REQUIRE(b >= 0 && n > 0 && m > 0 && c_known > 0 && known_pm && idx && weight && mlp && out, "fp_interp_mlp: bad arguments");
     PRB_REQUIRE(mlp->c_in == c_known + c_skip, "fp_interp_mlp: c_in %d != %d + %d", mlp->c_in, c_known, c_skip);
     PRB_REQUIRE(c_skip == 0 || skip, "fp_interp_mlp: skip features missing");
@@ -1013,7 +1031,7 @@ PRB_API int prb_fp_interp_mlp_ws(int b, int n, int m, int c_known, int c_skip, c
     io.base.mode_in = IN_FP; io.base.mode_out = OUT_FP;
     io.base.n = n; io.base.m = m; io.base.c_known = c_known; io.base.c_skip = c_skip;
     io.base.known_pm = known_pm; io.base.idx = idx; io.base.weight = weight; io.base.skip = skip;
-    io.base.out = out; io.base.out_stride_c = mlp->c_out[mlp->num_layers - 1]; io.base.out_c_off = 0;
+    io.base.out = out; io.base.out_pm = out_pm; io.base.out_stride_c = mlp->c_out[mlp->num_layers - 1]; io.base.out_c_off = 0;
     return run_chain(io, mlp, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -1039,12 +1057,12 @@ PRB_API int prb_mlp_rows(long rows, int c_in, const float *x_rows, const prb_mlp
 int prb_sa_group_mlp_max(int b, int n, int npoint, int nsample, int c_feat, const float *xyz, const float *new_xyz,
                          const float *feats_pm, const int *idx, const prb_mlp_desc *mlp, float *out, int out_stride_c,
                          int out_c_off, void *stream) {
-    return prb_sa_group_mlp_max_ws(b, n, npoint, nsample, c_feat, xyz, new_xyz, feats_pm, idx, mlp, out, out_stride_c, out_c_off,
-                                   nullptr, 0, stream);
+    return prb_sa_group_mlp_max_ws(b, n, npoint, nsample, c_feat, xyz, new_xyz, feats_pm, idx, mlp, out, nullptr, out_stride_c,
+                                   out_c_off, nullptr, 0, stream);
 }
 int prb_fp_interp_mlp(int b, int n, int m, int c_known, int c_skip, const float *known_pm, const int *idx, const float *weight,
                       const float *skip, const prb_mlp_desc *mlp, float *out, void *stream) {
-    return prb_fp_interp_mlp_ws(b, n, m, c_known, c_skip, known_pm, idx, weight, skip, mlp, out, nullptr, 0, stream);
+    return prb_fp_interp_mlp_ws(b, n, m, c_known, c_skip, known_pm, idx, weight, skip, mlp, out, nullptr, nullptr, 0, stream);
 }
 
 }  // extern "C"

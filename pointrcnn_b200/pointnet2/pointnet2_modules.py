@@ -109,6 +109,20 @@ class _FusedMLP:
         return desc
 
 
+def _attach_pm(t, pm):
+    """remember the point-major twin the kernel wrote next to `t`; valid while `t` is not modified in place"""
+    t._prb_pm = (pm, t._version)
+    return t
+
+
+def _point_major(t):
+    """(B,C,N) -> (B,N,C): the twin written by the producing kernel if it is still valid, else a transpose kernel"""
+    twin = getattr(t, "_prb_pm", None)
+    if twin is not None and twin[1] == t._version and twin[0].shape == (t.size(0), t.size(2), t.size(1)) and twin[0].device == t.device:
+        return twin[0]
+    return pointnet2_utils.transpose_bcn_to_bnc(t.contiguous())
+
+
 def _fused_enabled():
     return os.environ.get("PRB_DISABLE_FUSED", "0") != "1"
 
@@ -179,11 +193,13 @@ class _PointnetSAModuleBase(nn.Module):
         dev = xyz.device
         npoint = centres.size(1)
         c_feat = 0 if features is None else features.size(1)
-        feats_pm = pointnet2_utils.transpose_bcn_to_bnc(features.contiguous()) if features is not None else None
+        feats_pm = _point_major(features) if features is not None else None
         if self._fused is None or len(self._fused) != len(self.mlps):
             self._fused = [_FusedMLP() for _ in self.mlps]
         descs = [f.get(mlp, 0, c_feat, dev) for f, mlp in zip(self._fused, self.mlps)]
-        out = torch.empty((B, sum(f.c_out[-1] for f in self._fused), npoint), dtype=torch.float32, device=dev)
+        c_total = sum(f.c_out[-1] for f in self._fused)
+        out = torch.empty((B, c_total, npoint), dtype=torch.float32, device=dev)
+        out_pm = torch.empty((B, npoint, c_total), dtype=torch.float32, device=dev)   # twin for the next gather
         off = 0
         with torch.cuda.device(dev):
             for desc, fused, idx, ns in zip(descs, self._fused, idxs, nss):
@@ -192,10 +208,10 @@ class _PointnetSAModuleBase(nn.Module):
                 ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
                 with prof.region("sa_mlp"):
                     C.check(lib.prb_sa_group_mlp_max_ws(B, N, npoint, ns, c_feat, C.ptr(xyz), C.ptr(centres), C.ptr(feats_pm),
-                                                        C.ptr(idx), ctypes.byref(desc), C.ptr(out), out.size(1), off,
+                                                        C.ptr(idx), ctypes.byref(desc), C.ptr(out), C.ptr(out_pm), out.size(1), off,
                                                         C.ptr(ws), C.c_size_t(wsb), C.stream()), "sa_group_mlp_max")
                 off += fused.c_out[-1]
-        return out
+        return _attach_pm(out, out_pm)
 
     def _forward_fused(self, xyz, features, new_xyz):
         xyz = xyz.contiguous()
@@ -267,6 +283,7 @@ class PointnetFPModule(nn.Module):
         super().__init__()
         self.mlp = pt_utils.SharedMLP(mlp, bn=bn)
         self._fused = None
+        self.emit_point_major = True   # also write a (B,n,C) twin for the next FP level (skips its transpose kernel)
 
     def _can_fuse(self, unknown, known, unknow_feats, known_feats):
         if not _fused_enabled() or known is None or not unknown.is_cuda:
@@ -287,22 +304,23 @@ class PointnetFPModule(nn.Module):
         dev = known_feats.device
         B, c_known, m = known_feats.shape
         c_skip = 0 if unknow_feats is None else unknow_feats.size(1)
-        known_pm = pointnet2_utils.transpose_bcn_to_bnc(known_feats.contiguous())
+        known_pm = _point_major(known_feats)
         skip = unknow_feats.contiguous() if unknow_feats is not None else None
         if self._fused is None:
             self._fused = _FusedMLP()
         desc = self._fused.get(self.mlp, 1, c_known, dev)
         c_out = self._fused.c_out
         out = torch.empty((B, c_out[-1], n), dtype=torch.float32, device=dev)
+        out_pm = torch.empty((B, n, c_out[-1]), dtype=torch.float32, device=dev) if self.emit_point_major else None
         co_arr = (ctypes.c_int * 3)(*(c_out + [0] * (3 - len(c_out))))
         with torch.cuda.device(dev):
             wsb = lib.prb_fp_workspace_bytes(B, n, c_known, c_skip, desc.num_layers, co_arr)
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
             with prof.region("fp_mlp"):
                 C.check(lib.prb_fp_interp_mlp_ws(B, n, m, c_known, c_skip, C.ptr(known_pm), C.ptr(idx), C.ptr(weight), C.ptr(skip),
-                                                 ctypes.byref(desc), C.ptr(out), C.ptr(ws), C.c_size_t(wsb), C.stream()),
+                                                 ctypes.byref(desc), C.ptr(out), C.ptr(out_pm), C.ptr(ws), C.c_size_t(wsb), C.stream()),
                         "fp_interp_mlp")
-        return out
+        return _attach_pm(out, out_pm) if out_pm is not None else out
 
     def _forward_fused(self, unknown, known, unknow_feats, known_feats):
         idx, weight = self.fused_geometry(unknown, known)
