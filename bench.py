@@ -338,6 +338,9 @@ def main():
     for name in ("ball_query", "three_nn", "transpose"):
         if name in fam_ms:
             kernels.append({"name": name, "ms_per_step": fam_ms[name]})
+    for name in sorted(fam_ms):                      # PRB_PROF_DETAIL=1: one line per chain launch shape
+        if name.startswith(("sa_mlp ", "fp_mlp ")):
+            kernels.append({"name": name, "ms_per_step": fam_ms[name]})
     for k in kernels:
         if "achieved" in k:
             k["frac"] = k["achieved"] / k["peak"]

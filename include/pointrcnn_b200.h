@@ -125,6 +125,43 @@ PRB_API int prb_fp_interp_mlp(int b, int n, int m, int c_known, int c_skip, cons
                       const int *idx, const float *weight, const float *skip,
                       const prb_mlp_desc *mlp, float *out, void *stream);
 
+/* --- workspace-taking forms (what the Python mirror calls: no allocation inside the library) ---
+ * kind: 0 = SA rows [rel xyz | feats], 1 = FP rows [interp | skip], 2 = plain rows.  `split` is the
+ * channel where the first row source ends (3 for SA, c_known for FP, 0 for plain rows); it fixes
+ * how layer-0 weight columns are permuted into K-chunks. */
+PRB_API size_t prb_mlp_packed_bytes_ex(int kind, int split, int num_layers, int c_in, const int *c_out);
+PRB_API int prb_mlp_pack_weights_ex(int kind, int split, int num_layers, int c_in, const int *c_out,
+                                    const float *const *w, void *dst);
+PRB_API size_t prb_sa_workspace_bytes(int b, int npoint, int nsample, int c_feat, int num_layers, const int *c_out);
+PRB_API size_t prb_fp_workspace_bytes(int b, int n, int c_known, int c_skip, int num_layers, const int *c_out);
+PRB_API size_t prb_rows_workspace_bytes(long rows, int c_in, int num_layers, const int *c_out);
+/* as prb_sa_group_mlp_max / prb_fp_interp_mlp with caller scratch (device, *_workspace_bytes; may be
+ * NULL/0 when the chain fits one launch).  out_pm: NULL, or a second POINT-major copy of the result,
+ * (b, npoint, out_stride_c) at channel offset out_c_off for SA and (b, n, c_last) for FP -- the layout
+ * the next level's gather reads, so no transpose kernel runs between levels. */
+PRB_API int prb_sa_group_mlp_max_ws(int b, int n, int npoint, int nsample, int c_feat, const float *xyz,
+                                    const float *new_xyz, const float *feats_pm, const int *idx,
+                                    const prb_mlp_desc *mlp, float *out, float *out_pm, int out_stride_c,
+                                    int out_c_off, void *workspace, size_t workspace_bytes, void *stream);
+PRB_API int prb_fp_interp_mlp_ws(int b, int n, int m, int c_known, int c_skip, const float *known_pm,
+                                 const int *idx, const float *weight, const float *skip,
+                                 const prb_mlp_desc *mlp, float *out, float *out_pm, void *workspace,
+                                 size_t workspace_bytes, void *stream);
+/* plain row MLP: x_rows (rows, c_in) row-major -> out_rows (rows, out_pitch), out_pitch >= round_up(c_last,32);
+ * replaces a pt_utils.SharedMLP applied to (B,C,N,1) tensors (lib/net/rcnn_net.py:58-66 xyz_up_layer / merge_down_layer) */
+PRB_API int prb_mlp_rows(long rows, int c_in, const float *x_rows, const prb_mlp_desc *mlp, float *out_rows,
+                         int out_pitch, void *workspace, size_t workspace_bytes, void *stream);
+
+/* --- uniform-grid neighbour search: same results, bit for bit, as prb_ball_query(_msg2) / prb_three_nn
+ * (first-nsample-in-index-order and lexicographic (d2, idx) rules kept; queries the grid cannot answer
+ * exactly fall back to the exhaustive kernels inside the call).  Used for n >= a few thousand points. */
+PRB_API size_t prb_grid_workspace_bytes(int b, int n_points, int n_queries);
+PRB_API int prb_ball_query_grid(int b, int n, int m, int nr, const float *radius, const int *nsample,
+                                const float *new_xyz, const float *xyz, int *const *idx, void *workspace,
+                                size_t workspace_bytes, void *stream);
+PRB_API int prb_three_nn_grid(int b, int n, int m, const float *unknown, const float *known, float *dist2,
+                              int *idx, float *weight, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------ roipool3d_cuda ------
  * replaces lib/utils/roipool3d/src/roipool3d.cpp:48-79 (forward) -> roipool3d_kernel.cu:209-237.
  * xyz (B,N,3), boxes3d (B,M,7) ALREADY enlarged, pts_feature (B,N,C) -> pooled (B,M,S,3+C),

@@ -277,7 +277,6 @@ __global__ void __launch_bounds__(GR_THREADS) three_nn_grid_kernel(const GridNnP
     if (u >= p.n) return;
     const float *q = p.unknown + ((size_t)scene * p.n + u) * 3;
     const float ux = q[0], uy = q[1], uz = q[2];
-    const float *kn = p.known + (size_t)scene * p.m * 3;
     const float4 *nodes = p.g.nodes + (size_t)scene * p.m;
     const int *heads = p.g.heads + (size_t)scene * p.g.table_size;
     const double ih = p.g.inv_h[scene];

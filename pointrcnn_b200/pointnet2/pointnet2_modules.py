@@ -206,7 +206,7 @@ class _PointnetSAModuleBase(nn.Module):
                 co_arr = (ctypes.c_int * 3)(*(fused.c_out + [0] * (3 - len(fused.c_out))))
                 wsb = lib.prb_sa_workspace_bytes(B, npoint, ns, c_feat, desc.num_layers, co_arr)
                 ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-                with prof.region("sa_mlp"):
+                with prof.region("sa_mlp", "%dx%d [%d]+%s" % (B * npoint, ns, 3 + c_feat, fused.c_out)):
                     C.check(lib.prb_sa_group_mlp_max_ws(B, N, npoint, ns, c_feat, C.ptr(xyz), C.ptr(centres), C.ptr(feats_pm),
                                                         C.ptr(idx), ctypes.byref(desc), C.ptr(out), C.ptr(out_pm), out.size(1), off,
                                                         C.ptr(ws), C.c_size_t(wsb), C.stream()), "sa_group_mlp_max")
@@ -316,7 +316,7 @@ class PointnetFPModule(nn.Module):
         with torch.cuda.device(dev):
             wsb = lib.prb_fp_workspace_bytes(B, n, c_known, c_skip, desc.num_layers, co_arr)
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-            with prof.region("fp_mlp"):
+            with prof.region("fp_mlp", "%d [%d+%d]+%s" % (B * n, c_known, c_skip, c_out)):
                 C.check(lib.prb_fp_interp_mlp_ws(B, n, m, c_known, c_skip, C.ptr(known_pm), C.ptr(idx), C.ptr(weight), C.ptr(skip),
                                                  ctypes.byref(desc), C.ptr(out), C.ptr(out_pm), C.ptr(ws), C.c_size_t(wsb), C.stream()),
                         "fp_interp_mlp")

@@ -7,7 +7,10 @@ import contextlib
 
 import torch
 
+import os
+
 _on = False
+_detail = os.environ.get("PRB_PROF_DETAIL", "0") == "1"
 _events = []
 
 
@@ -23,7 +26,13 @@ def disable():
 
 
 @contextlib.contextmanager
-def region(name):
+def region(name, detail=None):
+    """detail: optional shape string; with PRB_PROF_DETAIL=1 it is appended to the family name"""
+    if _on and detail is not None and _detail:
+        with region("%s %s" % (name, detail)):   # the detailed line nests inside the family line
+            with region(name):
+                yield
+        return
     if not _on:
         yield
         return

@@ -104,6 +104,11 @@ def test_cabi_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "libpointrcnn_b200.so does not export %s" % n
     assert lib.prb_abi_version() == 1
     assert lib.prb_launch_count() == 0
+    # and the other way round: nothing is exported that the header does not declare
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (prb_\w+)", out)))
+    assert exported == names, set(exported) ^ set(names)
 
 
 def test_cabi_bad_arguments_raise_instead_of_exiting():

@@ -209,6 +209,14 @@ def test_sa_module_fused_vs_unfused_vs_oracle(cuda, npoint, radii, nsamples, mlp
     o_xyz, o_out, _ = O.sa_module_msg(xyz, feats, npoint, radii, nsamples, [_folded(m) for m in mod.mlps])
     assert np.array_equal(new_xyz.cpu().numpy(), o_xyz)
     assert np.abs(out.cpu().numpy() - o_out).max() <= 1e-2 * np.abs(o_out).max()
+    # the point-major twin written by the same launch is the exact transpose, and it is dropped once
+    # the channel-major tensor is modified in place
+    twin = out._prb_pm[0]
+    assert torch.equal(twin, out.transpose(1, 2).contiguous())
+    assert pm._point_major(out) is twin
+    out.mul_(2.0)
+    fresh = pm._point_major(out)
+    assert fresh is not twin and torch.equal(fresh, out.transpose(1, 2).contiguous())
 
 
 def test_sa_module_group_all_and_no_bn(cuda):
@@ -258,6 +266,11 @@ def test_fp_module_fused_vs_unfused_vs_oracle(cuda, n, m, c_known, c_skip, mlp):
     assert (out - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
     o = O.fp_module(unknown, known, sf, kf, _folded(mod.mlp))
     assert np.abs(out.cpu().numpy() - o).max() <= 1e-2 * np.abs(o).max()
+    assert torch.equal(out._prb_pm[0], out.transpose(1, 2).contiguous())
+    mod.emit_point_major = False
+    with torch.no_grad():
+        out2 = mod(tu, tk, tsf, tkf)
+    assert not hasattr(out2, "_prb_pm") and torch.equal(out2, out)
 
 
 def test_backbone_fused_vs_unfused(cuda):
