@@ -51,6 +51,11 @@ PRB_API unsigned long long prb_launch_count(void);
  * pointnet2_modules.py:32-35). */
 PRB_API int prb_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx,
                                 float *new_xyz, void *stream);
+/* same, with caller scratch (device, prb_fps_workspace_bytes; 0 = none needed).  With scratch, scenes of
+ * 4097..16384 points run the pruned single-CTA kernel (same indices and temp, bit for bit). */
+PRB_API size_t prb_fps_workspace_bytes(int b, int n);
+PRB_API int prb_furthest_point_sampling_ws(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                   float *new_xyz, void *workspace, size_t workspace_bytes, void *stream);
 
 /* gather_points_wrapper_fast / gather_points_grad_wrapper_fast, sampling.cpp:11-33 */
 PRB_API int prb_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx,

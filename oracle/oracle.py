@@ -67,10 +67,11 @@ def opt_n_threads(n):
 
 
 # ------------------------------------------------------------------ pointnet2 ops
-def fps(xyz, npoint, return_temp=False):
+def fps(xyz, npoint, return_temp=False, temp0=None):
+    """temp0: caller-initialised running minima (the reference's temp tensor is in/out); default 1e10 everywhere"""
     xyz = _f32(xyz)
     B, N, _ = xyz.shape
-    temp = np.full((B, N), 1e10, dtype=np.float32)
+    temp = np.full((B, N), 1e10, dtype=np.float32) if temp0 is None else np.ascontiguousarray(temp0, dtype=np.float32).copy()
     idx = np.zeros((B, npoint), dtype=np.int32)
     lib().orc_fps(B, N, int(npoint), _p(xyz), _p(temp), _p(idx))
     return (idx, temp) if return_temp else idx

@@ -43,6 +43,12 @@ def fps(xyz, npoint, return_temp=False):
     return (idx, temp) if return_temp else idx
 
 
+def fps_raw(xyz, temp, idx):
+    """the reference kernel on caller-owned temp (in/out) and idx"""
+    B, N, _ = xyz.shape
+    lib().ref_fps(B, N, int(idx.shape[1]), _p(xyz), _p(temp), _p(idx), _st())
+
+
 def gather(features, idx):
     B, C, N = features.shape
     M = idx.shape[1]

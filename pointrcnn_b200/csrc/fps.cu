@@ -20,6 +20,7 @@
 // peer's mbarrier (no cluster barrier in the loop).  A CTA mirrors only its OWN points in shared memory (<= 48 KB, so several clusters share an
 // SM); the winner's coordinates travel with the message.  new_xyz is emitted on the fly.
 #include <limits.h>
+#include <math_constants.h>
 
 #include "common.cuh"
 
@@ -307,6 +308,288 @@ static int dispatch_cs(const FpsParams &p, int threads, int ppt, size_t smem, cu
     return -1;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Pruned FPS (n in (2048, 16384]): one CTA per scene, exact.
+//
+// A round only changes temp[k] where |p_k - p_last|^2 < temp[k], i.e. inside the new sample's Voronoi cell (~n/j
+// points in round j).  Points are pre-sorted into spatially compact GROUPS of 32 (k-d ordered cells, counting sort
+// in fps_sort_kernel); every group caches its box and its best (temp, rank).  A group whose box is provably
+// farther from the new sample than its cached maximum cannot change and is skipped, so a round costs one box test
+// per group plus the few groups around the sample -- and the fixed reduction latency -- instead of n updates.
+// Exactness: a skipped update is a no-op of the reference (fminf(d, temp) == temp), the box test is conservative
+// (0.9999 safety factor against fp32 rounding of either side), and the winner is still (max temp, then min rank).
+//
+// Layout: group g = slot * 16 + warp (neighbouring groups go to different warps); lane l of warp w keeps temp and
+// rank of point l of its NS groups in registers (static indexing: the slot loop is unrolled and predicated on the
+// ballot of the box tests, where lane j tests slot j); coordinates live in shared memory as three planes.
+struct FpsSorted {
+    float *sx, *sy, *sz, *st;   // (b, np) sorted coordinates and running min distance (pads: st = -1)
+    int *srank;                 // (b, np) reference rank of the sorted point (pads: 0xffff)
+    int np;                     // padded points per scene = 16 warps x NS slots x 32
+};
+
+constexpr int kSortBits = 13;
+constexpr int kSortBins = 1 << kSortBits;
+
+__global__ void __launch_bounds__(1024, 1) fps_sort_kernel(const FpsParams p, const FpsSorted s) {
+    __shared__ unsigned s_cnt[kSortBins];
+    __shared__ float s_red[6][32];
+    __shared__ unsigned s_scan[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int scene = blockIdx.x, n = p.n, np = s.np;
+    const float *xyz = p.xyz + (size_t)scene * n * 3;
+    const float *temp = p.temp + (size_t)scene * n;
+    float *sx = s.sx + (size_t)scene * np, *sy = s.sy + (size_t)scene * np, *sz = s.sz + (size_t)scene * np;
+    float *st = s.st + (size_t)scene * np;
+    int *srank = s.srank + (size_t)scene * np;
+
+    for (int i = tid; i < kSortBins; i += 1024) s_cnt[i] = 0;
+    // scene box
+    float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    for (int k = tid; k < n; k += 1024) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = xyz[k * 3 + a];
+            lo[a] = fminf(lo[a], v);
+            hi[a] = fmaxf(hi[a], v);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) { s_red[a][warp] = lo[a]; s_red[3 + a][warp] = hi[a]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = s_red[a][0]; hi[a] = s_red[3 + a][0];
+        for (int w = 1; w < 32; ++w) { lo[a] = fminf(lo[a], s_red[a][w]); hi[a] = fmaxf(hi[a], s_red[3 + a][w]); }
+    }
+    // k-d style bit allocation: every split halves the currently longest cell edge
+    float edge[3];
+    int bits[3] = {0, 0, 0};
+    unsigned order = 0;   // 2 bits per split, first split in the low bits
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { edge[a] = hi[a] - lo[a]; if (!(edge[a] > 0.f) || !(edge[a] < CUDART_INF_F)) edge[a] = 0.f; }
+    for (int sidx = 0; sidx < kSortBits; ++sidx) {
+        int a = 0;
+        if (edge[1] > edge[a]) a = 1;
+        if (edge[2] > edge[a]) a = 2;
+        order |= (unsigned)a << (2 * sidx);
+        edge[a] *= 0.5f;
+        bits[a] += 1;
+    }
+    float inv[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float ext = hi[a] - lo[a];
+        inv[a] = (ext > 0.f && ext < CUDART_INF_F) ? (float)(1 << bits[a]) / ext : 0.f;
+    }
+    // bit of the quantised coordinate each split looks at (4 bits per split)
+    unsigned long long shifts = 0;
+    {
+        int rem0 = bits[0], rem1 = bits[1], rem2 = bits[2];
+        for (int sidx = 0; sidx < kSortBits; ++sidx) {
+            const int a = (order >> (2 * sidx)) & 3;
+            int sh;
+            if (a == 0) sh = --rem0; else if (a == 1) sh = --rem1; else sh = --rem2;
+            shifts |= (unsigned long long)sh << (4 * sidx);
+        }
+    }
+    const float lo0 = lo[0], lo1 = lo[1], lo2 = lo[2], inv0 = inv[0], inv1 = inv[1], inv2 = inv[2];
+    const int top0 = (1 << bits[0]) - 1, top1 = (1 << bits[1]) - 1, top2 = (1 << bits[2]) - 1;
+    auto quant = [](float c, float l, float iv, int top) -> int {
+        const float f = (c - l) * iv;
+        const int v = (f > 0.f) ? (int)fminf(f, 65535.f) : 0;   // NaN -> 0
+        return v > top ? top : v;
+    };
+    auto key_of = [&](float x, float y, float z) -> unsigned {
+        const int q0 = quant(x, lo0, inv0, top0), q1 = quant(y, lo1, inv1, top1), q2 = quant(z, lo2, inv2, top2);
+        unsigned key = 0;
+#pragma unroll
+        for (int sidx = 0; sidx < kSortBits; ++sidx) {
+            const int a = (order >> (2 * sidx)) & 3;
+            const int sh = (int)((shifts >> (4 * sidx)) & 15ull);
+            const int q = a == 0 ? q0 : (a == 1 ? q1 : q2);
+            key = (key << 1) | ((unsigned)(q >> sh) & 1u);
+        }
+        return key;
+    };
+    __syncthreads();
+    for (int k = tid; k < n; k += 1024) atomicAdd(&s_cnt[key_of(xyz[k * 3], xyz[k * 3 + 1], xyz[k * 3 + 2])], 1u);
+    __syncthreads();
+    // exclusive scan of the histogram: 8 consecutive bins per thread
+    {
+        constexpr int PER = kSortBins / 1024;
+        unsigned loc[PER], sum = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { loc[i] = s_cnt[tid * PER + i]; sum += loc[i]; }
+        unsigned inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_scan[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned v = s_scan[lane], iv = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned u = __shfl_up_sync(0xffffffffu, iv, o);
+                if (lane >= o) iv += u;
+            }
+            s_scan[lane] = iv - v;
+        }
+        __syncthreads();
+        unsigned run = s_scan[warp] + inc - sum;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { s_cnt[tid * PER + i] = run; run += loc[i]; }
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += 1024) {
+        const float x = xyz[k * 3], y = xyz[k * 3 + 1], z = xyz[k * 3 + 2];
+        const unsigned pos = atomicAdd(&s_cnt[key_of(x, y, z)], 1u);
+        sx[pos] = x; sy[pos] = y; sz[pos] = z;
+        st[pos] = temp[k];
+        srank[pos] = k_to_rank(k, p.S, p.logS, p.Q);
+    }
+    __syncthreads();   // CTA-scope visibility of the scatter above
+    for (int i = n + tid; i < np; i += 1024) {   // pads sit on the last sorted point and can never win
+        sx[i] = sx[n - 1]; sy[i] = sy[n - 1]; sz[i] = sz[n - 1];
+        st[i] = -1.f;
+        srank[i] = 0xffff;
+    }
+}
+
+__device__ __forceinline__ float redux_max_f32(float v) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float redux_min_f32(float v) {
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// one slot of the pruned round: update my point of group (J, warp), refresh the group's cached best.
+// The best is a (value, payload) pair reduced with two CREDUX ops: payload = (0x3fff - rank) << 5 | lane, so the
+// larger payload is the smaller rank and names the lane that holds the point (no vote / ffs / shuffle).
+#define PRB_FPS_SLOT(J)                                                                                      \
+    case J: {                                                                                                \
+        const int P = (((J) * W + warp) << 5) + lane;                                                        \
+        const float v = fminf(dist2_ref(px[P] - cx, py[P] - cy, pz[P] - cz), t[(J) < NS ? (J) : 0]);         \
+        t[(J) < NS ? (J) : 0] = v;                                                                           \
+        const float mx = redux_max_f32(v);                                                                   \
+        const unsigned mp = __reduce_max_sync(0xffffffffu, v == mx ? pay[(J) < NS ? (J) : 0] : 0u);          \
+        if (lane == (J)) { gval = mx; gpay = mp; }                                                           \
+    } break;
+
+template <int NS>
+__global__ void __launch_bounds__(512, 1) fps_pruned_kernel(const FpsParams p, const FpsSorted s) {
+    constexpr int W = 16;
+    constexpr int NP = W * NS * 32;
+    extern __shared__ __align__(16) float s_pl[];       // three planes of NP floats
+    __shared__ uint2 s_w[2][W];                         // per-warp winner {temp bits, (0x3fff - rank) << 14 | position}
+    float *px = s_pl, *py = s_pl + NP, *pz = s_pl + 2 * NP;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int scene = blockIdx.x, n = p.n, m = p.m;
+    const float *xyz = p.xyz + (size_t)scene * n * 3;
+    float *temp = p.temp + (size_t)scene * n;
+    int *idx = p.idx + (size_t)scene * m;
+    float *new_xyz = p.new_xyz ? p.new_xyz + (size_t)scene * m * 3 : nullptr;
+    {
+        const float4 *gx = reinterpret_cast<const float4 *>(s.sx + (size_t)scene * NP);
+        const float4 *gy = reinterpret_cast<const float4 *>(s.sy + (size_t)scene * NP);
+        const float4 *gz = reinterpret_cast<const float4 *>(s.sz + (size_t)scene * NP);
+        for (int i = tid; i < NP / 4; i += 512) {
+            reinterpret_cast<float4 *>(px)[i] = gx[i];
+            reinterpret_cast<float4 *>(py)[i] = gy[i];
+            reinterpret_cast<float4 *>(pz)[i] = gz[i];
+        }
+    }
+    __syncthreads();
+    // registers: running min distance and tie-break payload of my point in each of the warp's NS groups; lane j
+    // also owns the box and the cached best of slot j
+    float t[NS];
+    unsigned pay[NS];
+    float lox = 0.f, loy = 0.f, loz = 0.f, hix = 0.f, hiy = 0.f, hiz = 0.f, gval = -1.f;
+    unsigned gpay = 0u;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        const int P = ((j * W + warp) << 5) + lane;
+        t[j] = s.st[(size_t)scene * NP + P];
+        pay[j] = ((0x3fffu - ((unsigned)s.srank[(size_t)scene * NP + P] & 0x3fffu)) << 5) | (unsigned)lane;
+        const float x = px[P], y = py[P], z = pz[P];
+        const float ax = redux_min_f32(x), ay = redux_min_f32(y), az = redux_min_f32(z);
+        const float bx = redux_max_f32(x), by = redux_max_f32(y), bz = redux_max_f32(z);
+        const float mx = redux_max_f32(t[j]);
+        const unsigned mp = __reduce_max_sync(0xffffffffu, t[j] == mx ? pay[j] : 0u);
+        if (lane == j) { lox = ax; loy = ay; loz = az; hix = bx; hiy = by; hiz = bz; gval = mx; gpay = mp; }
+    }
+
+    float cx = xyz[0], cy = xyz[1], cz = xyz[2];
+    if (tid == 0) {
+        idx[0] = 0;   // ranks until the fix-up pass below (rank 0 == point 0)
+        if (new_xyz) { new_xyz[0] = cx; new_xyz[1] = cy; new_xyz[2] = cz; }
+    }
+    const unsigned my_group_base = (unsigned)((lane * W + warp) << 5);
+    for (int round = 1; round < m; ++round) {
+        const int par = round & 1;
+        // box test of my slot
+        const float ex = fmaxf(fmaxf(lox - cx, cx - hix), 0.f);
+        const float ey = fmaxf(fmaxf(loy - cy, cy - hiy), 0.f);
+        const float ez = fmaxf(fmaxf(loz - cz, cz - hiz), 0.f);
+        const float lb = ex * ex + ey * ey + ez * ez;
+        const bool untouched = (lb * 0.9999f >= gval) && (lb > 1e-30f);
+        unsigned mask = __ballot_sync(0xffffffffu, lane < NS && !untouched);
+        while (mask) {                       // warp-uniform walk over the touched slots, highest first
+            const int j = 31 - __clz(mask);
+            mask &= ~(1u << j);
+            switch (j) {
+                PRB_FPS_SLOT(0) PRB_FPS_SLOT(1) PRB_FPS_SLOT(2) PRB_FPS_SLOT(3) PRB_FPS_SLOT(4) PRB_FPS_SLOT(5) PRB_FPS_SLOT(6)
+                PRB_FPS_SLOT(7) PRB_FPS_SLOT(8) PRB_FPS_SLOT(9) PRB_FPS_SLOT(10) PRB_FPS_SLOT(11) PRB_FPS_SLOT(12)
+                PRB_FPS_SLOT(13) PRB_FPS_SLOT(14) PRB_FPS_SLOT(15) PRB_FPS_SLOT(16) PRB_FPS_SLOT(17) PRB_FPS_SLOT(18)
+                PRB_FPS_SLOT(19) PRB_FPS_SLOT(20) PRB_FPS_SLOT(21) PRB_FPS_SLOT(22) PRB_FPS_SLOT(23) PRB_FPS_SLOT(24)
+                PRB_FPS_SLOT(25) PRB_FPS_SLOT(26) PRB_FPS_SLOT(27) PRB_FPS_SLOT(28) PRB_FPS_SLOT(29) PRB_FPS_SLOT(30)
+                PRB_FPS_SLOT(31)
+            }
+        }
+        // warp winner over its slots, then CTA winner: (max temp, then min rank) as (value, payload) maxima
+        const float wm = redux_max_f32(gval);
+        const unsigned cand = ((gpay >> 5) << 14) | (my_group_base + (gpay & 31u));
+        const unsigned wp = __reduce_max_sync(0xffffffffu, gval == wm ? cand : 0u);
+        if (lane == 0) s_w[par][warp] = make_uint2(__float_as_uint(wm), wp);
+        __syncthreads();
+        const uint2 kv = lane < W ? s_w[par][lane] : make_uint2(__float_as_uint(-1.f), 0u);
+        const float cm = redux_max_f32(__uint_as_float(kv.x));
+        const unsigned cp = __reduce_max_sync(0xffffffffu, __uint_as_float(kv.x) == cm ? kv.y : 0u);
+        const unsigned pos = cp & 0x3fffu;
+        cx = px[pos]; cy = py[pos]; cz = pz[pos];
+        if (tid == 0) {
+            idx[round] = (int)(0x3fffu - (cp >> 14));
+            if (new_xyz) { new_xyz[round * 3 + 0] = cx; new_xyz[round * 3 + 1] = cy; new_xyz[round * 3 + 2] = cz; }
+        }
+    }
+    // running minimum distances back to the reference's temp (pads sit past n in the sorted order), ranks -> indices
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        const int P = ((j * W + warp) << 5) + lane;
+        if (P < n) {
+            const int k = rank_to_k((int)(0x3fffu - (pay[j] >> 5)), p.S, p.logS, p.Q);
+            if (k < n) temp[k] = t[j];
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < m; j += 512) idx[j] = rank_to_k(idx[j], p.S, p.logS, p.Q);
+}
+#undef PRB_FPS_SLOT
+
 static int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v ? atoi(v) : dflt;
@@ -316,8 +599,39 @@ static int env_int(const char *name, int dflt) {
 
 using namespace prb;
 
+// pruned path: slots per lane for n points (0 = not applicable)
+static int pruned_slots(int n) {
+    const int mode = env_int("PRB_FPS_PRUNE", 1);   // 0 off, 1 n > 4096, 2 n > 2048
+    if (mode == 0 || n > 16384) return 0;
+    if (n > 8192) return 32;
+    if (n > 4096) return 16;
+    if (n > 2048 && mode >= 2) return 8;
+    return 0;
+}
+
+template <int NS>
+static int launch_pruned(const FpsParams &p, const FpsSorted &s, cudaStream_t st) {
+    const size_t smem = (size_t)3 * 16 * NS * 32 * sizeof(float);
+    if (smem + 1024 > 48 * 1024)
+        PRB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fps_sort_kernel<<<p.b, 1024, 0, st>>>(p, s);
+    if (check_launch("fps_sort_kernel")) return -1;
+    fps_pruned_kernel<NS><<<p.b, 512, smem, st>>>(p, s);
+    return check_launch("fps_pruned_kernel");
+}
+
+extern "C" size_t prb_fps_workspace_bytes(int b, int n) {
+    const int ns = pruned_slots(n);
+    return ns ? (size_t)b * 16 * ns * 32 * 5 * sizeof(float) + 256 : 0;
+}
+
 extern "C" int prb_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx,
                                            float *new_xyz, void *stream) {
+    return prb_furthest_point_sampling_ws(b, n, m, xyz, temp, idx, new_xyz, nullptr, 0, stream);
+}
+
+extern "C" int prb_furthest_point_sampling_ws(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                              float *new_xyz, void *workspace, size_t workspace_bytes, void *stream) {
     PRB_REQUIRE(b >= 0 && n > 0 && xyz && temp && idx, "fps: bad arguments (b=%d n=%d)", b, n);
     if (m <= 0 || b == 0) return 0;  // reference kernel returns immediately for m <= 0
     cudaStream_t st = (cudaStream_t)stream;
@@ -328,6 +642,22 @@ extern "C" int prb_furthest_point_sampling(int b, int n, int m, const float *xyz
     p.S = 1 << logS; p.logS = logS; p.Q = ceil_div(n, p.S);
     p.xyz = xyz; p.temp = temp; p.idx = idx; p.new_xyz = new_xyz;
     const int n_pad = p.S * p.Q;
+
+    // exact pruned kernel (one CTA per scene) when the caller lent scratch memory
+    if (const int ns = pruned_slots(n); ns && workspace && m > 1) {
+        const size_t np = (size_t)16 * ns * 32;
+        PRB_REQUIRE(workspace_bytes >= (size_t)b * np * 5 * sizeof(float) + 256, "fps: workspace of %zu bytes is too small", workspace_bytes);
+        FpsSorted s;
+        float *w = reinterpret_cast<float *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+        s.sx = w; s.sy = w + b * np; s.sz = w + 2 * b * np; s.st = w + 3 * b * np;
+        s.srank = reinterpret_cast<int *>(w + 4 * b * np);
+        s.np = (int)np;
+        switch (ns) {
+            case 8: return launch_pruned<8>(p, s, st);
+            case 16: return launch_pruned<16>(p, s, st);
+            default: return launch_pruned<32>(p, s, st);
+        }
+    }
 
     // configuration: cluster size, threads per CTA, points per thread
     // A cluster of CS CTAs per scene cuts the per-round compute CS-fold; each CTA mirrors only its own slice of the

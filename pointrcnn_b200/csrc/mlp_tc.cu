@@ -872,7 +872,12 @@ static int launch_chain(ChainParams &p, cudaStream_t st) {
         if (depth >= 2 || occ == 1) break;
     }
     PRB_REQUIRE(smem <= (size_t)max_optin, "mlp: %zu bytes of shared memory needed, %d available", smem, max_optin);
-    int grid = num_sms() * occ;
+    // Tiles are dealt statically (tile += gridDim.x), so a CTA that cannot start with the first wave doubles the
+    // kernel's duration.  When other streams hold SMs (BatchPipeline: the single-CTA-per-scene FPS of the next
+    // batches), PRB_MLP_SMS sizes the grid for the SMs that are actually free.
+    int sms = num_sms();
+    if (const char *e = getenv("PRB_MLP_SMS")) { int v = atoi(e); if (v >= 1 && v < sms) sms = v; }
+    int grid = sms * occ;
     if (grid > p.num_tiles) grid = p.num_tiles;
 #define PRB_LAUNCH_CHAIN(NGV, MB)                                                                                              \
     do {                                                                                                                       \

@@ -57,8 +57,11 @@ def gather_points_grad_wrapper(b, c, n, npoints, grad_out, idx, grad_points):
 def furthest_point_sampling_wrapper(b, n, m, points, temp, idx):
     C.require_cuda(points, temp, idx); C.require_contig(points, temp, idx)
     with _guard(points):
-        C.check(C.lib().prb_furthest_point_sampling(int(b), int(n), int(m), C.ptr(points), C.ptr(temp), C.ptr(idx), None,
-                                                    C.stream()), "furthest_point_sampling")
+        lib = C.lib()
+        wsb = lib.prb_fps_workspace_bytes(int(b), int(n))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=points.device) if wsb else None
+        C.check(lib.prb_furthest_point_sampling_ws(int(b), int(n), int(m), C.ptr(points), C.ptr(temp), C.ptr(idx), None,
+                                                   C.ptr(ws), C.c_size_t(wsb), C.stream()), "furthest_point_sampling")
     return 1
 
 

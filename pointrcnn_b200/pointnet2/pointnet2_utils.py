@@ -63,6 +63,15 @@ def _three_nn_native(B, N, m, unknown, known, dist2, idx, weight):
         C.check(lib.prb_three_nn(B, N, m, C.ptr(unknown), C.ptr(known), C.ptr(dist2), C.ptr(idx), C.ptr(weight), C.stream()), "three_nn")
 
 
+def _fps_native(B, N, npoint, xyz, temp, idx, new_xyz):
+    """FPS through the C ABI, lending the library scratch memory (pruned kernel for big scenes)"""
+    lib = C.lib()
+    wsb = lib.prb_fps_workspace_bytes(B, N)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=xyz.device) if wsb else None
+    C.check(lib.prb_furthest_point_sampling_ws(B, N, int(npoint), C.ptr(xyz), C.ptr(temp), C.ptr(idx), C.ptr(new_xyz),
+                                               C.ptr(ws), C.c_size_t(wsb), C.stream()), "furthest_point_sampling")
+
+
 class FurthestPointSampling(Function):
     @staticmethod
     def forward(ctx, xyz: torch.Tensor, npoint: int) -> torch.Tensor:
@@ -91,8 +100,7 @@ def furthest_point_sample_xyz(xyz: torch.Tensor, npoint: int):
     new_xyz = _cuda_empty((B, npoint, 3), torch.float32, xyz)
     temp = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device)
     with torch.cuda.device(xyz.device), prof.region("fps"):
-        C.check(C.lib().prb_furthest_point_sampling(B, N, int(npoint), C.ptr(xyz), C.ptr(temp), C.ptr(idx), C.ptr(new_xyz),
-                                                    C.stream()), "furthest_point_sampling")
+        _fps_native(B, N, npoint, xyz, temp, idx, new_xyz)
     return idx, new_xyz
 
 

@@ -30,7 +30,11 @@ def T(a, dev):
 # ------------------------------------------------------------------------------------------------ FPS
 FPS_CASES = [
     # (B, N, M, cloud)            what it exercises
-    (2, 16384, 4096, "kitti"),    # cluster of 8 CTAs, 4095 rounds (RPN SA1 shape)
+    (2, 16384, 4096, "kitti"),    # pruned single-CTA kernel, 4095 rounds (RPN SA1 shape)
+    (2, 16384, 2048, "cube"),     # pruned, uniform cloud
+    (3, 10000, 700, "kitti"),     # pruned with 6384 pad points
+    (2, 5000, 5000, "kitti"),     # pruned, 16 slots, m == n
+    (2, 8192, 600, "dup"),        # pruned + ties
     (3, 4096, 1024, "kitti"),     # single CTA 512x8
     (3, 1024, 256, "cube"),
     (5, 256, 64, "kitti"),
@@ -67,10 +71,11 @@ def test_fps_index_exact(cuda, B, N, M, kind):
 
 
 @pytest.mark.parametrize("env", [{"PRB_FPS_CS": "1"}, {"PRB_FPS_CS": "2"}, {"PRB_FPS_CS": "4"}, {"PRB_FPS_CS": "8"},
-                                 {"PRB_FPS_GENERIC": "1"}, {"PRB_FPS_CS": "1", "PRB_FPS_THREADS": "1024"}])
+                                 {"PRB_FPS_GENERIC": "1"}, {"PRB_FPS_CS": "1", "PRB_FPS_THREADS": "1024"}, {"PRB_FPS_PRUNE": "1"}])
 def test_fps_all_kernel_variants_agree(cuda, env):
     xyz = synth.dup_cloud(2, 8192, 5, unique=3000)
     want = O.fps(xyz, 512)
+    env = dict({"PRB_FPS_PRUNE": "0"}, **env)     # the cluster / generic kernels unless the case asks for pruning
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
     try:
@@ -92,6 +97,33 @@ def test_fps_temp_writeback_and_m_edge(cuda):
     assert np.array_equal(temp.cpu().numpy(), want_temp)
     one = pu.furthest_point_sample(x, 1)
     assert torch.count_nonzero(one) == 0
+
+
+@pytest.mark.parametrize("N,M,prune", [(6000, 300, "1"), (16384, 1000, "1"), (3000, 200, "2")])
+def test_fps_pruned_kernel_resumes_from_caller_temp(cuda, N, M, prune):
+    """temp is in/out (sampling_gpu.cu:105-111): a caller-initialised temp steers the sampling and gets the final minima"""
+    from pointrcnn_b200.ext import pointnet2_cuda
+    xyz = synth.u_kitti(2, N, 17)
+    rng = np.random.default_rng(5)
+    t0 = (rng.random((2, N)) * 30.0).astype(np.float32)
+    t0[:, ::7] = 1e10
+    want, want_temp = O.fps(xyz, M, return_temp=True, temp0=t0)
+    x = T(xyz, cuda)
+    temp = T(t0.copy(), cuda)
+    idx = torch.empty((2, M), dtype=torch.int32, device=cuda)
+    old = os.environ.get("PRB_FPS_PRUNE")
+    os.environ["PRB_FPS_PRUNE"] = prune
+    try:
+        pointnet2_cuda.furthest_point_sampling_wrapper(2, N, M, x, temp, idx)
+    finally:
+        os.environ.pop("PRB_FPS_PRUNE", None) if old is None else os.environ.__setitem__("PRB_FPS_PRUNE", old)
+    assert np.array_equal(idx.cpu().numpy(), want)
+    assert np.array_equal(temp.cpu().numpy(), want_temp)
+    if HAVE_REF:
+        rt = T(t0.copy(), cuda)
+        ridx = torch.empty((2, M), dtype=torch.int32, device=cuda)
+        R.fps_raw(x, rt, ridx)
+        assert torch.equal(ridx, idx) and torch.equal(rt, temp)
 
 
 # ------------------------------------------------------------------------------------------------ ball query / grouping
