@@ -11,7 +11,7 @@ import torch
 
 
 class BatchPipeline:
-    def __init__(self, fn, inflight=4, device=None, fps_cluster=2):
+    def __init__(self, fn, inflight=6, device=None, fps_cluster=2):
         """fn: callable(batch_on_device) -> tensor or tuple of tensors; inflight: batches in flight (streams);
         fps_cluster: CTAs per scene for the big FPS levels while the pipeline runs (0 = single-batch heuristic).
         With several batches in flight SM-time matters more than latency: 2 CTAs per scene take 3.35 ms on 32 SMs,
@@ -23,22 +23,24 @@ class BatchPipeline:
         self.streams = [torch.cuda.Stream(self.device) for _ in range(max(1, inflight))]
         self._host = {}   # (slot, output index, shape, dtype) -> reusable pinned result buffer (cudaHostAlloc is slow)
 
-    def run(self, batches, to_host=False):
+    def run(self, batches, to_host=False, keep=True):
         """batches: iterable of tensors (device, or pinned host -> copied inside the pipeline).
-        Returns the list of results; with to_host=True results are pinned host tensors (valid after return)."""
+        Returns the list of results; with to_host=True results are pinned host tensors (valid after return).
+        keep=False drops every result as soon as its work is queued (a consumer inside fn has used it): the
+        caching allocator then recycles the output blocks instead of growing by one cudaMalloc per batch."""
         import os
         old_cs = os.environ.get("PRB_FPS_CS")
         if self.fps_cluster > 0 and len(self.streams) > 1:
             os.environ["PRB_FPS_CS"] = str(self.fps_cluster)
         try:
-            return self._run(batches, to_host)
+            return self._run(batches, to_host, keep)
         finally:
             if old_cs is None:
                 os.environ.pop("PRB_FPS_CS", None)
             else:
                 os.environ["PRB_FPS_CS"] = old_cs
 
-    def _run(self, batches, to_host):
+    def _run(self, batches, to_host, keep):
         caller = torch.cuda.current_stream(self.device)
         ready = torch.cuda.Event()
         ready.record(caller)
@@ -61,7 +63,8 @@ class BatchPipeline:
                         h.copy_(o, non_blocking=True)
                         host.append(h)
                     out = host[0] if len(host) == 1 else tuple(host)
-                results.append(out)
+                results.append(out if keep else None)
+                del out
         for s in self.streams:
             caller.wait_stream(s)
         if to_host:
