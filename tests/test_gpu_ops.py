@@ -367,20 +367,24 @@ def test_ball_query_grid_path_exact(cuda, kind, N, M, radii, nss):
         assert np.array_equal(g.cpu().numpy(), O.ball_query(r, ns, xyz, new_xyz)), "grid ball query differs (r=%g)" % r
 
 
+@pytest.mark.parametrize("cell", [None, "0.5", "4.0"])     # default edge; tiny cells (most queries go to the exhaustive scan); big cells
 @pytest.mark.parametrize("kind,n,m", [("kitti", 8192, 2048), ("cube", 2000, 500), ("dup", 1024, 256), ("cube", 100, 5),
                                       ("kitti", 300, 3), ("dup", 4096, 64)])
-def test_three_nn_grid_path_exact(cuda, kind, n, m):
+def test_three_nn_grid_path_exact(cuda, kind, n, m, cell):
     unknown = _cloud(kind, 2, n, 61 + n)
     known = np.ascontiguousarray(unknown[:, ::max(1, n // m)][:, :m])
     if kind == "kitti":
         unknown[0, :10] += 300.0         # far-away queries: third neighbour beyond one cell -> brute-force list
     d2, idx = O.three_nn(unknown, known)
-    old = pu.GRID_MIN_POINTS_NN
+    old, old_cell = pu.GRID_MIN_POINTS_NN, os.environ.get("PRB_NN_CELL")
     pu.GRID_MIN_POINTS_NN = 1
+    if cell is not None:
+        os.environ["PRB_NN_CELL"] = cell
     try:
         got_d2, got_idx, w = pu.three_nn_weights(T(unknown, cuda), T(known, cuda))
     finally:
         pu.GRID_MIN_POINTS_NN = old
+        os.environ.pop("PRB_NN_CELL", None) if old_cell is None else os.environ.__setitem__("PRB_NN_CELL", old_cell)
     assert np.array_equal(got_idx.cpu().numpy(), idx)
     assert np.array_equal(got_d2.cpu().numpy(), d2)
     np.testing.assert_allclose(w.cpu().numpy(), O.interp_weights(d2), rtol=2e-6, atol=1e-7)
