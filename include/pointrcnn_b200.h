@@ -106,7 +106,9 @@ typedef struct prb_mlp_desc {
     int c_in;                /* input channels of layer 0 (incl. the 3 xyz channels for SA) */
     int c_out[3];            /* output channels per layer */
     const float *packed_w;   /* device, from prb_mlp_pack_weights */
-    const float *scale;      /* device; layer after layer, each layer zero-padded to round_up(c_out,32) floats */
+    const float *scale;      /* device; layer after layer, each layer zero-padded to round_up(c_out,32) floats;
+                              * NULL = the scale is already folded into the packed weights (y = relu(W'x + shift)),
+                              * which lets the SA kernel pool raw accumulators and apply shift/ReLU once per centre */
     const float *shift;      /* device; same layout */
 } prb_mlp_desc;
 

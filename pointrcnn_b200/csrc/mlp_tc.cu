@@ -47,7 +47,8 @@ struct ChainParams {
     int np[MAX_LAYERS];        // padded N (multiple of 32)
     int dcol[MAX_LAYERS];      // TMEM column of the accumulator
     const float *w[MAX_LAYERS];      // packed weight images
-    const float *scale[MAX_LAYERS];  // np floats (zero padded)
+    const float *scale[MAX_LAYERS];  // np floats (zero padded); unused when unit_scale
+    int unit_scale;                  // 1: the per-channel scale is folded into the packed weights, epilogues only add shift
     const float *shift[MAX_LAYERS];
     // resources (sized per launch so that small layers run several CTAs per SM)
     int na, nb;                // ring depths
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
     }
     if (warp == 4 * NG + 1) tmem_alloc(s2u(&S.tmem_base), (uint32_t)p.tmem_cols);
     for (int l = 0; l < L; ++l)
-        for (int i = tid; i < p.np[l]; i += NTHREADS) { s_scale[sc_off[l] + i] = p.scale[l][i]; s_shift[sc_off[l] + i] = p.shift[l][i]; }
+        for (int i = tid; i < p.np[l]; i += NTHREADS) { s_scale[sc_off[l] + i] = p.unit_scale ? 1.f : p.scale[l][i]; s_shift[sc_off[l] + i] = p.shift[l][i]; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -572,15 +573,28 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                         tmem_ld16(tmem + lane_base + (uint32_t)(p.dcol[l - 1] + kc * KC + hh * 16), acc);
                         const float4 *sc4 = reinterpret_cast<const float4 *>(s_scale + sc_off[l - 1] + kc * KC + hh * 16);
                         const float4 *sh4 = reinterpret_cast<const float4 *>(s_shift + sc_off[l - 1] + kc * KC + hh * 16);
+                        if (p.unit_scale) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 a = sc4[j], b = sh4[j];     // broadcast LDS.128
-                            float4 o;
-                            o.x = relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 0]), a.x, b.x));
-                            o.y = relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 1]), a.y, b.y));
-                            o.z = relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 2]), a.z, b.z));
-                            o.w = relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 3]), a.w, b.w));
-                            *reinterpret_cast<float4 *>(A + swz(r, hh * 4 + j)) = o;
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 b = sh4[j];                 // broadcast LDS.128
+                                float4 o;
+                                o.x = relu_to_tf32(__uint_as_float(acc[4 * j + 0]) + b.x);
+                                o.y = relu_to_tf32(__uint_as_float(acc[4 * j + 1]) + b.y);
+                                o.z = relu_to_tf32(__uint_as_float(acc[4 * j + 2]) + b.z);
+                                o.w = relu_to_tf32(__uint_as_float(acc[4 * j + 3]) + b.w);
+                                *reinterpret_cast<float4 *>(A + swz(r, hh * 4 + j)) = o;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 a = sc4[j], b = sh4[j];     // broadcast LDS.128
+                                float4 o;
+                                o.x = relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 0]), a.x, b.x));
+                                o.y = relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 1]), a.y, b.y));
+                                o.z = relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 2]), a.z, b.z));
+                                o.w = relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 3]), a.w, b.w));
+                                *reinterpret_cast<float4 *>(A + swz(r, hh * 4 + j)) = o;
+                            }
                         }
                     }
                     tc_fence_before();
@@ -608,7 +622,23 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                 uint32_t acc[16];
                 tmem_ld16(tmem + lane_base + (uint32_t)(p.dcol[L - 1] + c0), acc);
                 float v[16];
-                {
+                // folded scale + max-pool: max_s relu(x_s + t) == relu(max_s x_s + t), so the raw accumulators are
+                // pooled and shift / ReLU are applied once per (centre, channel) after the reduction
+                const bool pool_raw = p.unit_scale && p.mode_out == OUT_SA_MAX;
+                if (pool_raw) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(acc[q]);
+                } else if (p.unit_scale) {
+                    const float4 *sh4 = reinterpret_cast<const float4 *>(sh + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 b = sh4[j];
+                        v[4 * j + 0] = fmaxf(__uint_as_float(acc[4 * j + 0]) + b.x, 0.f);
+                        v[4 * j + 1] = fmaxf(__uint_as_float(acc[4 * j + 1]) + b.y, 0.f);
+                        v[4 * j + 2] = fmaxf(__uint_as_float(acc[4 * j + 2]) + b.z, 0.f);
+                        v[4 * j + 3] = fmaxf(__uint_as_float(acc[4 * j + 3]) + b.w, 0.f);
+                    }
+                } else {
                     const float4 *sc4 = reinterpret_cast<const float4 *>(sc + c0), *sh4 = reinterpret_cast<const float4 *>(sh + c0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -673,6 +703,7 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                                 for (int s = 1; s < per; ++s) x = fmaxf(x, pool2[(g16 + s) * 16 + q]);
                             }
                         }
+                        if (pool_raw) x = fmaxf(x + sh[c0 + q], 0.f);
                         if (e_ok && c0 + q < Cl) {
                             p.out[e_off + (size_t)c0 * p.npoint] = x;
                             if (p.out_pm) p.out_pm[e_pm + c0] = x;
@@ -684,6 +715,7 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                             const int row0 = g16 * 16 + t * ns;
                             float x = pool[row0 * POOL_STRIDE + q];
                             for (int s = 1; s < ns; ++s) x = fmaxf(x, pool[(row0 + s) * POOL_STRIDE + q]);
+                            if (pool_raw) x = fmaxf(x + sh[c0 + q], 0.f);
                             const unsigned Rg = (unsigned)tile * TM + (unsigned)row0;
                             if ((long)Rg < p.total_rows && c0 + q < Cl) {
                                 const unsigned pr = Rg >> p.log_ns, scene = pr / (unsigned)p.npoint, pp = pr - scene * (unsigned)p.npoint;
@@ -858,9 +890,14 @@ static int launch_chain(ChainParams &p, cudaStream_t st) {
     const int sm_smem = 227 * 1024;
     int ng = 0;
     if (const char *e = getenv("PRB_MLP_NG")) ng = atoi(e);
+    const bool ng_forced = ng != 0;
     int occ = 1;
     if (ng == 0) ng = (cols <= 256) ? 1 : 2;
     if (ng == 1) occ = 512 / cols > 3 ? 3 : 512 / cols;
+    // 129..256 TMEM columns: two CTAs fit either way, and two CTAs of 8 row warps beat two of 4 (measured per level,
+    // profiles/r1_notes.md: FP0 0.201 -> 0.165 ms, SA2 0.311 -> 0.295); the 3-CTA build stays best below 128 columns
+    if (!ng_forced && ng == 1 && occ == 2) ng = 2;
+    if (ng == 2) occ = 512 / cols >= 2 ? 2 : 1;
     if (const char *e = getenv("PRB_MLP_OCC")) { int o = atoi(e); if (o >= 1 && o < occ) occ = o; }
     size_t smem = 0;
     for (;; --occ) {
@@ -886,6 +923,7 @@ static int launch_chain(ChainParams &p, cudaStream_t st) {
     } while (0)
     if (ng == 1 && occ >= 3) PRB_LAUNCH_CHAIN(1, 3);
     else if (ng == 1) PRB_LAUNCH_CHAIN(1, 2);
+    else if (ng == 2 && occ >= 2) PRB_LAUNCH_CHAIN(2, 2);
     else if (ng == 2) PRB_LAUNCH_CHAIN(2, 1);
     else PRB_LAUNCH_CHAIN(3, 1);
 #undef PRB_LAUNCH_CHAIN
@@ -942,6 +980,7 @@ static int run_chain(const ChainIO &io, const prb_mlp_desc *mlp, void *workspace
         int l1 = L;
         while (l1 > l0 + 1 && !fits(g, l0, l1)) --l1;
         ChainParams p = io.base;
+        p.unit_scale = mlp->scale ? 0 : 1;
         p.total_rows = io.rows;
         p.num_layers = l1 - l0;
         for (int l = l0; l < l1; ++l) {
@@ -949,7 +988,7 @@ static int run_chain(const ChainIO &io, const prb_mlp_desc *mlp, void *workspace
             p.nchunks[i] = g[l].k_chunks;
             p.np[i] = g[l].np;
             p.w[i] = mlp->packed_w + g[l].w_off;
-            p.scale[i] = mlp->scale + soff[l];
+            p.scale[i] = mlp->scale ? mlp->scale + soff[l] : nullptr;
             p.shift[i] = mlp->shift + soff[l];
         }
         if (l0 > 0) {  // continue from materialised rows

@@ -66,7 +66,7 @@ class _FusedMLP:
             if hasattr(layer, "bn"):
                 bn = layer.bn.bn
                 tensors += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
-        key = (kind, split, str(device)) + tuple((id(t), t._version) if t is not None else None for t in tensors)
+        key = (kind, split, str(device), _fold_scale()) + tuple((id(t), t._version) if t is not None else None for t in tensors)
         if key == self.key:
             return self.desc
         L = len(layers)
@@ -88,6 +88,8 @@ class _FusedMLP:
                     inv = torch.ones(co)
                     sh = conv.bias.detach().float().cpu() if conv.bias is not None else torch.zeros(co)
                 pad = _round_up(co, 32) - co
+                if _fold_scale():
+                    W = (W * inv[:, None]).contiguous()     # BN scale folded into the weights before TF32 rounding
                 ws.append(W)
                 scales.append(F.pad(inv, (0, pad)))
                 shifts.append(F.pad(sh, (0, pad)))
@@ -104,7 +106,7 @@ class _FusedMLP:
         desc.num_layers, desc.c_in = L, c_in
         for i in range(3):
             desc.c_out[i] = c_out[i] if i < L else 0
-        desc.packed_w, desc.scale, desc.shift = packed.data_ptr(), scale.data_ptr(), shift.data_ptr()
+        desc.packed_w, desc.scale, desc.shift = packed.data_ptr(), (None if _fold_scale() else scale.data_ptr()), shift.data_ptr()
         self.key, self.desc, self.tensors, self.c_out = key, desc, (packed, scale, shift), c_out
         return desc
 
@@ -121,6 +123,11 @@ def _point_major(t):
     if twin is not None and twin[1] == t._version and twin[0].shape == (t.size(0), t.size(2), t.size(1)) and twin[0].device == t.device:
         return twin[0]
     return pointnet2_utils.transpose_bcn_to_bnc(t.contiguous())
+
+
+def _fold_scale():
+    """PRB_MLP_FOLD=0 keeps the BN scale as a separate epilogue multiply (y = relu(s * (W x) + t))"""
+    return os.environ.get("PRB_MLP_FOLD", "1") != "0"
 
 
 def _fused_enabled():

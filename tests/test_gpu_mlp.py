@@ -74,7 +74,13 @@ def _rand_layers(rng, dims):
     return layers
 
 
-def _desc(layers, kind, split, dev):
+def _fold(layers):
+    """BN scale folded into the weights: (W, s, t) -> (s * W, 1, t), the form the modules hand to the kernel"""
+    return [((W * sc[:, None]).astype(np.float32), np.ones_like(sc), sh) for W, sc, sh in layers]
+
+
+def _desc(layers, kind, split, dev, folded=False):
+    """folded: `layers` come from _fold(); the descriptor then carries scale = NULL"""
     L = len(layers)
     c_in = layers[0][0].shape[1]
     c_out = [l[0].shape[0] for l in layers]
@@ -93,7 +99,7 @@ def _desc(layers, kind, split, dev):
     d.num_layers, d.c_in = L, c_in
     for i in range(3):
         d.c_out[i] = c_out[i] if i < L else 0
-    d.packed_w, d.scale, d.shift = keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr()
+    d.packed_w, d.scale, d.shift = keep[0].data_ptr(), (None if folded else keep[1].data_ptr()), keep[2].data_ptr()
     return d, keep, co
 
 
@@ -110,12 +116,15 @@ ROW_CASES = [
 ]
 
 
+@pytest.mark.parametrize("folded", [False, True])
 @pytest.mark.parametrize("rows,dims", ROW_CASES)
-def test_mlp_rows_tcgen05(cuda, rows, dims):
+def test_mlp_rows_tcgen05(cuda, rows, dims, folded):
     rng = np.random.default_rng(rows + len(dims))
     layers = _rand_layers(rng, dims)
+    if folded:
+        layers = _fold(layers)
     x = rng.standard_normal((rows, dims[0])).astype(np.float32)
-    d, keep, co = _desc(layers, 2, 0, cuda)
+    d, keep, co = _desc(layers, 2, 0, cuda, folded)
     lib = C.lib()
     np_last = (dims[-1] + 31) // 32 * 32
     out = torch.full((rows, np_last), float("nan"), device=cuda)
@@ -217,6 +226,37 @@ def test_sa_module_fused_vs_unfused_vs_oracle(cuda, npoint, radii, nsamples, mlp
     out.mul_(2.0)
     fresh = pm._point_major(out)
     assert fresh is not twin and torch.equal(fresh, out.transpose(1, 2).contiguous())
+
+
+@pytest.mark.parametrize("ns", [8, 16, 32, 64])
+def test_sa_module_scale_fold_modes_agree(cuda, ns):
+    """PRB_MLP_FOLD=1 (default: BN scale inside the weights, raw accumulators pooled, shift/ReLU after the max) against
+    PRB_MLP_FOLD=0 (scale as an epilogue multiply); negative BN scales included -- max_s relu(x_s + t) = relu(max_s x_s + t)"""
+    import os
+    torch.manual_seed(7)
+    mod = pm.PointnetSAModuleMSG(npoint=200, radii=[0.25], nsamples=[ns], mlps=[[24, 64, 48, 96]], bn=True).to(cuda).eval()
+    _randomise_bn(mod, 11)
+    with torch.no_grad():
+        for m in mod.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.data[::3] *= -1.0
+    x = torch.from_numpy(synth.u_cube(2, 3000, 77)).to(cuda)
+    f = torch.randn(2, 24, 3000, device=cuda)
+    outs = {}
+    old = os.environ.get("PRB_MLP_FOLD")
+    try:
+        for mode in ("0", "1"):
+            os.environ["PRB_MLP_FOLD"] = mode
+            with torch.no_grad():
+                outs[mode] = mod(x, f)[1]
+    finally:
+        os.environ.pop("PRB_MLP_FOLD", None) if old is None else os.environ.__setitem__("PRB_MLP_FOLD", old)
+    with torch.no_grad():
+        ref = _unfused(lambda: mod(x, f))[1]
+    scale = ref.abs().max().item()
+    for mode in ("0", "1"):
+        assert (outs[mode] - ref).abs().max().item() <= 1e-2 * scale, "fold mode %s differs from the fp32 op-by-op path" % mode
+    assert (outs["0"] - outs["1"]).abs().max().item() <= 1e-2 * scale
 
 
 def test_sa_module_group_all_and_no_bn(cuda):
