@@ -159,6 +159,9 @@ PRB_API int prb_fp_interp_mlp_ws(int b, int n, int m, int c_known, int c_skip, c
 PRB_API int prb_mlp_rows(long rows, int c_in, const float *x_rows, const prb_mlp_desc *mlp, float *out_rows,
                          int out_pitch, void *workspace, size_t workspace_bytes, void *stream);
 
+/* diagnostics (PRB_MLP_TRACE=1): clock64 stamps of CTA 0 at the phase boundaries of its first 32 tiles (32 x 16) */
+PRB_API int prb_debug_mlp_trace(long long *dst);
+
 /* --- uniform-grid neighbour search: same results, bit for bit, as prb_ball_query(_msg2) / prb_three_nn
  * (first-nsample-in-index-order and lexicographic (d2, idx) rules kept; queries the grid cannot answer
  * exactly fall back to the exhaustive kernels inside the call).  Used for n >= a few thousand points. */

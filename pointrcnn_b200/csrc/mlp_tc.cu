@@ -48,6 +48,8 @@ struct ChainParams {
     int dcol[MAX_LAYERS];      // TMEM column of the accumulator
     const float *w[MAX_LAYERS];      // packed weight images
     const float *scale[MAX_LAYERS];  // np floats (zero padded); unused when unit_scale
+    int sleepy;                      // bit 0: MMA issuer waits with a suspend hint, bit 1: weight producer does
+    int trace;                       // debug: record phase time stamps (see g_trace)
     int unit_scale;                  // 1: the per-channel scale is folded into the packed weights, epilogues only add shift
     const float *shift[MAX_LAYERS];
     // resources (sized per launch so that small layers run several CTAs per SM)
@@ -204,6 +206,14 @@ __device__ __forceinline__ uint32_t swz(int r, int j) { return (uint32_t)(r * 12
 
 // Shared memory is carved at run time (ring depths and the weight-stage size depend on the chain), so that
 // narrow layers (SA1/SA2) fit 2 CTAs per SM and overlap their latency-bound gathers.
+// warp-level float max over the lanes named by MASK (CREDUX.MAX.F32: ~28 cycles dependent, pipelined when independent)
+template <unsigned MASK>
+__device__ __forceinline__ float redux_max_f32(float v) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "n"(MASK));
+    return r;
+}
+
 constexpr int POOL_STRIDE = 20;      // floats per row of the max-pool staging tile (80 B: conflict-free 128-bit stores)
 struct SmemFixed {
     int row_src[TM][3];      // SA: global point row (slot 0); FP: 3 known rows
@@ -238,6 +248,10 @@ __device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, %0;" ::"n
 // NG row groups of 4 warps each (warp w: TMEM lane quarter w%4, group w/4) + producer warp + MMA warp.
 // The A chunks (and the 16-column epilogue batches) of a tile are dealt round-robin to the groups, so 4*NG warps
 // hide each other's latencies while the stage order seen by the MMA issuer stays sequential.
+// optional phase trace (PRB_MLP_TRACE=1): CTA 0 stamps clock64 at the phase boundaries of its first 32 tiles
+__device__ long long g_trace[32 * 16];
+#define PRB_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && tcount < 32 && r == 0) g_trace[tcount * 16 + (slot)] = clock64(); } while (0)
+
 template <int NG, int MINB>
 __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const ChainParams p) {
     constexpr int NTHREADS = 128 * NG + 64;
@@ -281,7 +295,7 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                         for (int h = 0; h < halves; ++h) {
                             const int rows = min(B_TILE_ROWS, p.np[l] - h * B_TILE_ROWS);
                             const uint32_t bytes = (uint32_t)rows * KC * 4;
-                            mbar_wait_sleepy(s2u(&S.b_empty[rb.stage]), rb.phase ^ 1);
+                            if (p.sleepy & 2) mbar_wait_sleepy(s2u(&S.b_empty[rb.stage]), rb.phase ^ 1); else mbar_wait(s2u(&S.b_empty[rb.stage]), rb.phase ^ 1);
                             mbar_expect_tx(s2u(&S.b_full[rb.stage]), bytes);
                             const float *src = p.w[l] + ((size_t)kc * p.np[l] + (size_t)h * B_TILE_ROWS) * KC;
                             bulk_g2s(s2u(sB + (size_t)rb.stage * p.b_stage_bytes), src, bytes, s2u(&S.b_full[rb.stage]));
@@ -306,11 +320,11 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                             valid = min(KC, p.seg_width[s] - c * KC);
                         }
                         const int ksteps = (valid + 7) >> 3;
-                        mbar_wait_sleepy(s2u(&S.a_full[ra.stage]), ra.phase);
+                        if (p.sleepy & 1) mbar_wait_sleepy(s2u(&S.a_full[ra.stage]), ra.phase); else mbar_wait(s2u(&S.a_full[ra.stage]), ra.phase);
                         const uint64_t adesc = make_desc(s2u(sA + (size_t)ra.stage * A_STAGE_BYTES));
                         for (int h = 0; h < halves; ++h) {
                             const int rows = min(B_TILE_ROWS, p.np[l] - h * B_TILE_ROWS);
-                            mbar_wait_sleepy(s2u(&S.b_full[rb.stage]), rb.phase);
+                            if (p.sleepy & 1) mbar_wait_sleepy(s2u(&S.b_full[rb.stage]), rb.phase); else mbar_wait(s2u(&S.b_full[rb.stage]), rb.phase);
                             tc_fence_after();
                             const uint64_t bdesc = make_desc(s2u(sB + (size_t)rb.stage * p.b_stage_bytes));
                             const uint32_t idesc = make_idesc(rows);
@@ -370,7 +384,10 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
         };
         fetch_meta(blockIdx.x);
 
+        int tcount = -1;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            ++tcount;
+            PRB_TRACE(0);
             const long R = (long)tile * TM + r;
             const bool valid = m_valid;
             const int my_scene = m_scene, my_u = m_u;
@@ -555,6 +572,7 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
             }
 
             retire_all();
+            PRB_TRACE(1);
 
             // next tile's metadata: issue the loads now, consume them at the top of the next iteration
             fetch_meta(tile + gridDim.x);
@@ -563,6 +581,7 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
             for (int l = 1; l < L; ++l) {
                 mbar_wait(s2u(&S.d_full[l - 1]), dphase);
                 tc_fence_after();
+                PRB_TRACE(2 * l);
                 for (int kc = 0; kc < p.nchunks[l]; ++kc, ++cc, ra.advance(NA)) {
                     if ((int)(cc % NG) != grp) continue;
                     mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
@@ -601,16 +620,28 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                     fence_async_smem();
                     mbar_arrive(s2u(&S.a_full[ra.stage]));
                 }
+                PRB_TRACE(2 * l + 1);
             }
 
             // ---- final epilogue: 16-column batches dealt round-robin to the row groups
             mbar_wait(s2u(&S.d_full[L - 1]), dphase);
             tc_fence_after();
+            PRB_TRACE(2 * L);
             const int Cl = p.c_last;
             const float *sc = s_scale + sc_off[L - 1], *sh = s_shift + sc_off[L - 1];
             // SA max-pool: thread (g16, q) owns 16-row segment g16 and channel q of every batch
             size_t e_off = 0, e_pm = 0;
             bool e_ok = false;
+            // butterfly pooling (nsample 16 / 32): my centre is the one my own row belongs to
+            size_t b_off = 0, b_pm = 0;
+            bool b_ok = false;
+            if (p.mode_out == OUT_SA_MAX && (p.ns == 16 || p.ns == 32)) {
+                const unsigned Rg = (unsigned)tile * TM + (unsigned)r;
+                b_ok = (long)Rg < p.total_rows;
+                const unsigned pr = Rg >> p.log_ns, scene = pr / (unsigned)p.npoint, pp = pr - scene * (unsigned)p.npoint;
+                b_off = ((size_t)scene * p.out_stride_c + p.out_c_off) * p.npoint + pp;
+                b_pm = ((size_t)scene * p.npoint + pp) * p.out_stride_c + p.out_c_off;
+            }
             if (p.mode_out == OUT_SA_MAX && p.ns >= 16) {
                 const unsigned Rg = (unsigned)tile * TM + (unsigned)(r >> 4) * 16u;
                 e_ok = (long)Rg < p.total_rows && (((r >> 4) & ((p.ns >> 4) - 1)) == 0);
@@ -685,6 +716,68 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                     // Groups are whole (total_rows is a multiple of nsample): tail groups past total_rows are skipped.
                     const int ns = p.ns;
                     const int g16 = r >> 4, q = r & 15;          // (segment of 16 rows, channel) handled by this thread
+                    if (ns == 32 || ns == 16) {
+                        // The nsample rows of a centre are lanes of ONE warp: halving butterfly, no staging tile and
+                        // no barriers.  Each step a lane keeps half of its channels (chosen by one lane-id bit),
+                        // sends the other half to its partner and takes the max -- 8+4+2+1 shuffles leave one channel
+                        // per lane: channel (lane>>1)&15 for 32 samples (one more step joins lanes 2k, 2k+1), channel
+                        // lane&15 for 16 samples.  (Measured per 16-column batch under load, scripts/mlp_trace.py:
+                        // staged tile + two named barriers ~1000 cycles, 16 CREDUX ~860, this butterfly see notes.)
+                        float w8[8], w4[4], w2[2], x;
+                        if (ns == 32) {
+                            const bool b4 = lane & 16;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float keep = b4 ? v[i + 8] : v[i], send = b4 ? v[i] : v[i + 8];
+                                w8[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+                            }
+                            const bool b3 = lane & 8;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float keep = b3 ? w8[i + 4] : w8[i], send = b3 ? w8[i] : w8[i + 4];
+                                w4[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+                            }
+                            const bool b2 = lane & 4;
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                const float keep = b2 ? w4[i + 2] : w4[i], send = b2 ? w4[i] : w4[i + 2];
+                                w2[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+                            }
+                            const bool b1 = lane & 2;
+                            x = fmaxf(b1 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, b1 ? w2[0] : w2[1], 2));
+                            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+                        } else {
+                            const bool b3 = lane & 8;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float keep = b3 ? v[i + 8] : v[i], send = b3 ? v[i] : v[i + 8];
+                                w8[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+                            }
+                            const bool b2 = lane & 4;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float keep = b2 ? w8[i + 4] : w8[i], send = b2 ? w8[i] : w8[i + 4];
+                                w4[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+                            }
+                            const bool b1 = lane & 2;
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                const float keep = b1 ? w4[i + 2] : w4[i], send = b1 ? w4[i] : w4[i + 2];
+                                w2[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+                            }
+                            const bool b0 = lane & 1;
+                            x = fmaxf(b0 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, b0 ? w2[0] : w2[1], 1));
+                        }
+                        // my channel and whether I store it: 32 samples -> even lanes, channel (lane >> 1) & 15;
+                        // 16 samples -> every lane, channel = the bit pattern the halving steps selected
+                        const int ch = ns == 32 ? ((lane >> 1) & 15) : (((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1));
+                        if (pool_raw) x = fmaxf(x + sh[c0 + ch], 0.f);
+                        if (b_ok && (ns == 16 || (lane & 1) == 0) && c0 + ch < Cl) {
+                            p.out[b_off + (size_t)(c0 + ch) * p.npoint] = x;
+                            if (p.out_pm) p.out_pm[b_pm + c0 + ch] = x;
+                        }
+                        continue;
+                    }
                     bar_group(grp);                              // previous readers of the staging tile are done
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
@@ -728,6 +821,7 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
             }
             tc_fence_before();
             dphase ^= 1;
+            PRB_TRACE(2 * L + 1);
         }
     }
 
@@ -981,6 +1075,9 @@ static int run_chain(const ChainIO &io, const prb_mlp_desc *mlp, void *workspace
         while (l1 > l0 + 1 && !fits(g, l0, l1)) --l1;
         ChainParams p = io.base;
         p.unit_scale = mlp->scale ? 0 : 1;
+        p.trace = getenv("PRB_MLP_TRACE") ? 1 : 0;
+        p.sleepy = 3;
+        if (const char *e = getenv("PRB_MLP_SLEEPY")) p.sleepy = atoi(e);
         p.total_rows = io.rows;
         p.num_layers = l1 - l0;
         for (int l = l0; l < l1; ++l) {
@@ -1029,6 +1126,15 @@ static int run_chain(const ChainIO &io, const prb_mlp_desc *mlp, void *workspace
 }  // namespace prb
 
 extern "C" {
+
+// debug: copy the phase trace of the last traced launch (32 tiles x 16 stamps, clock64 of CTA 0's row thread 0)
+PRB_API int prb_debug_mlp_trace(long long *dst) {
+    PRB_CUDA(cudaDeviceSynchronize());
+    PRB_CUDA(cudaMemcpyFromSymbol(dst, g_trace, sizeof(long long) * 32 * 16));
+    static long long zeros[32 * 16];
+    PRB_CUDA(cudaMemcpyToSymbol(g_trace, zeros, sizeof(zeros)));
+    return 0;
+}
 
 PRB_API size_t prb_sa_workspace_bytes(int b, int npoint, int nsample, int c_feat, int num_layers, const int *c_out) {
     return chain_workspace_bytes((long)b * npoint * nsample, num_layers, 0, 3 + c_feat, c_feat, c_out);
