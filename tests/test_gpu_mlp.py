@@ -339,3 +339,26 @@ def test_training_path_autograd(cuda):
     up.sum().backward()
     assert f.grad is not None and torch.isfinite(f.grad).all() and f.grad.abs().sum() > 0
     assert all(p.grad is not None for p in sa.parameters())
+
+
+def test_batch_pipeline_matches_sequential(cuda):
+    """independent batches on alternating streams give bit-identical results to the one-after-another loop"""
+    from pointrcnn_b200.pipeline import BatchPipeline
+    torch.manual_seed(4)
+    net = Pointnet2MSG(input_channels=1).to(cuda).eval()
+    _randomise_bn(net, 9)
+    batches = [torch.from_numpy(synth.u_kitti(2, 16384, 200 + i, channels=4)).to(cuda) for i in range(5)]
+    with torch.no_grad():
+        want = [net(b)[1].clone() for b in batches]
+        pipe = BatchPipeline(lambda x: net(x)[1], inflight=3, device=cuda)
+        got = pipe.run(batches)
+        torch.cuda.synchronize()
+        for w, g in zip(want, got):
+            assert torch.equal(w, g)
+        # host-side inputs and results (pinned), and the fire-and-forget mode
+        host = [b.cpu().pin_memory() for b in batches]
+        pipe2 = BatchPipeline(lambda x: net(x)[1].mean(dim=(1, 2)), inflight=2, device=cuda)
+        res = pipe2.run(host, to_host=True)
+        for w, r in zip(want, res):
+            assert not r.is_cuda and torch.allclose(r, w.mean(dim=(1, 2)).cpu(), rtol=1e-6, atol=1e-7)
+        assert pipe.run(batches, keep=False) == [None] * 5
