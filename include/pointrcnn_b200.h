@@ -159,6 +159,22 @@ PRB_API int prb_fp_interp_mlp_ws(int b, int n, int m, int c_known, int c_skip, c
 PRB_API int prb_mlp_rows(long rows, int c_in, const float *x_rows, const prb_mlp_desc *mlp, float *out_rows,
                          int out_pitch, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------ RPN proposal path (next to the hot path) -----
+ * prb_decode_rpn_proposals replaces decode_bbox_target as called by the proposal layer (lib/utils/bbox_transform.py:
+ * 24-121 from lib/rpn/proposal_layer.py:23-32): xyz (n,3), reg (n,c) -> out (n,7) [x, y = bottom centre, z, h, w, l, ry];
+ * anchor_hwl = 3 HOST floats (cfg.CLS_MEAN_SIZE[0]).  Every torch op of the reference is one fp32 rounding here too.
+ * prb_rpn_proposals replaces ProposalLayer.forward's per-scene loop (lib/rpn/proposal_layer.py:34-142): order = the
+ * indices of torch.sort(scores, descending) (b,n) int64; distance_based selects the (0,40] / (40,80] split with the
+ * 70/30 top-n quotas, otherwise the score-based variant; normal_nms: nms_normal_gpu instead of nms_gpu.  Outputs
+ * (b, post_nms_top_n, 7) and (b, post_nms_top_n), zero rows behind the survivors.  No host synchronisation. */
+PRB_API int prb_decode_rpn_proposals(long n, int c, const float *xyz, const float *reg, const float *anchor_hwl,
+                                     float loc_scope, float loc_bin_size, int num_head_bin, int get_xz_fine, float *out,
+                                     void *stream);
+PRB_API size_t prb_rpn_proposals_workspace_bytes(int b, int post_nms_top_n);
+PRB_API int prb_rpn_proposals(int b, int n, const float *boxes, const float *scores, const long long *order,
+                              int distance_based, int pre_nms_top_n, int post_nms_top_n, float nms_thresh, int normal_nms,
+                              float *out_boxes, float *out_scores, void *workspace, size_t workspace_bytes, void *stream);
+
 /* diagnostics (PRB_MLP_TRACE=1): clock64 stamps of CTA 0 at the phase boundaries of its first 32 tiles (32 x 16) */
 PRB_API int prb_debug_mlp_trace(long long *dst);
 

@@ -32,7 +32,7 @@ def lib():
         L.prb_launch_count.restype = ctypes.c_ulonglong
         for name in ("prb_nms_workspace_bytes", "prb_mlp_packed_bytes", "prb_mlp_packed_bytes_ex",
                      "prb_sa_workspace_bytes", "prb_fp_workspace_bytes", "prb_rows_workspace_bytes", "prb_grid_workspace_bytes",
-                     "prb_fps_workspace_bytes"):
+                     "prb_fps_workspace_bytes", "prb_rpn_proposals_workspace_bytes"):
             getattr(L, name).restype = c_size_t
         if L.prb_abi_version() != 1:
             raise RuntimeError("pointrcnn_b200: ABI version mismatch")

@@ -6,6 +6,7 @@ After this, with the reference tree on sys.path, `lib/net/*.py` and `tools/*.py`
     import pointnet2_cuda / iou3d_cuda / roipool3d_cuda                    -> pointrcnn_b200.ext.*
     pointnet2_lib.pointnet2.{pointnet2_utils,pointnet2_modules,pytorch_utils} -> pointrcnn_b200.pointnet2.*
     lib.utils.iou3d.iou3d_utils, lib.utils.roipool3d.roipool3d_utils       -> pointrcnn_b200.{iou3d,roipool3d}.*
+    lib.rpn.proposal_layer (ProposalLayer)                                 -> pointrcnn_b200.rpn.proposal_layer
 Optionally (compat=True) also provides the tiny stand-ins the 2019-era reference needs on a modern stack:
 `easydict`, `tensorboardX.SummaryWriter` (no-op), `fire`, and a default Loader for `yaml.load`
  -- none of them is on the operator path.
@@ -50,6 +51,15 @@ def activate(compat=False):
     from .roipool3d import roipool3d_utils
     _alias("lib.utils.iou3d.iou3d_utils", iou3d_utils)
     _alias("lib.utils.roipool3d.roipool3d_utils", roipool3d_utils)
+    # next to the hot path: the RPN proposal layer, same class and signature
+    try:
+        importlib.import_module("lib.rpn")
+    except ImportError:
+        m = types.ModuleType("lib.rpn")
+        m.__path__ = []
+        _alias("lib.rpn", m)
+    from .rpn import proposal_layer
+    _alias("lib.rpn.proposal_layer", proposal_layer)
 
 
 def _install_compat():

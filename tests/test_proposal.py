@@ -1,0 +1,90 @@
+"""RPN proposal path: decode_bbox_target + ProposalLayer.
+
+CPU: the numpy oracle (oracle/proposal.py) against the golden outputs of the reference's own Python
+(tests/golden/proposal_layer.npz, written by oracle/make_golden_proposal.py).
+GPU: the device path (pointrcnn_b200/rpn/proposal_layer.py -> csrc/proposal.cu) against the same golden vectors and the
+oracle, bit for bit."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+from make_golden_proposal import CASES, rpn_outputs  # noqa: E402
+from oracle import proposal as P  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "proposal_layer.npz")
+ANCHOR = np.array([1.52563191462, 1.62856739989, 3.88311640418], dtype=np.float32)     # tools/cfgs/default.yaml:19
+MODES = {"TEST": dict(pre_nms_top_n=9000, post_nms_top_n=100, nms_thresh=0.8),           # default.yaml:163-165
+         "TRAIN": dict(pre_nms_top_n=9000, post_nms_top_n=512, nms_thresh=0.85)}         # default.yaml:156-158
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLDEN)
+
+
+def test_decode_oracle_matches_reference_python(gold):
+    _, reg, xyz = rpn_outputs(2, 4096, 106)
+    d = P.decode_bbox_target(xyz.reshape(-1, 3), reg.reshape(-1, 76), ANCHOR, 3.0, 0.5, 12, True)
+    assert np.array_equal(d, gold["decode_boxes"])
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_proposal_oracle_matches_reference_python(gold, case):
+    name, mode, nms_type, dist_based, B, N, seed = case
+    scores, reg, xyz = rpn_outputs(B, N, seed, far_empty=name.endswith("far_area_empty"))
+    b, s = P.proposal_layer(scores, reg, xyz, ANCHOR, nms_type=nms_type, distance_based=dist_based, **MODES[mode])
+    assert np.array_equal(b, gold[name + "_boxes"]) and np.array_equal(s, gold[name + "_scores"])
+
+
+def _cfg(nms_type, dist_based):
+    ns = types.SimpleNamespace
+    cfg = {"TEST": ns(RPN_PRE_NMS_TOP_N=9000, RPN_POST_NMS_TOP_N=100, RPN_NMS_THRESH=0.8, RPN_DISTANCE_BASED_PROPOSE=dist_based),
+           "TRAIN": ns(RPN_PRE_NMS_TOP_N=9000, RPN_POST_NMS_TOP_N=512, RPN_NMS_THRESH=0.85, RPN_DISTANCE_BASED_PROPOSE=True)}
+
+    class Cfg(dict):
+        __getattr__ = dict.__getitem__
+    c = Cfg(cfg)
+    c["CLS_MEAN_SIZE"] = ANCHOR[None]
+    c["RPN"] = ns(LOC_SCOPE=3.0, LOC_BIN_SIZE=0.5, NUM_HEAD_BIN=12, LOC_XZ_FINE=True, NMS_TYPE=nms_type)
+    return c
+
+
+@pytest.mark.gpu
+def test_decode_kernel_bit_exact(cuda, gold):
+    from pointrcnn_b200.rpn.proposal_layer import decode_rpn_proposals
+    _, reg, xyz = rpn_outputs(2, 4096, 106)
+    got = decode_rpn_proposals(torch.from_numpy(xyz).to(cuda), torch.from_numpy(reg).to(cuda), ANCHOR, 3.0, 0.5, 12, True)
+    want = gold["decode_boxes"].copy()
+    want[:, 1] = want[:, 1] + want[:, 3] / np.float32(2)             # proposal_layer.py:32 is fused into the kernel
+    assert np.array_equal(got.cpu().numpy().reshape(-1, 7), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_proposal_layer_bit_exact(cuda, gold, case):
+    from pointrcnn_b200.rpn.proposal_layer import ProposalLayer
+    name, mode, nms_type, dist_based, B, N, seed = case
+    scores, reg, xyz = rpn_outputs(B, N, seed, far_empty=name.endswith("far_area_empty"))
+    layer = ProposalLayer(mode=mode, cfg=_cfg(nms_type, dist_based))
+    b, s = layer(torch.from_numpy(scores).to(cuda), torch.from_numpy(reg).to(cuda), torch.from_numpy(xyz).to(cuda))
+    assert tuple(b.shape) == gold[name + "_boxes"].shape
+    assert np.array_equal(s.cpu().numpy(), gold[name + "_scores"]), "kept scores differ from the reference's proposal layer"
+    assert np.array_equal(b.cpu().numpy(), gold[name + "_boxes"]), "proposals differ from the reference's proposal layer"
+
+
+@pytest.mark.gpu
+def test_proposal_layer_few_points_and_empty_ranges(cuda):
+    """fewer candidates than the quotas, survivors < post_nms_top_n (zero rows behind them), nothing in the far range"""
+    from pointrcnn_b200.rpn.proposal_layer import ProposalLayer
+    for seed, N, far_empty in ((7, 700, False), (8, 150, True), (9, 40, False)):
+        scores, reg, xyz = rpn_outputs(3, N, seed, far_empty=far_empty)
+        want_b, want_s = P.proposal_layer(scores, reg, xyz, ANCHOR, nms_type="rotate", distance_based=True, **MODES["TRAIN"])
+        layer = ProposalLayer(mode="TRAIN", cfg=_cfg("rotate", True))
+        b, s = layer(torch.from_numpy(scores).to(cuda), torch.from_numpy(reg).to(cuda), torch.from_numpy(xyz).to(cuda))
+        assert np.array_equal(s.cpu().numpy(), want_s) and np.array_equal(b.cpu().numpy(), want_b)
