@@ -13,7 +13,7 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.append(os.path.join(ROOT, "oracle"))
 from make_golden_proposal import CASES, rpn_outputs  # noqa: E402
 from oracle import proposal as P  # noqa: E402
 
