@@ -246,6 +246,13 @@ a, b = ref.Pointnet2MSG(input_channels=0), Pointnet2MSG(input_channels=0)
 assert list(a.state_dict()) == list(b.state_dict())
 assert type(a.SA_modules[0]).__module__.startswith('pointrcnn_b200')
 assert iu.__name__.startswith('pointrcnn_b200') and iu.kitti_utils.__name__ == 'lib.utils.kitti_utils'
+# the whole two-stage network of the reference builds on top of the B200 modules, proposal layer included
+cfg.RPN.ENABLED = True; cfg.RCNN.ENABLED = True
+from lib.net.point_rcnn import PointRCNN
+net = PointRCNN(num_classes=2, use_xyz=True, mode='TEST')
+assert type(net.rpn.proposal_layer).__module__ == 'pointrcnn_b200.rpn.proposal_layer'
+assert all(type(m).__module__.startswith('pointrcnn_b200') for m in net.rcnn_net.SA_modules)
+assert sum(p.numel() for p in net.parameters()) == 3887452
 print('OK')
 """ % ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
