@@ -110,6 +110,7 @@ typedef struct prb_mlp_desc {
                               * NULL = the scale is already folded into the packed weights (y = relu(W'x + shift)),
                               * which lets the SA kernel pool raw accumulators and apply shift/ReLU once per centre */
     const float *shift;      /* device; same layout */
+    int flags;               /* bit 0: the LAST layer is linear (no ReLU): y = W x + shift, e.g. detection heads */
 } prb_mlp_desc;
 
 /* bytes of the packed image for one MLP */

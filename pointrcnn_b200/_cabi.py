@@ -17,7 +17,7 @@ c_int, c_long, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_long, ctypes
 class MlpDesc(ctypes.Structure):
     """struct prb_mlp_desc"""
     _fields_ = [("num_layers", c_int), ("c_in", c_int), ("c_out", c_int * 3),
-                ("packed_w", c_void_p), ("scale", c_void_p), ("shift", c_void_p)]
+                ("packed_w", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("flags", c_int)]
 
 
 def lib():

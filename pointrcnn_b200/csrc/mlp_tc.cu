@@ -26,6 +26,8 @@
 
 #include <vector>
 
+#include <math_constants.h>
+
 #include "common.cuh"
 
 namespace prb {
@@ -57,6 +59,7 @@ struct ChainParams {
     int b_stage_bytes;         // weight stage size = min(256, max np) * 128
     int tmem_cols;             // power of two >= 32
     int gather_mode;           // layer-0 row gather: 0 registers (+cvt.rna), 1 cp.async.cg, 2 cp.async.ca
+    int linear_last;           // the last layer of the chain has no ReLU (heads: y = W x + shift)
     int round_out;             // OUT_ROWS: round to tf32 (intermediate segment of a split chain)
     // layer-0 K segments (each padded to a multiple of KC)
     int nseg, seg_chunks[2], seg_width[2];
@@ -656,6 +659,7 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                 // folded scale + max-pool: max_s relu(x_s + t) == relu(max_s x_s + t), so the raw accumulators are
                 // pooled and shift / ReLU are applied once per (centre, channel) after the reduction
                 const bool pool_raw = p.unit_scale && p.mode_out == OUT_SA_MAX;
+                const float lo = p.linear_last ? -CUDART_INF_F : 0.f;    // ReLU = max(., 0); a linear last layer keeps the sign
                 if (pool_raw) {
 #pragma unroll
                     for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(acc[q]);
@@ -664,20 +668,20 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float4 b = sh4[j];
-                        v[4 * j + 0] = fmaxf(__uint_as_float(acc[4 * j + 0]) + b.x, 0.f);
-                        v[4 * j + 1] = fmaxf(__uint_as_float(acc[4 * j + 1]) + b.y, 0.f);
-                        v[4 * j + 2] = fmaxf(__uint_as_float(acc[4 * j + 2]) + b.z, 0.f);
-                        v[4 * j + 3] = fmaxf(__uint_as_float(acc[4 * j + 3]) + b.w, 0.f);
+                        v[4 * j + 0] = fmaxf(__uint_as_float(acc[4 * j + 0]) + b.x, lo);
+                        v[4 * j + 1] = fmaxf(__uint_as_float(acc[4 * j + 1]) + b.y, lo);
+                        v[4 * j + 2] = fmaxf(__uint_as_float(acc[4 * j + 2]) + b.z, lo);
+                        v[4 * j + 3] = fmaxf(__uint_as_float(acc[4 * j + 3]) + b.w, lo);
                     }
                 } else {
                     const float4 *sc4 = reinterpret_cast<const float4 *>(sc + c0), *sh4 = reinterpret_cast<const float4 *>(sh + c0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float4 a = sc4[j], b = sh4[j];
-                        v[4 * j + 0] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 0]), a.x, b.x), 0.f);
-                        v[4 * j + 1] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 1]), a.y, b.y), 0.f);
-                        v[4 * j + 2] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 2]), a.z, b.z), 0.f);
-                        v[4 * j + 3] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 3]), a.w, b.w), 0.f);
+                        v[4 * j + 0] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 0]), a.x, b.x), lo);
+                        v[4 * j + 1] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 1]), a.y, b.y), lo);
+                        v[4 * j + 2] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 2]), a.z, b.z), lo);
+                        v[4 * j + 3] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 3]), a.w, b.w), lo);
                     }
                 }
                 if (p.mode_out == OUT_ROWS) {
@@ -771,7 +775,7 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                         // my channel and whether I store it: 32 samples -> even lanes, channel (lane >> 1) & 15;
                         // 16 samples -> every lane, channel = the bit pattern the halving steps selected
                         const int ch = ns == 32 ? ((lane >> 1) & 15) : (((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1));
-                        if (pool_raw) x = fmaxf(x + sh[c0 + ch], 0.f);
+                        if (pool_raw) x = fmaxf(x + sh[c0 + ch], lo);
                         if (b_ok && (ns == 16 || (lane & 1) == 0) && c0 + ch < Cl) {
                             p.out[b_off + (size_t)(c0 + ch) * p.npoint] = x;
                             if (p.out_pm) p.out_pm[b_pm + c0 + ch] = x;
@@ -796,7 +800,7 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                                 for (int s = 1; s < per; ++s) x = fmaxf(x, pool2[(g16 + s) * 16 + q]);
                             }
                         }
-                        if (pool_raw) x = fmaxf(x + sh[c0 + q], 0.f);
+                        if (pool_raw) x = fmaxf(x + sh[c0 + q], lo);
                         if (e_ok && c0 + q < Cl) {
                             p.out[e_off + (size_t)c0 * p.npoint] = x;
                             if (p.out_pm) p.out_pm[e_pm + c0] = x;
@@ -808,7 +812,7 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                             const int row0 = g16 * 16 + t * ns;
                             float x = pool[row0 * POOL_STRIDE + q];
                             for (int s = 1; s < ns; ++s) x = fmaxf(x, pool[(row0 + s) * POOL_STRIDE + q]);
-                            if (pool_raw) x = fmaxf(x + sh[c0 + q], 0.f);
+                            if (pool_raw) x = fmaxf(x + sh[c0 + q], lo);
                             const unsigned Rg = (unsigned)tile * TM + (unsigned)row0;
                             if ((long)Rg < p.total_rows && c0 + q < Cl) {
                                 const unsigned pr = Rg >> p.log_ns, scene = pr / (unsigned)p.npoint, pp = pr - scene * (unsigned)p.npoint;
@@ -1075,6 +1079,7 @@ static int run_chain(const ChainIO &io, const prb_mlp_desc *mlp, void *workspace
         while (l1 > l0 + 1 && !fits(g, l0, l1)) --l1;
         ChainParams p = io.base;
         p.unit_scale = mlp->scale ? 0 : 1;
+        p.linear_last = (l1 == L && (mlp->flags & 1)) ? 1 : 0;
         p.trace = getenv("PRB_MLP_TRACE") ? 1 : 0;
         p.sleepy = 3;
         if (const char *e = getenv("PRB_MLP_SLEEPY")) p.sleepy = atoi(e);

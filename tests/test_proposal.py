@@ -88,3 +88,50 @@ def test_proposal_layer_few_points_and_empty_ranges(cuda):
         layer = ProposalLayer(mode="TRAIN", cfg=_cfg("rotate", True))
         b, s = layer(torch.from_numpy(scores).to(cuda), torch.from_numpy(reg).to(cuda), torch.from_numpy(xyz).to(cuda))
         assert np.array_equal(s.cpu().numpy(), want_s) and np.array_equal(b.cpu().numpy(), want_b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_pts,with_twin", [(5000, False), (16384, True)])
+def test_fused_rpn_heads_match_torch(cuda, n_pts, with_twin):
+    """cls [128,128,1] + reg [128,128,76] head stacks (lib/net/rpn.py:19-47) as one two-layer tensor-core launch"""
+    import torch.nn as nn
+    from pointrcnn_b200.pointnet2 import pytorch_utils as pt_utils
+    from pointrcnn_b200.pointnet2 import pointnet2_modules as pm
+    from pointrcnn_b200.rpn.heads import rpn_heads
+    torch.manual_seed(5)
+
+    class Heads(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.rpn_cls_layer = nn.Sequential(pt_utils.Conv1d(128, 128, bn=True), nn.Dropout(0.5), pt_utils.Conv1d(128, 1, activation=None))
+            self.rpn_reg_layer = nn.Sequential(pt_utils.Conv1d(128, 128, bn=True), nn.Dropout(0.5), pt_utils.Conv1d(128, 76, activation=None))
+    h = Heads().to(cuda).eval()
+    g = torch.Generator().manual_seed(3)
+    for m in h.modules():
+        if isinstance(m, nn.BatchNorm1d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+    nn.init.normal_(h.rpn_cls_layer[2].conv.bias, mean=-2.0, std=0.1)
+    f = torch.randn(2, 128, n_pts, device=cuda)
+    if with_twin:
+        f = pm._attach_pm(f, f.transpose(1, 2).contiguous())
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want_c = h.rpn_cls_layer(f).transpose(1, 2).contiguous()
+            want_r = h.rpn_reg_layer(f).transpose(1, 2).contiguous()
+            got_c, got_r = rpn_heads(h, f)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert got_c.shape == want_c.shape == (2, n_pts, 1) and got_r.shape == want_r.shape == (2, n_pts, 76)
+    assert got_c.is_contiguous() and got_r.is_contiguous()
+    assert (got_r.min() < 0) and (got_c.min() < 0), "the last layer is linear: negative outputs must survive"
+    for got, want in ((got_c, want_c), (got_r, want_r)):
+        assert (got - want).abs().max().item() <= 1e-2 * want.abs().max().item()
+    # grad-enabled / training calls take the reference-shaped torch path
+    h.train()
+    c2, r2 = rpn_heads(h, f)
+    assert c2.requires_grad and r2.shape == (2, n_pts, 76)
