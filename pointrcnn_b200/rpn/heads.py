@@ -111,7 +111,7 @@ def rpn_heads(rpn_module, backbone_features):
     """eval-mode replacement of `rpn_cls_layer(f).transpose(1,2).contiguous()`, `rpn_reg_layer(f).transpose(...)`
     for a reference lib.net.rpn.RPN instance (or anything with the same two attributes)"""
     cache = rpn_module.__dict__.setdefault("_prb_heads", FusedRPNHeads())
-    fused_ok = (not torch.is_grad_enabled()) and not rpn_module.training and pm._fused_enabled() and \\
+    fused_ok = (not torch.is_grad_enabled()) and not rpn_module.training and pm._fused_enabled() and \
         FusedRPNHeads.supported(rpn_module.rpn_cls_layer, rpn_module.rpn_reg_layer)
     if not fused_ok:
         return (rpn_module.rpn_cls_layer(backbone_features).transpose(1, 2).contiguous(),
