@@ -51,6 +51,8 @@ struct ChainParams {
     const float *w[MAX_LAYERS];      // packed weight images
     const float *scale[MAX_LAYERS];  // np floats (zero padded); unused when unit_scale
     int sleepy;                      // bit 0: MMA issuer waits with a suspend hint, bit 1: weight producer does
+    int a_tmem;                      // layers >= 1 take their A operand from tensor memory: the epilogue rewrites the
+                                     // previous accumulator IN PLACE (relu(x + t) -> tf32), no shared-memory stage, no proxy fence
     int trace;                       // debug: record phase time stamps (see g_trace)
     int unit_scale;                  // 1: the per-channel scale is folded into the packed weights, epilogues only add shift
     const float *shift[MAX_LAYERS];
@@ -163,6 +165,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same with the A operand in tensor memory: lane = row, one 32-bit column per K element (8 columns per K=8 step)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns from registers (thread i writes lane base+i)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrives on the mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -332,8 +352,14 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                             const uint64_t bdesc = make_desc(s2u(sB + (size_t)rb.stage * p.b_stage_bytes));
                             const uint32_t idesc = make_idesc(rows);
                             const uint32_t d = tmem + (uint32_t)(p.dcol[l] + h * B_TILE_ROWS);
-                            for (int ks = 0; ks < ksteps; ++ks)  // +32 bytes (= 2 x 16 B) per K=8 step inside the swizzle row
-                                umma_tf32(d, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                            if (p.a_tmem && l > 0) {   // A = the rewritten accumulator of layer l-1: columns kc*32 + ks*8 ...
+                                const uint32_t a_t = tmem + (uint32_t)(p.dcol[l - 1] + kc * KC);
+                                for (int ks = 0; ks < ksteps; ++ks)
+                                    umma_tf32_ts(d, a_t + (uint32_t)(8 * ks), bdesc + (uint64_t)(2 * ks), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                            } else {
+                                for (int ks = 0; ks < ksteps; ++ks)  // +32 bytes (= 2 x 16 B) per K=8 step inside the swizzle row
+                                    umma_tf32(d, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                            }
                             umma_commit(s2u(&S.b_empty[rb.stage]));
                             rb.advance(NB);
                         }
@@ -589,6 +615,30 @@ __global__ void __launch_bounds__(128 * NG + 64, MINB) mlp_chain_kernel(const Ch
                     if ((int)(cc % NG) != grp) continue;
                     mbar_wait(s2u(&S.a_empty[ra.stage]), ra.phase ^ 1);
                     uint8_t *A = sA + (size_t)ra.stage * A_STAGE_BYTES;
+                    if (p.a_tmem) {
+                        // in place: D_{l-1}[:, chunk] -> relu(. + shift) as tf32 bit patterns -> the same TMEM columns
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const uint32_t col = tmem + lane_base + (uint32_t)(p.dcol[l - 1] + kc * KC + hh * 16);
+                            uint32_t acc[16];
+                            tmem_ld16(col, acc);
+                            const float4 *sc4 = reinterpret_cast<const float4 *>(s_scale + sc_off[l - 1] + kc * KC + hh * 16);
+                            const float4 *sh4 = reinterpret_cast<const float4 *>(s_shift + sc_off[l - 1] + kc * KC + hh * 16);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 a = sc4[j], b = sh4[j];
+                                acc[4 * j + 0] = __float_as_uint(relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 0]), a.x, b.x)));
+                                acc[4 * j + 1] = __float_as_uint(relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 1]), a.y, b.y)));
+                                acc[4 * j + 2] = __float_as_uint(relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 2]), a.z, b.z)));
+                                acc[4 * j + 3] = __float_as_uint(relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 3]), a.w, b.w)));
+                            }
+                            tmem_st16(col, acc);
+                        }
+                        tmem_st_wait();
+                        tc_fence_before();
+                        mbar_arrive(s2u(&S.a_full[ra.stage]));
+                        continue;
+                    }
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
                         uint32_t acc[16];
@@ -1081,6 +1131,8 @@ static int run_chain(const ChainIO &io, const prb_mlp_desc *mlp, void *workspace
         p.unit_scale = mlp->scale ? 0 : 1;
         p.linear_last = (l1 == L && (mlp->flags & 1)) ? 1 : 0;
         p.trace = getenv("PRB_MLP_TRACE") ? 1 : 0;
+        p.a_tmem = 1;   // measured (profiles/r1_notes.md): SA chains 1.124 -> 1.088 ms per batch; PRB_MLP_ATMEM=0 = shared-memory stages
+        if (const char *e = getenv("PRB_MLP_ATMEM")) p.a_tmem = atoi(e) ? 1 : 0;
         p.sleepy = 3;
         if (const char *e = getenv("PRB_MLP_SLEEPY")) p.sleepy = atoi(e);
         p.total_rows = io.rows;
