@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PRB_ABI_VERSION 1
+#define PRB_ABI_VERSION 2   /* 2: prb_mlp_desc.flags, out_pm arguments, workspace-taking FPS */
 #if defined(__GNUC__)
 #define PRB_API __attribute__((visibility("default")))
 #else

@@ -34,7 +34,7 @@ def lib():
                      "prb_sa_workspace_bytes", "prb_fp_workspace_bytes", "prb_rows_workspace_bytes", "prb_grid_workspace_bytes",
                      "prb_fps_workspace_bytes", "prb_rpn_proposals_workspace_bytes"):
             getattr(L, name).restype = c_size_t
-        if L.prb_abi_version() != 1:
+        if L.prb_abi_version() != 2:
             raise RuntimeError("pointrcnn_b200: ABI version mismatch")
         _lib = L
     return _lib

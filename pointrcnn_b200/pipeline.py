@@ -1,11 +1,12 @@
 """Batch pipelining: consecutive, independent batches on alternating CUDA streams.
 
-Furthest-point sampling is a dependency chain (4095 serial rounds for the first RPN level) that keeps only
-64 of 148 SMs busy, and nothing else of the SAME batch can run before it ends.  Consecutive batches are
+Furthest-point sampling is a dependency chain (4095 serial rounds for the first RPN level) that runs as one CTA per
+scene (16 of 148 SMs), and nothing else of the SAME batch can run before it ends.  Consecutive batches are
 independent (the reference's eval loop processes them one after another), so batch i+1's sampling chain can
 overlap batch i's neighbour searches and tensor-core MLPs.  Measured on B200 (RPN backbone, 16 scenes of 16384
-points per batch): 5.73 ms per batch back to back on one stream, 3.92 ms with two batches in flight, 3.55 ms with
-three (profiles/r1_notes.md).  Results are identical to the sequential loop -- only the stream assignment differs.
+points per batch): 4.68 ms per batch back to back on one stream, 2.13 ms with six batches in flight
+(profiles/r1_notes.md).  Results are identical to the sequential loop, bit for bit -- only the stream assignment
+differs (tests/test_gpu_mlp.py::test_batch_pipeline_matches_sequential).
 """
 import torch
 
@@ -13,9 +14,10 @@ import torch
 class BatchPipeline:
     def __init__(self, fn, inflight=6, device=None, fps_cluster=2):
         """fn: callable(batch_on_device) -> tensor or tuple of tensors; inflight: batches in flight (streams);
-        fps_cluster: CTAs per scene for the big FPS levels while the pipeline runs (0 = single-batch heuristic).
+        fps_cluster: CTAs per scene of the cluster FPS kernel while the pipeline runs (0 = single-batch heuristic);
+        only relevant for scenes the pruned single-CTA kernel does not take (> 16384 points or PRB_FPS_PRUNE=0).
         With several batches in flight SM-time matters more than latency: 2 CTAs per scene take 3.35 ms on 32 SMs,
-        4 CTAs 2.53 ms on 64 SMs."""
+        4 CTAs 2.53 ms on 64 SMs, the pruned kernel 1.95 ms on 16 SMs."""
         self.fps_cluster = int(fps_cluster)
         self.fn = fn
         self.device = torch.device(device if device is not None else "cuda", torch.cuda.current_device()) \
