@@ -111,6 +111,18 @@ def test_cabi_library_exports_every_declared_symbol():
     assert exported == names, set(exported) ^ set(names)
 
 
+def test_cabi_size_t_functions_have_a_64_bit_restype():
+    """ctypes defaults to a C int return: every size_t entry point of the header must be registered in _cabi.lib()"""
+    import ctypes
+    from pointrcnn_b200 import _cabi
+    lib = _cabi.lib()
+    hdr = open(os.path.join(ROOT, "include", "pointrcnn_b200.h")).read()
+    names = re.findall(r"PRB_API size_t (prb_\w+)\(", hdr)
+    assert len(names) >= 9
+    for n in names:
+        assert getattr(lib, n).restype is ctypes.c_size_t, "%s would be truncated to 32 bits" % n
+
+
 def test_cabi_bad_arguments_raise_instead_of_exiting():
     from pointrcnn_b200 import _cabi as C
     rc = C.lib().prb_ball_query(1, 10, 5, C.c_float(1.0), 0, None, None, None, None)
