@@ -6,23 +6,29 @@ on synthetic 16384x4 clouds, batch 16 per GPU (BASELINE.json configs[1]).
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
     python bench.py --impl reference ...      # the CPU restatement of the same path on the host cores
 
-One JSON line on rank 0.
-  value        device-resident throughput: K steps (one batch of 16 scenes each) through pointrcnn_b200.pipeline.
-               BatchPipeline with `--inflight` independent batches in flight, CUDA events around the K steps, max over
-               ranks; inputs rotate through a pool larger than L2.
-  e2e          the same K steps with pinned HOST inputs: H2D of every step's input and a D2H read of every step's
-               per-scene metric inside the timed region.
-  single_batch one batch at a time on one stream with an L2 flush in between (per-batch latency view).
+One JSON line on rank 0.  A "step" is one batch of 16 scenes per GPU.  Every timed region times EXACTLY K steps between
+a barrier + synchronize on both sides (CUDA events, max over ranks) and is REPEATED R >= 3 times so that at least
+~1 s is timed per leg; the line reports the median repeat (and min / max).
+
+  value         device-resident throughput: K steps through pointrcnn_b200.pipeline.BatchPipeline with `--inflight`
+                independent batches in flight (one CUDA graph per slot); inputs rotate through a pool larger than L2.
+  e2e           the whole RPN stage a caller runs (backbone -> fused cls/reg heads -> proposal layer, TEST quotas) from
+                pinned HOST input: H2D of every step's points and D2H of every step's proposals (B,100,7)+(B,100)
+                inside the timed region, handed to a host consumer per batch.
+  e2e_features  backbone only, returning the full (B,128,16384) feature tensor to the host (PCIe bound; secondary).
+  single_batch  one batch at a time on one stream with an L2 flush in between (per-batch latency view).
   roofline / kernels   per-kernel-family device times from CUDA events on the launching stream (sequential pass).
-  cpu_baseline oracle port on the host cores over a bounded sample of the same workload.
+  ref_cuda      the reference's own CUDA kernels (oracle/_ref, rebuilt for sm_100a) + stock cuDNN MLP in the reference's
+                call order, same process, same inputs: once single-stream, once with the same number of batches in
+                flight; vs_ref_cuda = ours / theirs for both.
+  strong_scaling  (N > 1) global batch 16: 16/N scenes per GPU per step, same pipeline.
+  cpu_baseline  oracle port on the host cores over a bounded sample of the same workload.
 """
 import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -33,6 +39,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 POINTS, CHANNELS, BATCH = 16384, 4, 16
 CONFIG_SEED = 2000  # seed = 1000*config + scene index
+METRIC = "scenes/sec RPN backbone fwd (16384 pts)"
+
+
+def workload_config(world):
+    """identical for the GPU arm and the reference (CPU) arm"""
+    return {"workload": "RPN PointNet++ backbone fwd: 4 SA-MSG + 4 FP (tools/cfgs/default.yaml), 16384x4 uniform KITTI-scope "
+                        "points, eval-mode BN (BASELINE configs[1])", "batch_per_gpu": BATCH, "global_batch": BATCH * world,
+            "parallelism": "dp%d (scene sharding, no data-path collective)" % world}
 
 
 def make_scenes(first, count):
@@ -40,23 +54,39 @@ def make_scenes(first, count):
     return np.concatenate([synth.u_kitti(1, POINTS, CONFIG_SEED + first + i, channels=CHANNELS) for i in range(count)], 0)
 
 
+def _randomise_bn(net):
+    import torch
+    g = torch.Generator().manual_seed(1)
+    for m in net.modules():   # non-trivial eval-mode BN (SURVEY.md 8d)
+        if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d)):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+
+
 def build_model(device):
     import torch
     from pointrcnn_b200.backbone import Pointnet2MSG
     torch.manual_seed(0)
     net = Pointnet2MSG(input_channels=CHANNELS - 3).eval()
-    g = torch.Generator().manual_seed(1)
-    for m in net.modules():   # non-trivial eval-mode BN (SURVEY.md 8d)
-        if isinstance(m, torch.nn.BatchNorm2d):
-            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
-            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+    _randomise_bn(net)
     return net.to(device)
+
+
+def build_rpn_stage(device, backbone):
+    """the RPN stage around the SAME backbone module (heads random-init, BN randomised)"""
+    import torch
+    from pointrcnn_b200.rpn.stage import RPNStage
+    torch.manual_seed(2)
+    stage = RPNStage(input_channels=CHANNELS - 3).eval()
+    _randomise_bn(stage)
+    stage.backbone_net = backbone
+    stage.backbone_net.FP_modules[0].emit_point_major = True
+    return stage.to(device)
 
 
 def mlp_flops_per_scene(net):
     """2*MAC of every SA / FP SharedMLP per scene (algorithmic FLOPs of the tensor-core kernels)"""
     sa = fp = 0
-    n = POINTS
     for mod in net.SA_modules:
         for grouper, mlp in zip(mod.groupers, mod.mlps):
             rows = mod.npoint * grouper.nsample
@@ -64,7 +94,6 @@ def mlp_flops_per_scene(net):
     npts = [POINTS] + [m.npoint for m in net.SA_modules]
     for k, mod in enumerate(net.FP_modules):
         fp += 2 * npts[k] * sum(l.conv.in_channels * l.conv.out_channels for l in mod.mlp.children())
-    del n
     return sa, fp
 
 
@@ -185,45 +214,56 @@ def peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
 
 
+def ncu_traffic():
+    """DRAM bytes per step of each kernel family, from the committed ncu --set full capture (profiles/r2_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum summed over the family's launches of one step), or {}"""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
+
+
 def run_reference_arm(args):
     """--impl reference: the reference has no CPU implementation of this path; the arm times the CPU restatement
     (oracle port) with all host threads on a bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    import torch
     from oracle import oracle as O
     net = build_model("cpu")
     specs = folded_specs(net)
     scenes = args.cpu_scenes
-    val, dt = time_cpu(specs, scenes, steps=max(1, args.steps), warmup=min(1, args.warmup))
+    steps, warm = max(1, args.steps), min(1, args.warmup)
+    val, dt = time_cpu(specs, scenes, steps=steps, warmup=warm)
     cores = O.num_threads()
-    line = {"impl": "reference", "metric": "scenes/sec RPN backbone fwd (16384 pts)", "value": val, "unit": "scenes/s",
-            "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": min(1, args.warmup), "ms_per_step": dt * 1e3,
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "scenes/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "RPN PointNet++ backbone fwd, 4 SA-MSG + 4 FP, 16384x4 pts (BASELINE configs[1])",
-                       "per_step": "%d scenes (bounded sample)" % scenes},
+            "config": workload_config(world),
             "cpu_baseline": {"value": val, "unit": "scenes/s", "cores": cores, "kind": "port",
-                             "sample": "%d scenes per step, oracle/pointops_oracle.c (OpenMP) + numpy fp32 MLP" % scenes},
+                             "sample": "%d scenes per step of the same workload (bounded sample of the batch of %d), oracle/pointops_oracle.c "
+                                       "(OpenMP) + numpy fp32 MLP; the reference itself has no CPU implementation of this path" % (scenes, BATCH)},
             "e2e": {"value": val, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    del torch
     print(json.dumps(line))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-scenes", type=int, default=2, help="scenes per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-CUDA comparator leg")
     ap.add_argument("--inflight", type=int, default=6, help="independent batches in flight (CUDA streams); 1 = sequential")
-    ap.add_argument("--fps-cluster", type=int, default=2, help="FPS cluster size while batches are pipelined (0 = the "
-                    "single-batch heuristic); measured: 5190 scenes/s with 4 CTAs per scene, 5650 with 2 (profiles/r1_notes.md)")
+    ap.add_argument("--graphs", type=int, default=1, help="1: one CUDA graph per pipeline slot (default), 0: eager launches")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="each leg repeats its K-step region until this much is timed (>= 3 repeats)")
     ap.add_argument("--pool", type=int, default=40, help="distinct input batches rotated through (40 x 4.2 MB > 126 MB L2)")
-    ap.add_argument("--profile-out", default=None, help="write the per-kernel-family table as JSON here")
+    ap.add_argument("--profile-out", default=None, help="write the line as indented JSON here as well")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -232,6 +272,7 @@ def main():
     import torch.distributed as dist
     from pointrcnn_b200 import _cabi, prof
     from pointrcnn_b200.parallel_utils import max_over_ranks
+    from pointrcnn_b200.pipeline import BatchPipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -243,54 +284,97 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W, K = max(3, args.warmup), max(1, args.steps)
+    F = max(1, args.inflight)
+    G = bool(args.graphs)
 
-    from pointrcnn_b200.pipeline import BatchPipeline
     net = build_model(dev)
+    stage = build_rpn_stage(dev, net)
     # input pool: distinct batches, together larger than the 126 MB L2, rotated through -> no step finds its input in L2
     P = max(1, args.pool)
     host_pool = [torch.from_numpy(make_scenes((rank * P + i) * BATCH, BATCH)).pin_memory() for i in range(P)]
     dev_pool = [h.to(dev) for h in host_pool]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2 (sequential pass)
-    F = max(1, args.inflight)
-    pipe = BatchPipeline(lambda x: net(x)[1], inflight=F, device=dev, fps_cluster=args.fps_cluster)
-    pipe_metric = BatchPipeline(lambda x: net(x)[1].mean(dim=(1, 2)), inflight=F, device=dev, fps_cluster=args.fps_cluster)
+    pipe = BatchPipeline(lambda x: net(x)[1], inflight=F, device=dev, graphs=G)
+    pipe_rpn = BatchPipeline(lambda x: stage(x), inflight=F, device=dev, graphs=G)
+    pipe_feat = BatchPipeline(lambda x: net(x)[1], inflight=min(F, 3), device=dev, graphs=G)
 
     def barrier():
         if world > 1:
             dist.barrier()
 
-    # clock / throttle sampling runs through every timed region; nvidia-smi is started before the warm-up because its
-    # start-up takes the driver lock for a few hundred ms (it once stalled a 70 ms timed region to 430 ms)
+    def timed(run_k, min_seconds):
+        """repeat the K-step region (barrier + sync on both sides, CUDA events, max over ranks) until min_seconds are
+        timed, at least 3 times; returns the list of ms per step"""
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        out, total, offset = [], 0.0, 0
+        while len(out) < 3 or (total < min_seconds and len(out) < 200):
+            barrier(); torch.cuda.synchronize()
+            t0.record()
+            run_k(offset)
+            t1.record()
+            torch.cuda.synchronize(); barrier()
+            ms = max_over_ranks(t0.elapsed_time(t1), device=dev)      # identical on every rank -> same repeat count
+            out.append(ms / K)
+            total += ms * 1e-3
+            offset += K
+        return out
+
+    def summary(ms_list):
+        return {"n": len(ms_list), "ms_per_step_median": statistics.median(ms_list), "ms_per_step_min": min(ms_list),
+                "ms_per_step_max": max(ms_list), "timed_seconds": sum(ms_list) * K * 1e-3}
+
+    checksum = [0.0]
+
+    def consume_rois(i, res):
+        rois, scores = res
+        checksum[0] += float(scores.numpy().sum())       # the host consumer: touches every batch's proposals
+        return None
+
     sampler = ClockSampler(local) if rank == 0 else None
     with torch.no_grad():
+        launches0 = _cabi.launch_count()
+        net(dev_pool[0])
+        torch.cuda.synchronize()
+        launches = _cabi.launch_count() - launches0                       # native kernels of one backbone forward
         for i in range(W):
             net(dev_pool[i % P])
-        pipe.run([dev_pool[i % P] for i in range(2 * F)], keep=False)
-        pipe_metric.run([host_pool[i % P] for i in range(K)], to_host=True)    # also allocates the pinned result buffers
+            stage(dev_pool[i % P])
+        pipe.run([dev_pool[i % P] for i in range(2 * F)], keep=False)       # captures the graphs
+        pipe_rpn.run([host_pool[i % P] for i in range(2 * F)], to_host=True, consume=consume_rois)
+        pipe_feat.run([host_pool[i % P] for i in range(4)], to_host=True, consume=lambda i, r: None)
         torch.cuda.synchronize()
         if sampler:
             sampler.wait_started()
             sampler.mark()
 
         # ---------------- device-resident throughput: K steps, F independent batches in flight
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = _cabi.launch_count()
-        barrier(); torch.cuda.synchronize()
-        t0.record()
-        pipe.run([dev_pool[(W + i) % P] for i in range(K)], keep=False)   # results are dropped as a consumer would
-        t1.record()
-        torch.cuda.synchronize(); barrier()
-        launches = (_cabi.launch_count() - launches0) // K
-        ms = max_over_ranks(t0.elapsed_time(t1) / K, device=dev)
+        ms_list = timed(lambda off: pipe.run([dev_pool[(off + i) % P] for i in range(K)], keep=False), args.min_seconds)
+        ms = statistics.median(ms_list)
 
-        # ---------------- end to end: pinned host input -> H2D -> backbone -> metric -> D2H, same pipeline
-        barrier(); torch.cuda.synchronize()
-        t0.record()
-        metrics = pipe_metric.run([host_pool[(W + i) % P] for i in range(K)], to_host=True)
-        t1.record()
-        torch.cuda.synchronize(); barrier()
-        ms_e2e = max_over_ranks(t0.elapsed_time(t1) / K, device=dev)
-        d2h_bytes = metrics[0].numel() * 4
+        # ---------------- end to end: pinned host input -> H2D -> backbone -> heads -> proposals -> D2H -> host consumer
+        e2e_list = timed(lambda off: pipe_rpn.run([host_pool[(off + i) % P] for i in range(K)], to_host=True, consume=consume_rois),
+                         args.min_seconds)
+        ms_e2e = statistics.median(e2e_list)
+        d2h_bytes = BATCH * 100 * 7 * 4 + BATCH * 100 * 4
+
+        # ---------------- secondary: the full feature tensor back on the host (PCIe bound)
+        feat_list = timed(lambda off: pipe_feat.run([host_pool[(off + i) % P] for i in range(K)], to_host=True,
+                                                    consume=lambda i, r: None), 0.0)
+        ms_feat = statistics.median(feat_list)
+
+        # ---------------- strong scaling: global batch 16 -> 16/world scenes per GPU per step
+        strong = None
+        if world > 1 and BATCH % world == 0:
+            bs = BATCH // world
+            Fs = min(24, F * max(1, world // 2))
+            pipe_s = BatchPipeline(lambda x: net(x)[1], inflight=Fs, device=dev, graphs=G)
+            small = [d[:bs] for d in dev_pool]
+            pipe_s.run([small[i % P] for i in range(2 * Fs)], keep=False)
+            s_list = timed(lambda off: pipe_s.run([small[(off + i) % P] for i in range(K)], keep=False), args.min_seconds)
+            ms_s = statistics.median(s_list)
+            strong = {"global_batch": BATCH, "scenes_per_gpu_per_step": bs, "batches_in_flight": Fs, "ms_per_step": ms_s,
+                      "value": BATCH / (ms_s * 1e-3), "unit": "scenes/s", "repeats": summary(s_list),
+                      "note": "same K steps, each step = 16 scenes over all GPUs; efficiency = value / (N=1 value)"}
 
         # ---------------- sequential pass (one batch at a time, L2 flushed in between): per-batch latency and the
         # per-kernel-family breakdown (CUDA events on the launching stream)
@@ -307,8 +391,48 @@ def main():
         prof.disable()
         fam = prof.collect()
         ms_seq = sum(a.elapsed_time(b_) for a, b_ in ev) / KS
-        host = host_pool[0]
     clocks = sampler.stop() if sampler else None
+
+    # ---------------- the reference's CUDA-extension build (oracle/_ref kernels + cuDNN MLP), same process, same inputs
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_ref_cuda:
+        try:
+            from oracle import refgpu
+            if not refgpu.available():
+                ref_cuda = {"unavailable": "oracle/_ref/libref_pointops.so not built"}
+            else:
+                from oracle.ref_backbone import backbone as ref_backbone
+                with torch.no_grad():
+                    for i in range(3):
+                        ref_backbone(net, dev_pool[i % P])
+                    torch.cuda.synchronize()
+                    KR = 5
+                    evr = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KR)]
+                    for i, (a, b_) in enumerate(evr):
+                        flush.fill_(1.0)
+                        a.record()
+                        ref_backbone(net, dev_pool[i % P])
+                        b_.record()
+                    torch.cuda.synchronize()
+                    ms_ref_single = sum(a.elapsed_time(b_) for a, b_ in evr) / KR
+                    pipe_ref = BatchPipeline(lambda x: ref_backbone(net, x)[1], inflight=F, device=dev, graphs=False)
+                    pipe_ref.run([dev_pool[i % P] for i in range(F)], keep=False)
+                    torch.cuda.synchronize()
+                    KP = 2 * F
+                    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    pipe_ref.run([dev_pool[i % P] for i in range(KP)], keep=False)
+                    b_.record()
+                    torch.cuda.synchronize()
+                    ms_ref_pipe = a.elapsed_time(b_) / KP
+                ref_cuda = {"impl": "reference CUDA kernels (oracle/_ref, unmodified sources rebuilt for sm_100a) + torch cuDNN/cuBLAS MLP, "
+                                    "reference call order (pointnet2_modules.py:19-55,127-156)",
+                            "single_stream": {"ms_per_step": ms_ref_single, "value": BATCH / (ms_ref_single * 1e-3), "steps": KR},
+                            "pipelined": {"ms_per_step": ms_ref_pipe, "value": BATCH / (ms_ref_pipe * 1e-3), "steps": KP,
+                                          "batches_in_flight": F, "graphs": False},
+                            "unit": "scenes/s", "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32)}
+        except Exception as e:      # the comparator must never take the bench line down
+            ref_cuda = {"unavailable": "%s: %s" % (type(e).__name__, e)}
 
     if world > 1:
         dist.destroy_process_group()
@@ -319,32 +443,35 @@ def main():
     sa_flops, fp_flops = mlp_flops_per_scene(net)
     tf32_peak = pk["bf16"] / 2.0          # tcgen05 kind::tf32 runs at half the bf16 rate; bf16 figure is the measured one
     fam_ms = {k: v[0] / KS for k, v in fam.items()}
+    traffic = ncu_traffic()
     kernels = []
     if "sa_mlp" in fam_ms:
-        kernels.append({"name": "mlp_chain_kernel (SA: gather + SharedMLP + max-pool)", "ms_per_step": fam_ms["sa_mlp"],
+        kernels.append({"name": "mlp_chain kernels (SA: gather + SharedMLP + max-pool)", "family": "sa_mlp", "ms_per_step": fam_ms["sa_mlp"],
                         "bound": "tensor", "achieved": sa_flops * BATCH / (fam_ms["sa_mlp"] * 1e-3) / 1e12, "peak": tf32_peak,
                         "unit": "TFLOP/s"})
     if "fp_mlp" in fam_ms:
-        kernels.append({"name": "mlp_chain_kernel (FP: interpolate + SharedMLP)", "ms_per_step": fam_ms["fp_mlp"],
+        kernels.append({"name": "mlp_chain kernels (FP: interpolate + SharedMLP)", "family": "fp_mlp", "ms_per_step": fam_ms["fp_mlp"],
                         "bound": "tensor", "achieved": fp_flops * BATCH / (fam_ms["fp_mlp"] * 1e-3) / 1e12, "peak": tf32_peak,
                         "unit": "TFLOP/s"})
     if "fps" in fam_ms:
         rounds = sum(m.npoint - 1 for m in net.SA_modules)
         npts = [POINTS] + [m.npoint for m in net.SA_modules]
         fps_bytes = sum(npts[i] * 12 + npts[i + 1] * 16 for i in range(len(net.SA_modules))) * BATCH
-        kernels.append({"name": "fps_pruned_kernel + fps_rank_kernel (dependency chain: %d serial rounds/scene)" % rounds, "ms_per_step": fam_ms["fps"],
-                        "bound": "hbm", "achieved": fps_bytes / (fam_ms["fps"] * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                        "us_per_round": fam_ms["fps"] * 1e3 / rounds})
+        kernels.append({"name": "fps_pruned_kernel + fps_rank_kernel (dependency chain: %d serial rounds/scene)" % rounds, "family": "fps",
+                        "ms_per_step": fam_ms["fps"], "bound": "hbm", "achieved": fps_bytes / (fam_ms["fps"] * 1e-3) / 1e9,
+                        "peak": pk["hbm"], "unit": "GB/s", "us_per_round": fam_ms["fps"] * 1e3 / rounds})
     for name in ("ball_query", "three_nn", "transpose"):
         if name in fam_ms:
-            kernels.append({"name": name, "ms_per_step": fam_ms[name]})
-    for name in sorted(fam_ms):                      # PRB_PROF_DETAIL=1: one line per chain launch shape
+            kernels.append({"name": name, "family": name, "ms_per_step": fam_ms[name]})
+    for name in sorted(fam_ms):                      # prof_detail: one line per chain launch shape
         if name.startswith(("sa_mlp ", "fp_mlp ")):
             kernels.append({"name": name, "ms_per_step": fam_ms[name]})
     for k in kernels:
         if "achieved" in k:
             k["frac"] = k["achieved"] / k["peak"]
         k["share"] = k["ms_per_step"] / ms_seq     # share of the sequential (single batch) step
+        if k.get("family") in traffic:
+            k["traffic"] = traffic[k["family"]]
     # Dominant kernel of the PIPELINED step = largest share of SM-time: a chain launch fills the GPU, while the
     # sampling kernels hold one CTA per scene (16 of the SMs) for their duration.
     n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -355,10 +482,14 @@ def main():
     dom = max((k for k in kernels if "achieved" in k), key=lambda k: k["sm_time_ms"], default=None)
     roofline = None
     if dom:
-        # dram traffic of this family per step from the committed ncu --set full captures (profiles/r1_notes.md), or null
         roofline = {"kernel": dom["name"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
-                    "frac": dom["frac"], "traffic": None, "peak_source": pk["src"] + (" bf16/2" if dom["bound"] == "tensor" else " copy"),
-                    "share_of_step": dom["share"], "share_of_sm_time": dom["sm_time_ms"] / sum(k.get("sm_time_ms", k["ms_per_step"]) for k in kernels if not k["name"].startswith(("sa_mlp ", "fp_mlp ")))}
+                    "frac": dom["frac"], "traffic": dom.get("traffic"),
+                    "traffic_source": traffic.get("_source") if dom.get("traffic") is not None else None,
+                    "algorithmic_flops_per_step": (sa_flops if dom.get("family") == "sa_mlp" else fp_flops) * BATCH if dom["bound"] == "tensor" else None,
+                    "peak_source": pk["src"] + (" bf16/2" if dom["bound"] == "tensor" else " copy"),
+                    "share_of_step": dom["share"],
+                    "share_of_sm_time": dom["sm_time_ms"] / sum(k.get("sm_time_ms", k["ms_per_step"]) for k in kernels if "family" in k),
+                    "timing": "CUDA events around the family's launches, sequential pass with L2 flush (single_batch), %d steps" % KS}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -368,18 +499,32 @@ def main():
                "sample": "%d scenes of the same workload, %.1f s (oracle C/OpenMP ops + numpy fp32 MLP)" % (args.cpu_scenes, cdt)}
 
     scenes = BATCH * world
-    line = {"metric": "scenes/sec RPN backbone fwd (16384 pts)", "value": scenes / (ms * 1e-3), "unit": "scenes/s", "n_gpus": world,
+    value = scenes / (ms * 1e-3)
+    single_val = BATCH / (ms_seq * 1e-3)
+    vs_ref = None
+    if ref_cuda and "pipelined" in ref_cuda:
+        vs_ref = {"pipelined": value / ref_cuda["pipelined"]["value"], "single_stream": single_val / ref_cuda["single_stream"]["value"],
+                  "note": "pipelined: both sides with %d batches in flight; single_stream: one batch at a time, L2 flushed" % F}
+    line = {"metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (tf32 tensor-core MLP, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": "RPN PointNet++ backbone fwd: 4 SA-MSG + 4 FP (tools/cfgs/default.yaml), 16384x4 uniform KITTI-scope "
-                                   "points, eval-mode BN (BASELINE configs[1])", "batch_per_gpu": BATCH, "global_batch": scenes,
-                       "parallelism": "dp%d (scene sharding, no data-path collective)" % world,
-                       "batches_in_flight": F, "fps_cluster_while_pipelined": args.fps_cluster, "l2": "inputs rotate through %d distinct batches (%.0f MB > 126 MB L2)" % (P, P * BATCH * POINTS * CHANNELS * 4 / 1e6)},
-            "single_batch": {"ms_per_step": ms_seq, "value": BATCH / (ms_seq * 1e-3), "unit": "scenes/s",
-                             "note": "one batch at a time on one stream, 256 MB L2 flush write between steps"},
+            "config": workload_config(world),
+            "pipeline": {"batches_in_flight": F, "cuda_graphs": G,
+                         "l2": "inputs rotate through %d distinct batches (%.0f MB > 126 MB L2)" % (P, P * BATCH * POINTS * CHANNELS * 4 / 1e6)},
+            "repeats": summary(ms_list),
+            "single_batch": {"ms_per_step": ms_seq, "value": single_val, "unit": "scenes/s",
+                             "note": "one batch at a time on one stream (eager launches), 256 MB L2 flush write between steps"},
             "e2e": {"value": scenes / (ms_e2e * 1e-3), "unit": "scenes/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": d2h_bytes},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
+                    "h2d_bytes_per_step": host_pool[0].numel() * 4, "d2h_bytes_per_step": d2h_bytes,
+                    "what": "RPN stage: pinned host points -> H2D -> backbone -> fused cls/reg heads -> proposal layer (TEST: 9000 pre-NMS, "
+                            "100 post-NMS, thr 0.8) -> D2H of rois (B,100,7) + scores (B,100) -> host consumer per batch",
+                    "repeats": summary(e2e_list), "consumer_checksum": checksum[0]},
+            "e2e_features": {"value": scenes / (ms_feat * 1e-3), "unit": "scenes/s", "ms_per_step": ms_feat,
+                             "h2d_bytes_per_step": host_pool[0].numel() * 4, "d2h_bytes_per_step": BATCH * 128 * POINTS * 4,
+                             "what": "backbone only, full (B,128,16384) features copied to pinned host memory every step (PCIe bound)",
+                             "repeats": summary(feat_list)},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+            "ref_cuda": ref_cuda, "vs_ref_cuda": vs_ref, "strong_scaling": strong}
     if args.profile_out:
         json.dump(line, open(args.profile_out, "w"), indent=1)
     print(json.dumps(line))

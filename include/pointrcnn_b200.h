@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PRB_ABI_VERSION 2   /* 2: prb_mlp_desc.flags, out_pm arguments, workspace-taking FPS */
+#define PRB_ABI_VERSION 3   /* 3: prb_options (per-thread tuning block; no per-call environment reads) */
 #if defined(__GNUC__)
 #define PRB_API __attribute__((visibility("default")))
 #else
@@ -40,6 +40,30 @@ PRB_API int prb_abi_version(void);
 PRB_API const char *prb_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 PRB_API unsigned long long prb_launch_count(void);
+
+/* Per-thread tuning block.  Every heuristic the kernels' launchers apply can be overridden here; 0 / the value
+ * prb_options_init() fills in means "library default".  The block is THREAD-LOCAL (each nn.DataParallel worker
+ * thread owns one), nothing is process-global, and no entry point reads the environment per call: PRB_*
+ * environment variables only seed the values prb_options_init() returns, once, when first used. */
+typedef struct prb_options {
+    int fps_cluster;   /* CTAs per scene of the cluster FPS kernel (1,2,4,8); 0 = heuristic */
+    int fps_prune;     /* 0: never use the pruned single-CTA kernel; 1: for 4097..16384 points; 2: also 2049..4096 */
+    int fps_threads;   /* threads per CTA of the rank kernel; 0 = heuristic */
+    int fps_generic;   /* 1: force the generic (reference-shaped) kernel */
+    int mlp_gather;    /* layer-0 row gather of the chain kernel: 0 registers (+tf32 rounding), 1 cp.async.cg, 2 cp.async.ca */
+    int mlp_ng;        /* row groups per CTA (legacy kernel); 0 = heuristic */
+    int mlp_occ;       /* cap on CTAs per SM; 0 = none */
+    int mlp_sms;       /* size the persistent grid for this many SMs; 0 = all */
+    int mlp_atmem;     /* 1: layers >= 1 take their A operand from tensor memory (legacy kernel) */
+    int mlp_sleepy;    /* bit 0: MMA issuer waits with a suspend hint, bit 1: weight producer does */
+    int mlp_trace;     /* 1: record the phase trace read by prb_debug_mlp_trace */
+    int mlp_pipeline;  /* 1: role-specialised pipelined chain kernel (gather of tile i+1 overlaps tile i); 0: legacy */
+    int grid_debug;    /* 1: print (and synchronise for) the 3-NN grid's fallback counts */
+    float nn_cell;     /* 3-NN grid cell edge in units of the mean point spacing (default 1.6) */
+} prb_options;
+PRB_API void prb_options_init(prb_options *o);                 /* library defaults */
+PRB_API int prb_set_thread_options(const prb_options *o);      /* NULL: back to the defaults */
+PRB_API void prb_get_thread_options(prb_options *o);
 
 /* ------------------------------------------------------------------ pointnet2_cuda ------
  * replaces pointnet2_lib/pointnet2/src/pointnet2_api.cpp:10-23 */

@@ -2,6 +2,7 @@
 
 There is deliberately no fallback: if the library is missing or a call fails, a RuntimeError is raised.
 """
+import contextlib
 import ctypes
 import os
 
@@ -20,6 +21,31 @@ class MlpDesc(ctypes.Structure):
                 ("packed_w", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("flags", c_int)]
 
 
+class Options(ctypes.Structure):
+    """struct prb_options (per-thread tuning block)"""
+    _fields_ = [(k, c_int) for k in ("fps_cluster", "fps_prune", "fps_threads", "fps_generic", "mlp_gather", "mlp_ng", "mlp_occ",
+                                     "mlp_sms", "mlp_atmem", "mlp_sleepy", "mlp_trace", "mlp_pipeline", "grid_debug")] + [("nn_cell", c_float)]
+
+
+@contextlib.contextmanager
+def options(**kw):
+    """with options(fps_cluster=2, mlp_gather=1): ...  -- overrides fields of THIS thread's prb_options for the block.
+    Thread-local inside the library (prb_set_thread_options): safe under nn.DataParallel worker threads."""
+    L = lib()
+    old, new = Options(), Options()
+    L.prb_get_thread_options(ctypes.byref(old))
+    L.prb_get_thread_options(ctypes.byref(new))
+    for k, v in kw.items():
+        if not hasattr(new, k):
+            raise TypeError("prb_options has no field %r" % k)
+        setattr(new, k, v)
+    L.prb_set_thread_options(ctypes.byref(new))
+    try:
+        yield new
+    finally:
+        L.prb_set_thread_options(ctypes.byref(old))
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -34,7 +60,9 @@ def lib():
                      "prb_sa_workspace_bytes", "prb_fp_workspace_bytes", "prb_rows_workspace_bytes", "prb_grid_workspace_bytes",
                      "prb_fps_workspace_bytes", "prb_rpn_proposals_workspace_bytes"):
             getattr(L, name).restype = c_size_t
-        if L.prb_abi_version() != 2:
+        L.prb_options_init.restype = None
+        L.prb_get_thread_options.restype = None
+        if L.prb_abi_version() != 3:
             raise RuntimeError("pointrcnn_b200: ABI version mismatch")
         _lib = L
     return _lib

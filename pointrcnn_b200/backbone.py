@@ -72,11 +72,11 @@ class Pointnet2MSG(nn.Module):
     # follow it level by level: the FPS of level k+1 and all neighbour searches overlap the MLP of level k.
     # Same kernels, same results as the level-by-level loop.
     def _plannable(self, xyz, features):
-        import os
+        from . import config
         # opt-in: measured on B200 (profiles/r1_notes.md) the side-stream plan does not pay at batch 16 -- every
         # kernel except the small FPS levels already fills the GPU, and the persistent MLP CTAs queue behind the
         # neighbour-search CTAs they share SMs with (7.66 ms planned vs 6.95 ms level-by-level).
-        if os.environ.get("PRB_ENABLE_PLAN", "0") != "1" or not xyz.is_cuda:
+        if not config.get("enable_plan") or not xyz.is_cuda:
             return False
         if not all(m._can_fuse(xyz, features, None) for m in self.SA_modules):
             return False

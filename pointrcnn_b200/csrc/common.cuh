@@ -52,6 +52,11 @@ __device__ __forceinline__ float dist2_ref(float dx, float dy, float dz) {
     return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
-int num_sms();
+int num_sms();   // SM count of the CURRENT device (cached per device)
+
+// per-thread tuning block (include/pointrcnn_b200.h: prb_options).  Environment variables seed the DEFAULTS once,
+// when the library is loaded; no entry point reads the environment per call, and a thread (e.g. a DataParallel
+// worker) that sets its own options never disturbs another.
+const prb_options &opts();
 
 }  // namespace prb

@@ -590,18 +590,13 @@ __global__ void __launch_bounds__(512, 1) fps_pruned_kernel(const FpsParams p, c
 }
 #undef PRB_FPS_SLOT
 
-static int env_int(const char *name, int dflt) {
-    const char *v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
-
 }  // namespace prb
 
 using namespace prb;
 
 // pruned path: slots per lane for n points (0 = not applicable)
 static int pruned_slots(int n) {
-    const int mode = env_int("PRB_FPS_PRUNE", 1);   // 0 off, 1 n > 4096, 2 n > 2048
+    const int mode = opts().fps_prune;   // 0 off, 1 n > 4096, 2 n > 2048
     if (mode == 0 || n > 16384) return 0;
     if (n > 8192) return 32;
     if (n > 4096) return 16;
@@ -615,7 +610,7 @@ static int launch_pruned(const FpsParams &p, const FpsSorted &s, cudaStream_t st
     if (smem + 1024 > 48 * 1024)
         PRB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fps_sort_kernel<<<p.b, 1024, 0, st>>>(p, s);
-    if (check_launch("fps_sort_kernel")) return -1;
+    if (int rc = check_launch("fps_sort_kernel")) return rc;
     fps_pruned_kernel<NS><<<p.b, 512, smem, st>>>(p, s);
     return check_launch("fps_pruned_kernel");
 }
@@ -663,7 +658,7 @@ extern "C" int prb_furthest_point_sampling_ws(int b, int n, int m, const float *
     // A cluster of CS CTAs per scene cuts the per-round compute CS-fold; each CTA mirrors only its own slice of the
     // scene in shared memory (<= 48 KB).  Measured (profiles/r1_fps_sweep.json, n=16384, m=4096, ns per round):
     // b=2: CS=8 538, CS=4 614, CS=2 803;  b=16: CS=8 691 (CTAs start sharing SMs), CS=4 617;  b=32: CS=4 617.
-    int cs = env_int("PRB_FPS_CS", 0);
+    int cs = opts().fps_cluster;
     if (cs != 0 && n_pad < 4096) cs = 1;       // the override is meant for the big levels only
     if (cs == 0) {
         cs = 1;
@@ -675,7 +670,7 @@ extern "C" int prb_furthest_point_sampling_ws(int b, int n, int m, const float *
     while (cs < 8 && ceil_div(n_pad, cs) > 8192) cs <<= 1;  // keep the register-resident path
     while (cs > 1 && (n_pad % (cs * 128)) != 0) cs >>= 1;
     int P = ceil_div(n_pad, cs);
-    int threads = env_int("PRB_FPS_THREADS", 0);
+    int threads = opts().fps_threads;
     if (threads == 0) {
         threads = 128;
         while (threads < 512 && threads * 4 < P) threads <<= 1;
@@ -683,7 +678,7 @@ extern "C" int prb_furthest_point_sampling_ws(int b, int n, int m, const float *
     }
     int ppt = 1;
     while (threads * ppt < P) ppt <<= 1;
-    bool generic = (ppt > 16) || (threads == 1024 && ppt > 8) || env_int("PRB_FPS_GENERIC", 0);
+    bool generic = (ppt > 16) || (threads == 1024 && ppt > 8) || opts().fps_generic;
     // round (threads, ppt) to an instantiated pair
     if (!generic) {
         if (threads == 128 && ppt > 4) { threads = 256; ppt = ppt / 2; }

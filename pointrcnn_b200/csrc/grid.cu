@@ -483,8 +483,7 @@ PRB_API int prb_three_nn_grid(int b, int n, int m, const float *unknown, const f
     // cell edge = factor * mean point spacing.  A query is certified only if its third neighbour is closer than one
     // cell, everything else falls back to the exhaustive scan; the centre-out walk skips cells beyond the current
     // third distance.  Measured on the RPN backbone (profiles/r1_notes.md): 1.3 -> 0.285 ms, 1.6 -> 0.272, 2.0 -> 0.288.
-    double factor = 1.6;
-    if (const char *e = getenv("PRB_NN_CELL")) { double v = atof(e); if (v > 0.2 && v < 50.0) factor = v; }
+    double factor = opts().nn_cell > 0.2f && opts().nn_cell < 50.f ? (double)opts().nn_cell : 1.6;
     grid_cell_from_bbox_kernel<<<b, 256, 0, st>>>(m, known, factor, w.inv_h, w.h);
     if (int rc = check_launch("grid_cell_from_bbox_kernel")) return rc;
     grid_insert_kernel<<<dim3(ceil_div(m, 256), b), 256, 0, st>>>(m, w.table, known, w.inv_h, w.heads, w.nodes);
@@ -496,7 +495,7 @@ PRB_API int prb_three_nn_grid(int b, int n, int m, const float *unknown, const f
     if (int rc = check_launch("three_nn_grid_kernel")) return rc;
     three_nn_overflow_kernel<<<4 * num_sms(), GR_THREADS, 0, st>>>(p);
     if (int rc = check_launch("three_nn_overflow_kernel")) return rc;
-    if (getenv("PRB_GRID_DEBUG")) {   // diagnostics only: synchronises
+    if (opts().grid_debug) {   // diagnostics only: synchronises
         int cnt = 0;
         PRB_CUDA(cudaMemcpyAsync(&cnt, w.overflow, 4, cudaMemcpyDeviceToHost, st));
         PRB_CUDA(cudaStreamSynchronize(st));

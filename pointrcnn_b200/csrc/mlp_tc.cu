@@ -1009,16 +1009,15 @@ namespace prb {
 
 // launch one fused segment of the chain: size rings / TMEM to the segment, pick the CTAs-per-SM it allows
 static int launch_chain(ChainParams &p, cudaStream_t st) {
-    static int max_optin = 0;
-    if (!max_optin) {
+    int max_optin = 0;
+    {
         int dev = 0;
         PRB_CUDA(cudaGetDevice(&dev));
         PRB_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     }
     p.num_tiles = (int)((p.total_rows + TM - 1) / TM);
     if (p.num_tiles == 0) return 0;
-    p.gather_mode = 0;   // measured (profiles/r1_notes.md): register gather 1.53 ms, cp.async.cg 1.66, cp.async.ca 1.67 per batch of SA chains
-    if (const char *e = getenv("PRB_MLP_GATHER")) p.gather_mode = atoi(e);
+    p.gather_mode = opts().mlp_gather;   // default 0; measured (profiles/r1_notes.md): register gather 1.53 ms, cp.async.cg 1.66, cp.async.ca 1.67 per batch of SA chains
     const int L = p.num_layers;
     int np_total = 0, np_max = 0;
     for (int l = 0; l < L; ++l) { np_total += p.np[l]; np_max = p.np[l] > np_max ? p.np[l] : np_max; }
@@ -1036,8 +1035,7 @@ static int launch_chain(ChainParams &p, cudaStream_t st) {
     // shared memory allow several CTAs per SM -- NG=1 with 2 or 3 independent CTAs (the 3-CTA build is capped at 112
     // registers per thread).
     const int sm_smem = 227 * 1024;
-    int ng = 0;
-    if (const char *e = getenv("PRB_MLP_NG")) ng = atoi(e);
+    int ng = opts().mlp_ng;
     const bool ng_forced = ng != 0;
     int occ = 1;
     if (ng == 0) ng = (cols <= 256) ? 1 : 2;
@@ -1046,7 +1044,7 @@ static int launch_chain(ChainParams &p, cudaStream_t st) {
     // profiles/r1_notes.md: FP0 0.201 -> 0.165 ms, SA2 0.311 -> 0.295); the 3-CTA build stays best below 128 columns
     if (!ng_forced && ng == 1 && occ == 2) ng = 2;
     if (ng == 2) occ = 512 / cols >= 2 ? 2 : 1;
-    if (const char *e = getenv("PRB_MLP_OCC")) { int o = atoi(e); if (o >= 1 && o < occ) occ = o; }
+    if (const int o = opts().mlp_occ; o >= 1 && o < occ) occ = o;
     size_t smem = 0;
     for (;; --occ) {
         int depth = occ >= 2 ? 3 : 4;
@@ -1061,7 +1059,7 @@ static int launch_chain(ChainParams &p, cudaStream_t st) {
     // kernel's duration.  When other streams hold SMs (BatchPipeline: the single-CTA-per-scene FPS of the next
     // batches), PRB_MLP_SMS sizes the grid for the SMs that are actually free.
     int sms = num_sms();
-    if (const char *e = getenv("PRB_MLP_SMS")) { int v = atoi(e); if (v >= 1 && v < sms) sms = v; }
+    if (const int v = opts().mlp_sms; v >= 1 && v < sms) sms = v;
     int grid = sms * occ;
     if (grid > p.num_tiles) grid = p.num_tiles;
 #define PRB_LAUNCH_CHAIN(NGV, MB)                                                                                              \
@@ -1130,11 +1128,9 @@ static int run_chain(const ChainIO &io, const prb_mlp_desc *mlp, void *workspace
         ChainParams p = io.base;
         p.unit_scale = mlp->scale ? 0 : 1;
         p.linear_last = (l1 == L && (mlp->flags & 1)) ? 1 : 0;
-        p.trace = getenv("PRB_MLP_TRACE") ? 1 : 0;
-        p.a_tmem = 1;   // measured (profiles/r1_notes.md): SA chains 1.124 -> 1.088 ms per batch; PRB_MLP_ATMEM=0 = shared-memory stages
-        if (const char *e = getenv("PRB_MLP_ATMEM")) p.a_tmem = atoi(e) ? 1 : 0;
-        p.sleepy = 3;
-        if (const char *e = getenv("PRB_MLP_SLEEPY")) p.sleepy = atoi(e);
+        p.trace = opts().mlp_trace ? 1 : 0;
+        p.a_tmem = opts().mlp_atmem ? 1 : 0;   // default 1; measured (profiles/r1_notes.md): SA chains 1.124 -> 1.088 ms per batch; 0 = shared-memory stages
+        p.sleepy = opts().mlp_sleepy;
         p.total_rows = io.rows;
         p.num_layers = l1 - l0;
         for (int l = l0; l < l1; ++l) {

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -18,16 +19,56 @@ void set_error(const char *fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 int num_sms() {
-    static int sms = 0;
+    static std::atomic<int> cache[64];   // per device ordinal; 0 = not queried yet
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;  // B200
+    int sms = cache[dev].load(std::memory_order_relaxed);
     if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-            sms = 148;  // B200
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        cache[dev].store(sms, std::memory_order_relaxed);
     }
     return sms;
 }
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+// process defaults: built-in values, overridden ONCE (first use) by PRB_* environment variables for experiment scripts
+static prb_options make_defaults() {
+    prb_options o;
+    o.fps_cluster = env_int("PRB_FPS_CS", 0);
+    o.fps_prune = env_int("PRB_FPS_PRUNE", 1);
+    o.fps_threads = env_int("PRB_FPS_THREADS", 0);
+    o.fps_generic = env_int("PRB_FPS_GENERIC", 0);
+    o.mlp_gather = env_int("PRB_MLP_GATHER", 0);
+    o.mlp_ng = env_int("PRB_MLP_NG", 0);
+    o.mlp_occ = env_int("PRB_MLP_OCC", 0);
+    o.mlp_sms = env_int("PRB_MLP_SMS", 0);
+    o.mlp_atmem = env_int("PRB_MLP_ATMEM", 1);
+    o.mlp_sleepy = env_int("PRB_MLP_SLEEPY", 3);
+    o.mlp_trace = env_int("PRB_MLP_TRACE", 0);
+    o.mlp_pipeline = env_int("PRB_MLP_PIPELINE", 1);
+    o.grid_debug = env_int("PRB_GRID_DEBUG", 0);
+    o.nn_cell = 1.6f;
+    if (const char *e = getenv("PRB_NN_CELL")) { float v = (float)atof(e); if (v > 0.2f && v < 50.f) o.nn_cell = v; }
+    return o;
+}
+static const prb_options &defaults() {
+    static const prb_options d = make_defaults();
+    return d;
+}
+static thread_local prb_options t_opts;
+static thread_local bool t_opts_set = false;
+const prb_options &opts() { return t_opts_set ? t_opts : defaults(); }
 }  // namespace prb
+
+extern "C" void prb_options_init(prb_options *o) { if (o) *o = prb::defaults(); }
+extern "C" int prb_set_thread_options(const prb_options *o) {
+    if (o) { prb::t_opts = *o; prb::t_opts_set = true; } else prb::t_opts_set = false;
+    return 0;
+}
+extern "C" void prb_get_thread_options(prb_options *o) { if (o) *o = prb::opts(); }
 
 extern "C" int prb_abi_version(void) { return PRB_ABI_VERSION; }
 extern "C" const char *prb_last_error(void) { return prb::g_err; }

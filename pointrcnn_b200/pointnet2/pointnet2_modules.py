@@ -9,10 +9,9 @@ Two execution paths per module, chosen per call:
            three_nn(+weights) -> ONE kernel that interpolates, concatenates the skip features and runs the MLP.
   unfused  (training / anything else): the reference's op-by-op sequence on the B200 natives with
            torch.nn convolutions, full autograd support.
-Set PRB_DISABLE_FUSED=1 to force the unfused path (used by tests to cross-check the two).
+`config.override(disable_fused=True)` forces the unfused path (used by tests to cross-check the two).
 """
 import ctypes
-import os
 from typing import List
 
 import numpy as np
@@ -21,6 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _cabi as C
+from .. import config
 from .. import prof
 from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
@@ -126,12 +126,12 @@ def _point_major(t):
 
 
 def _fold_scale():
-    """PRB_MLP_FOLD=0 keeps the BN scale as a separate epilogue multiply (y = relu(s * (W x) + t))"""
-    return os.environ.get("PRB_MLP_FOLD", "1") != "0"
+    """config.fold_scale=False keeps the BN scale as a separate epilogue multiply (y = relu(s * (W x) + t))"""
+    return config.get("fold_scale")
 
 
 def _fused_enabled():
-    return os.environ.get("PRB_DISABLE_FUSED", "0") != "1"
+    return not config.get("disable_fused")
 
 
 def _needs_graph(module, *tensors):

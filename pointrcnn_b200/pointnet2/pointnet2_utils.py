@@ -13,6 +13,7 @@ import torch.nn as nn
 from torch.autograd import Function
 
 from .. import _cabi as C
+from .. import config
 from .. import prof
 from ..ext import pointnet2_cuda as pointnet2
 
@@ -22,14 +23,13 @@ def _cuda_empty(shape, dtype, like):
 
 
 # Neighbour searches go through the hash grid (csrc/grid.cu) when the searched set is large enough to pay for the
-# build; results are identical to the brute-force kernels either way.  PRB_DISABLE_GRID=1 forces brute force.
+# build; results are identical to the brute-force kernels either way.  config.override(disable_grid=True) forces brute force.
 GRID_MIN_POINTS_BQ = 2048
 GRID_MIN_POINTS_NN = 512
 
 
 def _use_grid(n_points, threshold):
-    import os
-    return n_points >= threshold and os.environ.get("PRB_DISABLE_GRID", "0") != "1"
+    return n_points >= threshold and not config.get("disable_grid")
 
 
 def _ball_query_native(B, N, npoint, radii, nsamples, new_xyz, xyz, idxs):

@@ -7,10 +7,9 @@ import contextlib
 
 import torch
 
-import os
+from . import config
 
 _on = False
-_detail = os.environ.get("PRB_PROF_DETAIL", "0") == "1"
 _events = []
 
 
@@ -27,8 +26,8 @@ def disable():
 
 @contextlib.contextmanager
 def region(name, detail=None):
-    """detail: optional shape string; with PRB_PROF_DETAIL=1 it is appended to the family name"""
-    if _on and detail is not None and _detail:
+    """detail: optional shape string; with config prof_detail it is appended to the family name"""
+    if _on and detail is not None and config.get("prof_detail"):
         with region("%s %s" % (name, detail)):   # the detailed line nests inside the family line
             with region(name):
                 yield

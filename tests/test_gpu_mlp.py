@@ -52,10 +52,13 @@ def tf32_trunc(x):
 
 def mlp_tf32_ref(x, layers):
     """weights are rounded at pack time (host, ties away), every A operand built in registers with cvt.rn (ties even).  With the
-    optional cp.async gather (PRB_MLP_GATHER=1/2) layer-0 rows of 16-byte aligned pitch reach the tensor core unrounded
-    and are truncated there."""
-    import os
-    async_gather = os.environ.get("PRB_MLP_GATHER", "0") in ("1", "2")
+    optional cp.async gather (prb_options.mlp_gather = 1/2) layer-0 rows of 16-byte aligned pitch reach the tensor core
+    unrounded and are truncated there."""
+    import ctypes
+    from pointrcnn_b200 import _cabi
+    o = _cabi.Options()
+    _cabi.lib().prb_get_thread_options(ctypes.byref(o))
+    async_gather = o.mlp_gather in (1, 2)
     h = x.astype(np.float32)
     for li, (W, sc, sh) in enumerate(layers):
         a = tf32_trunc(h) if (async_gather and li == 0 and x.shape[1] % 4 == 0) else tf32_rn(h)
@@ -174,15 +177,15 @@ def _folded(mlp):
 
 
 def _unfused(fn):
-    import os
-    os.environ["PRB_DISABLE_FUSED"] = "1"
-    old = torch.backends.cudnn.allow_tf32
+    from pointrcnn_b200 import config
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     try:
-        return fn()
+        with config.override(disable_fused=True):
+            return fn()
     finally:
-        os.environ["PRB_DISABLE_FUSED"] = "0"
-        torch.backends.cudnn.allow_tf32 = old
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
 SA_CASES = [
@@ -230,9 +233,9 @@ def test_sa_module_fused_vs_unfused_vs_oracle(cuda, npoint, radii, nsamples, mlp
 
 @pytest.mark.parametrize("ns", [8, 16, 32, 64])
 def test_sa_module_scale_fold_modes_agree(cuda, ns):
-    """PRB_MLP_FOLD=1 (default: BN scale inside the weights, raw accumulators pooled, shift/ReLU after the max) against
-    PRB_MLP_FOLD=0 (scale as an epilogue multiply); negative BN scales included -- max_s relu(x_s + t) = relu(max_s x_s + t)"""
-    import os
+    """fold_scale=True (default: BN scale inside the weights, raw accumulators pooled, shift/ReLU after the max) against
+    fold_scale=False (scale as an epilogue multiply); negative BN scales included -- max_s relu(x_s + t) = relu(max_s x_s + t)"""
+    from pointrcnn_b200 import config
     torch.manual_seed(7)
     mod = pm.PointnetSAModuleMSG(npoint=200, radii=[0.25], nsamples=[ns], mlps=[[24, 64, 48, 96]], bn=True).to(cuda).eval()
     _randomise_bn(mod, 11)
@@ -243,14 +246,9 @@ def test_sa_module_scale_fold_modes_agree(cuda, ns):
     x = torch.from_numpy(synth.u_cube(2, 3000, 77)).to(cuda)
     f = torch.randn(2, 24, 3000, device=cuda)
     outs = {}
-    old = os.environ.get("PRB_MLP_FOLD")
-    try:
-        for mode in ("0", "1"):
-            os.environ["PRB_MLP_FOLD"] = mode
-            with torch.no_grad():
-                outs[mode] = mod(x, f)[1]
-    finally:
-        os.environ.pop("PRB_MLP_FOLD", None) if old is None else os.environ.__setitem__("PRB_MLP_FOLD", old)
+    for mode in ("0", "1"):
+        with torch.no_grad(), config.override(fold_scale=(mode == "1")):
+            outs[mode] = mod(x, f)[1]
     with torch.no_grad():
         ref = _unfused(lambda: mod(x, f))[1]
     scale = ref.abs().max().item()
@@ -362,3 +360,24 @@ def test_batch_pipeline_matches_sequential(cuda):
         for w, r in zip(want, res):
             assert not r.is_cuda and torch.allclose(r, w.mean(dim=(1, 2)).cpu(), rtol=1e-6, atol=1e-7)
         assert pipe.run(batches, keep=False) == [None] * 5
+        # results of an earlier run() stay valid after a later one (slot buffers are never handed out)
+        res2 = pipe2.run(host[::-1], to_host=True)
+        for w, r in zip(want, res):
+            assert torch.allclose(r, w.mean(dim=(1, 2)).cpu(), rtol=1e-6, atol=1e-7)
+        assert len(res2) == 5
+        # streaming consumer: called once per batch, in order of completion per slot, before the slot is reused
+        seen = []
+        out = pipe2.run(host, to_host=True, consume=lambda i, r: seen.append((i, r.clone())) or i)
+        assert out == list(range(5)) and sorted(i for i, _ in seen) == list(range(5))
+        for i, r in seen:
+            assert torch.allclose(r, want[i].mean(dim=(1, 2)).cpu(), rtol=1e-6, atol=1e-7)
+        # CUDA-graph replay per slot: same bits as the eager launches
+        pipe3 = BatchPipeline(lambda x: net(x)[1], inflight=2, device=cuda, graphs=True)
+        for rep in range(2):
+            got3 = pipe3.run(batches)
+            torch.cuda.synchronize()
+            for w, g in zip(want, got3):
+                assert torch.equal(w, g)
+        res3 = pipe3.run(host, to_host=True)
+        for w, r in zip(want, res3):
+            assert torch.equal(r, w.cpu())

@@ -70,20 +70,35 @@ def test_fps_index_exact(cuda, B, N, M, kind):
         assert np.array_equal(ref_temp.cpu().numpy(), want_temp), "oracle temp != reference temp"
 
 
-@pytest.mark.parametrize("env", [{"PRB_FPS_CS": "1"}, {"PRB_FPS_CS": "2"}, {"PRB_FPS_CS": "4"}, {"PRB_FPS_CS": "8"},
-                                 {"PRB_FPS_GENERIC": "1"}, {"PRB_FPS_CS": "1", "PRB_FPS_THREADS": "1024"}, {"PRB_FPS_PRUNE": "1"}])
-def test_fps_all_kernel_variants_agree(cuda, env):
+@pytest.mark.parametrize("opt", [{"fps_cluster": 1}, {"fps_cluster": 2}, {"fps_cluster": 4}, {"fps_cluster": 8},
+                                 {"fps_generic": 1}, {"fps_cluster": 1, "fps_threads": 1024}, {"fps_prune": 1}])
+def test_fps_all_kernel_variants_agree(cuda, opt):
+    from pointrcnn_b200 import _cabi
     xyz = synth.dup_cloud(2, 8192, 5, unique=3000)
     want = O.fps(xyz, 512)
-    env = dict({"PRB_FPS_PRUNE": "0"}, **env)     # the cluster / generic kernels unless the case asks for pruning
-    old = {k: os.environ.get(k) for k in env}
-    os.environ.update(env)
-    try:
+    opt = dict({"fps_prune": 0}, **opt)     # the cluster / generic kernels unless the case asks for pruning
+    with _cabi.options(**opt):              # per-thread prb_options, not the process environment
         got = pu.furthest_point_sample(T(xyz, cuda), 512)
-    finally:
-        for k, v in old.items():
-            os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
     assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_options_are_thread_local(cuda):
+    """natives are re-entered from nn.DataParallel worker threads; one thread's prb_options must not leak"""
+    import threading
+    from pointrcnn_b200 import _cabi
+    seen = {}
+
+    def worker():
+        o = _cabi.Options()
+        _cabi.lib().prb_get_thread_options(ctypes.byref(o))
+        seen["worker"] = (o.fps_cluster, o.fps_prune)
+    import ctypes
+    with _cabi.options(fps_cluster=8, fps_prune=0):
+        t = threading.Thread(target=worker); t.start(); t.join()
+        o = _cabi.Options()
+        _cabi.lib().prb_get_thread_options(ctypes.byref(o))
+        seen["main"] = (o.fps_cluster, o.fps_prune)
+    assert seen["main"] == (8, 0) and seen["worker"] != (8, 0)
 
 
 def test_fps_temp_writeback_and_m_edge(cuda):
@@ -99,7 +114,7 @@ def test_fps_temp_writeback_and_m_edge(cuda):
     assert torch.count_nonzero(one) == 0
 
 
-@pytest.mark.parametrize("N,M,prune", [(6000, 300, "1"), (16384, 1000, "1"), (3000, 200, "2")])
+@pytest.mark.parametrize("N,M,prune", [(6000, 300, 1), (16384, 1000, 1), (3000, 200, 2)])
 def test_fps_pruned_kernel_resumes_from_caller_temp(cuda, N, M, prune):
     """temp is in/out (sampling_gpu.cu:105-111): a caller-initialised temp steers the sampling and gets the final minima"""
     from pointrcnn_b200.ext import pointnet2_cuda
@@ -111,12 +126,9 @@ def test_fps_pruned_kernel_resumes_from_caller_temp(cuda, N, M, prune):
     x = T(xyz, cuda)
     temp = T(t0.copy(), cuda)
     idx = torch.empty((2, M), dtype=torch.int32, device=cuda)
-    old = os.environ.get("PRB_FPS_PRUNE")
-    os.environ["PRB_FPS_PRUNE"] = prune
-    try:
+    from pointrcnn_b200 import _cabi
+    with _cabi.options(fps_prune=prune):
         pointnet2_cuda.furthest_point_sampling_wrapper(2, N, M, x, temp, idx)
-    finally:
-        os.environ.pop("PRB_FPS_PRUNE", None) if old is None else os.environ.__setitem__("PRB_FPS_PRUNE", old)
     assert np.array_equal(idx.cpu().numpy(), want)
     assert np.array_equal(temp.cpu().numpy(), want_temp)
     if HAVE_REF:
@@ -367,7 +379,7 @@ def test_ball_query_grid_path_exact(cuda, kind, N, M, radii, nss):
         assert np.array_equal(g.cpu().numpy(), O.ball_query(r, ns, xyz, new_xyz)), "grid ball query differs (r=%g)" % r
 
 
-@pytest.mark.parametrize("cell", [None, "0.5", "4.0"])     # default edge; tiny cells (most queries go to the exhaustive scan); big cells
+@pytest.mark.parametrize("cell", [None, 0.5, 4.0])     # default edge; tiny cells (most queries go to the exhaustive scan); big cells
 @pytest.mark.parametrize("kind,n,m", [("kitti", 8192, 2048), ("cube", 2000, 500), ("dup", 1024, 256), ("cube", 100, 5),
                                       ("kitti", 300, 3), ("dup", 4096, 64)])
 def test_three_nn_grid_path_exact(cuda, kind, n, m, cell):
@@ -376,15 +388,14 @@ def test_three_nn_grid_path_exact(cuda, kind, n, m, cell):
     if kind == "kitti":
         unknown[0, :10] += 300.0         # far-away queries: third neighbour beyond one cell -> brute-force list
     d2, idx = O.three_nn(unknown, known)
-    old, old_cell = pu.GRID_MIN_POINTS_NN, os.environ.get("PRB_NN_CELL")
+    from pointrcnn_b200 import _cabi
+    old = pu.GRID_MIN_POINTS_NN
     pu.GRID_MIN_POINTS_NN = 1
-    if cell is not None:
-        os.environ["PRB_NN_CELL"] = cell
     try:
-        got_d2, got_idx, w = pu.three_nn_weights(T(unknown, cuda), T(known, cuda))
+        with _cabi.options(**({} if cell is None else {"nn_cell": cell})):
+            got_d2, got_idx, w = pu.three_nn_weights(T(unknown, cuda), T(known, cuda))
     finally:
         pu.GRID_MIN_POINTS_NN = old
-        os.environ.pop("PRB_NN_CELL", None) if old_cell is None else os.environ.__setitem__("PRB_NN_CELL", old_cell)
     assert np.array_equal(got_idx.cpu().numpy(), idx)
     assert np.array_equal(got_d2.cpu().numpy(), d2)
     np.testing.assert_allclose(w.cpu().numpy(), O.interp_weights(d2), rtol=2e-6, atol=1e-7)
