@@ -58,6 +58,8 @@ typedef struct prb_options {
     int mlp_sleepy;    /* bit 0: MMA issuer waits with a suspend hint, bit 1: weight producer does */
     int mlp_trace;     /* 1: record the phase trace read by prb_debug_mlp_trace */
     int mlp_pipeline;  /* 1: role-specialised pipelined chain kernel (gather of tile i+1 overlaps tile i); 0: legacy */
+    int mlp_ne, mlp_ngw;   /* pipelined kernel: epilogue / gather warp groups per CTA (1 or 2); 0 = plan rule */
+    int mlp_zs, mlp_nbuf;  /* pipelined kernel: last-layer slice width (multiple of 32) / slice buffers (1 or 2); 0 = plan rule */
     int grid_debug;    /* 1: print (and synchronise for) the 3-NN grid's fallback counts */
     float nn_cell;     /* 3-NN grid cell edge in units of the mean point spacing (default 1.6) */
 } prb_options;

@@ -1,0 +1,789 @@
+// mlp_pipe.cu -- the shared-MLP chain as a ROLE-SPECIALISED, tile-pipelined tcgen05 kernel.
+//
+// Same contract as the legacy kernel in mlp_tc.cu (gather -> SharedMLP layers -> max-pool / channel-major store;
+// replaces pointnet2_utils.py:249-257 + pointnet2_modules.py:40-52,144-156 + pytorch_utils.py:5-101 for eval-mode
+// forward), but the phases of consecutive 128-row tiles overlap instead of running one after another:
+//
+//   gather warps   (4*NGW) build the layer-0 A operand of tile i+1, i+2, ... in a shared-memory ring (K-major
+//                  SWIZZLE_128B chunks of 32 K-columns) while the tensor core and the epilogue warps are still busy
+//                  with tile i: neighbour-row gathers are L2 latency, and no longer hold tensor memory;
+//   issuer A       (1 thread) layer-0 MMAs: A from the ring, accumulator region X of tensor memory;
+//   issuer B       (1 thread) layers >= 1: A operand straight from tensor memory (the previous accumulator rewritten in
+//                  place by the epilogue warps), own accumulator regions Y / Z -- so X is free again as soon as layer 1 has
+//                  consumed it and tile i+1's layer 0 runs under tile i's later layers;
+//   producers      (2 threads) stream pre-packed weight tiles with cp.async.bulk into two rings (layer 0 / layers >= 1);
+//   epilogue warps (4*NE) mid layers: tcgen05.ld -> +shift -> relu -> tf32 -> tcgen05.st in place, chunk by chunk (the
+//                  next layer's MMAs start on the first chunk); last layer: computed in column SLICES through one or two
+//                  small TMEM buffers, so that pooling / storing slice s overlaps the MMAs of slice s+1 and a 256-wide
+//                  last layer does not need 256 columns next to its 224-column input.
+//
+// Tensor-memory plan: region l < L-1 at rcol[l] (np[l] columns each), last layer: nbuf buffers of zs columns at zcol[].
+// Hazards: X is released to issuer A by a tcgen05.commit of issuer B after layer 1's MMAs; regions written and read
+// by issuer B alone are ordered by the in-order execution of one thread's MMAs; slice buffers cycle through
+// z_full (commit) / z_free (epilogue arrive) barriers.
+#include "mlp_dev.cuh"
+
+namespace prb {
+
+constexpr int PIPE_MAX_A = 8;      // A-ring depth upper bound
+constexpr int PIPE_MAX_B = 4;
+
+struct PipeSmem {
+    uint64_t a_full[PIPE_MAX_A], a_empty[PIPE_MAX_A];
+    uint64_t b0_full[PIPE_MAX_B], b0_empty[PIPE_MAX_B], b1_full[PIPE_MAX_B], b1_empty[PIPE_MAX_B];
+    uint64_t r_full[2];          // accumulator of mid layer l complete
+    uint64_t x_free;             // region 0 consumed by layer 1
+    uint64_t ready[2][16];       // chunk kc of region l rewritten as the next layer's A operand
+    uint64_t z_full[2], z_free[2];
+    uint32_t tmem_base;
+    int row_src[2][TM][3];       // double-buffered by item parity. SA: global point row (slot 0); FP: 3 known rows
+    float row_aux[2][TM][3];     // SA: centre xyz; FP: 3 weights
+    int row_valid[2][TM];
+};
+
+__host__ __device__ inline size_t pipe_smem_bytes(int ne, int na, int nb0, int b0_bytes, int nb1, int b1_bytes, int np_total) {
+    return 1024 /*alignment slack*/ + (size_t)na * A_STAGE_BYTES + (size_t)nb0 * b0_bytes + (size_t)nb1 * b1_bytes +
+           (size_t)2 * np_total * sizeof(float) + (size_t)ne * (TM * POOL_STRIDE + 8 * 16) * sizeof(float) + 64;
+}
+
+__device__ __forceinline__ void bar_named(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int NE, int NGW, int MINB>
+__global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(const ChainParams p) {
+    constexpr int NTHREADS = (NE + NGW + 1) * 128;
+    constexpr int W_GATHER = 4 * NE, W_MISC = 4 * (NE + NGW);
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ PipeSmem S;
+    uint8_t *base = smem_raw + ((1024u - (s2u(smem_raw) & 1023u)) & 1023u);
+    const int L = p.num_layers;
+    int np_total = 0, sc_off[MAX_LAYERS];
+    for (int l = 0; l < L; ++l) { sc_off[l] = np_total; np_total += p.np[l]; }
+    uint8_t *sA = base;
+    uint8_t *sB0 = sA + (size_t)p.na * A_STAGE_BYTES;
+    uint8_t *sB1 = sB0 + (size_t)p.nb0 * p.b0_stage_bytes;
+    float *s_scale = reinterpret_cast<float *>(sB1 + (size_t)p.nb1 * p.b1_stage_bytes);
+    float *s_shift = s_scale + np_total;
+    float *s_pool = s_shift + np_total;                                  // NE x (TM x POOL_STRIDE + 8 x 16)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NA = p.na;
+
+    if (tid == 0) {
+        for (int i = 0; i < PIPE_MAX_A; ++i) { mbar_init(s2u(&S.a_full[i]), 128); mbar_init(s2u(&S.a_empty[i]), 1); }
+        for (int i = 0; i < PIPE_MAX_B; ++i) {
+            mbar_init(s2u(&S.b0_full[i]), 1); mbar_init(s2u(&S.b0_empty[i]), 1);
+            mbar_init(s2u(&S.b1_full[i]), 1); mbar_init(s2u(&S.b1_empty[i]), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(s2u(&S.r_full[i]), 1);
+            mbar_init(s2u(&S.z_full[i]), 1); mbar_init(s2u(&S.z_free[i]), 128 * NE);
+            for (int k = 0; k < 16; ++k) mbar_init(s2u(&S.ready[i][k]), 128);
+        }
+        mbar_init(s2u(&S.x_free), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == W_MISC + 2) tmem_alloc(s2u(&S.tmem_base), (uint32_t)p.tmem_cols);
+    for (int l = 0; l < L; ++l)
+        for (int i = tid; i < p.np[l]; i += NTHREADS) { s_scale[sc_off[l] + i] = p.unit_scale ? 1.f : p.scale[l][i]; s_shift[sc_off[l] + i] = p.shift[l][i]; }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+    const int nsplit = p.nsplit;
+
+    if (warp == W_MISC) {
+        // ===================================================== weight producer, layer 0
+        if (lane == 0) {
+            RingPos rb = {0, 0};
+            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+                const int sj = item % nsplit;
+                const int col0 = sj * p.split_w;
+                const int width = L == 1 ? min(p.split_w, p.np[0] - col0) : p.np[0];
+                const int halves = (width + B_TILE_ROWS - 1) / B_TILE_ROWS;
+                for (int kc = 0; kc < p.nchunks[0]; ++kc)
+                    for (int h = 0; h < halves; ++h) {
+                        const int rows = min(B_TILE_ROWS, width - h * B_TILE_ROWS);
+                        const uint32_t bytes = (uint32_t)rows * KC * 4;
+                        mbar_wait_sleepy(s2u(&S.b0_empty[rb.stage]), rb.phase ^ 1);
+                        mbar_expect_tx(s2u(&S.b0_full[rb.stage]), bytes);
+                        const float *src = p.w[0] + ((size_t)kc * p.np[0] + (size_t)(col0 + h * B_TILE_ROWS)) * KC;
+                        bulk_g2s(s2u(sB0 + (size_t)rb.stage * p.b0_stage_bytes), src, bytes, s2u(&S.b0_full[rb.stage]));
+                        rb.advance(p.nb0);
+                    }
+            }
+        }
+    } else if (warp == W_MISC + 1) {
+        // ===================================================== weight producer, layers >= 1
+        if (lane == 0 && L > 1) {
+            RingPos rb = {0, 0};
+            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+                for (int l = 1; l < L; ++l) {
+                    const bool last = l == L - 1;
+                    const int nsl = last ? p.nslice : 1;
+                    const int width = last ? p.zs : p.np[l];
+                    const int halves = (width + B_TILE_ROWS - 1) / B_TILE_ROWS;
+                    for (int s = 0; s < nsl; ++s)
+                        for (int kc = 0; kc < p.nchunks[l]; ++kc)
+                            for (int h = 0; h < halves; ++h) {
+                                const int rows = min(B_TILE_ROWS, width - h * B_TILE_ROWS);
+                                const uint32_t bytes = (uint32_t)rows * KC * 4;
+                                mbar_wait_sleepy(s2u(&S.b1_empty[rb.stage]), rb.phase ^ 1);
+                                mbar_expect_tx(s2u(&S.b1_full[rb.stage]), bytes);
+                                const float *src = p.w[l] + ((size_t)kc * p.np[l] + (size_t)(s * width + h * B_TILE_ROWS)) * KC;
+                                bulk_g2s(s2u(sB1 + (size_t)rb.stage * p.b1_stage_bytes), src, bytes, s2u(&S.b1_full[rb.stage]));
+                                rb.advance(p.nb1);
+                            }
+                }
+            }
+        }
+    } else if (warp == W_MISC + 2) {
+        // ===================================================== MMA issuer A: layer 0 (A operand from the shared-memory ring)
+        if (lane == 0) {
+            RingPos ra = {0, 0}, rb = {0, 0};
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+                const int sj = item % nsplit;
+                const int width = L == 1 ? min(p.split_w, p.np[0] - sj * p.split_w) : p.np[0];
+                const int halves = (width + B_TILE_ROWS - 1) / B_TILE_ROWS;
+                uint32_t dcol, buf = 0;
+                if (L > 1) {
+                    mbar_wait_sleepy(s2u(&S.x_free), (it & 1) ^ 1);       // layer 1 of the previous item has consumed X
+                    dcol = (uint32_t)p.rcol[0];
+                } else {
+                    buf = it % (uint32_t)p.nbuf;
+                    mbar_wait_sleepy(s2u(&S.z_free[buf]), ((it / (uint32_t)p.nbuf) & 1) ^ 1);
+                    dcol = (uint32_t)p.zcol[buf];
+                }
+                tc_fence_after();
+                for (int kc = 0; kc < p.nchunks[0]; ++kc) {
+                    int c = kc, sg = 0;
+                    if (p.nseg > 1 && c >= p.seg_chunks[0]) { c -= p.seg_chunks[0]; sg = 1; }
+                    const int valid = min(KC, p.seg_width[sg] - c * KC);
+                    const int ksteps = (valid + 7) >> 3;
+                    mbar_wait_sleepy(s2u(&S.a_full[ra.stage]), ra.phase);
+                    const uint64_t adesc = make_desc(s2u(sA + (size_t)ra.stage * A_STAGE_BYTES));
+                    for (int h = 0; h < halves; ++h) {
+                        const int rows = min(B_TILE_ROWS, width - h * B_TILE_ROWS);
+                        mbar_wait_sleepy(s2u(&S.b0_full[rb.stage]), rb.phase);
+                        tc_fence_after();
+                        const uint64_t bdesc = make_desc(s2u(sB0 + (size_t)rb.stage * p.b0_stage_bytes));
+                        const uint32_t idesc = make_idesc(rows);
+                        const uint32_t d = tmem + dcol + (uint32_t)(h * B_TILE_ROWS);
+                        for (int ks = 0; ks < ksteps; ++ks)  // +32 bytes (= 2 x 16 B) per K=8 step inside the swizzle row
+                            umma_tf32(d, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                        umma_commit(s2u(&S.b0_empty[rb.stage]));
+                        rb.advance(p.nb0);
+                    }
+                    umma_commit(s2u(&S.a_empty[ra.stage]));
+                    ra.advance(NA);
+                }
+                umma_commit(L > 1 ? s2u(&S.r_full[0]) : s2u(&S.z_full[buf]));
+            }
+        }
+    } else if (warp == W_MISC + 3) {
+        // ===================================================== MMA issuer B: layers >= 1 (A operand from tensor memory)
+        if (lane == 0 && L > 1) {
+            RingPos rb = {0, 0};
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+                for (int l = 1; l < L; ++l) {
+                    const bool last = l == L - 1;
+                    const int nsl = last ? p.nslice : 1;
+                    const int width = last ? p.zs : p.np[l];
+                    const int halves = (width + B_TILE_ROWS - 1) / B_TILE_ROWS;
+                    for (int s = 0; s < nsl; ++s) {
+                        uint32_t dcol, buf = 0;
+                        if (last) {
+                            const uint32_t u = it * (uint32_t)p.nslice + (uint32_t)s;
+                            buf = u % (uint32_t)p.nbuf;
+                            mbar_wait_sleepy(s2u(&S.z_free[buf]), ((u / (uint32_t)p.nbuf) & 1) ^ 1);   // the epilogue has drained this buffer
+                            dcol = (uint32_t)p.zcol[buf];
+                        } else {
+                            dcol = (uint32_t)p.rcol[l];
+                        }
+                        for (int kc = 0; kc < p.nchunks[l]; ++kc) {
+                            if (s == 0) mbar_wait_sleepy(s2u(&S.ready[l - 1][kc]), it & 1);   // chunk kc of the A operand is in place
+                            tc_fence_after();
+                            const uint32_t a_t = tmem + (uint32_t)(p.rcol[l - 1] + kc * KC);
+                            for (int h = 0; h < halves; ++h) {
+                                const int rows = min(B_TILE_ROWS, width - h * B_TILE_ROWS);
+                                mbar_wait_sleepy(s2u(&S.b1_full[rb.stage]), rb.phase);
+                                tc_fence_after();
+                                const uint64_t bdesc = make_desc(s2u(sB1 + (size_t)rb.stage * p.b1_stage_bytes));
+                                const uint32_t idesc = make_idesc(rows);
+                                const uint32_t d = tmem + dcol + (uint32_t)(h * B_TILE_ROWS);
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    umma_tf32_ts(d, a_t + (uint32_t)(8 * ks), bdesc + (uint64_t)(2 * ks), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                                umma_commit(s2u(&S.b1_empty[rb.stage]));
+                                rb.advance(p.nb1);
+                            }
+                        }
+                        umma_commit(last ? s2u(&S.z_full[buf]) : s2u(&S.r_full[l]));
+                    }
+                    if (l == 1) umma_commit(s2u(&S.x_free));      // region 0 may take the next item's layer 0
+                }
+            }
+        }
+    } else if (warp >= W_GATHER) {
+        // ===================================================== gather warps: layer-0 A chunks, running ahead of the MMAs
+        const int gw = warp - W_GATHER;
+        const int wq = gw & 3, grp = gw >> 2;
+        const int r = wq * 32 + lane;       // my row inside the tile
+        const int j8 = lane & 7;            // my 16-byte unit inside a 128-byte row
+        const int rsub = lane >> 3;         // which of the 4 rows a warp-wide gather step covers
+        RingPos ra = {0, 0};
+        uint32_t cc = 0, it = 0;
+        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+            const int tile = item / nsplit;
+            const int par = it & 1;
+            // ---- per-row metadata of this tile
+            const unsigned R = (unsigned)tile * TM + r;          // total_rows < 2^31 (checked on the host)
+            const bool valid = (long)R < p.total_rows;
+            int m_src[3] = {0, 0, 0};
+            float m_aux[3] = {0.f, 0.f, 0.f};
+            int my_scene = 0, my_u = 0;
+            if (p.mode_in == IN_SA) {
+                const unsigned pr = valid ? (R >> p.log_ns) : 0u;     // global centre index (nsample is a power of two)
+                const unsigned scene = pr / (unsigned)p.npoint;
+                m_src[0] = (int)scene * p.n + (valid ? __ldg(p.idx + R) : 0);
+                m_aux[0] = __ldg(p.new_xyz + (size_t)pr * 3 + 0);
+                m_aux[1] = __ldg(p.new_xyz + (size_t)pr * 3 + 1);
+                m_aux[2] = __ldg(p.new_xyz + (size_t)pr * 3 + 2);
+            } else if (p.mode_in == IN_FP) {
+                const unsigned rr = valid ? R : 0u;
+                const unsigned scene = rr / (unsigned)p.n;
+                my_scene = (int)scene; my_u = (int)(rr - scene * (unsigned)p.n);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    m_src[q] = (int)scene * p.m + __ldg(p.idx + (size_t)rr * 3 + q);
+                    m_aux[q] = __ldg(p.weight + (size_t)rr * 3 + q);
+                }
+            }
+            if (grp == 0) {
+                S.row_valid[par][r] = valid;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) { S.row_src[par][r][q] = m_src[q]; S.row_aux[par][r][q] = m_aux[q]; }
+            }
+            // one barrier per item: the table is double buffered, so the readers of item it-1 never see item it+1's rows
+            bar_named(5, 128 * NGW);
+
+            for (int kc = 0; kc < p.nchunks[0]; ++kc, ++cc, ra.advance(NA)) {
+                if ((int)(cc % NGW) != grp) continue;
+                int c = kc, seg = 0;
+                if (p.nseg > 1 && c >= p.seg_chunks[0]) { c -= p.seg_chunks[0]; seg = 1; }
+                const int k0 = c * KC;                       // first column of this chunk inside its segment
+                const int width = p.seg_width[seg];
+                uint8_t *A = sA + (size_t)ra.stage * A_STAGE_BYTES;
+                const uint32_t empty_bar = s2u(&S.a_empty[ra.stage]);
+                const uint32_t empty_par = ra.phase ^ 1;
+                const bool rows_seg = (p.mode_in == IN_DIRECT) || (p.mode_in == IN_SA && seg == 0 && p.c_feat > 5) ||
+                                      (p.mode_in == IN_FP && seg == 0);
+                if (rows_seg) {
+                    // point-major sources: 8 lanes cover one row's 128 bytes, a warp covers 4 rows per step, 8 steps.
+                    // All loads of a half chunk are issued before the first use (memory-level parallelism).
+                    const int kk = k0 + 4 * j8;
+                    if (p.mode_in == IN_FP) {
+                        const int C = p.c_known;
+                        const bool vec = (C & 3) == 0;
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            float4 t0[4], t1[4], t2[4];
+                            float w0[4], w1[4], w2[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int rr = wq * 32 + rsub + 4 * (half * 4 + i);
+                                t0[i] = t1[i] = t2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                w0[i] = S.row_aux[par][rr][0]; w1[i] = S.row_aux[par][rr][1]; w2[i] = S.row_aux[par][rr][2];
+                                if (S.row_valid[par][rr] && kk < width) {
+                                    const float *s0 = p.known_pm + (size_t)S.row_src[par][rr][0] * C + kk;
+                                    const float *s1 = p.known_pm + (size_t)S.row_src[par][rr][1] * C + kk;
+                                    const float *s2 = p.known_pm + (size_t)S.row_src[par][rr][2] * C + kk;
+                                    if (vec) {
+                                        t0[i] = __ldg((const float4 *)s0); t1[i] = __ldg((const float4 *)s1); t2[i] = __ldg((const float4 *)s2);
+                                    } else {
+                                        float a0[4], a1[4], a2[4];
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q) {
+                                            const bool in = kk + q < width;
+                                            a0[q] = in ? __ldg(s0 + q) : 0.f; a1[q] = in ? __ldg(s1 + q) : 0.f; a2[q] = in ? __ldg(s2 + q) : 0.f;
+                                        }
+                                        t0[i] = make_float4(a0[0], a0[1], a0[2], a0[3]);
+                                        t1[i] = make_float4(a1[0], a1[1], a1[2], a1[3]);
+                                        t2[i] = make_float4(a2[0], a2[1], a2[2], a2[3]);
+                                    }
+                                }
+                            }
+                            if (half == 0) mbar_wait(empty_bar, empty_par);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int rr = wq * 32 + rsub + 4 * (half * 4 + i);
+                                // same contraction as three_interpolate (reference SASS): fma(w2,p2, fma(w0,p0, w1*p1))
+                                float4 v;
+                                v.x = to_tf32(__fmaf_rn(w2[i], t2[i].x, __fmaf_rn(w0[i], t0[i].x, __fmul_rn(w1[i], t1[i].x))));
+                                v.y = to_tf32(__fmaf_rn(w2[i], t2[i].y, __fmaf_rn(w0[i], t0[i].y, __fmul_rn(w1[i], t1[i].y))));
+                                v.z = to_tf32(__fmaf_rn(w2[i], t2[i].z, __fmaf_rn(w0[i], t0[i].z, __fmul_rn(w1[i], t1[i].z))));
+                                v.w = to_tf32(__fmaf_rn(w2[i], t2[i].w, __fmaf_rn(w0[i], t0[i].w, __fmul_rn(w1[i], t1[i].w))));
+                                *reinterpret_cast<float4 *>(A + swz(rr, j8)) = v;
+                            }
+                        }
+                    } else {
+                        const int pitch = p.mode_in == IN_DIRECT ? p.x_pitch : p.c_feat;
+                        float4 t[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = wq * 32 + rsub + 4 * i;
+                            t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (S.row_valid[par][rr] && kk < width) {
+                                const float *src = p.mode_in == IN_DIRECT ? p.x_rows + ((size_t)tile * TM + rr) * pitch + kk
+                                                                          : p.feats_pm + (size_t)S.row_src[par][rr][0] * pitch + kk;
+                                if ((pitch & 3) == 0) {
+                                    t[i] = __ldg((const float4 *)src);
+                                } else {
+                                    float o[4];
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) o[q] = (kk + q < width) ? __ldg(src + q) : 0.f;
+                                    t[i] = make_float4(o[0], o[1], o[2], o[3]);
+                                }
+                            }
+                        }
+                        mbar_wait(empty_bar, empty_par);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = wq * 32 + rsub + 4 * i;
+                            float4 v = t[i];
+                            v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                            *reinterpret_cast<float4 *>(A + swz(rr, j8)) = v;
+                        }
+                    }
+                } else if (p.mode_in == IN_SA) {
+                    // relative xyz segment: [x - cx, y - cy, z - cz, (<= 5 feature channels,) 0 ...]; one K=8 step
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), v2 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid) {
+                        const float *q = p.xyz + (size_t)m_src[0] * 3;
+                        v.x = to_tf32(__ldg(q + 0) - m_aux[0]);
+                        v.y = to_tf32(__ldg(q + 1) - m_aux[1]);
+                        v.z = to_tf32(__ldg(q + 2) - m_aux[2]);
+                        if (p.c_feat > 0 && p.c_feat <= 5) {
+                            const float *f = p.feats_pm + (size_t)m_src[0] * p.c_feat;
+                            v.w = to_tf32(__ldg(f));
+                            if (p.c_feat > 1) v2.x = to_tf32(__ldg(f + 1));
+                            if (p.c_feat > 2) v2.y = to_tf32(__ldg(f + 2));
+                            if (p.c_feat > 3) v2.z = to_tf32(__ldg(f + 3));
+                            if (p.c_feat > 4) v2.w = to_tf32(__ldg(f + 4));
+                        }
+                    }
+                    mbar_wait(empty_bar, empty_par);
+                    *reinterpret_cast<float4 *>(A + swz(r, 0)) = v;
+                    *reinterpret_cast<float4 *>(A + swz(r, 1)) = v2;
+                } else {
+                    // FP skip segment: channel-major (b, c_skip, n); lanes run along consecutive points
+                    const float *bsrc = p.skip + (size_t)my_scene * p.c_skip * p.n + my_u;
+                    float o[32];
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const int ch = k0 + q;
+                        o[q] = (valid && ch < width) ? __ldg(bsrc + (size_t)ch * p.n) : 0.f;
+                    }
+                    mbar_wait(empty_bar, empty_par);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4 *>(A + swz(r, j)) =
+                            make_float4(to_tf32(o[4 * j]), to_tf32(o[4 * j + 1]), to_tf32(o[4 * j + 2]), to_tf32(o[4 * j + 3]));
+                }
+                fence_async_smem();
+                mbar_arrive(s2u(&S.a_full[ra.stage]));
+            }
+        }
+    } else {
+        // ===================================================== epilogue warps (warps 0 .. 4*NE-1)
+        const int wq = warp & 3, grp = warp >> 2;
+        const int r = wq * 32 + lane;       // my row inside the tile / my TMEM lane
+        const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+        float *pool = s_pool + grp * (TM * POOL_STRIDE + 128);
+        float *pool2 = pool + TM * POOL_STRIDE;   // 8 x 16 partial maxima (nsample > 32)
+        const int Cl = p.c_last;
+        const float *sc = s_scale + sc_off[L - 1], *sh = s_shift + sc_off[L - 1];
+        // mid layer l of item number `itn`: accumulator -> +shift -> ReLU -> tf32, rewritten in place as the next layer's A operand
+        auto mid_epilogue = [&](int l, uint32_t itn) {
+            mbar_wait(s2u(&S.r_full[l]), itn & 1);
+            tc_fence_after();
+            const int nch = p.np[l] / KC;
+            for (int kc = grp; kc < nch; kc += NE) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const uint32_t col = tmem + lane_base + (uint32_t)(p.rcol[l] + kc * KC + hh * 16);
+                    uint32_t acc[16];
+                    tmem_ld16(col, acc);
+                    const float4 *sc4 = reinterpret_cast<const float4 *>(s_scale + sc_off[l] + kc * KC + hh * 16);
+                    const float4 *sh4 = reinterpret_cast<const float4 *>(s_shift + sc_off[l] + kc * KC + hh * 16);
+                    if (p.unit_scale) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b = sh4[j];
+                            acc[4 * j + 0] = __float_as_uint(relu_to_tf32(__uint_as_float(acc[4 * j + 0]) + b.x));
+                            acc[4 * j + 1] = __float_as_uint(relu_to_tf32(__uint_as_float(acc[4 * j + 1]) + b.y));
+                            acc[4 * j + 2] = __float_as_uint(relu_to_tf32(__uint_as_float(acc[4 * j + 2]) + b.z));
+                            acc[4 * j + 3] = __float_as_uint(relu_to_tf32(__uint_as_float(acc[4 * j + 3]) + b.w));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 a = sc4[j], b = sh4[j];
+                            acc[4 * j + 0] = __float_as_uint(relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 0]), a.x, b.x)));
+                            acc[4 * j + 1] = __float_as_uint(relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 1]), a.y, b.y)));
+                            acc[4 * j + 2] = __float_as_uint(relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 2]), a.z, b.z)));
+                            acc[4 * j + 3] = __float_as_uint(relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 3]), a.w, b.w)));
+                        }
+                    }
+                    tmem_st16(col, acc);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(s2u(&S.ready[l][kc]));
+            }
+        };
+        // Skewed order: the first mid layer of item i+1 is handled BEFORE the last layer of item i.  Item i+1's layer-0
+        // accumulator is complete by then (region X was released when layer 1 of item i had run), so the round trips
+        // "rewritten chunk -> next layer's MMAs -> commit" of one item are covered by epilogue work of its neighbour
+        // instead of idling the epilogue warps.  Not when the last layer IS layer 1 and has more slices than buffers:
+        // X is released only after the last slice, which needs this item's final epilogue to drain buffers first.
+        const bool skew = (L == 3) || (L == 2 && p.nslice <= p.nbuf);
+        uint32_t it = 0;
+        if (skew && (int)blockIdx.x < p.num_items) mid_epilogue(0, 0u);
+        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+            const int tile = item / nsplit, sj = item - tile * nsplit;
+            const long R = (long)tile * TM + r;
+            const bool valid = R < p.total_rows;
+            int my_scene = 0, my_u = 0;
+            if (p.mode_out == OUT_FP) {
+                const unsigned rr = valid ? (unsigned)R : 0u;
+                const unsigned scene = rr / (unsigned)p.n;
+                my_scene = (int)scene; my_u = (int)(rr - scene * (unsigned)p.n);
+            }
+            if (skew) {
+                for (int l = 1; l + 1 < L; ++l) mid_epilogue(l, it);
+                if (item + (int)gridDim.x < p.num_items) mid_epilogue(0, it + 1);
+            } else {
+                for (int l = 0; l + 1 < L; ++l) mid_epilogue(l, it);
+            }
+
+            // ---- last layer, slice by slice
+            size_t e_off = 0, e_pm = 0;
+            bool e_ok = false;
+            size_t b_off = 0, b_pm = 0;
+            bool b_ok = false;
+            if (p.mode_out == OUT_SA_MAX && (p.ns == 16 || p.ns == 32)) {
+                const unsigned Rg = (unsigned)tile * TM + (unsigned)r;
+                b_ok = (long)Rg < p.total_rows;
+                const unsigned pr = Rg >> p.log_ns, scene = pr / (unsigned)p.npoint, pp = pr - scene * (unsigned)p.npoint;
+                b_off = ((size_t)scene * p.out_stride_c + p.out_c_off) * p.npoint + pp;
+                b_pm = ((size_t)scene * p.npoint + pp) * p.out_stride_c + p.out_c_off;
+            }
+            if (p.mode_out == OUT_SA_MAX && p.ns >= 16) {
+                const unsigned Rg = (unsigned)tile * TM + (unsigned)(r >> 4) * 16u;
+                e_ok = (long)Rg < p.total_rows && (((r >> 4) & ((p.ns >> 4) - 1)) == 0);
+                const unsigned pr = Rg >> p.log_ns, scene = pr / (unsigned)p.npoint, pp = pr - scene * (unsigned)p.npoint;
+                e_off = ((size_t)scene * p.out_stride_c + p.out_c_off + (r & 15)) * p.npoint + pp;
+                e_pm = ((size_t)scene * p.npoint + pp) * p.out_stride_c + p.out_c_off + (r & 15);
+            }
+            const bool pool_raw = p.unit_scale && p.mode_out == OUT_SA_MAX;
+            const float lo = p.linear_last ? -CUDART_INF_F : 0.f;    // ReLU = max(., 0); a linear last layer keeps the sign
+            const int nsl = L == 1 ? 1 : p.nslice;
+            for (int s = 0; s < nsl; ++s) {
+                const uint32_t u = it * (uint32_t)nsl + (uint32_t)s;
+                const uint32_t buf = u % (uint32_t)p.nbuf;
+                const int s_lo = L == 1 ? sj * p.split_w : s * p.zs;                  // first absolute column of this slice
+                const int s_hi = min(Cl, s_lo + (L == 1 ? p.split_w : p.zs));
+                mbar_wait(s2u(&S.z_full[buf]), (u / (uint32_t)p.nbuf) & 1);
+                tc_fence_after();
+                for (int c0 = s_lo + grp * 16; c0 < s_hi; c0 += 16 * NE) {
+                    uint32_t acc[16];
+                    tmem_ld16(tmem + lane_base + (uint32_t)(p.zcol[buf] + (c0 - s_lo)), acc);
+                    float v[16];
+                    // folded scale + max-pool: max_s relu(x_s + t) == relu(max_s x_s + t), so the raw accumulators are
+                    // pooled and shift / ReLU are applied once per (centre, channel) after the reduction
+                    if (pool_raw) {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(acc[q]);
+                    } else if (p.unit_scale) {
+                        const float4 *sh4 = reinterpret_cast<const float4 *>(sh + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b = sh4[j];
+                            v[4 * j + 0] = fmaxf(__uint_as_float(acc[4 * j + 0]) + b.x, lo);
+                            v[4 * j + 1] = fmaxf(__uint_as_float(acc[4 * j + 1]) + b.y, lo);
+                            v[4 * j + 2] = fmaxf(__uint_as_float(acc[4 * j + 2]) + b.z, lo);
+                            v[4 * j + 3] = fmaxf(__uint_as_float(acc[4 * j + 3]) + b.w, lo);
+                        }
+                    } else {
+                        const float4 *sc4 = reinterpret_cast<const float4 *>(sc + c0), *sh4 = reinterpret_cast<const float4 *>(sh + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 a = sc4[j], b = sh4[j];
+                            v[4 * j + 0] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 0]), a.x, b.x), lo);
+                            v[4 * j + 1] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 1]), a.y, b.y), lo);
+                            v[4 * j + 2] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 2]), a.z, b.z), lo);
+                            v[4 * j + 3] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 3]), a.w, b.w), lo);
+                        }
+                    }
+                    if (p.mode_out == OUT_ROWS) {
+                        if (valid) {
+                            float *o = p.out + (size_t)R * p.out_pitch + c0;
+                            if (p.round_out) {   // the next launch of a split chain reads these rows as its A operand
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) v[q] = to_tf32(v[q]);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 16; q += 4)
+                                *reinterpret_cast<float4 *>(o + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+                        }
+                    } else if (p.mode_out == OUT_FP) {
+                        if (valid) {
+                            float *o = p.out + ((size_t)my_scene * p.out_stride_c + p.out_c_off + c0) * p.n + my_u;
+#pragma unroll
+                            for (int q = 0; q < 16; ++q)
+                                if (c0 + q < Cl) o[(size_t)q * p.n] = v[q];
+                            if (p.out_pm) {   // point-major copy for the next consumer (no transpose kernel)
+                                float *o2 = p.out_pm + (size_t)R * p.out_stride_c + p.out_c_off + c0;
+                                if ((p.out_stride_c & 3) == 0 && c0 + 16 <= Cl) {
+#pragma unroll
+                                    for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4 *>(o2 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+                                } else {
+#pragma unroll
+                                    for (int q = 0; q < 16; ++q)
+                                        if (c0 + q < Cl) o2[q] = v[q];
+                                }
+                            }
+                        }
+                    } else {
+                        // max over the nsample consecutive rows of each centre
+                        const int ns = p.ns;
+                        const int g16 = r >> 4, q = r & 15;          // (segment of 16 rows, channel) handled by this thread
+                        if (ns == 32 || ns == 16) {
+                            // The nsample rows of a centre are lanes of ONE warp: halving butterfly, no staging tile and
+                            // no barriers.  Each step a lane keeps half of its channels (chosen by one lane-id bit),
+                            // sends the other half to its partner and takes the max -- 8+4+2+1 shuffles leave one channel
+                            // per lane: channel (lane>>1)&15 for 32 samples (one more step joins lanes 2k, 2k+1), channel
+                            // lane&15 (bit-permuted) for 16 samples.
+                            float w8[8], w4[4], w2[2], x;
+                            if (ns == 32) {
+                                const bool b4 = lane & 16;
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float keep = b4 ? v[i + 8] : v[i], send = b4 ? v[i] : v[i + 8];
+                                    w8[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+                                }
+                                const bool b3 = lane & 8;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float keep = b3 ? w8[i + 4] : w8[i], send = b3 ? w8[i] : w8[i + 4];
+                                    w4[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+                                }
+                                const bool b2 = lane & 4;
+#pragma unroll
+                                for (int i = 0; i < 2; ++i) {
+                                    const float keep = b2 ? w4[i + 2] : w4[i], send = b2 ? w4[i] : w4[i + 2];
+                                    w2[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+                                }
+                                const bool b1 = lane & 2;
+                                x = fmaxf(b1 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, b1 ? w2[0] : w2[1], 2));
+                                x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+                            } else {
+                                const bool b3 = lane & 8;
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float keep = b3 ? v[i + 8] : v[i], send = b3 ? v[i] : v[i + 8];
+                                    w8[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+                                }
+                                const bool b2 = lane & 4;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float keep = b2 ? w8[i + 4] : w8[i], send = b2 ? w8[i] : w8[i + 4];
+                                    w4[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+                                }
+                                const bool b1 = lane & 2;
+#pragma unroll
+                                for (int i = 0; i < 2; ++i) {
+                                    const float keep = b1 ? w4[i + 2] : w4[i], send = b1 ? w4[i] : w4[i + 2];
+                                    w2[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+                                }
+                                const bool b0 = lane & 1;
+                                x = fmaxf(b0 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, b0 ? w2[0] : w2[1], 1));
+                            }
+                            const int ch = ns == 32 ? ((lane >> 1) & 15) : (((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1));
+                            if (pool_raw) x = fmaxf(x + sh[c0 + ch], lo);
+                            if (b_ok && (ns == 16 || (lane & 1) == 0) && c0 + ch < Cl) {
+                                p.out[b_off + (size_t)(c0 + ch) * p.npoint] = x;
+                                if (p.out_pm) p.out_pm[b_pm + c0 + ch] = x;
+                            }
+                            continue;
+                        }
+                        bar_named(2 + grp, 128);                     // previous readers of the staging tile are done
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<float4 *>(pool + r * POOL_STRIDE + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        bar_named(2 + grp, 128);
+                        if (ns >= 16) {
+                            float x = pool[(g16 * 16) * POOL_STRIDE + q];
+#pragma unroll
+                            for (int t = 1; t < 16; ++t) x = fmaxf(x, pool[(g16 * 16 + t) * POOL_STRIDE + q]);
+                            if (ns > 32) {
+                                pool2[g16 * 16 + q] = x;
+                                bar_named(2 + grp, 128);
+                                const int per = ns >> 4;
+                                if ((g16 % per) == 0) {
+                                    for (int t = 1; t < per; ++t) x = fmaxf(x, pool2[(g16 + t) * 16 + q]);
+                                }
+                            }
+                            if (pool_raw) x = fmaxf(x + sh[c0 + q], lo);
+                            if (e_ok && c0 + q < Cl) {
+                                p.out[e_off + (size_t)c0 * p.npoint] = x;
+                                if (p.out_pm) p.out_pm[e_pm + c0] = x;
+                            }
+                        } else {
+                            // nsample 4 or 8: 128/ns centres per tile, 16 channels each -> (16/ns) items per thread
+                            const int per16 = 16 / ns;
+                            for (int t = 0; t < per16; ++t) {
+                                const int row0 = g16 * 16 + t * ns;
+                                float x = pool[row0 * POOL_STRIDE + q];
+                                for (int t2 = 1; t2 < ns; ++t2) x = fmaxf(x, pool[(row0 + t2) * POOL_STRIDE + q]);
+                                if (pool_raw) x = fmaxf(x + sh[c0 + q], lo);
+                                const unsigned Rg = (unsigned)tile * TM + (unsigned)row0;
+                                if ((long)Rg < p.total_rows && c0 + q < Cl) {
+                                    const unsigned pr = Rg >> p.log_ns, scene = pr / (unsigned)p.npoint, pp = pr - scene * (unsigned)p.npoint;
+                                    p.out[((size_t)scene * p.out_stride_c + p.out_c_off + c0 + q) * p.npoint + pp] = x;
+                                    if (p.out_pm) p.out_pm[((size_t)scene * p.npoint + pp) * p.out_stride_c + p.out_c_off + c0 + q] = x;
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(s2u(&S.z_free[buf]));        // all 128*NE epilogue threads: this slice buffer may be overwritten
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_MISC + 2) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+// Can this chain segment run on the pipelined kernel, and with which tensor-memory plan?  Fills the plan fields of p.
+// Returns the CTAs per SM the plan allows (0 = not supported: the caller falls back to the legacy kernel).
+struct PipePlan {
+    int ne, ngw, occ, zs, nbuf, nslice, cols, na, nb0, nb1, b0_bytes, b1_bytes, nsplit, split_w;
+    size_t smem;
+};
+
+// Plan rules (tunable through prb_options.mlp_ne / mlp_ngw / mlp_zs / mlp_nbuf for sweeps):
+//  * last layer: slice width zs (divides np_last) x nbuf buffers next to the mid regions; prefer a plan of <= 256 columns
+//    (two CTAs per SM), then double buffering, then wide slices;
+//  * <= 256 columns: two CTAs of 4 epilogue + 4 gather warps (384 threads, 85 registers);
+//    otherwise one CTA with 8 epilogue warps and 8 (layer 0 has >= 2 K chunks) or 4 gather warps.
+static bool pipe_plan(const ChainParams &p, int max_optin, PipePlan *out) {
+    const int L = p.num_layers;
+    const int np_last = p.np[L - 1];
+    int np_total = 0, mid = 0;
+    for (int l = 0; l < L; ++l) { np_total += p.np[l]; if (l + 1 < L) mid += p.np[l]; }
+    if (mid + 32 > 512) return false;
+    const int k0 = p.nchunks[0];
+    const prb_options &o = opts();
+    PipePlan best;
+    long best_score = -1;
+    for (int nbuf = 2; nbuf >= 1; --nbuf) {
+        if (o.mlp_nbuf && nbuf != o.mlp_nbuf) continue;
+        for (int zs = 256; zs >= 32; zs -= 32) {
+            int nslice = 1, nsplit = 1, split_w = np_last, z = zs;
+            if (L == 1) {
+                // single layer: no slicing (the A chunks stream by once); wide layers are dealt to nsplit work items
+                if (zs != 256) continue;
+                nsplit = (np_last + 255) / 256;
+                if (o.mlp_zs >= 32 && o.mlp_zs < np_last) nsplit = (np_last + o.mlp_zs - 1) / o.mlp_zs;
+                split_w = ((np_last + nsplit - 1) / nsplit + 31) / 32 * 32;
+                z = split_w;
+            } else {
+                if (zs > np_last || np_last % zs) continue;
+                if (o.mlp_zs && zs != o.mlp_zs) continue;
+                nslice = np_last / zs;
+            }
+            const int need = mid + nbuf * z;
+            if (need > 512) continue;
+            int cols = 32;
+            while (cols < need) cols <<= 1;
+            PipePlan pl;
+            pl.zs = z; pl.nbuf = nbuf; pl.nslice = nslice; pl.cols = cols; pl.nsplit = nsplit; pl.split_w = split_w;
+            pl.occ = cols <= 256 ? 2 : 1;
+            if (o.mlp_occ == 1) pl.occ = 1;
+            pl.ne = pl.occ == 2 ? 1 : 2;
+            pl.ngw = pl.occ == 2 ? 1 : (k0 >= 2 ? 2 : 1);
+            if (o.mlp_ne) { pl.ne = o.mlp_ne; if (pl.ne + pl.ngw > 2) pl.occ = 1; }
+            if (o.mlp_ngw) { pl.ngw = o.mlp_ngw > 1 && k0 >= 2 ? 2 : 1; if (pl.ne + pl.ngw > 2) pl.occ = 1; }
+            const int b0_rows = L == 1 ? (z < 256 ? z : 256) : (p.np[0] < 256 ? p.np[0] : 256);
+            int b1_rows = 32;
+            for (int l = 1; l < L; ++l) { const int w = (l == L - 1) ? z : p.np[l]; const int r = w < 256 ? w : 256; if (r > b1_rows) b1_rows = r; }
+            pl.b0_bytes = b0_rows * KC * 4; pl.b1_bytes = L > 1 ? b1_rows * KC * 4 : 0;
+            const size_t budget = (size_t)(227 * 1024) / pl.occ - 1024 - sizeof(PipeSmem) - 512;
+            bool ok = false;
+            // A ring: as deep as fits (one whole item ahead + 2 when possible); weight rings 3 deep, 2 if tight
+            for (int nb = 3; nb >= 2 && !ok; --nb)
+                for (int na = (k0 + 2 < PIPE_MAX_A ? (k0 + 2 > 3 ? k0 + 2 : 3) : PIPE_MAX_A); na >= 2 && !ok; --na) {
+                    const size_t smem = pipe_smem_bytes(pl.ne, na, nb, pl.b0_bytes, L > 1 ? nb : 0, pl.b1_bytes, np_total);
+                    if (smem <= budget && smem <= (size_t)max_optin && (nb == 2 || na >= (k0 < 4 ? k0 : 4))) {
+                        pl.na = na; pl.nb0 = nb; pl.nb1 = L > 1 ? nb : 0; pl.smem = smem; ok = true;
+                    }
+                }
+            if (!ok) continue;
+            const long score = (long)pl.occ * 1000000L + nbuf * 1000L + z;
+            if (score > best_score) { best_score = score; best = pl; }
+        }
+    }
+    if (best_score < 0) return false;
+    *out = best;
+    return true;
+}
+
+// launch one fused segment on the pipelined kernel; returns -2 when the segment is not supported (caller falls back)
+int launch_chain_pipe(ChainParams &p, cudaStream_t st) {
+    int max_optin = 0;
+    {
+        int dev = 0;
+        PRB_CUDA(cudaGetDevice(&dev));
+        PRB_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    }
+    p.num_tiles = (int)((p.total_rows + TM - 1) / TM);
+    if (p.num_tiles == 0) return 0;
+    const int L = p.num_layers;
+    PipePlan pl;
+    PRB_REQUIRE(pipe_plan(p, max_optin, &pl), "mlp: no tensor-memory / shared-memory plan for this chain segment");
+    int col = 0;
+    for (int l = 0; l + 1 < L; ++l) { p.rcol[l] = col; col += p.np[l]; }
+    p.zcol[0] = col; p.zcol[1] = col + pl.zs;
+    p.zs = pl.zs; p.nslice = pl.nslice; p.nbuf = pl.nbuf;
+    p.tmem_cols = pl.cols;
+    p.na = pl.na; p.nb0 = pl.nb0; p.nb1 = pl.nb1 > 0 ? pl.nb1 : 1;
+    p.b0_stage_bytes = pl.b0_bytes; p.b1_stage_bytes = pl.b1_bytes;
+    p.nsplit = pl.nsplit; p.split_w = pl.split_w;
+    p.num_items = p.num_tiles * pl.nsplit;
+    int sms = num_sms();
+    if (const int v = opts().mlp_sms; v >= 1 && v < sms) sms = v;
+    int grid = sms * pl.occ;
+    if (grid > p.num_items) grid = p.num_items;
+    const size_t smem = pl.smem;
+#define PRB_LAUNCH_PIPE(NE, NGW, MB)                                                                                         \
+    do {                                                                                                                     \
+        PRB_CUDA(cudaFuncSetAttribute(mlp_pipe_kernel<NE, NGW, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        mlp_pipe_kernel<NE, NGW, MB><<<grid, (NE + NGW + 1) * 128, smem, st>>>(p);                                            \
+    } while (0)
+    if (pl.ne == 1 && pl.ngw == 1) { if (pl.occ >= 2) PRB_LAUNCH_PIPE(1, 1, 2); else PRB_LAUNCH_PIPE(1, 1, 1); }
+    else if (pl.ne == 1) PRB_LAUNCH_PIPE(1, 2, 1);
+    else if (pl.ngw == 1) PRB_LAUNCH_PIPE(2, 1, 1);
+    else PRB_LAUNCH_PIPE(2, 2, 1);
+#undef PRB_LAUNCH_PIPE
+    return check_launch("mlp_pipe_kernel");
+}
+
+}  // namespace prb

@@ -26,246 +26,9 @@
 
 #include <vector>
 
-#include <math_constants.h>
-
-#include "common.cuh"
+#include "mlp_dev.cuh"
 
 namespace prb {
-
-constexpr int TM = 128;              // rows per tile (= TMEM lanes, UMMA M)
-constexpr int KC = 32;               // K columns per chunk (128 bytes of fp32/tf32)
-constexpr int A_STAGE_BYTES = TM * KC * 4;        // 16 KB
-constexpr int B_TILE_ROWS = 256;                  // max N per MMA / per weight tile
-constexpr int MAX_STAGES = 4;        // ring depth upper bound (runtime depth in ChainParams)
-constexpr int MAX_LAYERS = 3;
-constexpr int MAX_NP = 512;
-
-enum { IN_SA = 0, IN_FP = 1, IN_DIRECT = 2 };
-enum { OUT_ROWS = 0, OUT_SA_MAX = 1, OUT_FP = 2 };
-
-struct ChainParams {
-    int mode_in, mode_out, num_layers;
-    int nchunks[MAX_LAYERS];   // K chunks per layer
-    int np[MAX_LAYERS];        // padded N (multiple of 32)
-    int dcol[MAX_LAYERS];      // TMEM column of the accumulator
-    const float *w[MAX_LAYERS];      // packed weight images
-    const float *scale[MAX_LAYERS];  // np floats (zero padded); unused when unit_scale
-    int sleepy;                      // bit 0: MMA issuer waits with a suspend hint, bit 1: weight producer does
-    int a_tmem;                      // layers >= 1 take their A operand from tensor memory: the epilogue rewrites the
-                                     // previous accumulator IN PLACE (relu(x + t) -> tf32), no shared-memory stage, no proxy fence
-    int trace;                       // debug: record phase time stamps (see g_trace)
-    int unit_scale;                  // 1: the per-channel scale is folded into the packed weights, epilogues only add shift
-    const float *shift[MAX_LAYERS];
-    // resources (sized per launch so that small layers run several CTAs per SM)
-    int na, nb;                // ring depths
-    int b_stage_bytes;         // weight stage size = min(256, max np) * 128
-    int tmem_cols;             // power of two >= 32
-    int gather_mode;           // layer-0 row gather: 0 registers (+cvt.rna), 1 cp.async.cg, 2 cp.async.ca
-    int linear_last;           // the last layer of the chain has no ReLU (heads: y = W x + shift)
-    int round_out;             // OUT_ROWS: round to tf32 (intermediate segment of a split chain)
-    // layer-0 K segments (each padded to a multiple of KC)
-    int nseg, seg_chunks[2], seg_width[2];
-    long total_rows;
-    int num_tiles;
-    // SA
-    int n, npoint, ns, log_ns, c_feat;
-    const float *xyz, *new_xyz, *feats_pm;
-    const int *idx;
-    // FP
-    int m, c_known, c_skip;
-    const float *known_pm, *weight, *skip;
-    // DIRECT
-    const float *x_rows;
-    int x_pitch;
-    // output
-    float *out;
-    float *out_pm;       // optional second copy of the final output in point-major layout (rows x out_stride_c)
-    int c_last;          // true channel count of the last layer
-    int out_stride_c, out_c_off, out_pitch;
-};
-
-// ------------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t s2u(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "W_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra D_%=;\n\t"
-        "bra W_%=;\n\t"
-        "D_%=:\n\t}" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-// same, with a suspend-time hint: the single producer / MMA-issuer threads should sleep in hardware instead of
-// spinning in the issue slots of the row warps that share their scheduler
-__device__ __forceinline__ void mbar_wait_sleepy(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "W_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra D_%=;\n\t"
-        "bra W_%=;\n\t"
-        "D_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(20000u)
-        : "memory");
-}
-// one non-blocking probe of a phase (true = completed)
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-// 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void *src, uint32_t src_bytes) {   // also allocates in L1
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {   // ncols: power of two >= 32
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, tf32 inputs, fp32 accumulate, M=128
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// same with the A operand in tensor memory: lane = row, one 32-bit column per K element (8 columns per K=8 step)
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// 32 lanes x 16 consecutive 32-bit columns from registers (thread i writes lane base+i)
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// arrives on the mbarrier once all previously issued MMAs of this thread have completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// 32 lanes x 16 consecutive fp32 columns: thread i of the warp receives lane (base+i)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-// relu + round-to-nearest-even to tf32 in ONE instruction (F2FP.RELU.TF32.F32)
-__device__ __forceinline__ float relu_to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rn.relu.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-// round-to-nearest-even to tf32: one F2FP instruction (cvt.rna expands to a 4-instruction sequence)
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rn.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-
-// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row atoms of 1024 bytes (SBO), version 1
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address
-    d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset
-    d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
-    return d;
-}
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-    // c=f32 (1<<4), a=tf32 (2<<7), b=tf32 (2<<10), a,b K-major, N>>3 at bit 17, M>>4 at bit 24
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-}
-// byte offset of (row r, 16-byte unit j) inside a K-major SWIZZLE_128B stage
-__device__ __forceinline__ uint32_t swz(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
-
-// Shared memory is carved at run time (ring depths and the weight-stage size depend on the chain), so that
-// narrow layers (SA1/SA2) fit 2 CTAs per SM and overlap their latency-bound gathers.
-// warp-level float max over the lanes named by MASK (CREDUX.MAX.F32: ~28 cycles dependent, pipelined when independent)
-template <unsigned MASK>
-__device__ __forceinline__ float redux_max_f32(float v) {
-    float r;
-    asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "n"(MASK));
-    return r;
-}
-
-constexpr int POOL_STRIDE = 20;      // floats per row of the max-pool staging tile (80 B: conflict-free 128-bit stores)
-struct SmemFixed {
-    int row_src[TM][3];      // SA: global point row (slot 0); FP: 3 known rows
-    float row_aux[TM][3];    // SA: centre xyz; FP: 3 weights
-    int row_valid[TM];
-    uint64_t a_full[MAX_STAGES], a_empty[MAX_STAGES], b_full[MAX_STAGES], b_empty[MAX_STAGES], d_full[MAX_LAYERS];
-    uint32_t tmem_base;
-};
-
-__host__ __device__ inline size_t chain_smem_bytes(int ng, int na, int nb, int b_stage_bytes, int np_total) {
-    return 1024 /*alignment slack*/ + (size_t)na * A_STAGE_BYTES + (size_t)nb * b_stage_bytes + (size_t)2 * np_total * sizeof(float) +
-           (size_t)ng * (TM * POOL_STRIDE + 8 * 16) * sizeof(float) + sizeof(SmemFixed) + 64;
-}
-
-struct RingPos {
-    uint32_t stage, phase;
-    __device__ void advance(int depth) {
-        if (++stage == (uint32_t)depth) { stage = 0; phase ^= 1; }
-    }
-};
-
-// barrier over one row group (128 threads) / over all row threads
-__device__ __forceinline__ void bar_group(int grp) {
-    if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
-    else if (grp == 1) asm volatile("bar.sync 3, 128;" ::: "memory");
-    else asm volatile("bar.sync 4, 128;" ::: "memory");
-}
-template <int NG>
-__device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, %0;" ::"n"(128 * NG) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------ kernel
 // NG row groups of 4 warps each (warp w: TMEM lane quarter w%4, group w/4) + producer warp + MMA warp.
@@ -1007,8 +770,15 @@ int prb_mlp_pack_weights(int num_layers, int c_in, const int *c_out, const float
 
 namespace prb {
 
+int launch_chain_pipe(ChainParams &p, cudaStream_t st);   // mlp_pipe.cu
+
+// the pipelined kernel takes every segment unless the caller asks for the legacy one (prb_options.mlp_pipeline = 0) or
+// for the cp.async gather experiment, which only the legacy kernel implements
+static bool use_pipe() { return opts().mlp_pipeline != 0 && opts().mlp_gather == 0; }
+
 // launch one fused segment of the chain: size rings / TMEM to the segment, pick the CTAs-per-SM it allows
 static int launch_chain(ChainParams &p, cudaStream_t st) {
+    if (use_pipe()) return launch_chain_pipe(p, st);
     int max_optin = 0;
     {
         int dev = 0;
@@ -1076,13 +846,23 @@ static int launch_chain(ChainParams &p, cudaStream_t st) {
     return check_launch("mlp_chain_kernel");
 }
 
-// TMEM feasibility of fusing layers [l0, l1): accumulators ping-pong between column 0 and the top
-static bool fits(const LayerGeom *g, int l0, int l1) {
+// TMEM feasibility of fusing layers [l0, l1).  Legacy kernel: accumulators ping-pong between column 0 and the top.
+// Pipelined kernel: every mid layer owns a region, the last layer needs at least one 32-column slice buffer.
+static bool fits_legacy(const LayerGeom *g, int l0, int l1) {
     const int n = l1 - l0;
     if (n == 1) return g[l0].np <= 512;
     if (n == 2) return g[l0].np + g[l0 + 1].np <= 512;
     return g[l0].np + g[l0 + 1].np <= 512 && g[l0 + 2].np + g[l0 + 1].np <= 512;
 }
+static bool fits_pipe(const LayerGeom *g, int l0, int l1) {
+    int mid = 0;
+    for (int l = l0; l + 1 < l1; ++l) mid += g[l].np;
+    // keep at least two 64-column slice buffers (or the whole last layer) next to the mid regions
+    const int last = g[l1 - 1].np;
+    const int z = last < 64 ? last : 64;
+    return g[l1 - 1].np <= 512 && mid + (l1 - l0 > 1 ? 2 * z : 0) <= 512;
+}
+static bool fits(const LayerGeom *g, int l0, int l1) { return use_pipe() ? fits_pipe(g, l0, l1) : fits_legacy(g, l0, l1); }
 
 struct ChainIO {
     int kind, split;          // packing kind (0 SA, 1 FP, 2 DIRECT) and its split argument
@@ -1098,7 +878,7 @@ static size_t chain_workspace_bytes(long rows, int L, int kind, int c_in, int sp
     // worst case: two ping-pong row buffers of the widest padded layer
     int wmax = 0;
     for (int l = 0; l < L; ++l) wmax = g[l].np > wmax ? g[l].np : wmax;
-    bool split_needed = !fits(g, 0, L);
+    bool split_needed = !fits_legacy(g, 0, L) || !fits_pipe(g, 0, L);   // either kernel may be chosen at launch time
     const size_t rows_pad = (size_t)((rows + TM - 1) / TM * TM);
     return split_needed ? 2 * (rows_pad * wmax * sizeof(float) + 256) : 256;
 }
