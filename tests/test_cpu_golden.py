@@ -89,3 +89,34 @@ def test_roipool3d_golden(gold):
     assert same.mean() >= 0.95   # host cosf/sinf vs libdevice: only borderline points may differ
     for b, m in zip(*np.nonzero(~same)):
         assert O.pts_in_boxes3d_margin(xyz[b], boxes[b, m:m + 1].astype(np.float32))[0].min() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ CPU twins (row a17)
+TWINS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "roipool3d_cpu_twins.npz")
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_cpu_twins_match_the_reference_extension(case):
+    """pts_in_boxes3d_cpu / roipool_pc_cpu / roipool3d_cpu of the mirror (numpy twins in ext/roipool3d_cuda.py) against
+    the outputs of the reference's OWN roipool3d.cpp (:82-195) + roipool3d_utils.py (:31-108), compiled and run in the
+    build container by oracle/make_golden_cpu_twins.py"""
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    from make_golden_cpu_twins import CASES, scene
+    from pointrcnn_b200.roipool3d import roipool3d_utils as ru
+    g = np.load(TWINS)
+    name, N, M, C, S, extra, seed = [c for c in CASES if c[0] == case][0]
+    pts, boxes, feat = scene(N, M, C, seed)
+    masks = ru.pts_in_boxes3d_cpu(torch.from_numpy(pts), torch.from_numpy(boxes))
+    assert np.array_equal(np.stack([m.numpy() for m in masks]), g[name + "_mask"])
+    pp, pf, pe = ru.roipool_pc_cpu(torch.from_numpy(pts), torch.from_numpy(feat), torch.from_numpy(boxes), S)
+    assert np.array_equal(pe.numpy(), g[name + "_pc_empty"])
+    assert np.array_equal(pp.numpy(), g[name + "_pc_pts"]) and np.array_equal(pf.numpy(), g[name + "_pc_feat"])
+    ex = feat[:, :2].copy()
+    a, b, e = ru.roipool3d_cpu(boxes, pts, feat, ex, extra, sampled_pt_num=S, canonical_transform=False)
+    assert np.array_equal(e, g[name + "_rp_empty"]) and np.array_equal(a, g[name + "_rp_input"]) and np.array_equal(b, g[name + "_rp_feat"])
+    keep = g[name + "_rpc_keep"]
+    a2, b2 = ru.roipool3d_cpu(boxes[keep], pts, feat, ex, extra, sampled_pt_num=S, canonical_transform=True)
+    assert np.array_equal(b2, g[name + "_rpc_feat"])
+    # the canonical rotation goes through float64 cos/sin + np.dot in the reference (kitti_utils.py:33-43): same here
+    np.testing.assert_allclose(a2, g[name + "_rpc_input"], rtol=0, atol=1e-6)

@@ -8,7 +8,8 @@ pinned by any reference test.  Two checks:
           everywhere.  Chains: an intermediate activation that sits on a TF32 rounding boundary may round the
           other way (1 tf32 ulp = 1e-3 rel) and moves every output of the next layer a little, so for chains
           97% of the outputs must meet 2e-4 and all of them 5e-3.
-  loose : against the plain fp32 oracle: |err| <= 1e-2 * max|ref| (three chained TF32 layers).
+  fp32  : against the plain fp32 oracle / fp32 torch evaluation: max|err| <= 2e-3 * max|ref| -- the a6 / a11 contract of
+          SURVEY.md 8(c) (TF32 operands, fp32 accumulation, up to three chained layers).
 """
 import ctypes
 
@@ -24,7 +25,12 @@ pytestmark = pytest.mark.gpu
 from pointrcnn_b200 import _cabi as C  # noqa: E402
 from pointrcnn_b200.backbone import Pointnet2MSG  # noqa: E402
 from pointrcnn_b200.pointnet2 import pointnet2_modules as pm  # noqa: E402
+from pointrcnn_b200.pointnet2 import pointnet2_utils as pu  # noqa: E402
 
+
+
+TOL_BACKBONE = 5e-3   # the whole backbone chains 8 levels (20 TF32 layers); per-op contract is TOL
+TOL = 2e-3      # a6 / a11 parity vs an fp32 evaluation of the same weights (norm-wise: max|err| / max|ref|)
 
 def tf32(x):
     """cvt.rna.tf32.f32 on a numpy array"""
@@ -147,7 +153,7 @@ def test_mlp_rows_tcgen05(cuda, rows, dims, folded):
     else:
         assert ok.mean() >= 0.97 and (err <= 5e-3 * (1 + np.abs(tight))).all(), "tight check failed: %g ok, max err %g" % (ok.mean(), err.max())
     loose = O.shared_mlp(x, layers)
-    assert np.abs(got - loose).max() <= 1e-2 * np.abs(loose).max()
+    assert np.abs(got - loose).max() <= TOL * np.abs(loose).max()
     if np_last > dims[-1]:
         assert np.count_nonzero(out.cpu().numpy()[:, dims[-1]:]) == 0, "padding channels must be exactly zero"
 
@@ -216,11 +222,11 @@ def test_sa_module_fused_vs_unfused_vs_oracle(cuda, npoint, radii, nsamples, mlp
     assert torch.equal(new_xyz, ref_xyz)
     assert out.shape == ref_out.shape == (B, sum(m[-1] for m in mlps), npoint)
     scale = ref_out.abs().max().item()
-    assert (out - ref_out).abs().max().item() <= 1e-2 * scale, "fused SA differs from the op-by-op fp32 path"
+    assert (out - ref_out).abs().max().item() <= TOL * scale, "fused SA differs from the op-by-op fp32 path"
     # CPU oracle (fp32) of the whole module
     o_xyz, o_out, _ = O.sa_module_msg(xyz, feats, npoint, radii, nsamples, [_folded(m) for m in mod.mlps])
     assert np.array_equal(new_xyz.cpu().numpy(), o_xyz)
-    assert np.abs(out.cpu().numpy() - o_out).max() <= 1e-2 * np.abs(o_out).max()
+    assert np.abs(out.cpu().numpy() - o_out).max() <= TOL * np.abs(o_out).max()
     # the point-major twin written by the same launch is the exact transpose, and it is dropped once
     # the channel-major tensor is modified in place
     twin = out._prb_pm[0]
@@ -253,8 +259,8 @@ def test_sa_module_scale_fold_modes_agree(cuda, ns):
         ref = _unfused(lambda: mod(x, f))[1]
     scale = ref.abs().max().item()
     for mode in ("0", "1"):
-        assert (outs[mode] - ref).abs().max().item() <= 1e-2 * scale, "fold mode %s differs from the fp32 op-by-op path" % mode
-    assert (outs["0"] - outs["1"]).abs().max().item() <= 1e-2 * scale
+        assert (outs[mode] - ref).abs().max().item() <= TOL * scale, "fold mode %s differs from the fp32 op-by-op path" % mode
+    assert (outs["0"] - outs["1"]).abs().max().item() <= TOL * scale
 
 
 def test_sa_module_group_all_and_no_bn(cuda):
@@ -271,7 +277,7 @@ def test_sa_module_group_all_and_no_bn(cuda):
         rx, ref = _unfused(lambda: mod(xyz, f))
     assert nx is None and rx is None
     assert out.shape == ref.shape == (B, 512, 1)
-    assert (out - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    assert (out - ref).abs().max().item() <= TOL * ref.abs().max().item()
 
 
 FP_CASES = [
@@ -301,9 +307,9 @@ def test_fp_module_fused_vs_unfused_vs_oracle(cuda, n, m, c_known, c_skip, mlp):
         out = mod(tu, tk, tsf, tkf)
         ref = _unfused(lambda: mod(tu, tk, tsf, tkf))
     assert out.shape == ref.shape == (B, mlp[-1], n)
-    assert (out - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    assert (out - ref).abs().max().item() <= TOL * ref.abs().max().item()
     o = O.fp_module(unknown, known, sf, kf, _folded(mod.mlp))
-    assert np.abs(out.cpu().numpy() - o).max() <= 1e-2 * np.abs(o).max()
+    assert np.abs(out.cpu().numpy() - o).max() <= TOL * np.abs(o).max()
     assert torch.equal(out._prb_pm[0], out.transpose(1, 2).contiguous())
     mod.emit_point_major = False
     with torch.no_grad():
@@ -322,7 +328,47 @@ def test_backbone_fused_vs_unfused(cuda):
     assert feats.shape == (2, 128, 16384)
     assert torch.equal(xyz, rxyz)
     rel = (feats - rfeats).abs().max().item() / rfeats.abs().max().item()
-    assert rel <= 2e-2, "backbone output differs: %g" % rel
+    assert rel <= TOL_BACKBONE, "backbone output differs: %g" % rel
+
+
+def test_backbone_b16_against_the_cpu_oracle(cuda):
+    """BASELINE configs[1] at its stated shape (B=16, 16384x4 points): the fused backbone against the CPU oracle
+    (O.sa_module_msg / O.fp_module, fp32 MLP, exact index ops) -- sampled centres exact, features within TOL_BACKBONE"""
+    import bench
+    torch.manual_seed(3)
+    net = Pointnet2MSG(input_channels=1).to(cuda).eval()
+    _randomise_bn(net, 5)
+    pc = bench.make_scenes(700, 16)
+    with torch.no_grad():
+        xyz, feats = net(torch.from_numpy(pc).to(cuda))
+    want = bench.cpu_backbone(pc, *bench.folded_specs(net))
+    got = feats.cpu().numpy()
+    assert got.shape == want.shape == (16, 128, 16384)
+    rel = np.abs(got - want).max() / np.abs(want).max()
+    assert rel <= TOL_BACKBONE, "backbone output differs from the oracle: %g" % rel
+
+
+def test_c1_single_sa_layer_at_baseline_shape(cuda):
+    """BASELINE configs[0] / SURVEY 8(d) C1 at its stated shape: one SA layer (npoint 4096, r 0.1, nsample 32, MLP [1+3,16,32])
+    on one 16384x4 cloud (U-CUBE: dense balls): FPS and ball-query indices exact, grouped features exact, pooled output
+    within the MLP tolerance"""
+    torch.manual_seed(11)
+    pc = synth.u_cube(1, 16384, 1001)
+    inten = (np.random.default_rng(1001).random((1, 1, 16384), dtype=np.float32) - np.float32(0.5))
+    mod = pm.PointnetSAModuleMSG(npoint=4096, radii=[0.1], nsamples=[32], mlps=[[1, 16, 32]], bn=True).to(cuda).eval()
+    _randomise_bn(mod, 3)
+    x, f = torch.from_numpy(pc).to(cuda), torch.from_numpy(inten).to(cuda)
+    with torch.no_grad():
+        new_xyz, out = mod(x, f)
+        idx = pu.ball_query(0.1, 32, x, new_xyz)
+        grouped = mod.groupers[0](x, new_xyz, f)
+    o_xyz, o_out, _ = O.sa_module_msg(pc, inten, 4096, [0.1], [32], [_folded(mod.mlps[0])])
+    assert np.array_equal(new_xyz.cpu().numpy(), o_xyz), "FPS picks differ"
+    o_idx = O.ball_query(0.1, 32, pc, o_xyz)
+    assert np.array_equal(idx.cpu().numpy(), o_idx), "ball-query indices differ"
+    o_grouped = O.query_and_group(0.1, 32, pc, o_xyz, inten)
+    np.testing.assert_allclose(grouped.cpu().numpy(), o_grouped, rtol=1e-5, atol=0)
+    assert np.abs(out.cpu().numpy() - o_out).max() <= TOL * np.abs(o_out).max()
 
 
 def test_training_path_autograd(cuda):
