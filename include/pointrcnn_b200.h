@@ -224,6 +224,14 @@ PRB_API int prb_three_nn_grid(int b, int n, int m, const float *unknown, const f
 PRB_API int prb_roipool3d(int B, int N, int M, int C, int S, const float *xyz, const float *boxes3d,
                   const float *pts_feature, float *pooled, int *empty_flag,
                   const float *rois_canonical, void *stream);
+/* two-pass form (what the Python mirror calls): pass A reads a scene's points once per tile of boxes and writes the
+ * per-box index lists into caller scratch (prb_roipool3d_workspace_bytes), pass B streams the pooled rows with
+ * 128-bit stores.  zero_fill_empty != 0: the kernel zeroes the rows of empty boxes itself, so `pooled` may be
+ * uninitialised (saves the caller's 558 MB memset at C4); 0: untouched, as the reference leaves them. */
+PRB_API size_t prb_roipool3d_workspace_bytes(int B, int M, int S);
+PRB_API int prb_roipool3d_ws(int B, int N, int M, int C, int S, const float *xyz, const float *boxes3d,
+                     const float *pts_feature, float *pooled, int *empty_flag, const float *rois_canonical,
+                     int zero_fill_empty, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------ iou3d_cuda ----------
  * replaces lib/utils/iou3d/src/iou3d.cpp:31-71 (matrices) and :73-170 (NMS) */

@@ -50,6 +50,135 @@ __device__ __forceinline__ bool pt_in_box(const BoxConst &c, float x, float y, f
            ((double)z_rot <= c.half_w);
 }
 
+// ------------------------------------------------------------------------------------------------ two-pass form
+// Pass A (assign): one CTA per (scene, tile of RA_BOXES boxes).  The scene's points are read ONCE per tile (the
+// reference and the one-pass kernel above re-read all N points for every box: 2048 x 196 KB at C4).  Warp w owns the
+// contiguous point range [w*N/8, (w+1)*N/8): it appends the hits of every box to its own ordered list in shared memory
+// (ballot + popc prefix, no CTA barrier inside the scan); the lists are then concatenated in warp order, which IS
+// point-index order, and cut at S -> idx (B,M,S) int32 + cnt (B,M) in caller scratch.
+// Pass B (copy): one CTA per box streams the S x (3+C) output as ONE flat array with 128-bit stores (rows are
+// 532 bytes at C4, so row-aligned stores are 4 bytes per lane); sources are read through L1 (a box holds a few dozen
+// distinct rows that are repeated cyclically).  Empty boxes set the flag and, when asked, zero their rows, so the caller
+// need not pre-zero the 558 MB output.
+constexpr int RA_BOXES = 4;
+constexpr int RA_WARPS = 8;
+
+__global__ void __launch_bounds__(32 * RA_WARPS) roipool3d_assign_kernel(int N, int M, int S, const float *__restrict__ xyz,
+                                                                        const float *__restrict__ boxes3d,
+                                                                        int *__restrict__ idx_out, int *__restrict__ cnt_out) {
+    extern __shared__ int s_list[];                 // [RA_BOXES][RA_WARPS][S]
+    __shared__ int s_cnt[RA_BOXES][RA_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int box0 = blockIdx.x * RA_BOXES, scene = blockIdx.y;
+    const int nb = min(RA_BOXES, M - box0);
+    BoxConst bc[RA_BOXES];
+#pragma unroll
+    for (int b = 0; b < RA_BOXES; ++b) bc[b] = make_box(boxes3d + ((size_t)scene * M + box0 + (b < nb ? b : 0)) * 7);
+    const float *pts = xyz + (size_t)scene * N * 3;
+    const int per = (N + RA_WARPS - 1) / RA_WARPS;
+    const int lo = warp * per, hi = min(N, lo + per);
+    int cnt[RA_BOXES];
+#pragma unroll
+    for (int b = 0; b < RA_BOXES; ++b) cnt[b] = 0;
+    for (int k0 = lo; k0 < hi; k0 += 32) {
+        const int k = k0 + lane;
+        float x = 0.f, y = 0.f, z = 0.f;
+        const bool ok = k < hi;
+        if (ok) { x = __ldg(pts + (size_t)k * 3); y = __ldg(pts + (size_t)k * 3 + 1); z = __ldg(pts + (size_t)k * 3 + 2); }
+#pragma unroll
+        for (int b = 0; b < RA_BOXES; ++b) {
+            const bool in = ok && b < nb && pt_in_box(bc[b], x, y, z);
+            const unsigned hits = __ballot_sync(0xffffffffu, in);
+            if (hits) {
+                const int pos = cnt[b] + __popc(hits & ((1u << lane) - 1));
+                if (in && pos < S) s_list[((size_t)b * RA_WARPS + warp) * S + pos] = k;
+                cnt[b] = min(S, cnt[b] + __popc(hits));
+            }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < RA_BOXES; ++b) s_cnt[b][warp] = cnt[b];
+    }
+    __syncthreads();
+    // concatenate the per-warp lists (warp order = point order), cut at S
+    for (int b = 0; b < nb; ++b) {
+        int off = 0;
+        for (int w = 0; w < RA_WARPS; ++w) {
+            const int c = s_cnt[b][w];
+            const int take = min(c, S - off);
+            int *dst = idx_out + ((size_t)scene * M + box0 + b) * S + off;
+            for (int j = tid; j < take; j += 32 * RA_WARPS) dst[j] = s_list[((size_t)b * RA_WARPS + w) * S + j];
+            off += take;
+            if (off >= S) break;
+        }
+        if (tid == 0) cnt_out[(size_t)scene * M + box0 + b] = off;
+    }
+}
+
+__global__ void __launch_bounds__(RP_THREADS) roipool3d_copy_kernel(int N, int M, int C, int S, const float *__restrict__ xyz,
+                                                                    const float *__restrict__ pts_feature,
+                                                                    const int *__restrict__ idx_in, const int *__restrict__ cnt_in,
+                                                                    float *__restrict__ pooled, int *__restrict__ empty_flag,
+                                                                    const float *__restrict__ rois, int zero_fill) {
+    extern __shared__ int s_idx[];  // S selected point indices
+    const int tid = threadIdx.x;
+    const int box = blockIdx.x, scene = blockIdx.y;
+    const size_t bi = (size_t)scene * M + box;
+    const int cnt = cnt_in[bi];
+    const int W = 3 + C;
+    const long total = (long)S * W;
+    float *dst = pooled + bi * (size_t)total;
+    const bool vec = (total & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    if (cnt == 0) {
+        if (tid == 0) empty_flag[bi] = 1;
+        if (zero_fill) {
+            if (vec) for (long e = 4L * tid; e < total; e += 4L * RP_THREADS) *reinterpret_cast<float4 *>(dst + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+            else for (long e = tid; e < total; e += RP_THREADS) dst[e] = 0.f;
+        }
+        return;
+    }
+    for (int j = tid; j < S; j += RP_THREADS) s_idx[j] = idx_in[bi * S + (j < cnt ? j : j % cnt)];
+    __syncthreads();
+    // canonical transform constants (rcnn_net.py:146-152): xyz -= roi centre, rotate (x,z) by roi ry
+    float rcx = 0.f, rcy = 0.f, rcz = 0.f, rcos = 1.f, rsin = 0.f;
+    if (rois) {
+        const float *r = rois + bi * 7;
+        rcx = r[0]; rcy = r[1]; rcz = r[2];
+        rcos = cosf(r[6]); rsin = sinf(r[6]);
+    }
+    const float *pts = xyz + (size_t)scene * N * 3;
+    const float *feat = pts_feature + (size_t)scene * N * C;
+    auto value = [&](int row, int col) -> float {
+        const int k = s_idx[row];
+        if (col >= 3) return __ldg(feat + (size_t)k * C + (col - 3));
+        if (!rois) return __ldg(pts + (size_t)k * 3 + col);
+        const float x = __ldg(pts + (size_t)k * 3) - rcx, y = __ldg(pts + (size_t)k * 3 + 1) - rcy, z = __ldg(pts + (size_t)k * 3 + 2) - rcz;
+        // [x z] @ [[cos,-sin],[sin,cos]]^T : x' = x*cos - z*sin, z' = x*sin + z*cos
+        return col == 0 ? __fmaf_rn(x, rcos, -__fmul_rn(z, rsin)) : (col == 1 ? y : __fmaf_rn(x, rsin, __fmul_rn(z, rcos)));
+    };
+    if (vec) {
+        // thread t owns float4 units t, t + T, ...: (row, col) of the unit's first float advance by a constant stride
+        const int step = 4 * RP_THREADS;
+        const int d_row = step / W, d_col = step % W;
+        int row = (4 * tid) / W, col = (4 * tid) % W;
+        for (long e = 4L * tid; e < total; e += step) {
+            float v[4];
+            int r = row, c = col;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                v[q] = value(r, c);
+                if (++c == W) { c = 0; ++r; }
+            }
+            *reinterpret_cast<float4 *>(dst + e) = make_float4(v[0], v[1], v[2], v[3]);
+            row += d_row; col += d_col;
+            if (col >= W) { col -= W; ++row; }
+        }
+    } else {
+        for (long e = tid; e < total; e += RP_THREADS) dst[e] = value((int)(e / W), (int)(e % W));
+    }
+}
+
 __global__ void __launch_bounds__(RP_THREADS) roipool3d_kernel(int N, int M, int C, int S, const float *__restrict__ xyz,
                                                                const float *__restrict__ boxes3d,
                                                                const float *__restrict__ pts_feature,
@@ -120,6 +249,35 @@ __global__ void __launch_bounds__(RP_THREADS) roipool3d_kernel(int N, int M, int
 }  // namespace prb
 
 using namespace prb;
+
+extern "C" size_t prb_roipool3d_workspace_bytes(int B, int M, int S) {
+    return ((size_t)B * M * S + (size_t)B * M) * sizeof(int) + 256;
+}
+
+// two-pass form with caller scratch; zero_fill_empty != 0: rows of empty boxes are zeroed by the kernel (the caller may
+// pass an uninitialised `pooled`), 0: they are left untouched like the reference (caller pre-zeroes)
+extern "C" int prb_roipool3d_ws(int B, int N, int M, int C, int S, const float *xyz, const float *boxes3d,
+                                const float *pts_feature, float *pooled, int *empty_flag, const float *rois_canonical,
+                                int zero_fill_empty, void *workspace, size_t workspace_bytes, void *stream) {
+    PRB_REQUIRE(B >= 0 && N >= 0 && M >= 0 && C >= 0 && S > 0 && xyz && boxes3d && pooled && empty_flag && (C == 0 || pts_feature),
+                "roipool3d: bad arguments");
+    if (B == 0 || M == 0) return 0;
+    PRB_REQUIRE(workspace && workspace_bytes >= prb_roipool3d_workspace_bytes(B, M, S), "roipool3d: workspace too small");
+    const size_t smem_a = (size_t)RA_BOXES * RA_WARPS * S * sizeof(int), smem_b = (size_t)S * sizeof(int);
+    PRB_REQUIRE(smem_a <= 200 * 1024, "roipool3d: sampled_pts_num %d too large", S);
+    int *idx = reinterpret_cast<int *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    int *cnt = idx + (size_t)B * M * S;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (smem_a > 48 * 1024)
+        PRB_CUDA(cudaFuncSetAttribute(roipool3d_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    roipool3d_assign_kernel<<<dim3(ceil_div(M, RA_BOXES), B), 32 * RA_WARPS, smem_a, st>>>(N, M, S, xyz, boxes3d, idx, cnt);
+    if (int rc = check_launch("roipool3d_assign_kernel")) return rc;
+    if (smem_b > 48 * 1024)
+        PRB_CUDA(cudaFuncSetAttribute(roipool3d_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    roipool3d_copy_kernel<<<dim3(M, B), RP_THREADS, smem_b, st>>>(N, M, C, S, xyz, pts_feature, idx, cnt, pooled, empty_flag,
+                                                                 rois_canonical, zero_fill_empty);
+    return check_launch("roipool3d_copy_kernel");
+}
 
 extern "C" int prb_roipool3d(int B, int N, int M, int C, int S, const float *xyz, const float *boxes3d,
                              const float *pts_feature, float *pooled, int *empty_flag, const float *rois_canonical,

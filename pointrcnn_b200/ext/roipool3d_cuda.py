@@ -10,11 +10,34 @@ import torch
 from .. import _cabi as C
 
 
-def forward(xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag, rois_canonical=None):
+def forward(xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag, rois_canonical=None, zero_fill_empty=False):
+    """reference signature (roipool3d.cpp:48): the caller pre-zeroes `pooled_features` / `pooled_empty_flag`.
+    zero_fill_empty=True (extra): the kernel zeroes the rows of empty boxes, `pooled_features` may be torch.empty"""
     for t, nm in ((xyz, "xyz"), (boxes3d, "boxes3d"), (pts_feature, "pts_feature"), (pooled_features, "pooled_features"),
                   (pooled_empty_flag, "pooled_empty_flag")):
         if not (t.is_cuda and t.is_contiguous()):
             raise RuntimeError("%s must be a contiguous CUDA tensor" % nm)  # CHECK_INPUT, roipool3d.cpp:21-25
+    B, N = int(xyz.size(0)), int(xyz.size(1))
+    M, Cf, S = int(boxes3d.size(1)), int(pts_feature.size(2)), int(pooled_features.size(2))
+    for t, nm, dt in ((xyz, "xyz", torch.float32), (boxes3d, "boxes3d", torch.float32), (pts_feature, "pts_feature", torch.float32),
+                      (pooled_features, "pooled_features", torch.float32), (pooled_empty_flag, "pooled_empty_flag", torch.int32)):
+        if t.dtype != dt:
+            raise RuntimeError("%s must be %s" % (nm, dt))     # the reference's .data<float>() / .data<int>() throw as well
+    if tuple(pooled_features.shape) != (B, M, S, 3 + Cf) or pooled_empty_flag.numel() != B * M or boxes3d.size(0) != B or \
+            pts_feature.size(0) != B or pts_feature.size(1) != N:
+        raise RuntimeError("roipool3d: inconsistent tensor shapes")
+    lib = C.lib()
+    with torch.cuda.device(xyz.device):
+        wsb = lib.prb_roipool3d_workspace_bytes(B, M, S)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=xyz.device)
+        C.check(lib.prb_roipool3d_ws(B, N, M, Cf, S, C.ptr(xyz), C.ptr(boxes3d), C.ptr(pts_feature), C.ptr(pooled_features),
+                                     C.ptr(pooled_empty_flag), C.ptr(rois_canonical), int(bool(zero_fill_empty)), C.ptr(ws),
+                                     C.c_size_t(wsb), C.stream()), "roipool3d")
+    return 1
+
+
+def forward_one_pass(xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag, rois_canonical=None):
+    """the one-kernel form (prb_roipool3d: no scratch, every box rescans the scene) -- kept for A/B measurements"""
     B, N = int(xyz.size(0)), int(xyz.size(1))
     M, Cf, S = int(boxes3d.size(1)), int(pts_feature.size(2)), int(pooled_features.size(2))
     with torch.cuda.device(xyz.device):
