@@ -60,6 +60,8 @@ typedef struct prb_options {
     int mlp_pipeline;  /* 1: role-specialised pipelined chain kernel (gather of tile i+1 overlaps tile i); 0: legacy */
     int mlp_ne, mlp_ngw;   /* pipelined kernel: epilogue / gather warp groups per CTA (1 or 2); 0 = plan rule */
     int mlp_zs, mlp_nbuf;  /* pipelined kernel: last-layer slice width (multiple of 32) / slice buffers (1 or 2); 0 = plan rule */
+    int mlp_brows;     /* pipelined kernel: rows per weight stage / MMA N (32..256); 0 = 64 */
+    int mlp_pool;      /* SA max-pool over 16/32 samples: 0 = CREDUX (warp-wide max per channel), 1 = shuffle butterfly */
     int grid_debug;    /* 1: print (and synchronise for) the 3-NN grid's fallback counts */
     float nn_cell;     /* 3-NN grid cell edge in units of the mean point spacing (default 1.6) */
 } prb_options;
@@ -239,6 +241,14 @@ PRB_API int prb_boxes_overlap_bev(int num_a, const float *boxes_a, int num_b, co
                           float *ans_overlap, void *stream);
 PRB_API int prb_boxes_iou_bev(int num_a, const float *boxes_a, int num_b, const float *boxes_b,
                       float *ans_iou, void *stream);
+
+/* fused 3D IoU: what iou3d_utils.boxes_iou3d_gpu (lib/utils/iou3d/iou3d_utils.py:21-53) computes with two BEV
+ * conversions, the overlap kernel and ~12 torch ops, in ONE launch and with the same fp32 roundings.
+ * prb_boxes_iou3d: boxes_a (batch,na,7), boxes_b (batch,nb,7) [x,y,z,h,w,l,ry] -> out (batch,na,nb): all (RoI x GT)
+ * pairs of a batch at once (lib/rpn/proposal_target_layer.py:104 calls the reference once per scene).
+ * prb_boxes_iou3d_aligned: out[k] = IoU3D(boxes_a[k], boxes_b[k]) -- the aug loop's 1x1 calls (:232), batched. */
+PRB_API int prb_boxes_iou3d(int batch, int na, const float *boxes_a, int nb, const float *boxes_b, float *out, void *stream);
+PRB_API int prb_boxes_iou3d_aligned(int n, const float *boxes_a, const float *boxes_b, float *out, void *stream);
 
 /* scratch for one NMS call over n boxes */
 PRB_API size_t prb_nms_workspace_bytes(int n);

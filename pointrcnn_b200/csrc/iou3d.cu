@@ -173,9 +173,67 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_global_kernel(int n, co
     if (tid == 0) *num_out = s_num;
 }
 
+// ---------------------------------------------------------------- fused 3D IoU (boxes_iou3d_gpu in one launch)
+// lib/utils/iou3d/iou3d_utils.py:21-53 runs: 2 x boxes3d_to_bev (kitti_utils.py:134-147), the overlap kernel, ~12 small
+// torch kernels for the height overlap / volumes / division -- and lib/rpn/proposal_target_layer.py calls that once per
+// scene for (RoIs x GTs) and up to 10 times per RoI for single pairs (:104, :232).  Here one thread per pair does all of
+// it; every torch op of the reference is one fp32 rounding here too (explicit _rn intrinsics: no FMA contraction), so
+// the values equal the reference's op sequence on its own overlap kernel bit for bit.
+//   mode 0: matrix, out[s][i][j] = iou(a[s][i], b[s][j]) for s < batch; mode 1: aligned pairs, out[k] = iou(a[k], b[k])
+__device__ __forceinline__ void box7_to_bev(const float *b, float *bev) {
+    const float half_l = __fmul_rn(b[5], 0.5f), half_w = __fmul_rn(b[4], 0.5f);
+    bev[0] = __fsub_rn(b[0], half_l); bev[1] = __fsub_rn(b[2], half_w);
+    bev[2] = __fadd_rn(b[0], half_l); bev[3] = __fadd_rn(b[2], half_w);
+    bev[4] = b[6];
+}
+__device__ __forceinline__ float iou3d_pair(const float *a, const float *b) {
+    float abev[5], bbev[5];
+    box7_to_bev(a, abev);
+    box7_to_bev(b, bbev);
+    const float ov_bev = box_overlap(abev, bbev);
+    const float a_min = __fsub_rn(a[1], a[3]), b_min = __fsub_rn(b[1], b[3]);       // y - h .. y (y points down)
+    const float ov_h = fmaxf(__fsub_rn(fminf(a[1], b[1]), fmaxf(a_min, b_min)), 0.f);
+    const float ov3d = __fmul_rn(ov_bev, ov_h);
+    const float va = __fmul_rn(__fmul_rn(a[3], a[4]), a[5]), vb = __fmul_rn(__fmul_rn(b[3], b[4]), b[5]);
+    return __fdiv_rn(ov3d, fmaxf(__fsub_rn(__fadd_rn(va, vb), ov3d), 1e-7f));
+}
+__global__ void __launch_bounds__(128) iou3d_kernel(int mode, int batch, int na, int nb, const float *__restrict__ boxes_a,
+                                                    const float *__restrict__ boxes_b, float *__restrict__ out) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    float a[7], b[7];
+    if (mode == 1) {
+        if (t >= na) return;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) { a[q] = boxes_a[t * 7 + q]; b[q] = boxes_b[t * 7 + q]; }
+        out[t] = iou3d_pair(a, b);
+        return;
+    }
+    const long per = (long)na * nb;
+    if (t >= per * batch) return;
+    const long s = t / per, e = t - s * per;
+    const long i = e / nb, j = e - i * nb;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) { a[q] = boxes_a[(s * na + i) * 7 + q]; b[q] = boxes_b[(s * nb + j) * 7 + q]; }
+    out[t] = iou3d_pair(a, b);
+}
+
 }  // namespace prb
 
 using namespace prb;
+
+extern "C" int prb_boxes_iou3d(int batch, int na, const float *boxes_a, int nb, const float *boxes_b, float *out, void *stream) {
+    PRB_REQUIRE(batch >= 0 && na >= 0 && nb >= 0 && boxes_a && boxes_b && out, "boxes_iou3d: bad arguments");
+    const long total = (long)batch * na * nb;
+    if (total == 0) return 0;
+    iou3d_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(0, batch, na, nb, boxes_a, boxes_b, out);
+    return check_launch("iou3d_kernel");
+}
+extern "C" int prb_boxes_iou3d_aligned(int n, const float *boxes_a, const float *boxes_b, float *out, void *stream) {
+    PRB_REQUIRE(n >= 0 && boxes_a && boxes_b && out, "boxes_iou3d_aligned: bad arguments");
+    if (n == 0) return 0;
+    iou3d_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(1, 1, n, 1, boxes_a, boxes_b, out);
+    return check_launch("iou3d_kernel");
+}
 
 static int pair_matrix(bool iou, int na, const float *a, int nb, const float *b, float *out, void *stream) {
     PRB_REQUIRE(na >= 0 && nb >= 0 && a && b && out, "boxes matrix: bad arguments");
@@ -246,8 +304,12 @@ extern "C" int prb_nms_host(const float *boxes, int n, float thresh, int normal,
     int *num_dev = (int *)(ws + (size_t)n * cb * 8 + (size_t)n * 8);
     int rc = prb_nms_device(boxes, n, thresh, normal, keep_dev, num_dev, workspace, stream);
     if (rc) return rc;
+    // like the reference (iou3d.cpp:105-116) only keep_host[0 .. num_out) is written: count first, then that many indices
     PRB_CUDA(cudaMemcpyAsync(num_out, num_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
-    PRB_CUDA(cudaMemcpyAsync(keep_host, keep_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     PRB_CUDA(cudaStreamSynchronize(st));
+    if (*num_out > 0) {
+        PRB_CUDA(cudaMemcpyAsync(keep_host, keep_dev, (size_t)*num_out * 8, cudaMemcpyDeviceToHost, st));
+        PRB_CUDA(cudaStreamSynchronize(st));
+    }
     return 0;
 }

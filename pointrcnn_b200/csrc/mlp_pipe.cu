@@ -26,7 +26,7 @@
 namespace prb {
 
 constexpr int PIPE_MAX_A = 8;      // A-ring depth upper bound
-constexpr int PIPE_MAX_B = 4;
+constexpr int PIPE_MAX_B = 12;    // weight rings: many SMALL stages (64 rows x 128 B) -> enough bytes in flight to cover the L2 latency
 
 struct PipeSmem {
     uint64_t a_full[PIPE_MAX_A], a_empty[PIPE_MAX_A];
@@ -50,8 +50,30 @@ __device__ __forceinline__ void bar_named(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int NE, int NGW, int MINB>
-__global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(const ChainParams p) {
+// position of a running element index inside consecutive segments ("scenes") of `period` elements: advanced by a
+// constant stride per tile without any division in the loop
+struct Cursor {
+    int scene, pos, adv_scene, adv_pos, period;
+    __device__ __forceinline__ void init(int start, int step, int per) {
+        period = per;
+        scene = start / per; pos = start - scene * per;
+        adv_scene = step / per; adv_pos = step - adv_scene * per;
+    }
+    __device__ __forceinline__ void advance() {
+        scene += adv_scene; pos += adv_pos;
+        if (pos >= period) { pos -= period; ++scene; }
+    }
+    __device__ __forceinline__ void at(int off, int &sc, int &ps) const {
+        sc = scene; ps = pos + off;
+        while (ps >= period) { ps -= period; ++sc; }
+    }
+};
+
+// every wait parks the warp in hardware (try_wait with a suspend hint) instead of spinning in the issue slots
+__device__ __forceinline__ void bwait(uint64_t *bar, uint32_t parity) { mbar_wait_sleepy(s2u(bar), parity); }
+
+template <int NE, int NGW, int MINB, int MIN, int MOUT>
+__global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(const __grid_constant__ ChainParams p) {
     constexpr int NTHREADS = (NE + NGW + 1) * 128;
     constexpr int W_GATHER = 4 * NE, W_MISC = 4 * (NE + NGW);
     extern __shared__ uint8_t smem_raw[];
@@ -67,7 +89,6 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
     float *s_shift = s_scale + np_total;
     float *s_pool = s_shift + np_total;                                  // NE x (TM x POOL_STRIDE + 8 x 16)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int NA = p.na;
 
     if (tid == 0) {
         for (int i = 0; i < PIPE_MAX_A; ++i) { mbar_init(s2u(&S.a_full[i]), 128); mbar_init(s2u(&S.a_empty[i]), 1); }
@@ -90,26 +111,33 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
+    // work items: the grid is a multiple of nsplit, so a CTA keeps its column group and walks tiles with a fixed stride
+    const int brows = p.b_rows;          // rows (output channels) per weight stage / per MMA
     const int nsplit = p.nsplit;
+    const int sj = (int)blockIdx.x % nsplit;
+    const int tile0 = (int)blockIdx.x / nsplit, tstep = (int)gridDim.x / nsplit;
+    const int ntiles = p.num_tiles;
 
     if (warp == W_MISC) {
         // ===================================================== weight producer, layer 0
         if (lane == 0) {
             RingPos rb = {0, 0};
-            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-                const int sj = item % nsplit;
-                const int col0 = sj * p.split_w;
-                const int width = L == 1 ? min(p.split_w, p.np[0] - col0) : p.np[0];
-                const int halves = (width + B_TILE_ROWS - 1) / B_TILE_ROWS;
-                for (int kc = 0; kc < p.nchunks[0]; ++kc)
+            const int col0 = sj * p.split_w;
+            const int width = L == 1 ? min(p.split_w, p.np[0] - col0) : p.np[0];
+            const int halves = (width + brows - 1) / brows;
+            const int nch = p.nchunks[0], nb = p.nb0;
+            const uint32_t stage_bytes = (uint32_t)p.b0_stage_bytes;
+            const float *w0 = p.w[0] + (size_t)col0 * KC;
+            const size_t chunk_stride = (size_t)p.np[0] * KC;
+            for (int tile = tile0; tile < ntiles; tile += tstep) {
+                const float *src = w0;
+                for (int kc = 0; kc < nch; ++kc, src += chunk_stride)
                     for (int h = 0; h < halves; ++h) {
-                        const int rows = min(B_TILE_ROWS, width - h * B_TILE_ROWS);
-                        const uint32_t bytes = (uint32_t)rows * KC * 4;
-                        mbar_wait_sleepy(s2u(&S.b0_empty[rb.stage]), rb.phase ^ 1);
+                        const uint32_t bytes = (uint32_t)min(brows, width - h * brows) * KC * 4;
+                        bwait(&S.b0_empty[rb.stage], rb.phase ^ 1);
                         mbar_expect_tx(s2u(&S.b0_full[rb.stage]), bytes);
-                        const float *src = p.w[0] + ((size_t)kc * p.np[0] + (size_t)(col0 + h * B_TILE_ROWS)) * KC;
-                        bulk_g2s(s2u(sB0 + (size_t)rb.stage * p.b0_stage_bytes), src, bytes, s2u(&S.b0_full[rb.stage]));
-                        rb.advance(p.nb0);
+                        bulk_g2s(s2u(sB0) + rb.stage * stage_bytes, src + (size_t)h * brows * KC, bytes, s2u(&S.b0_full[rb.stage]));
+                        rb.advance(nb);
                     }
             }
         }
@@ -117,23 +145,27 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
         // ===================================================== weight producer, layers >= 1
         if (lane == 0 && L > 1) {
             RingPos rb = {0, 0};
-            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+            const int nb = p.nb1;
+            const uint32_t stage_bytes = (uint32_t)p.b1_stage_bytes;
+            for (int tile = tile0; tile < ntiles; tile += tstep) {
                 for (int l = 1; l < L; ++l) {
                     const bool last = l == L - 1;
                     const int nsl = last ? p.nslice : 1;
                     const int width = last ? p.zs : p.np[l];
-                    const int halves = (width + B_TILE_ROWS - 1) / B_TILE_ROWS;
-                    for (int s = 0; s < nsl; ++s)
-                        for (int kc = 0; kc < p.nchunks[l]; ++kc)
+                    const int halves = (width + brows - 1) / brows;
+                    const int nch = p.nchunks[l];
+                    const size_t chunk_stride = (size_t)p.np[l] * KC;
+                    for (int s = 0; s < nsl; ++s) {
+                        const float *src = p.w[l] + (size_t)s * width * KC;
+                        for (int kc = 0; kc < nch; ++kc, src += chunk_stride)
                             for (int h = 0; h < halves; ++h) {
-                                const int rows = min(B_TILE_ROWS, width - h * B_TILE_ROWS);
-                                const uint32_t bytes = (uint32_t)rows * KC * 4;
-                                mbar_wait_sleepy(s2u(&S.b1_empty[rb.stage]), rb.phase ^ 1);
+                                const uint32_t bytes = (uint32_t)min(brows, width - h * brows) * KC * 4;
+                                bwait(&S.b1_empty[rb.stage], rb.phase ^ 1);
                                 mbar_expect_tx(s2u(&S.b1_full[rb.stage]), bytes);
-                                const float *src = p.w[l] + ((size_t)kc * p.np[l] + (size_t)(s * width + h * B_TILE_ROWS)) * KC;
-                                bulk_g2s(s2u(sB1 + (size_t)rb.stage * p.b1_stage_bytes), src, bytes, s2u(&S.b1_full[rb.stage]));
-                                rb.advance(p.nb1);
+                                bulk_g2s(s2u(sB1) + rb.stage * stage_bytes, src + (size_t)h * brows * KC, bytes, s2u(&S.b1_full[rb.stage]));
+                                rb.advance(nb);
                             }
+                    }
                 }
             }
         }
@@ -141,42 +173,43 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
         // ===================================================== MMA issuer A: layer 0 (A operand from the shared-memory ring)
         if (lane == 0) {
             RingPos ra = {0, 0}, rb = {0, 0};
+            const int width = L == 1 ? min(p.split_w, p.np[0] - sj * p.split_w) : p.np[0];
+            const int halves = (width + brows - 1) / brows;
+            const int nch = p.nchunks[0], na = p.na, nb = p.nb0;
+            const uint32_t a_base = s2u(sA), b_base = s2u(sB0), b_bytes = (uint32_t)p.b0_stage_bytes;
+            const uint32_t nbuf = (uint32_t)p.nbuf;
             uint32_t it = 0;
-            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-                const int sj = item % nsplit;
-                const int width = L == 1 ? min(p.split_w, p.np[0] - sj * p.split_w) : p.np[0];
-                const int halves = (width + B_TILE_ROWS - 1) / B_TILE_ROWS;
+            for (int tile = tile0; tile < ntiles; tile += tstep, ++it) {
                 uint32_t dcol, buf = 0;
                 if (L > 1) {
-                    mbar_wait_sleepy(s2u(&S.x_free), (it & 1) ^ 1);       // layer 1 of the previous item has consumed X
+                    bwait(&S.x_free, (it & 1) ^ 1);       // layer 1 of the previous item has consumed X
                     dcol = (uint32_t)p.rcol[0];
                 } else {
-                    buf = it % (uint32_t)p.nbuf;
-                    mbar_wait_sleepy(s2u(&S.z_free[buf]), ((it / (uint32_t)p.nbuf) & 1) ^ 1);
+                    buf = nbuf == 2 ? (it & 1) : 0u;
+                    bwait(&S.z_free[buf], ((nbuf == 2 ? (it >> 1) : it) & 1) ^ 1);
                     dcol = (uint32_t)p.zcol[buf];
                 }
                 tc_fence_after();
-                for (int kc = 0; kc < p.nchunks[0]; ++kc) {
+                for (int kc = 0; kc < nch; ++kc) {
                     int c = kc, sg = 0;
                     if (p.nseg > 1 && c >= p.seg_chunks[0]) { c -= p.seg_chunks[0]; sg = 1; }
-                    const int valid = min(KC, p.seg_width[sg] - c * KC);
-                    const int ksteps = (valid + 7) >> 3;
-                    mbar_wait_sleepy(s2u(&S.a_full[ra.stage]), ra.phase);
-                    const uint64_t adesc = make_desc(s2u(sA + (size_t)ra.stage * A_STAGE_BYTES));
+                    const int ksteps = (min(KC, p.seg_width[sg] - c * KC) + 7) >> 3;
+                    bwait(&S.a_full[ra.stage], ra.phase);
+                    const uint64_t adesc = make_desc(a_base + ra.stage * A_STAGE_BYTES);
                     for (int h = 0; h < halves; ++h) {
-                        const int rows = min(B_TILE_ROWS, width - h * B_TILE_ROWS);
-                        mbar_wait_sleepy(s2u(&S.b0_full[rb.stage]), rb.phase);
+                        const int rows = min(brows, width - h * brows);
+                        bwait(&S.b0_full[rb.stage], rb.phase);
                         tc_fence_after();
-                        const uint64_t bdesc = make_desc(s2u(sB0 + (size_t)rb.stage * p.b0_stage_bytes));
+                        const uint64_t bdesc = make_desc(b_base + rb.stage * b_bytes);
                         const uint32_t idesc = make_idesc(rows);
-                        const uint32_t d = tmem + dcol + (uint32_t)(h * B_TILE_ROWS);
+                        const uint32_t d = tmem + dcol + (uint32_t)(h * brows);
                         for (int ks = 0; ks < ksteps; ++ks)  // +32 bytes (= 2 x 16 B) per K=8 step inside the swizzle row
                             umma_tf32(d, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
                         umma_commit(s2u(&S.b0_empty[rb.stage]));
-                        rb.advance(p.nb0);
+                        rb.advance(nb);
                     }
                     umma_commit(s2u(&S.a_empty[ra.stage]));
-                    ra.advance(NA);
+                    ra.advance(na);
                 }
                 umma_commit(L > 1 ? s2u(&S.r_full[0]) : s2u(&S.z_full[buf]));
             }
@@ -185,39 +218,44 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
         // ===================================================== MMA issuer B: layers >= 1 (A operand from tensor memory)
         if (lane == 0 && L > 1) {
             RingPos rb = {0, 0};
-            uint32_t it = 0;
-            for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+            const int nb = p.nb1;
+            const uint32_t b_base = s2u(sB1), b_bytes = (uint32_t)p.b1_stage_bytes;
+            const uint32_t nbuf = (uint32_t)p.nbuf, nslice = (uint32_t)p.nslice;
+            uint32_t it = 0, u = 0;      // u: running slice number (buffer = u mod nbuf)
+            for (int tile = tile0; tile < ntiles; tile += tstep, ++it) {
                 for (int l = 1; l < L; ++l) {
                     const bool last = l == L - 1;
-                    const int nsl = last ? p.nslice : 1;
+                    const uint32_t nsl = last ? nslice : 1u;
                     const int width = last ? p.zs : p.np[l];
-                    const int halves = (width + B_TILE_ROWS - 1) / B_TILE_ROWS;
-                    for (int s = 0; s < nsl; ++s) {
+                    const int halves = (width + brows - 1) / brows;
+                    const int nch = p.nchunks[l];
+                    const uint32_t a_col = tmem + (uint32_t)p.rcol[l - 1];
+                    for (uint32_t s = 0; s < nsl; ++s) {
                         uint32_t dcol, buf = 0;
                         if (last) {
-                            const uint32_t u = it * (uint32_t)p.nslice + (uint32_t)s;
-                            buf = u % (uint32_t)p.nbuf;
-                            mbar_wait_sleepy(s2u(&S.z_free[buf]), ((u / (uint32_t)p.nbuf) & 1) ^ 1);   // the epilogue has drained this buffer
+                            buf = nbuf == 2 ? (u & 1) : 0u;
+                            bwait(&S.z_free[buf], ((nbuf == 2 ? (u >> 1) : u) & 1) ^ 1);   // the epilogue has drained this buffer
                             dcol = (uint32_t)p.zcol[buf];
+                            ++u;
                         } else {
                             dcol = (uint32_t)p.rcol[l];
                         }
-                        for (int kc = 0; kc < p.nchunks[l]; ++kc) {
-                            if (s == 0) mbar_wait_sleepy(s2u(&S.ready[l - 1][kc]), it & 1);   // chunk kc of the A operand is in place
+                        for (int kc = 0; kc < nch; ++kc) {
+                            if (s == 0) bwait(&S.ready[l - 1][kc], it & 1);   // chunk kc of the A operand is in place
                             tc_fence_after();
-                            const uint32_t a_t = tmem + (uint32_t)(p.rcol[l - 1] + kc * KC);
+                            const uint32_t a_t = a_col + (uint32_t)(kc * KC);
                             for (int h = 0; h < halves; ++h) {
-                                const int rows = min(B_TILE_ROWS, width - h * B_TILE_ROWS);
-                                mbar_wait_sleepy(s2u(&S.b1_full[rb.stage]), rb.phase);
+                                const int rows = min(brows, width - h * brows);
+                                bwait(&S.b1_full[rb.stage], rb.phase);
                                 tc_fence_after();
-                                const uint64_t bdesc = make_desc(s2u(sB1 + (size_t)rb.stage * p.b1_stage_bytes));
+                                const uint64_t bdesc = make_desc(b_base + rb.stage * b_bytes);
                                 const uint32_t idesc = make_idesc(rows);
-                                const uint32_t d = tmem + dcol + (uint32_t)(h * B_TILE_ROWS);
+                                const uint32_t d = tmem + dcol + (uint32_t)(h * brows);
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks)
                                     umma_tf32_ts(d, a_t + (uint32_t)(8 * ks), bdesc + (uint64_t)(2 * ks), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
                                 umma_commit(s2u(&S.b1_empty[rb.stage]));
-                                rb.advance(p.nb1);
+                                rb.advance(nb);
                             }
                         }
                         umma_commit(last ? s2u(&S.z_full[buf]) : s2u(&S.r_full[l]));
@@ -233,58 +271,74 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
         const int r = wq * 32 + lane;       // my row inside the tile
         const int j8 = lane & 7;            // my 16-byte unit inside a 128-byte row
         const int rsub = lane >> 3;         // which of the 4 rows a warp-wide gather step covers
+        const int na = p.na, nch0 = p.nchunks[0];
+        const int rows = p.rows32;
         RingPos ra = {0, 0};
         uint32_t cc = 0, it = 0;
-        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-            const int tile = item / nsplit;
-            const int par = it & 1;
-            // ---- per-row metadata of this tile
-            const unsigned R = (unsigned)tile * TM + r;          // total_rows < 2^31 (checked on the host)
-            const bool valid = (long)R < p.total_rows;
-            int m_src[3] = {0, 0, 0};
-            float m_aux[3] = {0.f, 0.f, 0.f};
+        Cursor cur;
+        if (MIN == IN_SA) cur.init(tile0 * (TM >> p.log_ns), tstep * (TM >> p.log_ns), p.npoint);
+        else if (MIN == IN_FP) cur.init(tile0 * TM, tstep * TM, p.n);
+        else cur.init(0, 0, 1);
+        for (int tile = tile0; tile < ntiles; tile += tstep, ++it, cur.advance()) {
+            const int R = tile * TM + r;
+            const bool valid = R < rows;
+            // ---- per-row metadata of this tile (registers; FP also a shared table: 8 lanes cooperate on one row)
+            int src = -1;                     // SA: global point row of my sample (-1 = padding row)
+            float cx = 0.f, cy = 0.f, cz = 0.f;
             int my_scene = 0, my_u = 0;
-            if (p.mode_in == IN_SA) {
-                const unsigned pr = valid ? (R >> p.log_ns) : 0u;     // global centre index (nsample is a power of two)
-                const unsigned scene = pr / (unsigned)p.npoint;
-                m_src[0] = (int)scene * p.n + (valid ? __ldg(p.idx + R) : 0);
-                m_aux[0] = __ldg(p.new_xyz + (size_t)pr * 3 + 0);
-                m_aux[1] = __ldg(p.new_xyz + (size_t)pr * 3 + 1);
-                m_aux[2] = __ldg(p.new_xyz + (size_t)pr * 3 + 2);
-            } else if (p.mode_in == IN_FP) {
-                const unsigned rr = valid ? R : 0u;
-                const unsigned scene = rr / (unsigned)p.n;
-                my_scene = (int)scene; my_u = (int)(rr - scene * (unsigned)p.n);
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    m_src[q] = (int)scene * p.m + __ldg(p.idx + (size_t)rr * 3 + q);
-                    m_aux[q] = __ldg(p.weight + (size_t)rr * 3 + q);
+            const int par = it & 1;
+            if (MIN == IN_SA) {
+                int sc, pp;
+                cur.at(r >> p.log_ns, sc, pp);
+                if (valid) {
+                    src = sc * p.n + __ldg(p.idx + R);
+                    const float *ctr = p.new_xyz + ((size_t)sc * p.npoint + pp) * 3;
+                    cx = __ldg(ctr); cy = __ldg(ctr + 1); cz = __ldg(ctr + 2);
                 }
-            }
-            if (grp == 0) {
-                S.row_valid[par][r] = valid;
+            } else if (MIN == IN_FP) {
+                cur.at(r, my_scene, my_u);
+                int m_src[3] = {0, 0, 0};
+                float m_w[3] = {0.f, 0.f, 0.f};
+                if (valid) {
 #pragma unroll
-                for (int q = 0; q < 3; ++q) { S.row_src[par][r][q] = m_src[q]; S.row_aux[par][r][q] = m_aux[q]; }
+                    for (int q = 0; q < 3; ++q) {
+                        m_src[q] = my_scene * p.m + __ldg(p.idx + (size_t)R * 3 + q);
+                        m_w[q] = __ldg(p.weight + (size_t)R * 3 + q);
+                    }
+                }
+                if (grp == 0) {
+                    S.row_valid[par][r] = valid;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { S.row_src[par][r][q] = m_src[q]; S.row_aux[par][r][q] = m_w[q]; }
+                }
+                // one barrier per item: the table is double buffered, so the readers of item it-1 never see item it+1's rows
+                bar_named(5, 128 * NGW);
             }
-            // one barrier per item: the table is double buffered, so the readers of item it-1 never see item it+1's rows
-            bar_named(5, 128 * NGW);
+            // sources of the 8 rows my lane group helps to gather (rows of my own warp: shuffles instead of a table)
+            int s8[8];
+            if (MIN == IN_SA) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s8[i] = __shfl_sync(0xffffffffu, src, rsub + 4 * i);
+            } else if (MIN == IN_DIRECT) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const int rr = tile * TM + wq * 32 + rsub + 4 * i; s8[i] = rr < rows ? rr : -1; }
+            }
 
-            for (int kc = 0; kc < p.nchunks[0]; ++kc, ++cc, ra.advance(NA)) {
-                if ((int)(cc % NGW) != grp) continue;
+            for (int kc = 0; kc < nch0; ++kc, ++cc, ra.advance(na)) {
+                if (NGW > 1 && (int)(cc % NGW) != grp) continue;
                 int c = kc, seg = 0;
                 if (p.nseg > 1 && c >= p.seg_chunks[0]) { c -= p.seg_chunks[0]; seg = 1; }
                 const int k0 = c * KC;                       // first column of this chunk inside its segment
                 const int width = p.seg_width[seg];
                 uint8_t *A = sA + (size_t)ra.stage * A_STAGE_BYTES;
-                const uint32_t empty_bar = s2u(&S.a_empty[ra.stage]);
+                uint64_t *empty_bar = &S.a_empty[ra.stage];
                 const uint32_t empty_par = ra.phase ^ 1;
-                const bool rows_seg = (p.mode_in == IN_DIRECT) || (p.mode_in == IN_SA && seg == 0 && p.c_feat > 5) ||
-                                      (p.mode_in == IN_FP && seg == 0);
+                const bool rows_seg = (MIN == IN_DIRECT) || (MIN == IN_SA && seg == 0 && p.c_feat > 5) || (MIN == IN_FP && seg == 0);
                 if (rows_seg) {
                     // point-major sources: 8 lanes cover one row's 128 bytes, a warp covers 4 rows per step, 8 steps.
-                    // All loads of a half chunk are issued before the first use (memory-level parallelism).
+                    // All loads of a (half) chunk are issued before the first use (memory-level parallelism).
                     const int kk = k0 + 4 * j8;
-                    if (p.mode_in == IN_FP) {
+                    if (MIN == IN_FP) {
                         const int C = p.c_known;
                         const bool vec = (C & 3) == 0;
 #pragma unroll
@@ -315,7 +369,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                                     }
                                 }
                             }
-                            if (half == 0) mbar_wait(empty_bar, empty_par);
+                            if (half == 0) bwait(empty_bar, empty_par);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const int rr = wq * 32 + rsub + 4 * (half * 4 + i);
@@ -329,26 +383,25 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                             }
                         }
                     } else {
-                        const int pitch = p.mode_in == IN_DIRECT ? p.x_pitch : p.c_feat;
+                        const int pitch = MIN == IN_DIRECT ? p.x_pitch : p.c_feat;
+                        const float *srcbase = MIN == IN_DIRECT ? p.x_rows : p.feats_pm;
                         float4 t[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const int rr = wq * 32 + rsub + 4 * i;
                             t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (S.row_valid[par][rr] && kk < width) {
-                                const float *src = p.mode_in == IN_DIRECT ? p.x_rows + ((size_t)tile * TM + rr) * pitch + kk
-                                                                          : p.feats_pm + (size_t)S.row_src[par][rr][0] * pitch + kk;
+                            if (s8[i] >= 0 && kk < width) {
+                                const float *sp = srcbase + (size_t)s8[i] * pitch + kk;
                                 if ((pitch & 3) == 0) {
-                                    t[i] = __ldg((const float4 *)src);
+                                    t[i] = __ldg((const float4 *)sp);
                                 } else {
                                     float o[4];
 #pragma unroll
-                                    for (int q = 0; q < 4; ++q) o[q] = (kk + q < width) ? __ldg(src + q) : 0.f;
+                                    for (int q = 0; q < 4; ++q) o[q] = (kk + q < width) ? __ldg(sp + q) : 0.f;
                                     t[i] = make_float4(o[0], o[1], o[2], o[3]);
                                 }
                             }
                         }
-                        mbar_wait(empty_bar, empty_par);
+                        bwait(empty_bar, empty_par);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int rr = wq * 32 + rsub + 4 * i;
@@ -357,27 +410,28 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                             *reinterpret_cast<float4 *>(A + swz(rr, j8)) = v;
                         }
                     }
-                } else if (p.mode_in == IN_SA) {
+                } else if (MIN == IN_SA) {
                     // relative xyz segment: [x - cx, y - cy, z - cz, (<= 5 feature channels,) 0 ...]; one K=8 step
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f), v2 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (valid) {
-                        const float *q = p.xyz + (size_t)m_src[0] * 3;
-                        v.x = to_tf32(__ldg(q + 0) - m_aux[0]);
-                        v.y = to_tf32(__ldg(q + 1) - m_aux[1]);
-                        v.z = to_tf32(__ldg(q + 2) - m_aux[2]);
-                        if (p.c_feat > 0 && p.c_feat <= 5) {
-                            const float *f = p.feats_pm + (size_t)m_src[0] * p.c_feat;
+                        const float *q = p.xyz + (size_t)src * 3;
+                        v.x = to_tf32(__ldg(q + 0) - cx);
+                        v.y = to_tf32(__ldg(q + 1) - cy);
+                        v.z = to_tf32(__ldg(q + 2) - cz);
+                        const int cf = p.c_feat;
+                        if (cf > 0 && cf <= 5) {
+                            const float *f = p.feats_pm + (size_t)src * cf;
                             v.w = to_tf32(__ldg(f));
-                            if (p.c_feat > 1) v2.x = to_tf32(__ldg(f + 1));
-                            if (p.c_feat > 2) v2.y = to_tf32(__ldg(f + 2));
-                            if (p.c_feat > 3) v2.z = to_tf32(__ldg(f + 3));
-                            if (p.c_feat > 4) v2.w = to_tf32(__ldg(f + 4));
+                            if (cf > 1) v2.x = to_tf32(__ldg(f + 1));
+                            if (cf > 2) v2.y = to_tf32(__ldg(f + 2));
+                            if (cf > 3) v2.z = to_tf32(__ldg(f + 3));
+                            if (cf > 4) v2.w = to_tf32(__ldg(f + 4));
                         }
                     }
-                    mbar_wait(empty_bar, empty_par);
+                    bwait(empty_bar, empty_par);
                     *reinterpret_cast<float4 *>(A + swz(r, 0)) = v;
                     *reinterpret_cast<float4 *>(A + swz(r, 1)) = v2;
-                } else {
+                } else if (MIN == IN_FP) {
                     // FP skip segment: channel-major (b, c_skip, n); lanes run along consecutive points
                     const float *bsrc = p.skip + (size_t)my_scene * p.c_skip * p.n + my_u;
                     float o[32];
@@ -386,7 +440,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                         const int ch = k0 + q;
                         o[q] = (valid && ch < width) ? __ldg(bsrc + (size_t)ch * p.n) : 0.f;
                     }
-                    mbar_wait(empty_bar, empty_par);
+                    bwait(empty_bar, empty_par);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<float4 *>(A + swz(r, j)) =
@@ -400,45 +454,50 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
         // ===================================================== epilogue warps (warps 0 .. 4*NE-1)
         const int wq = warp & 3, grp = warp >> 2;
         const int r = wq * 32 + lane;       // my row inside the tile / my TMEM lane
-        const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+        const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
         float *pool = s_pool + grp * (TM * POOL_STRIDE + 128);
         float *pool2 = pool + TM * POOL_STRIDE;   // 8 x 16 partial maxima (nsample > 32)
         const int Cl = p.c_last;
+        const int rows = p.rows32;
         const float *sc = s_scale + sc_off[L - 1], *sh = s_shift + sc_off[L - 1];
+        const bool unit = p.unit_scale != 0;
+        const bool pool_raw = unit && MOUT == OUT_SA_MAX;
+        const float lo = p.linear_last ? -CUDART_INF_F : 0.f;    // ReLU = max(., 0); a linear last layer keeps the sign
+        const uint32_t nbuf = (uint32_t)p.nbuf;
+        const int nsl = L == 1 ? 1 : p.nslice;
+        const int slice_w = L == 1 ? p.split_w : p.zs;
+        const int ns = p.ns;
         // mid layer l of item number `itn`: accumulator -> +shift -> ReLU -> tf32, rewritten in place as the next layer's A operand
         auto mid_epilogue = [&](int l, uint32_t itn) {
-            mbar_wait(s2u(&S.r_full[l]), itn & 1);
+            bwait(&S.r_full[l], itn & 1);
             tc_fence_after();
             const int nch = p.np[l] / KC;
+            const uint32_t col0 = trow + (uint32_t)p.rcol[l];
             for (int kc = grp; kc < nch; kc += NE) {
+                uint32_t acc[32];
+                tmem_ld32(col0 + (uint32_t)(kc * KC), acc);
+                const float4 *sh4 = reinterpret_cast<const float4 *>(s_shift + sc_off[l] + kc * KC);
+                if (unit) {
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const uint32_t col = tmem + lane_base + (uint32_t)(p.rcol[l] + kc * KC + hh * 16);
-                    uint32_t acc[16];
-                    tmem_ld16(col, acc);
-                    const float4 *sc4 = reinterpret_cast<const float4 *>(s_scale + sc_off[l] + kc * KC + hh * 16);
-                    const float4 *sh4 = reinterpret_cast<const float4 *>(s_shift + sc_off[l] + kc * KC + hh * 16);
-                    if (p.unit_scale) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 b = sh4[j];
-                            acc[4 * j + 0] = __float_as_uint(relu_to_tf32(__uint_as_float(acc[4 * j + 0]) + b.x));
-                            acc[4 * j + 1] = __float_as_uint(relu_to_tf32(__uint_as_float(acc[4 * j + 1]) + b.y));
-                            acc[4 * j + 2] = __float_as_uint(relu_to_tf32(__uint_as_float(acc[4 * j + 2]) + b.z));
-                            acc[4 * j + 3] = __float_as_uint(relu_to_tf32(__uint_as_float(acc[4 * j + 3]) + b.w));
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 a = sc4[j], b = sh4[j];
-                            acc[4 * j + 0] = __float_as_uint(relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 0]), a.x, b.x)));
-                            acc[4 * j + 1] = __float_as_uint(relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 1]), a.y, b.y)));
-                            acc[4 * j + 2] = __float_as_uint(relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 2]), a.z, b.z)));
-                            acc[4 * j + 3] = __float_as_uint(relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 3]), a.w, b.w)));
-                        }
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = sh4[j];                 // broadcast LDS.128
+                        acc[4 * j + 0] = __float_as_uint(relu_to_tf32(__uint_as_float(acc[4 * j + 0]) + b.x));
+                        acc[4 * j + 1] = __float_as_uint(relu_to_tf32(__uint_as_float(acc[4 * j + 1]) + b.y));
+                        acc[4 * j + 2] = __float_as_uint(relu_to_tf32(__uint_as_float(acc[4 * j + 2]) + b.z));
+                        acc[4 * j + 3] = __float_as_uint(relu_to_tf32(__uint_as_float(acc[4 * j + 3]) + b.w));
                     }
-                    tmem_st16(col, acc);
+                } else {
+                    const float4 *sc4 = reinterpret_cast<const float4 *>(s_scale + sc_off[l] + kc * KC);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 a = sc4[j], b = sh4[j];
+                        acc[4 * j + 0] = __float_as_uint(relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 0]), a.x, b.x)));
+                        acc[4 * j + 1] = __float_as_uint(relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 1]), a.y, b.y)));
+                        acc[4 * j + 2] = __float_as_uint(relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 2]), a.z, b.z)));
+                        acc[4 * j + 3] = __float_as_uint(relu_to_tf32(fmaf(__uint_as_float(acc[4 * j + 3]), a.w, b.w)));
+                    }
                 }
+                tmem_st32(col0 + (uint32_t)(kc * KC), acc);
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(s2u(&S.ready[l][kc]));
@@ -450,64 +509,58 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
         // instead of idling the epilogue warps.  Not when the last layer IS layer 1 and has more slices than buffers:
         // X is released only after the last slice, which needs this item's final epilogue to drain buffers first.
         const bool skew = (L == 3) || (L == 2 && p.nslice <= p.nbuf);
-        uint32_t it = 0;
-        if (skew && (int)blockIdx.x < p.num_items) mid_epilogue(0, 0u);
-        for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-            const int tile = item / nsplit, sj = item - tile * nsplit;
-            const long R = (long)tile * TM + r;
-            const bool valid = R < p.total_rows;
-            int my_scene = 0, my_u = 0;
-            if (p.mode_out == OUT_FP) {
-                const unsigned rr = valid ? (unsigned)R : 0u;
-                const unsigned scene = rr / (unsigned)p.n;
-                my_scene = (int)scene; my_u = (int)(rr - scene * (unsigned)p.n);
-            }
+        Cursor cur;
+        if (MOUT == OUT_SA_MAX) cur.init(tile0 * (TM >> p.log_ns), tstep * (TM >> p.log_ns), p.npoint);
+        else if (MOUT == OUT_FP) cur.init(tile0 * TM, tstep * TM, p.n);
+        else cur.init(0, 0, 1);
+        uint32_t it = 0, u = 0;
+        if (skew && tile0 < ntiles) mid_epilogue(0, 0u);
+        for (int tile = tile0; tile < ntiles; tile += tstep, ++it, cur.advance()) {
+            const int R = tile * TM + r;
+            const bool valid = R < rows;
             if (skew) {
                 for (int l = 1; l + 1 < L; ++l) mid_epilogue(l, it);
-                if (item + (int)gridDim.x < p.num_items) mid_epilogue(0, it + 1);
+                if (tile + tstep < ntiles) mid_epilogue(0, it + 1);
             } else {
                 for (int l = 0; l + 1 < L; ++l) mid_epilogue(l, it);
             }
 
-            // ---- last layer, slice by slice
-            size_t e_off = 0, e_pm = 0;
-            bool e_ok = false;
-            size_t b_off = 0, b_pm = 0;
-            bool b_ok = false;
-            if (p.mode_out == OUT_SA_MAX && (p.ns == 16 || p.ns == 32)) {
-                const unsigned Rg = (unsigned)tile * TM + (unsigned)r;
-                b_ok = (long)Rg < p.total_rows;
-                const unsigned pr = Rg >> p.log_ns, scene = pr / (unsigned)p.npoint, pp = pr - scene * (unsigned)p.npoint;
-                b_off = ((size_t)scene * p.out_stride_c + p.out_c_off) * p.npoint + pp;
-                b_pm = ((size_t)scene * p.npoint + pp) * p.out_stride_c + p.out_c_off;
+            // ---- last layer, slice by slice: per-row output coordinates first
+            size_t off_cm = 0, off_pm = 0;   // SA: (scene, centre) of my row / my 16-row segment; FP: (scene, point); ROWS: row
+            bool ok = valid;
+            if (MOUT == OUT_SA_MAX) {
+                // 16 / 32 samples: the centre of my own row; other sample counts: the centre of my 16-row segment
+                const int rowc = (ns == 16 || ns == 32) ? r : (r & ~15);
+                int scn, pp;
+                cur.at(rowc >> p.log_ns, scn, pp);
+                ok = tile * TM + rowc < rows;
+                off_cm = ((size_t)scn * p.out_stride_c + p.out_c_off) * p.npoint + pp;
+                off_pm = ((size_t)scn * p.npoint + pp) * p.out_stride_c + p.out_c_off;
+            } else if (MOUT == OUT_FP) {
+                int scn, uu;
+                cur.at(r, scn, uu);
+                off_cm = ((size_t)scn * p.out_stride_c + p.out_c_off) * p.n + uu;
+                off_pm = (size_t)R * p.out_stride_c + p.out_c_off;
+            } else {
+                off_cm = (size_t)R * p.out_pitch;
             }
-            if (p.mode_out == OUT_SA_MAX && p.ns >= 16) {
-                const unsigned Rg = (unsigned)tile * TM + (unsigned)(r >> 4) * 16u;
-                e_ok = (long)Rg < p.total_rows && (((r >> 4) & ((p.ns >> 4) - 1)) == 0);
-                const unsigned pr = Rg >> p.log_ns, scene = pr / (unsigned)p.npoint, pp = pr - scene * (unsigned)p.npoint;
-                e_off = ((size_t)scene * p.out_stride_c + p.out_c_off + (r & 15)) * p.npoint + pp;
-                e_pm = ((size_t)scene * p.npoint + pp) * p.out_stride_c + p.out_c_off + (r & 15);
-            }
-            const bool pool_raw = p.unit_scale && p.mode_out == OUT_SA_MAX;
-            const float lo = p.linear_last ? -CUDART_INF_F : 0.f;    // ReLU = max(., 0); a linear last layer keeps the sign
-            const int nsl = L == 1 ? 1 : p.nslice;
-            for (int s = 0; s < nsl; ++s) {
-                const uint32_t u = it * (uint32_t)nsl + (uint32_t)s;
-                const uint32_t buf = u % (uint32_t)p.nbuf;
-                const int s_lo = L == 1 ? sj * p.split_w : s * p.zs;                  // first absolute column of this slice
-                const int s_hi = min(Cl, s_lo + (L == 1 ? p.split_w : p.zs));
-                mbar_wait(s2u(&S.z_full[buf]), (u / (uint32_t)p.nbuf) & 1);
+            for (int s = 0; s < nsl; ++s, ++u) {
+                const uint32_t buf = nbuf == 2 ? (u & 1) : 0u;
+                const int s_lo = L == 1 ? sj * slice_w : s * slice_w;                  // first absolute column of this slice
+                const int s_hi = min(Cl, s_lo + slice_w);
+                bwait(&S.z_full[buf], (nbuf == 2 ? (u >> 1) : u) & 1);
                 tc_fence_after();
+                const uint32_t zc = trow + (uint32_t)p.zcol[buf];
                 for (int c0 = s_lo + grp * 16; c0 < s_hi; c0 += 16 * NE) {
                     uint32_t acc[16];
-                    tmem_ld16(tmem + lane_base + (uint32_t)(p.zcol[buf] + (c0 - s_lo)), acc);
+                    tmem_ld16(zc + (uint32_t)(c0 - s_lo), acc);
                     float v[16];
                     // folded scale + max-pool: max_s relu(x_s + t) == relu(max_s x_s + t), so the raw accumulators are
                     // pooled and shift / ReLU are applied once per (centre, channel) after the reduction
                     if (pool_raw) {
 #pragma unroll
                         for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(acc[q]);
-                    } else if (p.unit_scale) {
+                    } else if (unit) {
                         const float4 *sh4 = reinterpret_cast<const float4 *>(sh + c0);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -528,9 +581,9 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                             v[4 * j + 3] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 3]), a.w, b.w), lo);
                         }
                     }
-                    if (p.mode_out == OUT_ROWS) {
+                    if (MOUT == OUT_ROWS) {
                         if (valid) {
-                            float *o = p.out + (size_t)R * p.out_pitch + c0;
+                            float *o = p.out + off_cm + c0;
                             if (p.round_out) {   // the next launch of a split chain reads these rows as its A operand
 #pragma unroll
                                 for (int q = 0; q < 16; ++q) v[q] = to_tf32(v[q]);
@@ -539,14 +592,14 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                             for (int q = 0; q < 16; q += 4)
                                 *reinterpret_cast<float4 *>(o + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
                         }
-                    } else if (p.mode_out == OUT_FP) {
+                    } else if (MOUT == OUT_FP) {
                         if (valid) {
-                            float *o = p.out + ((size_t)my_scene * p.out_stride_c + p.out_c_off + c0) * p.n + my_u;
+                            float *o = p.out + off_cm + (size_t)c0 * p.n;
 #pragma unroll
                             for (int q = 0; q < 16; ++q)
                                 if (c0 + q < Cl) o[(size_t)q * p.n] = v[q];
                             if (p.out_pm) {   // point-major copy for the next consumer (no transpose kernel)
-                                float *o2 = p.out_pm + (size_t)R * p.out_stride_c + p.out_c_off + c0;
+                                float *o2 = p.out_pm + off_pm + c0;
                                 if ((p.out_stride_c & 3) == 0 && c0 + 16 <= Cl) {
 #pragma unroll
                                     for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4 *>(o2 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
@@ -557,17 +610,41 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                                 }
                             }
                         }
-                    } else {
-                        // max over the nsample consecutive rows of each centre
-                        const int ns = p.ns;
-                        const int g16 = r >> 4, q = r & 15;          // (segment of 16 rows, channel) handled by this thread
-                        if (ns == 32 || ns == 16) {
-                            // The nsample rows of a centre are lanes of ONE warp: halving butterfly, no staging tile and
-                            // no barriers.  Each step a lane keeps half of its channels (chosen by one lane-id bit),
-                            // sends the other half to its partner and takes the max -- 8+4+2+1 shuffles leave one channel
-                            // per lane: channel (lane>>1)&15 for 32 samples (one more step joins lanes 2k, 2k+1), channel
-                            // lane&15 (bit-permuted) for 16 samples.
-                            float w8[8], w4[4], w2[2], x;
+                    } else if (ns == 32 || ns == 16) {
+                        // The nsample rows of a centre are lanes of ONE warp.
+                        float x;
+                        int ch;
+                        if (p.pool_mode == 0) {
+                            // one warp-wide (or half-warp-wide) CREDUX.MAX per channel, then every lane picks the channel
+                            // named by its low four lane bits through a 15-select tree
+                            if (ns == 32) {
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) v[q] = redux_max_f32<0xffffffffu>(v[q]);
+                            } else if (lane < 16) {
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) v[q] = redux_max_f32<0x0000ffffu>(v[q]);
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) v[q] = redux_max_f32<0xffff0000u>(v[q]);
+                            }
+                            const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8;
+                            float t8[8], t4[4];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) t8[i] = b0 ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) t4[i] = b1 ? t8[2 * i + 1] : t8[2 * i];
+                            const float t20 = b2 ? t4[1] : t4[0], t21 = b2 ? t4[3] : t4[2];
+                            x = b3 ? t21 : t20;
+                            ch = lane & 15;
+                            if (pool_raw) x = fmaxf(x + sh[c0 + ch], lo);
+                            if (ok && (ns == 16 || lane < 16) && c0 + ch < Cl) {
+                                p.out[off_cm + (size_t)(c0 + ch) * p.npoint] = x;
+                                if (p.out_pm) p.out_pm[off_pm + c0 + ch] = x;
+                            }
+                        } else {
+                            // halving shuffle butterfly: each step a lane keeps half of its channels (chosen by one lane-id
+                            // bit), sends the other half to its partner and takes the max
+                            float w8[8], w4[4], w2[2];
                             if (ns == 32) {
                                 const bool b4 = lane & 16;
 #pragma unroll
@@ -590,6 +667,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                                 const bool b1 = lane & 2;
                                 x = fmaxf(b1 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, b1 ? w2[0] : w2[1], 2));
                                 x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+                                ch = (lane >> 1) & 15;
                             } else {
                                 const bool b3 = lane & 8;
 #pragma unroll
@@ -611,15 +689,18 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                                 }
                                 const bool b0 = lane & 1;
                                 x = fmaxf(b0 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, b0 ? w2[0] : w2[1], 1));
+                                ch = ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1);
                             }
-                            const int ch = ns == 32 ? ((lane >> 1) & 15) : (((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1));
                             if (pool_raw) x = fmaxf(x + sh[c0 + ch], lo);
-                            if (b_ok && (ns == 16 || (lane & 1) == 0) && c0 + ch < Cl) {
-                                p.out[b_off + (size_t)(c0 + ch) * p.npoint] = x;
-                                if (p.out_pm) p.out_pm[b_pm + c0 + ch] = x;
+                            if (ok && (ns == 16 || (lane & 1) == 0) && c0 + ch < Cl) {
+                                p.out[off_cm + (size_t)(c0 + ch) * p.npoint] = x;
+                                if (p.out_pm) p.out_pm[off_pm + c0 + ch] = x;
                             }
-                            continue;
                         }
+                    } else {
+                        // other sample counts: max over the nsample consecutive rows of each centre through a staging tile:
+                        // thread (seg, q) reduces the <=16 rows of one 16-row segment for channel c0+q
+                        const int g16 = r >> 4, q = r & 15;
                         bar_named(2 + grp, 128);                     // previous readers of the staging tile are done
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
@@ -629,18 +710,17 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                             float x = pool[(g16 * 16) * POOL_STRIDE + q];
 #pragma unroll
                             for (int t = 1; t < 16; ++t) x = fmaxf(x, pool[(g16 * 16 + t) * POOL_STRIDE + q]);
-                            if (ns > 32) {
-                                pool2[g16 * 16 + q] = x;
-                                bar_named(2 + grp, 128);
-                                const int per = ns >> 4;
-                                if ((g16 % per) == 0) {
-                                    for (int t = 1; t < per; ++t) x = fmaxf(x, pool2[(g16 + t) * 16 + q]);
-                                }
+                            const int per = ns >> 4;
+                            pool2[g16 * 16 + q] = x;
+                            bar_named(2 + grp, 128);
+                            const bool head = (g16 % per) == 0;
+                            if (head) {
+                                for (int t = 1; t < per; ++t) x = fmaxf(x, pool2[(g16 + t) * 16 + q]);
                             }
                             if (pool_raw) x = fmaxf(x + sh[c0 + q], lo);
-                            if (e_ok && c0 + q < Cl) {
-                                p.out[e_off + (size_t)c0 * p.npoint] = x;
-                                if (p.out_pm) p.out_pm[e_pm + c0] = x;
+                            if (ok && head && c0 + q < Cl) {
+                                p.out[off_cm + (size_t)(c0 + q) * p.npoint] = x;
+                                if (p.out_pm) p.out_pm[off_pm + c0 + q] = x;
                             }
                         } else {
                             // nsample 4 or 8: 128/ns centres per tile, 16 channels each -> (16/ns) items per thread
@@ -650,11 +730,11 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                                 float x = pool[row0 * POOL_STRIDE + q];
                                 for (int t2 = 1; t2 < ns; ++t2) x = fmaxf(x, pool[(row0 + t2) * POOL_STRIDE + q]);
                                 if (pool_raw) x = fmaxf(x + sh[c0 + q], lo);
-                                const unsigned Rg = (unsigned)tile * TM + (unsigned)row0;
-                                if ((long)Rg < p.total_rows && c0 + q < Cl) {
-                                    const unsigned pr = Rg >> p.log_ns, scene = pr / (unsigned)p.npoint, pp = pr - scene * (unsigned)p.npoint;
-                                    p.out[((size_t)scene * p.out_stride_c + p.out_c_off + c0 + q) * p.npoint + pp] = x;
-                                    if (p.out_pm) p.out_pm[((size_t)scene * p.npoint + pp) * p.out_stride_c + p.out_c_off + c0 + q] = x;
+                                int scn, pp;
+                                cur.at(row0 >> p.log_ns, scn, pp);
+                                if (tile * TM + row0 < rows && c0 + q < Cl) {
+                                    p.out[((size_t)scn * p.out_stride_c + p.out_c_off + c0 + q) * p.npoint + pp] = x;
+                                    if (p.out_pm) p.out_pm[((size_t)scn * p.npoint + pp) * p.out_stride_c + p.out_c_off + c0 + q] = x;
                                 }
                             }
                         }
@@ -675,7 +755,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
 // Can this chain segment run on the pipelined kernel, and with which tensor-memory plan?  Fills the plan fields of p.
 // Returns the CTAs per SM the plan allows (0 = not supported: the caller falls back to the legacy kernel).
 struct PipePlan {
-    int ne, ngw, occ, zs, nbuf, nslice, cols, na, nb0, nb1, b0_bytes, b1_bytes, nsplit, split_w;
+    int ne, ngw, occ, zs, nbuf, nslice, cols, na, nb0, nb1, b0_bytes, b1_bytes, nsplit, split_w, brows;
     size_t smem;
 };
 
@@ -718,24 +798,29 @@ static bool pipe_plan(const ChainParams &p, int max_optin, PipePlan *out) {
             pl.zs = z; pl.nbuf = nbuf; pl.nslice = nslice; pl.cols = cols; pl.nsplit = nsplit; pl.split_w = split_w;
             pl.occ = cols <= 256 ? 2 : 1;
             if (o.mlp_occ == 1) pl.occ = 1;
-            pl.ne = pl.occ == 2 ? 1 : 2;
-            pl.ngw = pl.occ == 2 ? 1 : (k0 >= 2 ? 2 : 1);
-            if (o.mlp_ne) { pl.ne = o.mlp_ne; if (pl.ne + pl.ngw > 2) pl.occ = 1; }
-            if (o.mlp_ngw) { pl.ngw = o.mlp_ngw > 1 && k0 >= 2 ? 2 : 1; if (pl.ne + pl.ngw > 2) pl.occ = 1; }
-            const int b0_rows = L == 1 ? (z < 256 ? z : 256) : (p.np[0] < 256 ? p.np[0] : 256);
-            int b1_rows = 32;
-            for (int l = 1; l < L; ++l) { const int w = (l == L - 1) ? z : p.np[l]; const int r = w < 256 ? w : 256; if (r > b1_rows) b1_rows = r; }
-            pl.b0_bytes = b0_rows * KC * 4; pl.b1_bytes = L > 1 ? b1_rows * KC * 4 : 0;
+            pl.ne = pl.ngw = pl.occ == 2 ? 1 : 2;         // two builds: 4+4 row warps x 2 CTAs, or 8+8 row warps x 1 CTA
+            if (o.mlp_ne == 1) pl.ne = pl.ngw = 1;
+            if (o.mlp_ne == 2) { pl.ne = pl.ngw = 2; pl.occ = 1; }
+            // weight stages: BROWS rows of one 32-column K chunk (BROWS x 128 bytes); many small stages keep more bulk copies in
+            // flight than a few large ones (a 3-deep ring of 28 KB stages delivered ~10 B/cycle: every copy is a full round trip
+            // MMA commit -> producer -> L2 -> mbarrier)
+            const int brows = o.mlp_brows >= 32 ? o.mlp_brows : 64;
+            pl.brows = brows;
+            pl.b0_bytes = brows * KC * 4; pl.b1_bytes = L > 1 ? brows * KC * 4 : 0;
             const size_t budget = (size_t)(227 * 1024) / pl.occ - 1024 - sizeof(PipeSmem) - 512;
             bool ok = false;
-            // A ring: as deep as fits (one whole item ahead + 2 when possible); weight rings 3 deep, 2 if tight
-            for (int nb = 3; nb >= 2 && !ok; --nb)
-                for (int na = (k0 + 2 < PIPE_MAX_A ? (k0 + 2 > 3 ? k0 + 2 : 3) : PIPE_MAX_A); na >= 2 && !ok; --na) {
-                    const size_t smem = pipe_smem_bytes(pl.ne, na, nb, pl.b0_bytes, L > 1 ? nb : 0, pl.b1_bytes, np_total);
-                    if (smem <= budget && smem <= (size_t)max_optin && (nb == 2 || na >= (k0 < 4 ? k0 : 4))) {
-                        pl.na = na; pl.nb0 = nb; pl.nb1 = L > 1 ? nb : 0; pl.smem = smem; ok = true;
-                    }
+            // A ring first (>= 3 stages, up to one whole item + 1), the rest goes to the weight rings (<= PIPE_MAX_B stages each)
+            for (int na = (k0 + 1 < PIPE_MAX_A ? (k0 + 1 > 3 ? k0 + 1 : 3) : PIPE_MAX_A); na >= 2 && !ok; --na) {
+                const size_t fixed = pipe_smem_bytes(pl.ne, na, 0, 0, 0, 0, np_total);
+                if (fixed + (size_t)(L > 1 ? 4 : 2) * pl.b0_bytes > budget) continue;
+                int nb = (int)((budget - fixed) / ((size_t)pl.b0_bytes * (L > 1 ? 2 : 1)));
+                if (nb > PIPE_MAX_B) nb = PIPE_MAX_B;
+                if (na > 3 && nb < 6 && (L > 1 ? 2 : 1) * pl.b0_bytes * 6 + pipe_smem_bytes(pl.ne, na - 1, 0, 0, 0, 0, np_total) <= budget) continue;   // prefer deeper weight rings
+                const size_t smem = pipe_smem_bytes(pl.ne, na, nb, pl.b0_bytes, L > 1 ? nb : 0, pl.b1_bytes, np_total);
+                if (nb >= 2 && smem <= budget && smem <= (size_t)max_optin) {
+                    pl.na = na; pl.nb0 = nb; pl.nb1 = L > 1 ? nb : 0; pl.smem = smem; ok = true;
                 }
+            }
             if (!ok) continue;
             const long score = (long)pl.occ * 1000000L + nbuf * 1000L + z;
             if (score > best_score) { best_score = score; best = pl; }
@@ -767,21 +852,39 @@ int launch_chain_pipe(ChainParams &p, cudaStream_t st) {
     p.na = pl.na; p.nb0 = pl.nb0; p.nb1 = pl.nb1 > 0 ? pl.nb1 : 1;
     p.b0_stage_bytes = pl.b0_bytes; p.b1_stage_bytes = pl.b1_bytes;
     p.nsplit = pl.nsplit; p.split_w = pl.split_w;
+    p.b_rows = pl.brows;
     p.num_items = p.num_tiles * pl.nsplit;
     int sms = num_sms();
     if (const int v = opts().mlp_sms; v >= 1 && v < sms) sms = v;
     int grid = sms * pl.occ;
     if (grid > p.num_items) grid = p.num_items;
+    grid = grid / pl.nsplit * pl.nsplit;         // a CTA keeps its column group: tiles advance by grid / nsplit
+    if (grid < pl.nsplit) grid = pl.nsplit;
+    p.rows32 = (int)p.total_rows;
+    p.pool_mode = opts().mlp_pool;
     const size_t smem = pl.smem;
-#define PRB_LAUNCH_PIPE(NE, NGW, MB)                                                                                         \
-    do {                                                                                                                     \
-        PRB_CUDA(cudaFuncSetAttribute(mlp_pipe_kernel<NE, NGW, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        mlp_pipe_kernel<NE, NGW, MB><<<grid, (NE + NGW + 1) * 128, smem, st>>>(p);                                            \
+#define PRB_LAUNCH_PIPE(NE, NGW, MB, MI, MO)                                                                                   \
+    do {                                                                                                                       \
+        PRB_CUDA(cudaFuncSetAttribute(mlp_pipe_kernel<NE, NGW, MB, MI, MO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        mlp_pipe_kernel<NE, NGW, MB, MI, MO><<<grid, (NE + NGW + 1) * 128, smem, st>>>(p);                                      \
     } while (0)
-    if (pl.ne == 1 && pl.ngw == 1) { if (pl.occ >= 2) PRB_LAUNCH_PIPE(1, 1, 2); else PRB_LAUNCH_PIPE(1, 1, 1); }
-    else if (pl.ne == 1) PRB_LAUNCH_PIPE(1, 2, 1);
-    else if (pl.ngw == 1) PRB_LAUNCH_PIPE(2, 1, 1);
-    else PRB_LAUNCH_PIPE(2, 2, 1);
+#define PRB_LAUNCH_PIPE_IO(NE, NGW, MB)                                                                    \
+    do {                                                                                                   \
+        const int key = p.mode_in * 3 + p.mode_out;                                                        \
+        switch (key) {                                                                                     \
+            case IN_SA * 3 + OUT_ROWS: PRB_LAUNCH_PIPE(NE, NGW, MB, IN_SA, OUT_ROWS); break;              \
+            case IN_SA * 3 + OUT_SA_MAX: PRB_LAUNCH_PIPE(NE, NGW, MB, IN_SA, OUT_SA_MAX); break;          \
+            case IN_FP * 3 + OUT_ROWS: PRB_LAUNCH_PIPE(NE, NGW, MB, IN_FP, OUT_ROWS); break;              \
+            case IN_FP * 3 + OUT_FP: PRB_LAUNCH_PIPE(NE, NGW, MB, IN_FP, OUT_FP); break;                  \
+            case IN_DIRECT * 3 + OUT_ROWS: PRB_LAUNCH_PIPE(NE, NGW, MB, IN_DIRECT, OUT_ROWS); break;      \
+            case IN_DIRECT * 3 + OUT_SA_MAX: PRB_LAUNCH_PIPE(NE, NGW, MB, IN_DIRECT, OUT_SA_MAX); break;  \
+            case IN_DIRECT * 3 + OUT_FP: PRB_LAUNCH_PIPE(NE, NGW, MB, IN_DIRECT, OUT_FP); break;          \
+            default: set_error("mlp: unsupported input / output mode pair %d / %d", p.mode_in, p.mode_out); return -1; \
+        }                                                                                                  \
+    } while (0)
+    if (pl.ne == 1 && pl.ngw == 1) PRB_LAUNCH_PIPE_IO(1, 1, 2);      // launch bounds only cap the registers; occ 1 runs the same build
+    else PRB_LAUNCH_PIPE_IO(2, 2, 1);
+#undef PRB_LAUNCH_PIPE_IO
 #undef PRB_LAUNCH_PIPE
     return check_launch("mlp_pipe_kernel");
 }

@@ -34,6 +34,10 @@ def _nms(boxes, keep, thresh, normal):
     n = int(boxes.size(0))
     if n == 0:
         return 0
+    if boxes.dim() != 2 or boxes.size(1) != 5:
+        raise RuntimeError("boxes must be (N, 5)")
+    if keep.numel() < n:
+        raise RuntimeError("keep must hold at least N = %d entries" % n)   # the reference would overrun it silently
     with torch.cuda.device(boxes.device):
         ws = torch.empty(C.lib().prb_nms_workspace_bytes(n), dtype=torch.uint8, device=boxes.device)
         num = ctypes.c_int(0)
@@ -62,3 +66,30 @@ def nms_device(boxes, thresh, normal):
             C.check(C.lib().prb_nms_device(C.ptr(boxes), n, C.c_float(thresh), int(normal), C.ptr(keep), C.ptr(num),
                                            C.ptr(ws), C.stream()), "nms_device")
     return keep, num
+
+
+def boxes_iou3d(boxes_a, boxes_b):
+    """extension: fused boxes_iou3d_gpu.  boxes_a (M,7) x boxes_b (N,7) -> (M,N); or batched (B,M,7) x (B,N,7) -> (B,M,N)"""
+    _check_boxes(boxes_a, "boxes_a"); _check_boxes(boxes_b, "boxes_b")
+    batched = boxes_a.dim() == 3
+    a3 = boxes_a if batched else boxes_a.unsqueeze(0)
+    b3 = boxes_b if batched else boxes_b.unsqueeze(0)
+    if a3.size(-1) != 7 or b3.size(-1) != 7 or a3.size(0) != b3.size(0):
+        raise RuntimeError("boxes_iou3d: expected (.., 7) boxes with equal batch sizes")
+    out = torch.empty((a3.size(0), a3.size(1), b3.size(1)), dtype=torch.float32, device=boxes_a.device)
+    with torch.cuda.device(boxes_a.device):
+        C.check(C.lib().prb_boxes_iou3d(int(a3.size(0)), int(a3.size(1)), C.ptr(a3), int(b3.size(1)), C.ptr(b3), C.ptr(out), C.stream()),
+                "boxes_iou3d")
+    return out if batched else out[0]
+
+
+def boxes_iou3d_aligned(boxes_a, boxes_b):
+    """extension: out[k] = IoU3D(boxes_a[k], boxes_b[k]) for (K,7) x (K,7)"""
+    _check_boxes(boxes_a, "boxes_a"); _check_boxes(boxes_b, "boxes_b")
+    if boxes_a.shape != boxes_b.shape or boxes_a.dim() != 2 or boxes_a.size(1) != 7:
+        raise RuntimeError("boxes_iou3d_aligned: expected two (K, 7) tensors")
+    out = torch.empty(boxes_a.size(0), dtype=torch.float32, device=boxes_a.device)
+    with torch.cuda.device(boxes_a.device):
+        C.check(C.lib().prb_boxes_iou3d_aligned(int(boxes_a.size(0)), C.ptr(boxes_a), C.ptr(boxes_b), C.ptr(out), C.stream()),
+                "boxes_iou3d_aligned")
+    return out

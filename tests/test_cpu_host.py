@@ -269,3 +269,19 @@ print('OK')
 """ % ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
+def test_options_struct_matches_the_header():
+    """ctypes mirror of struct prb_options: same fields, same order as include/pointrcnn_b200.h"""
+    import re
+    from pointrcnn_b200 import _cabi
+    hdr = open(os.path.join(ROOT, "include", "pointrcnn_b200.h")).read()
+    body = hdr[hdr.index("typedef struct prb_options {"):hdr.index("} prb_options;")]
+    names = []
+    for line in body.split("\n")[1:]:
+        for grp in re.findall(r"(?:int|float)\s+([\w, ]+);", line.split("/*")[0]):
+            names += [n.strip() for n in grp.split(",")]
+    assert names == [f[0] for f in _cabi.Options._fields_]
+    o = _cabi.Options()
+    _cabi.lib().prb_options_init(ctypes.byref(o))
+    assert o.fps_prune == 1 and o.mlp_pipeline == 1 and abs(o.nn_cell - 1.6) < 1e-6

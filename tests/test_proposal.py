@@ -157,3 +157,64 @@ def test_golden_holds_with_the_reference_nms_kernel(cuda, gold, case, monkeypatc
     scores, reg, xyz = rpn_outputs(B, N, seed, far_empty=name.endswith("far_area_empty"))
     b, s = P.proposal_layer(scores, reg, xyz, ANCHOR, nms_type=nms_type, distance_based=dist_based, **MODES[mode])
     assert np.array_equal(s, gold[name + "_scores"]) and np.array_equal(b, gold[name + "_boxes"])
+
+
+# ------------------------------------------------------------------------------------------------ RCNN target layer (8(f) rank 2)
+TARGET_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "proposal_target_layer.npz")
+
+
+def _target_cfg(aug_times, aug_data):
+    from pointrcnn_b200.rpn import proposal_target_layer as ptl
+    d = dict(ptl.DEFAULT_CFG, AUG_DATA=aug_data)
+    d["RCNN"] = dict(d["RCNN"], ROI_FG_AUG_TIMES=aug_times)
+    return ptl._ns(d)
+
+
+@pytest.mark.gpu
+def test_proposal_target_layer_matches_reference_python(cuda):
+    """deterministic configuration (no jitter loop, no augmentation): the device layer against the outputs of the reference's
+    own Python (oracle/make_golden_proposal_target.py), same numpy / torch seeds -> same sampled RoIs, labels and pooled points"""
+    from make_golden_proposal_target import SEED, inputs
+    from pointrcnn_b200.rpn.proposal_target_layer import ProposalTargetLayer
+    g = np.load(TARGET_GOLDEN)
+    layer = ProposalTargetLayer(cfg=_target_cfg(0, False))
+    inp = {k: torch.from_numpy(v).to(cuda) for k, v in inputs().items()}
+    np.random.seed(SEED)
+    torch.manual_seed(SEED)
+    with torch.no_grad():
+        out = layer(inp)
+    assert np.array_equal(out["roi_boxes3d"].cpu().numpy(), g["roi_boxes3d"]), "sampled RoIs differ"
+    assert np.array_equal(out["cls_label"].cpu().numpy(), g["cls_label"]) and np.array_equal(out["reg_valid_mask"].cpu().numpy(), g["reg_valid_mask"])
+    np.testing.assert_allclose(out["gt_iou"].cpu().numpy(), g["gt_iou"], rtol=1e-4, atol=1e-6)       # CPU libm vs device in the overlap
+    np.testing.assert_allclose(out["gt_of_rois"].cpu().numpy(), g["gt_of_rois"], rtol=1e-5, atol=2e-5)
+    assert np.array_equal(out["pts_feature"].cpu().numpy(), g["pts_feature"]), "pooled features differ"
+    np.testing.assert_allclose(out["sampled_pts"].cpu().numpy(), g["sampled_pts"], rtol=0, atol=3e-5)
+
+
+@pytest.mark.gpu
+def test_proposal_target_layer_jitter_loop_properties(cuda):
+    """batched jitter loop (ROI_FG_AUG_TIMES = 10) + augmentation: every reported IoU is the true IoU of the returned (pre-
+    augmentation) RoI with its GT, foreground jitter stops at the threshold, labels follow the IoU rules"""
+    from make_golden_proposal_target import inputs
+    from pointrcnn_b200.ext import iou3d_cuda
+    from pointrcnn_b200.rpn.proposal_target_layer import ProposalTargetLayer
+    layer = ProposalTargetLayer(cfg=_target_cfg(10, False))
+    inp = {k: torch.from_numpy(v).to(cuda) for k, v in inputs().items()}
+    np.random.seed(3)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        rois, gts, iou = layer.sample_rois_for_rcnn(inp["roi_boxes3d"], inp["gt_boxes3d"])
+    true_iou = iou3d_cuda.boxes_iou3d_aligned(rois.reshape(-1, 7).contiguous(), gts.reshape(-1, 7).contiguous()).view(iou.shape)
+    assert torch.allclose(iou, true_iou, rtol=1e-6, atol=1e-7), "reported IoU is not the IoU of the returned RoI"
+    B, Rn = iou.shape
+    assert Rn == 64 and (iou[:, :32] >= 0).all()
+    # jittered boxes differ from every source RoI for most samples (p = 0.8 per draw), but stay near their GT cluster
+    src = inp["roi_boxes3d"]
+    same = (rois.unsqueeze(2) == src.unsqueeze(1)).all(dim=3).any(dim=2).float().mean().item()
+    assert same < 0.6, "the jitter loop left %.0f%% of the RoIs untouched" % (100 * same)
+    layer2 = ProposalTargetLayer(cfg=_target_cfg(10, True))
+    with torch.no_grad():
+        out = layer2(inp)
+    assert out["sampled_pts"].shape == (B * 64, 512, 3) and torch.isfinite(out["sampled_pts"]).all()
+    lab, giou = out["cls_label"], out["gt_iou"]
+    assert ((lab == 1) <= (giou > 0.6)).all() and ((giou < 0.45) <= (lab <= 0)).all()
