@@ -50,135 +50,7 @@ __device__ __forceinline__ bool pt_in_box(const BoxConst &c, float x, float y, f
            ((double)z_rot <= c.half_w);
 }
 
-// ------------------------------------------------------------------------------------------------ two-pass form
-// Pass A (assign): one CTA per (scene, tile of RA_BOXES boxes).  The scene's points are read ONCE per tile (the
-// reference and the one-pass kernel above re-read all N points for every box: 2048 x 196 KB at C4).  Warp w owns the
-// contiguous point range [w*N/8, (w+1)*N/8): it appends the hits of every box to its own ordered list in shared memory
-// (ballot + popc prefix, no CTA barrier inside the scan); the lists are then concatenated in warp order, which IS
-// point-index order, and cut at S -> idx (B,M,S) int32 + cnt (B,M) in caller scratch.
-// Pass B (copy): one CTA per box streams the S x (3+C) output as ONE flat array with 128-bit stores (rows are
-// 532 bytes at C4, so row-aligned stores are 4 bytes per lane); sources are read through L1 (a box holds a few dozen
-// distinct rows that are repeated cyclically).  Empty boxes set the flag and, when asked, zero their rows, so the caller
-// need not pre-zero the 558 MB output.
-constexpr int RA_BOXES = 4;
-constexpr int RA_WARPS = 8;
-
-__global__ void __launch_bounds__(32 * RA_WARPS) roipool3d_assign_kernel(int N, int M, int S, const float *__restrict__ xyz,
-                                                                        const float *__restrict__ boxes3d,
-                                                                        int *__restrict__ idx_out, int *__restrict__ cnt_out) {
-    extern __shared__ int s_list[];                 // [RA_BOXES][RA_WARPS][S]
-    __shared__ int s_cnt[RA_BOXES][RA_WARPS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int box0 = blockIdx.x * RA_BOXES, scene = blockIdx.y;
-    const int nb = min(RA_BOXES, M - box0);
-    BoxConst bc[RA_BOXES];
-#pragma unroll
-    for (int b = 0; b < RA_BOXES; ++b) bc[b] = make_box(boxes3d + ((size_t)scene * M + box0 + (b < nb ? b : 0)) * 7);
-    const float *pts = xyz + (size_t)scene * N * 3;
-    const int per = (N + RA_WARPS - 1) / RA_WARPS;
-    const int lo = warp * per, hi = min(N, lo + per);
-    int cnt[RA_BOXES];
-#pragma unroll
-    for (int b = 0; b < RA_BOXES; ++b) cnt[b] = 0;
-    for (int k0 = lo; k0 < hi; k0 += 32) {
-        const int k = k0 + lane;
-        float x = 0.f, y = 0.f, z = 0.f;
-        const bool ok = k < hi;
-        if (ok) { x = __ldg(pts + (size_t)k * 3); y = __ldg(pts + (size_t)k * 3 + 1); z = __ldg(pts + (size_t)k * 3 + 2); }
-#pragma unroll
-        for (int b = 0; b < RA_BOXES; ++b) {
-            const bool in = ok && b < nb && pt_in_box(bc[b], x, y, z);
-            const unsigned hits = __ballot_sync(0xffffffffu, in);
-            if (hits) {
-                const int pos = cnt[b] + __popc(hits & ((1u << lane) - 1));
-                if (in && pos < S) s_list[((size_t)b * RA_WARPS + warp) * S + pos] = k;
-                cnt[b] = min(S, cnt[b] + __popc(hits));
-            }
-        }
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int b = 0; b < RA_BOXES; ++b) s_cnt[b][warp] = cnt[b];
-    }
-    __syncthreads();
-    // concatenate the per-warp lists (warp order = point order), cut at S
-    for (int b = 0; b < nb; ++b) {
-        int off = 0;
-        for (int w = 0; w < RA_WARPS; ++w) {
-            const int c = s_cnt[b][w];
-            const int take = min(c, S - off);
-            int *dst = idx_out + ((size_t)scene * M + box0 + b) * S + off;
-            for (int j = tid; j < take; j += 32 * RA_WARPS) dst[j] = s_list[((size_t)b * RA_WARPS + w) * S + j];
-            off += take;
-            if (off >= S) break;
-        }
-        if (tid == 0) cnt_out[(size_t)scene * M + box0 + b] = off;
-    }
-}
-
-__global__ void __launch_bounds__(RP_THREADS) roipool3d_copy_kernel(int N, int M, int C, int S, const float *__restrict__ xyz,
-                                                                    const float *__restrict__ pts_feature,
-                                                                    const int *__restrict__ idx_in, const int *__restrict__ cnt_in,
-                                                                    float *__restrict__ pooled, int *__restrict__ empty_flag,
-                                                                    const float *__restrict__ rois, int zero_fill) {
-    extern __shared__ int s_idx[];  // S selected point indices
-    const int tid = threadIdx.x;
-    const int box = blockIdx.x, scene = blockIdx.y;
-    const size_t bi = (size_t)scene * M + box;
-    const int cnt = cnt_in[bi];
-    const int W = 3 + C;
-    const long total = (long)S * W;
-    float *dst = pooled + bi * (size_t)total;
-    const bool vec = (total & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-    if (cnt == 0) {
-        if (tid == 0) empty_flag[bi] = 1;
-        if (zero_fill) {
-            if (vec) for (long e = 4L * tid; e < total; e += 4L * RP_THREADS) *reinterpret_cast<float4 *>(dst + e) = make_float4(0.f, 0.f, 0.f, 0.f);
-            else for (long e = tid; e < total; e += RP_THREADS) dst[e] = 0.f;
-        }
-        return;
-    }
-    for (int j = tid; j < S; j += RP_THREADS) s_idx[j] = idx_in[bi * S + (j < cnt ? j : j % cnt)];
-    __syncthreads();
-    // canonical transform constants (rcnn_net.py:146-152): xyz -= roi centre, rotate (x,z) by roi ry
-    float rcx = 0.f, rcy = 0.f, rcz = 0.f, rcos = 1.f, rsin = 0.f;
-    if (rois) {
-        const float *r = rois + bi * 7;
-        rcx = r[0]; rcy = r[1]; rcz = r[2];
-        rcos = cosf(r[6]); rsin = sinf(r[6]);
-    }
-    const float *pts = xyz + (size_t)scene * N * 3;
-    const float *feat = pts_feature + (size_t)scene * N * C;
-    auto value = [&](int row, int col) -> float {
-        const int k = s_idx[row];
-        if (col >= 3) return __ldg(feat + (size_t)k * C + (col - 3));
-        if (!rois) return __ldg(pts + (size_t)k * 3 + col);
-        const float x = __ldg(pts + (size_t)k * 3) - rcx, y = __ldg(pts + (size_t)k * 3 + 1) - rcy, z = __ldg(pts + (size_t)k * 3 + 2) - rcz;
-        // [x z] @ [[cos,-sin],[sin,cos]]^T : x' = x*cos - z*sin, z' = x*sin + z*cos
-        return col == 0 ? __fmaf_rn(x, rcos, -__fmul_rn(z, rsin)) : (col == 1 ? y : __fmaf_rn(x, rsin, __fmul_rn(z, rcos)));
-    };
-    if (vec) {
-        // thread t owns float4 units t, t + T, ...: (row, col) of the unit's first float advance by a constant stride
-        const int step = 4 * RP_THREADS;
-        const int d_row = step / W, d_col = step % W;
-        int row = (4 * tid) / W, col = (4 * tid) % W;
-        for (long e = 4L * tid; e < total; e += step) {
-            float v[4];
-            int r = row, c = col;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                v[q] = value(r, c);
-                if (++c == W) { c = 0; ++r; }
-            }
-            *reinterpret_cast<float4 *>(dst + e) = make_float4(v[0], v[1], v[2], v[3]);
-            row += d_row; col += d_col;
-            if (col >= W) { col -= W; ++row; }
-        }
-    } else {
-        for (long e = tid; e < total; e += RP_THREADS) dst[e] = value((int)(e / W), (int)(e % W));
-    }
-}
-
+// ------------------------------------------------------------------------------------------------ one-pass form (prb_roipool3d: no scratch)
 __global__ void __launch_bounds__(RP_THREADS) roipool3d_kernel(int N, int M, int C, int S, const float *__restrict__ xyz,
                                                                const float *__restrict__ boxes3d,
                                                                const float *__restrict__ pts_feature,
@@ -213,6 +85,15 @@ __global__ void __launch_bounds__(RP_THREADS) roipool3d_kernel(int N, int M, int
     }
     if (cnt == 0) {
         if (tid == 0) empty_flag[(size_t)scene * M + box] = 1;
+        if (rois) {   // the reference applies the canonical transform to the (zero) rows of empty boxes as well
+            const float *r = rois + ((size_t)scene * M + box) * 7;
+            const float c = cosf(r[6]), s = sinf(r[6]);
+            const float x = 0.f - r[0], y = 0.f - r[1], z = 0.f - r[2];
+            const float ex = __fmaf_rn(x, c, -__fmul_rn(z, s)), ez = __fmaf_rn(x, s, __fmul_rn(z, c));
+            const int W = 3 + C;
+            float *dst = pooled + ((size_t)scene * M + box) * (size_t)S * W;
+            for (int row = tid; row < S; row += RP_THREADS) { dst[(size_t)row * W] = ex; dst[(size_t)row * W + 1] = y; dst[(size_t)row * W + 2] = ez; }
+        }
         return;
     }
 
@@ -246,6 +127,198 @@ __global__ void __launch_bounds__(RP_THREADS) roipool3d_kernel(int N, int M, int
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ two-pass form
+// Pass A (assign): one CTA per (scene, tile of RA_BOXES boxes).  The scene's points are read ONCE per tile (the
+// reference and the one-pass kernel above re-read all N points for every box: 2048 x 196 KB at C4).  Warp w owns the
+// contiguous point range [w*N/8, (w+1)*N/8): it appends the hits of every box to its own ordered list in shared memory
+// (ballot + popc prefix, no CTA barrier inside the scan); the lists are then concatenated in warp order, which IS
+// point-index order, and cut at S -> idx (B,M,S) int32 + cnt (B,M) in caller scratch.
+// Pass B (copy): one CTA per box streams the S x (3+C) output as ONE flat array with 128-bit stores (rows are
+// 532 bytes at C4, so row-aligned stores are 4 bytes per lane); sources are read through L1 (a box holds a few dozen
+// distinct rows that are repeated cyclically).  Empty boxes set the flag and, when asked, zero their rows, so the caller
+// need not pre-zero the 558 MB output.
+constexpr int RA_BOXES = 4;
+constexpr int RA_WARPS = 8;
+constexpr int RA_UNROLL = 4;     // points per lane per step: 12 coordinate loads in flight per lane
+
+// IdxT: unsigned short when the scene has <= 65536 points (half the shared memory -> twice the resident CTAs), else int
+template <typename IdxT>
+__global__ void __launch_bounds__(32 * RA_WARPS) roipool3d_assign_kernel(int N, int M, int S, const float *__restrict__ xyz,
+                                                                        const float *__restrict__ boxes3d,
+                                                                        int *__restrict__ idx_out, int *__restrict__ cnt_out) {
+    extern __shared__ unsigned char s_raw[];
+    IdxT *s_list = reinterpret_cast<IdxT *>(s_raw);      // [RA_BOXES][RA_WARPS][S]
+    __shared__ int s_cnt[RA_BOXES][RA_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int box0 = blockIdx.x * RA_BOXES, scene = blockIdx.y;
+    const int nb = min(RA_BOXES, M - box0);
+    BoxConst bc[RA_BOXES];
+#pragma unroll
+    for (int b = 0; b < RA_BOXES; ++b) bc[b] = make_box(boxes3d + ((size_t)scene * M + box0 + (b < nb ? b : 0)) * 7);
+    const float *pts = xyz + (size_t)scene * N * 3;
+    const int per = (N + RA_WARPS - 1) / RA_WARPS;
+    const int lo = warp * per, hi = min(N, lo + per);
+    int cnt[RA_BOXES];
+#pragma unroll
+    for (int b = 0; b < RA_BOXES; ++b) cnt[b] = 0;
+    for (int k0 = lo; k0 < hi; k0 += 32 * RA_UNROLL) {
+        float x[RA_UNROLL], y[RA_UNROLL], z[RA_UNROLL];
+#pragma unroll
+        for (int j = 0; j < RA_UNROLL; ++j) {          // all loads of the step first
+            const int k = k0 + 32 * j + lane;
+            x[j] = y[j] = z[j] = 0.f;
+            if (k < hi) { x[j] = __ldg(pts + (size_t)k * 3); y[j] = __ldg(pts + (size_t)k * 3 + 1); z[j] = __ldg(pts + (size_t)k * 3 + 2); }
+        }
+#pragma unroll
+        for (int j = 0; j < RA_UNROLL; ++j) {          // then the tests, in point order
+            const int k = k0 + 32 * j + lane;
+            const bool ok = k < hi;
+#pragma unroll
+            for (int b = 0; b < RA_BOXES; ++b) {
+                const bool in = ok && b < nb && pt_in_box(bc[b], x[j], y[j], z[j]);
+                const unsigned hits = __ballot_sync(0xffffffffu, in);
+                if (hits) {
+                    const int pos = cnt[b] + __popc(hits & ((1u << lane) - 1));
+                    if (in && pos < S) s_list[((size_t)b * RA_WARPS + warp) * S + pos] = (IdxT)k;
+                    cnt[b] = min(S, cnt[b] + __popc(hits));
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < RA_BOXES; ++b) s_cnt[b][warp] = cnt[b];
+    }
+    __syncthreads();
+    // concatenate the per-warp lists (warp order = point order), cut at S
+    for (int b = 0; b < nb; ++b) {
+        int off = 0;
+        for (int w = 0; w < RA_WARPS; ++w) {
+            const int c = s_cnt[b][w];
+            const int take = min(c, S - off);
+            int *dst = idx_out + ((size_t)scene * M + box0 + b) * S + off;
+            for (int j = tid; j < take; j += 32 * RA_WARPS) dst[j] = (int)s_list[((size_t)b * RA_WARPS + w) * S + j];
+            off += take;
+            if (off >= S) break;
+        }
+        if (tid == 0) cnt_out[(size_t)scene * M + box0 + b] = off;
+    }
+}
+
+// Pass B.  A box usually holds far fewer than S points, so its S output rows are `cnt` distinct rows repeated cyclically:
+// flat, the output IS the cnt x (3+C) source block repeated -- out[e] = block[e mod (cnt*(3+C))].  The block is staged in
+// shared memory once (coalesced row reads, canonical transform applied there) and streamed out with 128-bit stores;
+// boxes with more points than the staging area holds take the direct path (sources through L1).
+constexpr int RB_STAGE_FLOATS = 12 * 1024;   // 48 KB: 92 rows of 133 floats
+
+__global__ void __launch_bounds__(RP_THREADS) roipool3d_copy_kernel(int N, int M, int C, int S, const float *__restrict__ xyz,
+                                                                    const float *__restrict__ pts_feature,
+                                                                    const int *__restrict__ idx_in, const int *__restrict__ cnt_in,
+                                                                    float *__restrict__ pooled, int *__restrict__ empty_flag,
+                                                                    const float *__restrict__ rois, int zero_fill) {
+    extern __shared__ float s_blk[];          // RB_STAGE_FLOATS floats, then S ints (direct path)
+    int *s_idx = reinterpret_cast<int *>(s_blk + RB_STAGE_FLOATS);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int box = blockIdx.x, scene = blockIdx.y;
+    const size_t bi = (size_t)scene * M + box;
+    const int cnt = cnt_in[bi];
+    const int W = 3 + C;
+    const long total = (long)S * W;
+    float *dst = pooled + bi * (size_t)total;
+    const bool vec = (total & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    // canonical transform constants (rcnn_net.py:146-152): xyz -= roi centre, rotate (x,z) by roi ry
+    float rcx = 0.f, rcy = 0.f, rcz = 0.f, rcos = 1.f, rsin = 0.f;
+    if (rois) {
+        const float *r = rois + bi * 7;
+        rcx = r[0]; rcy = r[1]; rcz = r[2];
+        rcos = cosf(r[6]); rsin = sinf(r[6]);
+    }
+    auto canon = [&](float px, float py, float pz, int col) -> float {
+        const float x = px - rcx, y = py - rcy, z = pz - rcz;
+        // [x z] @ [[cos,-sin],[sin,cos]]^T : x' = x*cos - z*sin, z' = x*sin + z*cos
+        return col == 0 ? __fmaf_rn(x, rcos, -__fmul_rn(z, rsin)) : (col == 1 ? y : __fmaf_rn(x, rsin, __fmul_rn(z, rcos)));
+    };
+    if (cnt == 0) {
+        if (tid == 0) empty_flag[bi] = 1;
+        // The reference leaves the rows of an empty box zero -- and then applies the canonical transform to those zeros too
+        // (rcnn_net.py:146-152 runs over every RoI).  With the transform fused, an empty box's xyz columns get the
+        // transformed origin; without it the rows are zero-filled on request or left to the caller's memset.
+        if (rois) {
+            const float ex = canon(0.f, 0.f, 0.f, 0), ey = canon(0.f, 0.f, 0.f, 1), ez = canon(0.f, 0.f, 0.f, 2);
+            for (long e = tid; e < total; e += RP_THREADS) { const int c = (int)(e % W); dst[e] = c == 0 ? ex : (c == 1 ? ey : (c == 2 ? ez : 0.f)); }
+        } else if (zero_fill) {
+            if (vec) for (long e = 4L * tid; e < total; e += 4L * RP_THREADS) *reinterpret_cast<float4 *>(dst + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+            else for (long e = tid; e < total; e += RP_THREADS) dst[e] = 0.f;
+        }
+        return;
+    }
+    const float *pts = xyz + (size_t)scene * N * 3;
+    const float *feat = pts_feature + (size_t)scene * N * C;
+    const int *idx = idx_in + bi * S;
+    if ((long)cnt * W <= RB_STAGE_FLOATS && vec) {
+        // ---- stage the cnt distinct rows (warp per row, lanes along the row), then stream the block cyclically
+        for (int j = warp; j < cnt; j += RP_WARPS) {
+            const int k = idx[j];
+            float *row = s_blk + (size_t)j * W;
+            if (lane < 3) {
+                const float px = __ldg(pts + (size_t)k * 3), py = __ldg(pts + (size_t)k * 3 + 1), pz = __ldg(pts + (size_t)k * 3 + 2);
+                row[lane] = rois ? canon(px, py, pz, lane) : (lane == 0 ? px : (lane == 1 ? py : pz));
+            }
+            const float *f = feat + (size_t)k * C;
+            for (int c = lane; c < C; c += 32) row[3 + c] = __ldg(f + c);
+        }
+        __syncthreads();
+        const int P = cnt * W;                       // period of the output, in floats
+        const int step = (4 * RP_THREADS) % P;
+        int m = (4 * tid) % P;
+        for (long e = 4L * tid; e < total; e += 4L * RP_THREADS) {
+            float4 v;
+            if (m + 3 < P) {
+                v = make_float4(s_blk[m], s_blk[m + 1], s_blk[m + 2], s_blk[m + 3]);
+            } else {                                 // the unit wraps around the end of the block
+                float t[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { int mm = m + q; if (mm >= P) mm -= P; t[q] = s_blk[mm]; }
+                v = make_float4(t[0], t[1], t[2], t[3]);
+            }
+            *reinterpret_cast<float4 *>(dst + e) = v;
+            m += step;
+            if (m >= P) m -= P;
+        }
+        return;
+    }
+    // ---- direct path: many points in the box (or an unaligned output): sources through L1
+    for (int j = tid; j < S; j += RP_THREADS) s_idx[j] = idx[j < cnt ? j : j % cnt];
+    __syncthreads();
+    auto value = [&](int row, int col) -> float {
+        const int k = s_idx[row];
+        if (col >= 3) return __ldg(feat + (size_t)k * C + (col - 3));
+        if (!rois) return __ldg(pts + (size_t)k * 3 + col);
+        return canon(__ldg(pts + (size_t)k * 3), __ldg(pts + (size_t)k * 3 + 1), __ldg(pts + (size_t)k * 3 + 2), col);
+    };
+    if (vec) {
+        // thread t owns float4 units t, t + T, ...: (row, col) of the unit's first float advance by a constant stride
+        const int step = 4 * RP_THREADS;
+        const int d_row = step / W, d_col = step % W;
+        int row = (4 * tid) / W, col = (4 * tid) % W;
+        for (long e = 4L * tid; e < total; e += step) {
+            float v[4];
+            int r = row, c = col;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                v[q] = value(r, c);
+                if (++c == W) { c = 0; ++r; }
+            }
+            *reinterpret_cast<float4 *>(dst + e) = make_float4(v[0], v[1], v[2], v[3]);
+            row += d_row; col += d_col;
+            if (col >= W) { col -= W; ++row; }
+        }
+    } else {
+        for (long e = tid; e < total; e += RP_THREADS) dst[e] = value((int)(e / W), (int)(e % W));
+    }
+}
+
 }  // namespace prb
 
 using namespace prb;
@@ -263,14 +336,22 @@ extern "C" int prb_roipool3d_ws(int B, int N, int M, int C, int S, const float *
                 "roipool3d: bad arguments");
     if (B == 0 || M == 0) return 0;
     PRB_REQUIRE(workspace && workspace_bytes >= prb_roipool3d_workspace_bytes(B, M, S), "roipool3d: workspace too small");
-    const size_t smem_a = (size_t)RA_BOXES * RA_WARPS * S * sizeof(int), smem_b = (size_t)S * sizeof(int);
-    PRB_REQUIRE(smem_a <= 200 * 1024, "roipool3d: sampled_pts_num %d too large", S);
+    const bool small_idx = N <= 65536;
+    const size_t smem_a = (size_t)RA_BOXES * RA_WARPS * S * (small_idx ? sizeof(unsigned short) : sizeof(int));
+    const size_t smem_b = (size_t)RB_STAGE_FLOATS * sizeof(float) + (size_t)S * sizeof(int);
+    PRB_REQUIRE(smem_a <= 200 * 1024 && smem_b <= 200 * 1024, "roipool3d: sampled_pts_num %d too large", S);
     int *idx = reinterpret_cast<int *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     int *cnt = idx + (size_t)B * M * S;
     cudaStream_t st = (cudaStream_t)stream;
-    if (smem_a > 48 * 1024)
-        PRB_CUDA(cudaFuncSetAttribute(roipool3d_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
-    roipool3d_assign_kernel<<<dim3(ceil_div(M, RA_BOXES), B), 32 * RA_WARPS, smem_a, st>>>(N, M, S, xyz, boxes3d, idx, cnt);
+    if (small_idx) {
+        if (smem_a > 48 * 1024)
+            PRB_CUDA(cudaFuncSetAttribute(roipool3d_assign_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+        roipool3d_assign_kernel<unsigned short><<<dim3(ceil_div(M, RA_BOXES), B), 32 * RA_WARPS, smem_a, st>>>(N, M, S, xyz, boxes3d, idx, cnt);
+    } else {
+        if (smem_a > 48 * 1024)
+            PRB_CUDA(cudaFuncSetAttribute(roipool3d_assign_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+        roipool3d_assign_kernel<int><<<dim3(ceil_div(M, RA_BOXES), B), 32 * RA_WARPS, smem_a, st>>>(N, M, S, xyz, boxes3d, idx, cnt);
+    }
     if (int rc = check_launch("roipool3d_assign_kernel")) return rc;
     if (smem_b > 48 * 1024)
         PRB_CUDA(cudaFuncSetAttribute(roipool3d_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));

@@ -24,6 +24,24 @@ for p in lin.parameters():
     p.grad = torch.full_like(p, float(rank + 1))
 allreduce_grads(lin.parameters(), world)
 assert all(torch.allclose(p.grad, torch.full_like(p, 1.5)) for p in lin.parameters())
+# bucketed reducer: two ranks, different data, same weights -> averaged gradients equal the full-batch gradient
+from pointrcnn_b200.parallel_utils import GradBucketReducer
+torch.manual_seed(0)
+net = torch.nn.Sequential(torch.nn.Linear(6, 32), torch.nn.ReLU(), torch.nn.Linear(32, 32), torch.nn.ReLU(), torch.nn.Linear(32, 3))
+ref = torch.nn.Sequential(torch.nn.Linear(6, 32), torch.nn.ReLU(), torch.nn.Linear(32, 32), torch.nn.ReLU(), torch.nn.Linear(32, 3))
+ref.load_state_dict(net.state_dict())
+red = GradBucketReducer(net.parameters(), world=world, bucket_mb=0.002)      # several buckets
+assert len(red.buckets) >= 3
+g = torch.Generator().manual_seed(5)
+x = torch.randn(8, 6, generator=g)
+for step in range(2):                                # twice: reset() must keep the gradients inside the buckets
+    red.reset()
+    net(x[rank * 4:(rank + 1) * 4]).pow(2).mean().backward()
+    red.finish()
+ref(x).pow(2).mean().backward()
+for a, b in zip(net.parameters(), ref.parameters()):
+    assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-6), (a.grad - b.grad).abs().max()
+    assert a.grad.data_ptr() >= red.buckets[red._owner[a]]["flat"].data_ptr()
 dist.barrier()
 if rank == 0: print('DIST_OK')
 """ % ROOT

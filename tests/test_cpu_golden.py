@@ -120,3 +120,29 @@ def test_cpu_twins_match_the_reference_extension(case):
     assert np.array_equal(b2, g[name + "_rpc_feat"])
     # the canonical rotation goes through float64 cos/sin + np.dot in the reference (kitti_utils.py:33-43): same here
     np.testing.assert_allclose(a2, g[name + "_rpc_input"], rtol=0, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ host-side torch mirrors
+def test_decode_and_losses_match_the_reference_python():
+    """bbox_transform.decode_bbox_target and train.losses against the outputs of the reference's own
+    lib/utils/bbox_transform.py / loss_utils.py (oracle/make_golden_head_math.py)"""
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import make_golden_head_math as G
+    from pointrcnn_b200 import bbox_transform as bt
+    from pointrcnn_b200.train import losses as L
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "head_math.npz"))
+    anchor = torch.tensor(G.ANCHOR)
+    for i, case in enumerate(G.DECODE_CASES):
+        scope, bs, nh, fine, ybin, cols = case
+        roi, reg = G.decode_inputs(i, case)
+        got = bt.decode_bbox_target(roi, reg, scope, bs, nh, anchor, True, ybin, 0.5, 0.25, fine).numpy()
+        assert np.array_equal(got, g["decode_%d" % i]), "decode case %d" % i
+    for i, case in enumerate(G.LOSS_CASES):
+        scope, nh, fine, ybin = case
+        pred, lab = G.loss_inputs(i, case)
+        loc, ang, size, _ = L.get_reg_loss(pred, lab, scope, 0.5, nh, anchor, True, ybin, 0.5, 0.25, fine)
+        np.testing.assert_allclose([float(loc), float(ang), float(size)], g["reg_loss_%d" % i], rtol=2e-6, atol=1e-6)
+    logits, tgt, w = G.cls_inputs()
+    assert np.array_equal(L.SigmoidFocalClassificationLoss(2.0, 0.25)(logits, tgt, w).numpy(), g["focal"])
+    np.testing.assert_allclose(float(L.DiceLoss()(logits, tgt)), g["dice"][0], rtol=1e-6)
