@@ -22,6 +22,8 @@ a barrier + synchronize on both sides (CUDA events, max over ranks) and is REPEA
                 call order, same process, same inputs: once single-stream, once with the same number of batches in
                 flight; vs_ref_cuda = ours / theirs for both.
   strong_scaling  (N > 1) global batch 16: 16/N scenes per GPU per step, same pipeline.
+  train_step    BASELINE configs[2]: RPN training step, 16 scenes per GPU, NCCL gradient all-reduce overlapped with backward.
+  rcnn_stage    BASELINE configs[3]: roipool3d on 4 x 512 RoIs x 512 points + the RCNN PointNet++ stack (rank 0).
   cpu_baseline  oracle port on the host cores over a bounded sample of the same workload.
 """
 import argparse
@@ -259,6 +261,8 @@ def main():
     ap.add_argument("--cpu-scenes", type=int, default=2, help="scenes per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-CUDA comparator leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the RPN training-step leg (BASELINE configs[2])")
+    ap.add_argument("--no-rcnn", action="store_true", help="skip the RCNN stage-2 leg (BASELINE configs[3])")
     ap.add_argument("--inflight", type=int, default=6, help="independent batches in flight (CUDA streams); 1 = sequential")
     ap.add_argument("--graphs", type=int, default=1, help="1: one CUDA graph per pipeline slot (default), 0: eager launches")
     ap.add_argument("--min-seconds", type=float, default=1.0, help="each leg repeats its K-step region until this much is timed (>= 3 repeats)")
@@ -391,6 +395,44 @@ def main():
         prof.disable()
         fam = prof.collect()
         ms_seq = sum(a.elapsed_time(b_) for a, b_ in ev) / KS
+    # ---------------- BASELINE configs[2]: RPN training step, data parallel over the ranks (16 scenes per GPU), gradient
+    # all-reduce bucketed and overlapped with backward (parallel_utils.GradBucketReducer over NCCL)
+    train = None
+    if not args.no_train:
+        from pointrcnn_b200.train.step import RPNTrainer, synthetic_labels
+        tr = RPNTrainer(input_channels=CHANNELS - 3, device=dev, world=world)
+        labels = [synthetic_labels(dev_pool[i], seed=rank * 100 + i) for i in range(4)]
+        KT = min(K, 10)
+        for i in range(2):
+            tr.step(dev_pool[i % 4], *labels[i % 4], grad_norm_clip=1.0)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); torch.cuda.synchronize()
+        t0.record()
+        for i in range(KT):
+            loss_t, _ = tr.step(dev_pool[i % 4], *labels[i % 4], grad_norm_clip=1.0)
+        t1.record()
+        torch.cuda.synchronize(); barrier()
+        ms_t = max_over_ranks(t0.elapsed_time(t1) / KT, device=dev)
+        train = {"what": "RPN training step (BASELINE configs[2]): train-mode forward on the index natives + cuDNN MLPs, bin-based loss, "
+                         "backward (scatter kernels K3/K6/K9), bucketed NCCL all-reduce overlapped with backward, fused Adam",
+                 "ms_per_step": ms_t, "value": BATCH * world / (ms_t * 1e-3), "unit": "scenes/s", "steps": KT, "batch_per_gpu": BATCH,
+                 "allreduce_bytes_per_step": tr.reducer.bytes_per_step if world > 1 else 0, "buckets": len(tr.reducer.buckets),
+                 "collective": "ncclAllReduce(sum) x %d buckets per step on a side stream" % len(tr.reducer.buckets) if world > 1 else None,
+                 "final_loss": float(loss_t)}
+        tr.reducer.remove()
+        del tr
+        torch.cuda.empty_cache()
+
+    # ---------------- BASELINE configs[3]: RCNN stage 2 (roipool3d of 4 x 512 RoIs x 512 points + RCNN PointNet++), rank 0 only
+    rcnn = None
+    if not args.no_rcnn and rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        try:
+            import bench_rcnn_stage
+            rcnn = bench_rcnn_stage.measure(dev, steps=min(K, 10), warm=3)
+        except Exception as e:
+            rcnn = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+        torch.cuda.empty_cache()
     clocks = sampler.stop() if sampler else None
 
     # ---------------- the reference's CUDA-extension build (oracle/_ref kernels + cuDNN MLP), same process, same inputs
@@ -524,7 +566,7 @@ def main():
                              "what": "backbone only, full (B,128,16384) features copied to pinned host memory every step (PCIe bound)",
                              "repeats": summary(feat_list)},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
-            "ref_cuda": ref_cuda, "vs_ref_cuda": vs_ref, "strong_scaling": strong}
+            "ref_cuda": ref_cuda, "vs_ref_cuda": vs_ref, "strong_scaling": strong, "train_step": train, "rcnn_stage": rcnn}
     if args.profile_out:
         json.dump(line, open(args.profile_out, "w"), indent=1)
     print(json.dumps(line))

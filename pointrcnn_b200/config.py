@@ -7,6 +7,7 @@ environment variables ONCE at import; at run time they are changed with `overrid
     disable_grid    always use the exhaustive ball-query / 3-NN kernels
     enable_plan     side-stream plan of the backbone forward (measured slower at batch 16, opt-in)
     prof_detail     per-shape lines in prof.collect()
+    fp_project      FP modules: project the known points through layer 0 before interpolating (linearity), default on
 """
 import contextlib
 import os
@@ -18,6 +19,7 @@ _DEFAULTS = dict(
     disable_grid=os.environ.get("PRB_DISABLE_GRID", "0") == "1",
     enable_plan=os.environ.get("PRB_ENABLE_PLAN", "0") == "1",
     prof_detail=os.environ.get("PRB_PROF_DETAIL", "0") == "1",
+    fp_project=os.environ.get("PRB_FP_PROJECT", "1") != "0",
 )
 _local = threading.local()
 

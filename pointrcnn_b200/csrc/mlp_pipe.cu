@@ -21,6 +21,8 @@
 // Hazards: X is released to issuer A by a tcgen05.commit of issuer B after layer 1's MMAs; regions written and read
 // by issuer B alone are ordered by the in-order execution of one thread's MMAs; slice buffers cycle through
 // z_full (commit) / z_free (epilogue arrive) barriers.
+#include <type_traits>
+
 #include "mlp_dev.cuh"
 
 namespace prb {
@@ -71,6 +73,83 @@ struct Cursor {
 
 // every wait parks the warp in hardware (try_wait with a suspend hint) instead of spinning in the issue slots
 __device__ __forceinline__ void bwait(uint64_t *bar, uint32_t parity) { mbar_wait_sleepy(s2u(bar), parity); }
+// roles that run AHEAD of their consumer (gather warps, weight producers: a full ring is the normal state) poll rarely:
+// a try_wait wakes on every barrier event of the CTA, ~100 polls per tile and warp were 23 % of all issued instructions
+__device__ __forceinline__ void bwait_lazy(uint64_t *bar, uint32_t parity) {
+    const uint32_t b = s2u(bar);
+    while (!mbar_test(b, parity)) __nanosleep(400);
+}
+
+// SA max-pool of one 16-column batch when the nsample rows of a centre are lanes of ONE warp (NS = 16 / 32).
+// POOL 0: one warp-wide (half-warp-wide) CREDUX.MAX per channel, then every lane picks the channel named by its low four
+// lane bits through a 15-select tree.  POOL 1: halving shuffle butterfly.  Returns the pooled value of channel `ch(lane)`.
+template <int NS, int POOL>
+__device__ __forceinline__ float pool_batch(float (&v)[16], int lane) {
+    if (POOL == 0) {
+        if (NS == 32) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = redux_max_f32<0xffffffffu>(v[q]);
+        } else if (lane < 16) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = redux_max_f32<0x0000ffffu>(v[q]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = redux_max_f32<0xffff0000u>(v[q]);
+        }
+        const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8;
+        float t8[8], t4[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t8[i] = b0 ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t4[i] = b1 ? t8[2 * i + 1] : t8[2 * i];
+        const float t20 = b2 ? t4[1] : t4[0], t21 = b2 ? t4[3] : t4[2];
+        return b3 ? t21 : t20;                      // channel lane & 15
+    }
+    float w8[8], w4[4], w2[2], x;
+    if (NS == 32) {
+        const bool b4 = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float keep = b4 ? v[i + 8] : v[i], send = b4 ? v[i] : v[i + 8];
+            w8[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+        }
+        const bool b3 = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float keep = b3 ? w8[i + 4] : w8[i], send = b3 ? w8[i] : w8[i + 4];
+            w4[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+        }
+        const bool b2 = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float keep = b2 ? w4[i + 2] : w4[i], send = b2 ? w4[i] : w4[i + 2];
+            w2[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+        }
+        const bool b1 = lane & 2;
+        x = fmaxf(b1 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, b1 ? w2[0] : w2[1], 2));
+        return fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));      // channel (lane >> 1) & 15
+    }
+    const bool b3 = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float keep = b3 ? v[i + 8] : v[i], send = b3 ? v[i] : v[i + 8];
+        w8[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+    }
+    const bool b2 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float keep = b2 ? w8[i + 4] : w8[i], send = b2 ? w8[i] : w8[i + 4];
+        w4[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+    }
+    const bool b1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float keep = b1 ? w4[i + 2] : w4[i], send = b1 ? w4[i] : w4[i + 2];
+        w2[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+    }
+    const bool b0 = lane & 1;
+    return fmaxf(b0 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, b0 ? w2[0] : w2[1], 1));   // channel bit-reversed-ish, see caller
+}
 
 template <int NE, int NGW, int MINB, int MIN, int MOUT>
 __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(const __grid_constant__ ChainParams p) {
@@ -134,7 +213,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                 for (int kc = 0; kc < nch; ++kc, src += chunk_stride)
                     for (int h = 0; h < halves; ++h) {
                         const uint32_t bytes = (uint32_t)min(brows, width - h * brows) * KC * 4;
-                        bwait(&S.b0_empty[rb.stage], rb.phase ^ 1);
+                        bwait_lazy(&S.b0_empty[rb.stage], rb.phase ^ 1);
                         mbar_expect_tx(s2u(&S.b0_full[rb.stage]), bytes);
                         bulk_g2s(s2u(sB0) + rb.stage * stage_bytes, src + (size_t)h * brows * KC, bytes, s2u(&S.b0_full[rb.stage]));
                         rb.advance(nb);
@@ -160,7 +239,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                         for (int kc = 0; kc < nch; ++kc, src += chunk_stride)
                             for (int h = 0; h < halves; ++h) {
                                 const uint32_t bytes = (uint32_t)min(brows, width - h * brows) * KC * 4;
-                                bwait(&S.b1_empty[rb.stage], rb.phase ^ 1);
+                                bwait_lazy(&S.b1_empty[rb.stage], rb.phase ^ 1);
                                 mbar_expect_tx(s2u(&S.b1_full[rb.stage]), bytes);
                                 bulk_g2s(s2u(sB1) + rb.stage * stage_bytes, src + (size_t)h * brows * KC, bytes, s2u(&S.b1_full[rb.stage]));
                                 rb.advance(nb);
@@ -369,7 +448,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                                     }
                                 }
                             }
-                            if (half == 0) bwait(empty_bar, empty_par);
+                            if (half == 0) bwait_lazy(empty_bar, empty_par);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const int rr = wq * 32 + rsub + 4 * (half * 4 + i);
@@ -401,7 +480,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                                 }
                             }
                         }
-                        bwait(empty_bar, empty_par);
+                        bwait_lazy(empty_bar, empty_par);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int rr = wq * 32 + rsub + 4 * i;
@@ -428,7 +507,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                             if (cf > 4) v2.w = to_tf32(__ldg(f + 4));
                         }
                     }
-                    bwait(empty_bar, empty_par);
+                    bwait_lazy(empty_bar, empty_par);
                     *reinterpret_cast<float4 *>(A + swz(r, 0)) = v;
                     *reinterpret_cast<float4 *>(A + swz(r, 1)) = v2;
                 } else if (MIN == IN_FP) {
@@ -440,7 +519,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                         const int ch = k0 + q;
                         o[q] = (valid && ch < width) ? __ldg(bsrc + (size_t)ch * p.n) : 0.f;
                     }
-                    bwait(empty_bar, empty_par);
+                    bwait_lazy(empty_bar, empty_par);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<float4 *>(A + swz(r, j)) =
@@ -551,6 +630,56 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                 bwait(&S.z_full[buf], (nbuf == 2 ? (u >> 1) : u) & 1);
                 tc_fence_after();
                 const uint32_t zc = trow + (uint32_t)p.zcol[buf];
+                if (MOUT == OUT_SA_MAX && (ns == 32 || ns == 16)) {
+                    // ---- fast path: dispatched ONCE per slice on (nsample, pooling kind); everything that does not depend on
+                    // the 16-column batch is computed before the batch loop
+                    auto slice_loop = [&](auto ns_c, auto pool_c) {
+                        constexpr int NSC = decltype(ns_c)::value, POOLC = decltype(pool_c)::value;
+                        const int ch = POOLC == 0 ? (lane & 15)
+                                                  : (NSC == 32 ? ((lane >> 1) & 15)
+                                                               : (((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1)));
+                        const bool st_lane = ok && (NSC == 16 || (POOLC == 1 ? (lane & 1) == 0 : lane < 16));
+                        const int c_first = s_lo + grp * 16;
+                        float *ocm = p.out + off_cm + (size_t)(c_first + ch) * p.npoint;
+                        float *opm = p.out_pm ? p.out_pm + off_pm + c_first + ch : nullptr;
+                        const size_t cm_step = (size_t)(16 * NE) * p.npoint;
+                        const float *shp = sh + c_first + ch;
+                        uint32_t taddr = zc + (uint32_t)(c_first - s_lo);
+                        const int n_ok = Cl - ch;                   // channel c0 + ch exists iff c0 < n_ok
+                        for (int c0 = c_first; c0 < s_hi; c0 += 16 * NE, ocm += cm_step, shp += 16 * NE, taddr += 16 * NE, opm += (opm ? 16 * NE : 0)) {
+                            uint32_t acc[16];
+                            tmem_ld16(taddr, acc);
+                            float v[16];
+                            if (pool_raw) {
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(acc[q]);
+                            } else {
+                                // scale not folded (or a linear last layer): activation first, then the max
+                                const float4 *sh4 = reinterpret_cast<const float4 *>(sh + c0), *sc4 = reinterpret_cast<const float4 *>(sc + c0);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float4 a = sc4[j], b = sh4[j];
+                                    v[4 * j + 0] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 0]), a.x, b.x), lo);
+                                    v[4 * j + 1] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 1]), a.y, b.y), lo);
+                                    v[4 * j + 2] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 2]), a.z, b.z), lo);
+                                    v[4 * j + 3] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 3]), a.w, b.w), lo);
+                                }
+                            }
+                            float x = pool_batch<NSC, POOLC>(v, lane);
+                            if (pool_raw) x = fmaxf(x + *shp, lo);
+                            if (st_lane && c0 < n_ok) {
+                                *ocm = x;
+                                if (opm) *opm = x;
+                            }
+                        }
+                    };
+                    using I16 = std::integral_constant<int, 16>;
+                    using I32 = std::integral_constant<int, 32>;
+                    using P0 = std::integral_constant<int, 0>;
+                    using P1 = std::integral_constant<int, 1>;
+                    if (ns == 32) { if (p.pool_mode == 0) slice_loop(I32{}, P0{}); else slice_loop(I32{}, P1{}); }
+                    else { if (p.pool_mode == 0) slice_loop(I16{}, P0{}); else slice_loop(I16{}, P1{}); }
+                } else
                 for (int c0 = s_lo + grp * 16; c0 < s_hi; c0 += 16 * NE) {
                     uint32_t acc[16];
                     tmem_ld16(zc + (uint32_t)(c0 - s_lo), acc);
@@ -608,93 +737,6 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                                     for (int q = 0; q < 16; ++q)
                                         if (c0 + q < Cl) o2[q] = v[q];
                                 }
-                            }
-                        }
-                    } else if (ns == 32 || ns == 16) {
-                        // The nsample rows of a centre are lanes of ONE warp.
-                        float x;
-                        int ch;
-                        if (p.pool_mode == 0) {
-                            // one warp-wide (or half-warp-wide) CREDUX.MAX per channel, then every lane picks the channel
-                            // named by its low four lane bits through a 15-select tree
-                            if (ns == 32) {
-#pragma unroll
-                                for (int q = 0; q < 16; ++q) v[q] = redux_max_f32<0xffffffffu>(v[q]);
-                            } else if (lane < 16) {
-#pragma unroll
-                                for (int q = 0; q < 16; ++q) v[q] = redux_max_f32<0x0000ffffu>(v[q]);
-                            } else {
-#pragma unroll
-                                for (int q = 0; q < 16; ++q) v[q] = redux_max_f32<0xffff0000u>(v[q]);
-                            }
-                            const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8;
-                            float t8[8], t4[4];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) t8[i] = b0 ? v[2 * i + 1] : v[2 * i];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) t4[i] = b1 ? t8[2 * i + 1] : t8[2 * i];
-                            const float t20 = b2 ? t4[1] : t4[0], t21 = b2 ? t4[3] : t4[2];
-                            x = b3 ? t21 : t20;
-                            ch = lane & 15;
-                            if (pool_raw) x = fmaxf(x + sh[c0 + ch], lo);
-                            if (ok && (ns == 16 || lane < 16) && c0 + ch < Cl) {
-                                p.out[off_cm + (size_t)(c0 + ch) * p.npoint] = x;
-                                if (p.out_pm) p.out_pm[off_pm + c0 + ch] = x;
-                            }
-                        } else {
-                            // halving shuffle butterfly: each step a lane keeps half of its channels (chosen by one lane-id
-                            // bit), sends the other half to its partner and takes the max
-                            float w8[8], w4[4], w2[2];
-                            if (ns == 32) {
-                                const bool b4 = lane & 16;
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float keep = b4 ? v[i + 8] : v[i], send = b4 ? v[i] : v[i + 8];
-                                    w8[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
-                                }
-                                const bool b3 = lane & 8;
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const float keep = b3 ? w8[i + 4] : w8[i], send = b3 ? w8[i] : w8[i + 4];
-                                    w4[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
-                                }
-                                const bool b2 = lane & 4;
-#pragma unroll
-                                for (int i = 0; i < 2; ++i) {
-                                    const float keep = b2 ? w4[i + 2] : w4[i], send = b2 ? w4[i] : w4[i + 2];
-                                    w2[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 4));
-                                }
-                                const bool b1 = lane & 2;
-                                x = fmaxf(b1 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, b1 ? w2[0] : w2[1], 2));
-                                x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
-                                ch = (lane >> 1) & 15;
-                            } else {
-                                const bool b3 = lane & 8;
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float keep = b3 ? v[i + 8] : v[i], send = b3 ? v[i] : v[i + 8];
-                                    w8[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
-                                }
-                                const bool b2 = lane & 4;
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const float keep = b2 ? w8[i + 4] : w8[i], send = b2 ? w8[i] : w8[i + 4];
-                                    w4[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 4));
-                                }
-                                const bool b1 = lane & 2;
-#pragma unroll
-                                for (int i = 0; i < 2; ++i) {
-                                    const float keep = b1 ? w4[i + 2] : w4[i], send = b1 ? w4[i] : w4[i + 2];
-                                    w2[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 2));
-                                }
-                                const bool b0 = lane & 1;
-                                x = fmaxf(b0 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, b0 ? w2[0] : w2[1], 1));
-                                ch = ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1);
-                            }
-                            if (pool_raw) x = fmaxf(x + sh[c0 + ch], lo);
-                            if (ok && (ns == 16 || (lane & 1) == 0) && c0 + ch < Cl) {
-                                p.out[off_cm + (size_t)(c0 + ch) * p.npoint] = x;
-                                if (p.out_pm) p.out_pm[off_pm + c0 + ch] = x;
                             }
                         }
                     } else {
@@ -801,26 +843,27 @@ static bool pipe_plan(const ChainParams &p, int max_optin, PipePlan *out) {
             pl.ne = pl.ngw = pl.occ == 2 ? 1 : 2;         // two builds: 4+4 row warps x 2 CTAs, or 8+8 row warps x 1 CTA
             if (o.mlp_ne == 1) pl.ne = pl.ngw = 1;
             if (o.mlp_ne == 2) { pl.ne = pl.ngw = 2; pl.occ = 1; }
-            // weight stages: BROWS rows of one 32-column K chunk (BROWS x 128 bytes); many small stages keep more bulk copies in
-            // flight than a few large ones (a 3-deep ring of 28 KB stages delivered ~10 B/cycle: every copy is a full round trip
-            // MMA commit -> producer -> L2 -> mbarrier)
-            const int brows = o.mlp_brows >= 32 ? o.mlp_brows : 64;
+            // weight stages: up to BROWS rows (output channels) of one 32-column K chunk.  Measured (profiles/r2_notes.md): 64-row
+            // stages with 8-12 deep rings are SLOWER than 256-row stages 3 deep (SA3 0.178 vs 0.131 ms, FP1 0.242 vs 0.158):
+            // every stage costs two single-thread barrier round trips and an N=64 MMA per K step, which outweighs the
+            // extra bytes in flight.
+            const int brows = o.mlp_brows >= 32 ? o.mlp_brows : 256;
             pl.brows = brows;
-            pl.b0_bytes = brows * KC * 4; pl.b1_bytes = L > 1 ? brows * KC * 4 : 0;
+            int b0_rows = L == 1 ? z : p.np[0], b1_rows = 32;
+            for (int l = 1; l < L; ++l) { const int w = (l == L - 1) ? z : p.np[l]; if (w > b1_rows) b1_rows = w; }
+            if (b0_rows > brows) b0_rows = brows;
+            if (b1_rows > brows) b1_rows = brows;
+            pl.b0_bytes = b0_rows * KC * 4; pl.b1_bytes = L > 1 ? b1_rows * KC * 4 : 0;
             const size_t budget = (size_t)(227 * 1024) / pl.occ - 1024 - sizeof(PipeSmem) - 512;
             bool ok = false;
-            // A ring first (>= 3 stages, up to one whole item + 1), the rest goes to the weight rings (<= PIPE_MAX_B stages each)
-            for (int na = (k0 + 1 < PIPE_MAX_A ? (k0 + 1 > 3 ? k0 + 1 : 3) : PIPE_MAX_A); na >= 2 && !ok; --na) {
-                const size_t fixed = pipe_smem_bytes(pl.ne, na, 0, 0, 0, 0, np_total);
-                if (fixed + (size_t)(L > 1 ? 4 : 2) * pl.b0_bytes > budget) continue;
-                int nb = (int)((budget - fixed) / ((size_t)pl.b0_bytes * (L > 1 ? 2 : 1)));
-                if (nb > PIPE_MAX_B) nb = PIPE_MAX_B;
-                if (na > 3 && nb < 6 && (L > 1 ? 2 : 1) * pl.b0_bytes * 6 + pipe_smem_bytes(pl.ne, na - 1, 0, 0, 0, 0, np_total) <= budget) continue;   // prefer deeper weight rings
-                const size_t smem = pipe_smem_bytes(pl.ne, na, nb, pl.b0_bytes, L > 1 ? nb : 0, pl.b1_bytes, np_total);
-                if (nb >= 2 && smem <= budget && smem <= (size_t)max_optin) {
-                    pl.na = na; pl.nb0 = nb; pl.nb1 = L > 1 ? nb : 0; pl.smem = smem; ok = true;
+            // weight rings 3 deep (2 if tight); the A ring as deep as fits, up to one whole item + 2
+            for (int nb = 3; nb >= 2 && !ok; --nb)
+                for (int na = (k0 + 2 < PIPE_MAX_A ? (k0 + 2 > 3 ? k0 + 2 : 3) : PIPE_MAX_A); na >= 2 && !ok; --na) {
+                    const size_t smem = pipe_smem_bytes(pl.ne, na, nb, pl.b0_bytes, L > 1 ? nb : 0, pl.b1_bytes, np_total);
+                    if (smem <= budget && smem <= (size_t)max_optin && (nb == 2 || na >= (k0 < 4 ? k0 : 4))) {
+                        pl.na = na; pl.nb0 = nb; pl.nb1 = L > 1 ? nb : 0; pl.smem = smem; ok = true;
+                    }
                 }
-            }
             if (!ok) continue;
             const long score = (long)pl.occ * 1000000L + nbuf * 1000L + z;
             if (score > best_score) { best_score = score; best = pl; }

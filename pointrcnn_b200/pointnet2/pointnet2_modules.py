@@ -58,7 +58,11 @@ class _FusedMLP:
                 return False
         return True
 
-    def get(self, mlp: nn.Sequential, kind: int, split: int, device):
+    def get(self, mlp: nn.Sequential, kind: int, split: int, device, project_known: bool = False):
+        """project_known (FP chains, kind 1): layer 0 is split by linearity -- interp(known) @ W0k^T == interp(known @ W0k^T) --
+        into a per-KNOWN-point projection (a separate, 4x smaller row GEMM: `self.proj`, linear, no shift) and a main chain
+        whose layer 0 reads [interp(projected rows) | skip] through the weight [I | W0s]: the gather moves c_out0 instead of
+        c_known floats per neighbour and layer 0 contracts over c_out0 + c_skip instead of c_known + c_skip columns."""
         layers = list(mlp.children())
         tensors = []
         for layer in layers:
@@ -66,7 +70,7 @@ class _FusedMLP:
             if hasattr(layer, "bn"):
                 bn = layer.bn.bn
                 tensors += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
-        key = (kind, split, str(device), _fold_scale()) + tuple((id(t), t._version) if t is not None else None for t in tensors)
+        key = (kind, split, str(device), _fold_scale(), project_known) + tuple((id(t), t._version) if t is not None else None for t in tensors)
         if key == self.key:
             return self.desc
         L = len(layers)
@@ -94,6 +98,14 @@ class _FusedMLP:
                 scales.append(F.pad(inv, (0, pad)))
                 shifts.append(F.pad(sh, (0, pad)))
         lib = C.lib()
+        self.proj = None
+        if project_known:
+            # ws[0] is (c_out0, c_known + c_skip) with the BN scale already folded in: W0k -> projection, W0s stays
+            W0 = ws[0]
+            c1, c_known = W0.shape[0], split
+            self.proj = self._pack(lib, 2, 0, c_known, [c1], [W0[:, :c_known].contiguous()], torch.zeros(_round_up(c1, 32)), device, flags=1)
+            ws[0] = torch.cat([torch.eye(c1), W0[:, c_known:]], dim=1).contiguous()
+            c_in, split = c1 + (c_in - c_known), c1
         co_arr = (ctypes.c_int * 3)(*(c_out + [0] * (3 - L)))
         nbytes = lib.prb_mlp_packed_bytes_ex(kind, split, L, c_in, co_arr)
         host = np.zeros(nbytes // 4, dtype=np.float32)
@@ -109,6 +121,24 @@ class _FusedMLP:
         desc.packed_w, desc.scale, desc.shift = packed.data_ptr(), (None if _fold_scale() else scale.data_ptr()), shift.data_ptr()
         self.key, self.desc, self.tensors, self.c_out = key, desc, (packed, scale, shift), c_out
         return desc
+
+    @staticmethod
+    def _pack(lib, kind, split, c_in, c_out, ws, shift, device, flags=0):
+        """pack a chain whose scale is already folded into `ws`; returns dict(desc, keep-alive tensors, c_out)"""
+        L = len(ws)
+        co_arr = (ctypes.c_int * 3)(*(c_out + [0] * (3 - L)))
+        nbytes = lib.prb_mlp_packed_bytes_ex(kind, split, L, c_in, co_arr)
+        host = np.zeros(nbytes // 4, dtype=np.float32)
+        wp = (ctypes.c_void_p * L)(*[w.data_ptr() for w in ws])
+        C.check(lib.prb_mlp_pack_weights_ex(kind, split, L, c_in, co_arr, wp, host.ctypes.data_as(ctypes.c_void_p)), "mlp_pack")
+        packed = torch.from_numpy(host).to(device)
+        shift = shift.contiguous().to(device)
+        desc = C.MlpDesc()
+        desc.num_layers, desc.c_in = L, c_in
+        for i in range(3):
+            desc.c_out[i] = c_out[i] if i < L else 0
+        desc.packed_w, desc.scale, desc.shift, desc.flags = packed.data_ptr(), None, shift.data_ptr(), flags
+        return dict(desc=desc, keep=(packed, shift, ws), c_out=c_out, co_arr=co_arr)
 
 
 def _attach_pm(t, pm):
@@ -291,6 +321,7 @@ class PointnetFPModule(nn.Module):
         self.mlp = pt_utils.SharedMLP(mlp, bn=bn)
         self._fused = None
         self.emit_point_major = True   # also write a (B,n,C) twin for the next FP level (skips its transpose kernel)
+        self.project_known = True      # split layer 0 by linearity when it narrows the gathered rows (see _FusedMLP.get)
 
     def _can_fuse(self, unknown, known, unknow_feats, known_feats):
         if not _fused_enabled() or known is None or not unknown.is_cuda:
@@ -315,8 +346,25 @@ class PointnetFPModule(nn.Module):
         skip = unknow_feats.contiguous() if unknow_feats is not None else None
         if self._fused is None:
             self._fused = _FusedMLP()
-        desc = self._fused.get(self.mlp, 1, c_known, dev)
+        c1 = list(self.mlp.children())[0].conv.out_channels
+        # interpolation commutes with the (linear) first layer: project the m known points once instead of gathering
+        # c_known floats for each of the 3 neighbours of every one of the n >= m unknown points
+        project = self.project_known and config.get("fp_project") and _fold_scale() and c1 < c_known and n >= m
+        desc = self._fused.get(self.mlp, 1, c_known, dev, project_known=project)
         c_out = self._fused.c_out
+        if project:
+            pj = self._fused.proj
+            pitch = _round_up(c1, 32)
+            rows = B * m
+            proj_rows = torch.empty((rows, pitch), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                wsb = lib.prb_rows_workspace_bytes(C.c_long(rows), c_known, 1, pj["co_arr"])
+                wsp = torch.empty(wsb, dtype=torch.uint8, device=dev)
+                with prof.region("fp_mlp", "%d proj [%d]+[%d]" % (rows, c_known, c1)):
+                    C.check(lib.prb_mlp_rows(C.c_long(rows), c_known, C.ptr(known_pm), ctypes.byref(pj["desc"]), C.ptr(proj_rows), pitch,
+                                             C.ptr(wsp), C.c_size_t(wsb), C.stream()), "mlp_rows(fp projection)")
+            known_pm = proj_rows if pitch == c1 else proj_rows[:, :c1].contiguous()
+            c_known = c1
         out = torch.empty((B, c_out[-1], n), dtype=torch.float32, device=dev)
         out_pm = torch.empty((B, n, c_out[-1]), dtype=torch.float32, device=dev) if self.emit_point_major else None
         co_arr = (ctypes.c_int * 3)(*(c_out + [0] * (3 - len(c_out))))

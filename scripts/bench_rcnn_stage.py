@@ -45,8 +45,7 @@ def flops_per_roi(net):
     return 2 * f
 
 
-def main(steps=10, warm=3):
-    dev = torch.device("cuda", 0)
+def measure(dev, steps=10, warm=3):
     torch.manual_seed(0)
     net = RCNNStage().to(dev).eval()
     inp = make_inputs(dev)
@@ -85,9 +84,8 @@ def main(steps=10, warm=3):
            "rcnn_net": {"algorithmic_TFLOP": fl / 1e12, "achieved_TFLOPs": fl / t_net / 1e9, "peak_TFLOPs_tf32": peaks["bf16_tflops"] / 2,
                         "frac": fl / t_net / 1e9 / (peaks["bf16_tflops"] / 2)},
            "families_ms": fam, "non_empty_rois": int((empty == 0).sum()), "checksum": float(cls.double().mean() + reg.double().mean())}
-    print(json.dumps(out))
     return out
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(measure(torch.device("cuda", 0))))
