@@ -206,6 +206,10 @@ PRB_API int prb_rpn_proposals(int b, int n, const float *boxes, const float *sco
 
 /* diagnostics (PRB_MLP_TRACE=1): clock64 stamps of CTA 0 at the phase boundaries of its first 32 tiles (32 x 16) */
 PRB_API int prb_debug_mlp_trace(long long *dst);
+/* pipelined kernel (prb_options.mlp_trace): cycles CTA 0's roles spent in each class of barrier wait during the last traced
+ * launch, 8 x 4 int64: rows = issuer A {x/z_free, a_full, b0_full, total}, issuer B {z_free, ready, b1_full, total}, weight
+ * producer 0 {b0_empty, -, -, total}, producer 1 {b1_empty, ...}, gather warp 0 {a_empty, ...}, epilogue warp 0 {r_full, z_full, -, total} */
+PRB_API int prb_debug_pipe_trace(long long *dst);
 
 /* --- uniform-grid neighbour search: same results, bit for bit, as prb_ball_query(_msg2) / prb_three_nn
  * (first-nsample-in-index-order and lexicographic (d2, idx) rules kept; queries the grid cannot answer

@@ -151,6 +151,26 @@ __device__ __forceinline__ float pool_batch(float (&v)[16], int lane) {
     return fmaxf(b0 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, b0 ? w2[0] : w2[1], 1));   // channel bit-reversed-ish, see caller
 }
 
+// optional wait-time trace (prb_options.mlp_trace): CTA 0 accumulates the cycles each role spends in each class of wait
+// and the total cycles of its item loop; read back with prb_debug_pipe_trace.  Slots: 0 issuer A {x_free|z_free, a_full,
+// b0_full, total}, 1 issuer B {z_free, ready, b1_full, total}, 2 producer 0 {b0_empty, total}, 3 producer 1 {b1_empty,
+// total}, 4 gather warp 0 {a_empty, total}, 5 epilogue warp 0 {r_full, z_full, total}
+__device__ long long g_pipe_trace[8][4];
+struct TraceTimer {
+    bool on;
+    long long acc[3], t0;
+    __device__ __forceinline__ void start(bool enable) { on = enable; acc[0] = acc[1] = acc[2] = 0; t0 = on ? clock64() : 0; }
+    template <class F>
+    __device__ __forceinline__ void timed(int k, F &&f) {
+        if (on) { const long long t = clock64(); f(); acc[k] += clock64() - t; } else f();
+    }
+    __device__ __forceinline__ void finish(int slot, int nclass) {
+        if (!on) return;
+        for (int k = 0; k < nclass; ++k) g_pipe_trace[slot][k] = acc[k];
+        g_pipe_trace[slot][3] = clock64() - t0;
+    }
+};
+
 template <int NE, int NGW, int MINB, int MIN, int MOUT>
 __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(const __grid_constant__ ChainParams p) {
     constexpr int NTHREADS = (NE + NGW + 1) * 128;
@@ -196,6 +216,8 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
     const int sj = (int)blockIdx.x % nsplit;
     const int tile0 = (int)blockIdx.x / nsplit, tstep = (int)gridDim.x / nsplit;
     const int ntiles = p.num_tiles;
+    TraceTimer tt;
+    tt.start(p.trace != 0 && blockIdx.x == 0 && lane == 0 && (warp >= W_MISC || warp == W_GATHER || warp == 0));
 
     if (warp == W_MISC) {
         // ===================================================== weight producer, layer 0
@@ -213,7 +235,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                 for (int kc = 0; kc < nch; ++kc, src += chunk_stride)
                     for (int h = 0; h < halves; ++h) {
                         const uint32_t bytes = (uint32_t)min(brows, width - h * brows) * KC * 4;
-                        bwait_lazy(&S.b0_empty[rb.stage], rb.phase ^ 1);
+                        tt.timed(0, [&] { bwait_lazy(&S.b0_empty[rb.stage], rb.phase ^ 1); });
                         mbar_expect_tx(s2u(&S.b0_full[rb.stage]), bytes);
                         bulk_g2s(s2u(sB0) + rb.stage * stage_bytes, src + (size_t)h * brows * KC, bytes, s2u(&S.b0_full[rb.stage]));
                         rb.advance(nb);
@@ -239,7 +261,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                         for (int kc = 0; kc < nch; ++kc, src += chunk_stride)
                             for (int h = 0; h < halves; ++h) {
                                 const uint32_t bytes = (uint32_t)min(brows, width - h * brows) * KC * 4;
-                                bwait_lazy(&S.b1_empty[rb.stage], rb.phase ^ 1);
+                                tt.timed(0, [&] { bwait_lazy(&S.b1_empty[rb.stage], rb.phase ^ 1); });
                                 mbar_expect_tx(s2u(&S.b1_full[rb.stage]), bytes);
                                 bulk_g2s(s2u(sB1) + rb.stage * stage_bytes, src + (size_t)h * brows * KC, bytes, s2u(&S.b1_full[rb.stage]));
                                 rb.advance(nb);
@@ -261,11 +283,11 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
             for (int tile = tile0; tile < ntiles; tile += tstep, ++it) {
                 uint32_t dcol, buf = 0;
                 if (L > 1) {
-                    bwait(&S.x_free, (it & 1) ^ 1);       // layer 1 of the previous item has consumed X
+                    tt.timed(0, [&] { bwait(&S.x_free, (it & 1) ^ 1); });       // layer 1 of the previous item has consumed X
                     dcol = (uint32_t)p.rcol[0];
                 } else {
                     buf = nbuf == 2 ? (it & 1) : 0u;
-                    bwait(&S.z_free[buf], ((nbuf == 2 ? (it >> 1) : it) & 1) ^ 1);
+                    tt.timed(0, [&] { bwait(&S.z_free[buf], ((nbuf == 2 ? (it >> 1) : it) & 1) ^ 1); });
                     dcol = (uint32_t)p.zcol[buf];
                 }
                 tc_fence_after();
@@ -273,11 +295,11 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                     int c = kc, sg = 0;
                     if (p.nseg > 1 && c >= p.seg_chunks[0]) { c -= p.seg_chunks[0]; sg = 1; }
                     const int ksteps = (min(KC, p.seg_width[sg] - c * KC) + 7) >> 3;
-                    bwait(&S.a_full[ra.stage], ra.phase);
+                    tt.timed(1, [&] { bwait(&S.a_full[ra.stage], ra.phase); });
                     const uint64_t adesc = make_desc(a_base + ra.stage * A_STAGE_BYTES);
                     for (int h = 0; h < halves; ++h) {
                         const int rows = min(brows, width - h * brows);
-                        bwait(&S.b0_full[rb.stage], rb.phase);
+                        tt.timed(2, [&] { bwait(&S.b0_full[rb.stage], rb.phase); });
                         tc_fence_after();
                         const uint64_t bdesc = make_desc(b_base + rb.stage * b_bytes);
                         const uint32_t idesc = make_idesc(rows);
@@ -313,19 +335,19 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                         uint32_t dcol, buf = 0;
                         if (last) {
                             buf = nbuf == 2 ? (u & 1) : 0u;
-                            bwait(&S.z_free[buf], ((nbuf == 2 ? (u >> 1) : u) & 1) ^ 1);   // the epilogue has drained this buffer
+                            tt.timed(0, [&] { bwait(&S.z_free[buf], ((nbuf == 2 ? (u >> 1) : u) & 1) ^ 1); });   // the epilogue has drained this buffer
                             dcol = (uint32_t)p.zcol[buf];
                             ++u;
                         } else {
                             dcol = (uint32_t)p.rcol[l];
                         }
                         for (int kc = 0; kc < nch; ++kc) {
-                            if (s == 0) bwait(&S.ready[l - 1][kc], it & 1);   // chunk kc of the A operand is in place
+                            if (s == 0) tt.timed(1, [&] { bwait(&S.ready[l - 1][kc], it & 1); });   // chunk kc of the A operand is in place
                             tc_fence_after();
                             const uint32_t a_t = a_col + (uint32_t)(kc * KC);
                             for (int h = 0; h < halves; ++h) {
                                 const int rows = min(brows, width - h * brows);
-                                bwait(&S.b1_full[rb.stage], rb.phase);
+                                tt.timed(2, [&] { bwait(&S.b1_full[rb.stage], rb.phase); });
                                 tc_fence_after();
                                 const uint64_t bdesc = make_desc(b_base + rb.stage * b_bytes);
                                 const uint32_t idesc = make_idesc(rows);
@@ -448,7 +470,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                                     }
                                 }
                             }
-                            if (half == 0) bwait_lazy(empty_bar, empty_par);
+                            if (half == 0) tt.timed(0, [&] { bwait_lazy(empty_bar, empty_par); });
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const int rr = wq * 32 + rsub + 4 * (half * 4 + i);
@@ -480,7 +502,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                                 }
                             }
                         }
-                        bwait_lazy(empty_bar, empty_par);
+                        tt.timed(0, [&] { bwait_lazy(empty_bar, empty_par); });
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int rr = wq * 32 + rsub + 4 * i;
@@ -507,7 +529,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                             if (cf > 4) v2.w = to_tf32(__ldg(f + 4));
                         }
                     }
-                    bwait_lazy(empty_bar, empty_par);
+                    tt.timed(0, [&] { bwait_lazy(empty_bar, empty_par); });
                     *reinterpret_cast<float4 *>(A + swz(r, 0)) = v;
                     *reinterpret_cast<float4 *>(A + swz(r, 1)) = v2;
                 } else if (MIN == IN_FP) {
@@ -519,7 +541,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                         const int ch = k0 + q;
                         o[q] = (valid && ch < width) ? __ldg(bsrc + (size_t)ch * p.n) : 0.f;
                     }
-                    bwait_lazy(empty_bar, empty_par);
+                    tt.timed(0, [&] { bwait_lazy(empty_bar, empty_par); });
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<float4 *>(A + swz(r, j)) =
@@ -548,7 +570,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
         const int ns = p.ns;
         // mid layer l of item number `itn`: accumulator -> +shift -> ReLU -> tf32, rewritten in place as the next layer's A operand
         auto mid_epilogue = [&](int l, uint32_t itn) {
-            bwait(&S.r_full[l], itn & 1);
+            tt.timed(0, [&] { bwait(&S.r_full[l], itn & 1); });
             tc_fence_after();
             const int nch = p.np[l] / KC;
             const uint32_t col0 = trow + (uint32_t)p.rcol[l];
@@ -627,7 +649,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                 const uint32_t buf = nbuf == 2 ? (u & 1) : 0u;
                 const int s_lo = L == 1 ? sj * slice_w : s * slice_w;                  // first absolute column of this slice
                 const int s_hi = min(Cl, s_lo + slice_w);
-                bwait(&S.z_full[buf], (nbuf == 2 ? (u >> 1) : u) & 1);
+                tt.timed(1, [&] { bwait(&S.z_full[buf], (nbuf == 2 ? (u >> 1) : u) & 1); });
                 tc_fence_after();
                 const uint32_t zc = trow + (uint32_t)p.zcol[buf];
                 if (MOUT == OUT_SA_MAX && (ns == 32 || ns == 16)) {
@@ -788,6 +810,14 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
         }
     }
 
+    if (tt.on) {
+        if (warp == W_MISC + 2) tt.finish(0, 3);
+        else if (warp == W_MISC + 3) tt.finish(1, 3);
+        else if (warp == W_MISC) tt.finish(2, 1);
+        else if (warp == W_MISC + 1) tt.finish(3, 1);
+        else if (warp == W_GATHER) tt.finish(4, 1);
+        else if (warp == 0) tt.finish(5, 2);
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == W_MISC + 2) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
@@ -823,9 +853,17 @@ static bool pipe_plan(const ChainParams &p, int max_optin, PipePlan *out) {
             if (L == 1) {
                 // single layer: no slicing (the A chunks stream by once); wide layers are dealt to nsplit work items
                 if (zs != 256) continue;
+                // ... and launches with few tiles are dealt to MORE items than the accumulator width requires, until every SM
+                // has one (each item re-gathers its A rows from L2; the small levels -- 32 to 256 tiles -- otherwise run on a
+                // fraction of the GPU with one long K loop per CTA)
                 nsplit = (np_last + 255) / 256;
+                const int want = (num_sms() + p.num_tiles - 1) / p.num_tiles;
+                if (want > nsplit) nsplit = want;
+                if (nsplit > np_last / 64) nsplit = np_last / 64 > 0 ? np_last / 64 : 1;
+                if (nsplit < (np_last + 255) / 256) nsplit = (np_last + 255) / 256;
                 if (o.mlp_zs >= 32 && o.mlp_zs < np_last) nsplit = (np_last + o.mlp_zs - 1) / o.mlp_zs;
                 split_w = ((np_last + nsplit - 1) / nsplit + 31) / 32 * 32;
+                nsplit = (np_last + split_w - 1) / split_w;
                 z = split_w;
             } else {
                 if (zs > np_last || np_last % zs) continue;
@@ -903,6 +941,7 @@ int launch_chain_pipe(ChainParams &p, cudaStream_t st) {
     if (grid > p.num_items) grid = p.num_items;
     grid = grid / pl.nsplit * pl.nsplit;         // a CTA keeps its column group: tiles advance by grid / nsplit
     if (grid < pl.nsplit) grid = pl.nsplit;
+    p.trace = opts().mlp_trace ? 1 : 0;
     p.rows32 = (int)p.total_rows;
     p.pool_mode = opts().mlp_pool;
     const size_t smem = pl.smem;
@@ -933,3 +972,13 @@ int launch_chain_pipe(ChainParams &p, cudaStream_t st) {
 }
 
 }  // namespace prb
+
+// wait-time trace of the last traced pipelined launch: 8 roles x {3 wait classes, total cycles} (see g_pipe_trace); also
+// reports the plan of that launch in plan[0..7] = {ne, ngw, occ, zs, nbuf, na, nb, tmem columns}
+extern "C" int prb_debug_pipe_trace(long long *dst) {
+    PRB_CUDA(cudaDeviceSynchronize());
+    PRB_CUDA(cudaMemcpyFromSymbol(dst, prb::g_pipe_trace, sizeof(long long) * 32));
+    static long long zeros[32];
+    PRB_CUDA(cudaMemcpyToSymbol(prb::g_pipe_trace, zeros, sizeof(zeros)));
+    return 0;
+}
