@@ -195,7 +195,9 @@ PRB_API int prb_mlp_rows(long rows, int c_in, const float *x_rows, const prb_mlp
  * prb_rpn_proposals replaces ProposalLayer.forward's per-scene loop (lib/rpn/proposal_layer.py:34-142): order = the
  * indices of torch.sort(scores, descending) (b,n) int64; distance_based selects the (0,40] / (40,80] split with the
  * 70/30 top-n quotas, otherwise the score-based variant; normal_nms: nms_normal_gpu instead of nms_gpu.  Outputs
- * (b, post_nms_top_n, 7) and (b, post_nms_top_n), zero rows behind the survivors.  No host synchronisation. */
+ * (b, post_nms_top_n, 7) and (b, post_nms_top_n), zero rows behind the survivors.  No host synchronisation.
+ * Deviations on degenerate inputs: equal scores keep the order of `order` (the reference re-sorts each slice with an
+ * unstable sort); an empty near range yields zero rows (the reference asserts). */
 PRB_API int prb_decode_rpn_proposals(long n, int c, const float *xyz, const float *reg, const float *anchor_hwl,
                                      float loc_scope, float loc_bin_size, int num_head_bin, int get_xz_fine, float *out,
                                      void *stream);

@@ -181,6 +181,16 @@ class _PointnetSAModuleBase(nn.Module):
         self.pool_method = 'max_pool'
         self._fused = None
 
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .half() / .float() / .cuda() replace parameter storage without bumping tensor versions: drop the packed images
+        self._fused = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def invalidate_fused(self):
+        """call after editing weights through `.data` (EMA, weight averaging): such writes do not bump the version counters the
+        packed-weight cache keys on"""
+        self._fused = None
+
     # ------------------------------------------------------------------ fused (tensor-core) path
     def _can_fuse(self, xyz, features, new_xyz):
         if not _fused_enabled() or not xyz.is_cuda or self.pool_method != 'max_pool':
@@ -322,6 +332,13 @@ class PointnetFPModule(nn.Module):
         self._fused = None
         self.emit_point_major = True   # also write a (B,n,C) twin for the next FP level (skips its transpose kernel)
         self.project_known = True      # split layer 0 by linearity when it narrows the gathered rows (see _FusedMLP.get)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._fused = None             # see _PointnetSAModuleBase._apply
+        return super()._apply(fn, *args, **kwargs)
+
+    def invalidate_fused(self):
+        self._fused = None
 
     def _can_fuse(self, unknown, known, unknow_feats, known_feats):
         if not _fused_enabled() or known is None or not unknown.is_cuda:
