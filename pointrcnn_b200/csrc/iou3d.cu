@@ -18,51 +18,73 @@
 namespace prb {
 
 // ---------------------------------------------------------------- pairwise matrices
+// 16 x 16 pairs per CTA; the 32 boxes of the tile are precomputed once (BoxPre: centre, cos/sin, rotated corners), the
+// intersection polygon of each pair lives in a shared-memory column of its thread (no local memory).
 constexpr int PM_T = 16;
+constexpr int POLY_SLOTS = 16;         // an intersection polygon has at most 8 + 8 vertices
 template <bool IOU>
 __global__ void __launch_bounds__(PM_T * PM_T) pair_matrix_kernel(int num_a, const float *__restrict__ boxes_a, int num_b,
                                                                   const float *__restrict__ boxes_b, float *__restrict__ out) {
-    __shared__ float sa[PM_T * 5], sb[PM_T * 5];
+    extern __shared__ float s_poly[];                     // 3 x POLY_SLOTS x 256 floats
+    __shared__ BoxPre sa[PM_T], sb[PM_T];
     const int a0 = blockIdx.y * PM_T, b0 = blockIdx.x * PM_T;
     const int t = threadIdx.y * PM_T + threadIdx.x;
-    if (t < PM_T * 5) {
-        int i = a0 * 5 + t;
-        sa[t] = i < num_a * 5 ? boxes_a[i] : 0.f;
-    } else if (t < 2 * PM_T * 5) {
-        int i = b0 * 5 + (t - PM_T * 5);
-        sb[t - PM_T * 5] = i < num_b * 5 ? boxes_b[i] : 0.f;
+    if (t < PM_T) {
+        if (a0 + t < num_a) box_pre(boxes_a + (size_t)(a0 + t) * 5, sa[t]);
+    } else if (t < 2 * PM_T) {
+        if (b0 + t - PM_T < num_b) box_pre(boxes_b + (size_t)(b0 + t - PM_T) * 5, sb[t - PM_T]);
     }
     __syncthreads();
     const int ai = a0 + threadIdx.y, bi = b0 + threadIdx.x;
     if (ai >= num_a || bi >= num_b) return;
-    const float *A = sa + threadIdx.y * 5, *Bx = sb + threadIdx.x * 5;
-    out[(size_t)ai * num_b + bi] = IOU ? iou_bev(A, Bx) : box_overlap(A, Bx);
+    constexpr int NT = PM_T * PM_T;
+    float *px = s_poly + t, *py = px + POLY_SLOTS * NT, *pa = py + POLY_SLOTS * NT;
+    out[(size_t)ai * num_b + bi] = IOU ? iou_bev_pre(sa[threadIdx.y], sb[threadIdx.x], px, py, pa, NT)
+                                       : box_overlap_pre(sa[threadIdx.y], sb[threadIdx.x], px, py, pa, NT);
 }
 
 // ---------------------------------------------------------------- NMS mask (upper-triangle tiles)
+// One CTA of 8 warps per 64 x 64 tile.  Warp w takes rows w, w+8, ...; lane l tests columns l and l+32 of the row and two
+// ballots assemble the 64-bit mask word (the reference and the round-1 kernel: one thread per row, 64 pairs in sequence).
+// Rotated: the 128 boxes of the tile are precomputed once; axis-aligned: plain extents.
+constexpr int NM_THREADS = 256;
 template <bool NORMAL>
-__global__ void __launch_bounds__(64) nms_mask_kernel(int n, float thresh, const float *__restrict__ boxes,
-                                                      unsigned long long *__restrict__ mask) {
+__global__ void __launch_bounds__(NM_THREADS) nms_mask_kernel(int n, float thresh, const float *__restrict__ boxes,
+                                                              unsigned long long *__restrict__ mask) {
+    extern __shared__ float s_poly[];                     // rotated only: 3 x POLY_SLOTS x 256 floats
+    __shared__ BoxPre cpre[NORMAL ? 1 : 64], rpre[NORMAL ? 1 : 64];
+    __shared__ float cbx[NORMAL ? 64 * 5 : 1], rbx[NORMAL ? 64 * 5 : 1];
     const int row_blk = blockIdx.y, col_blk = blockIdx.x;
     const int col_blocks = ceil_div(n, 64);
     const int row_size = min(n - row_blk * 64, 64), col_size = min(n - col_blk * 64, 64);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (row_blk > col_blk) {  // never read by the scan; keep the buffer defined
-        if ((int)threadIdx.x < row_size) mask[(size_t)(row_blk * 64 + threadIdx.x) * col_blocks + col_blk] = 0ull;
+        if (tid < row_size) mask[(size_t)(row_blk * 64 + tid) * col_blocks + col_blk] = 0ull;
         return;
     }
-    __shared__ float cbx[64 * 5], rbx[64 * 5];
-    for (int i = threadIdx.x; i < col_size * 5; i += 64) cbx[i] = boxes[(size_t)col_blk * 64 * 5 + i];
-    for (int i = threadIdx.x; i < row_size * 5; i += 64) rbx[i] = boxes[(size_t)row_blk * 64 * 5 + i];
+    if (NORMAL) {
+        for (int i = tid; i < col_size * 5; i += NM_THREADS) cbx[i] = boxes[(size_t)col_blk * 64 * 5 + i];
+        for (int i = tid; i < row_size * 5; i += NM_THREADS) rbx[i] = boxes[(size_t)row_blk * 64 * 5 + i];
+    } else {
+        if (tid < col_size) box_pre(boxes + (size_t)(col_blk * 64 + tid) * 5, cpre[tid]);
+        else if (tid >= 64 && tid - 64 < row_size) box_pre(boxes + (size_t)(row_blk * 64 + tid - 64) * 5, rpre[tid - 64]);
+    }
     __syncthreads();
-    if ((int)threadIdx.x < row_size) {
-        const float *cur = rbx + threadIdx.x * 5;
-        unsigned long long t = 0;
-        const int start = (row_blk == col_blk) ? threadIdx.x + 1 : 0;
-        for (int i = start; i < col_size; i++) {
-            const float v = NORMAL ? iou_normal(cur, cbx + i * 5) : iou_bev(cur, cbx + i * 5);
-            if (v > thresh) t |= 1ULL << i;
+    float *px = s_poly + tid, *py = px + POLY_SLOTS * NM_THREADS, *pa = py + POLY_SLOTS * NM_THREADS;
+    for (int r = warp; r < row_size; r += NM_THREADS / 32) {
+        const int start = (row_blk == col_blk) ? r + 1 : 0;        // inside a diagonal tile only columns behind the row
+        bool hit[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = lane + 32 * h;
+            hit[h] = false;
+            if (c >= start && c < col_size) {
+                const float v = NORMAL ? iou_normal(rbx + r * 5, cbx + c * 5) : iou_bev_pre(rpre[r], cpre[c], px, py, pa, NM_THREADS);
+                hit[h] = v > thresh;
+            }
         }
-        mask[(size_t)(row_blk * 64 + threadIdx.x) * col_blocks + col_blk] = t;
+        const unsigned lo = __ballot_sync(0xffffffffu, hit[0]), hi = __ballot_sync(0xffffffffu, hit[1]);
+        if (lane == 0) mask[(size_t)(row_blk * 64 + r) * col_blocks + col_blk] = ((unsigned long long)hi << 32) | lo;
     }
 }
 
@@ -186,11 +208,14 @@ __device__ __forceinline__ void box7_to_bev(const float *b, float *bev) {
     bev[2] = __fadd_rn(b[0], half_l); bev[3] = __fadd_rn(b[2], half_w);
     bev[4] = b[6];
 }
-__device__ __forceinline__ float iou3d_pair(const float *a, const float *b) {
+__device__ __forceinline__ float iou3d_pair(const float *a, const float *b, float *px, float *py, float *pa, int stride) {
     float abev[5], bbev[5];
     box7_to_bev(a, abev);
     box7_to_bev(b, bbev);
-    const float ov_bev = box_overlap(abev, bbev);
+    BoxPre A, Bp;
+    box_pre(abev, A);
+    box_pre(bbev, Bp);
+    const float ov_bev = box_overlap_pre(A, Bp, px, py, pa, stride);
     const float a_min = __fsub_rn(a[1], a[3]), b_min = __fsub_rn(b[1], b[3]);       // y - h .. y (y points down)
     const float ov_h = fmaxf(__fsub_rn(fminf(a[1], b[1]), fmaxf(a_min, b_min)), 0.f);
     const float ov3d = __fmul_rn(ov_bev, ov_h);
@@ -199,13 +224,15 @@ __device__ __forceinline__ float iou3d_pair(const float *a, const float *b) {
 }
 __global__ void __launch_bounds__(128) iou3d_kernel(int mode, int batch, int na, int nb, const float *__restrict__ boxes_a,
                                                     const float *__restrict__ boxes_b, float *__restrict__ out) {
+    __shared__ float s_poly[3 * POLY_SLOTS * 128];
+    float *px = s_poly + threadIdx.x, *py = px + POLY_SLOTS * 128, *pa = py + POLY_SLOTS * 128;
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     float a[7], b[7];
     if (mode == 1) {
         if (t >= na) return;
 #pragma unroll
         for (int q = 0; q < 7; ++q) { a[q] = boxes_a[t * 7 + q]; b[q] = boxes_b[t * 7 + q]; }
-        out[t] = iou3d_pair(a, b);
+        out[t] = iou3d_pair(a, b, px, py, pa, 128);
         return;
     }
     const long per = (long)na * nb;
@@ -214,7 +241,7 @@ __global__ void __launch_bounds__(128) iou3d_kernel(int mode, int batch, int na,
     const long i = e / nb, j = e - i * nb;
 #pragma unroll
     for (int q = 0; q < 7; ++q) { a[q] = boxes_a[(s * na + i) * 7 + q]; b[q] = boxes_b[(s * nb + j) * 7 + q]; }
-    out[t] = iou3d_pair(a, b);
+    out[t] = iou3d_pair(a, b, px, py, pa, 128);
 }
 
 }  // namespace prb
@@ -239,8 +266,14 @@ static int pair_matrix(bool iou, int na, const float *a, int nb, const float *b,
     PRB_REQUIRE(na >= 0 && nb >= 0 && a && b && out, "boxes matrix: bad arguments");
     if (na == 0 || nb == 0) return 0;
     dim3 grid(ceil_div(nb, PM_T), ceil_div(na, PM_T)), block(PM_T, PM_T);
-    if (iou) pair_matrix_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(na, a, nb, b, out);
-    else pair_matrix_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(na, a, nb, b, out);
+    const size_t smem = (size_t)3 * POLY_SLOTS * PM_T * PM_T * sizeof(float);      // 48 KB
+    if (iou) {
+        PRB_CUDA(cudaFuncSetAttribute(pair_matrix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pair_matrix_kernel<true><<<grid, block, smem, (cudaStream_t)stream>>>(na, a, nb, b, out);
+    } else {
+        PRB_CUDA(cudaFuncSetAttribute(pair_matrix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pair_matrix_kernel<false><<<grid, block, smem, (cudaStream_t)stream>>>(na, a, nb, b, out);
+    }
     return check_launch("pair_matrix_kernel");
 }
 
@@ -256,8 +289,13 @@ extern "C" int prb_nms_mask(const float *boxes, int n, float thresh, int normal,
     if (n == 0) return 0;
     const int cb = ceil_div(n, 64);
     dim3 grid(cb, cb);
-    if (normal) nms_mask_kernel<true><<<grid, 64, 0, (cudaStream_t)stream>>>(n, thresh, boxes, mask);
-    else nms_mask_kernel<false><<<grid, 64, 0, (cudaStream_t)stream>>>(n, thresh, boxes, mask);
+    if (normal) {
+        nms_mask_kernel<true><<<grid, NM_THREADS, 0, (cudaStream_t)stream>>>(n, thresh, boxes, mask);
+    } else {
+        const size_t smem = (size_t)3 * POLY_SLOTS * NM_THREADS * sizeof(float);    // 48 KB of polygon scratch
+        PRB_CUDA(cudaFuncSetAttribute(nms_mask_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_mask_kernel<false><<<grid, NM_THREADS, smem, (cudaStream_t)stream>>>(n, thresh, boxes, mask);
+    }
     return check_launch("nms_mask_kernel");
 }
 

@@ -138,4 +138,103 @@ __device__ __forceinline__ float iou_normal(const float *a, const float *b) {
     return interS / fmaxf(Sa + Sb - interS, EPS);
 }
 
+// ---------------------------------------------------------------------------------------------- per-box precompute
+// box_overlap above recomputes, for EVERY PAIR, the four rotated corners of both boxes (2 sincos) and calls in_box2d eight
+// times (8 x cos(-ry), sin(-ry)), and its bubble sort calls atan2f twice per comparison: ~20 sincosf + up to ~200 atan2f per
+// pair, with the intersection polygon `cp[16]` in local memory.  BoxPre holds what depends on ONE box only -- centre,
+// cos / sin of its heading, rotated corners -- computed once per box per tile (the same expressions, so the same bits:
+// cosf is even and sinf odd on the device, `sin(-a)` is replaced by `-sin(a)`), the polygon lives in a caller-provided
+// (shared-memory) scratch column, and the polar angles are computed once per polygon vertex.  The comparisons, the
+// centroid and the fan area see the same floats in the same order as box_overlap, hence bit-identical results
+// (tests/test_gpu_ops.py compares masks / matrices with the reference kernel by torch.equal).
+struct BoxPre {
+    float x1, y1, x2, y2;      // axis-aligned extent before rotation
+    float cx, cy, c, s;        // centre, cos(ry), sin(ry)
+    P2 k[4];                   // rotated corners
+};
+
+__device__ __forceinline__ void box_pre(const float *box, BoxPre &b) {
+    b.x1 = box[0]; b.y1 = box[1]; b.x2 = box[2]; b.y2 = box[3];
+    const float ang = box[4];
+    b.cx = (b.x1 + b.x2) / 2;
+    b.cy = (b.y1 + b.y2) / 2;
+    b.c = cos(ang);
+    b.s = sin(ang);
+    const P2 ctr = mk(b.cx, b.cy);
+    b.k[0] = mk(b.x1, b.y1); b.k[1] = mk(b.x2, b.y1); b.k[2] = mk(b.x2, b.y2); b.k[3] = mk(b.x1, b.y2);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) rot_center(ctr, b.c, b.s, b.k[q]);
+}
+
+// in_box2d with the box's precomputed centre and cos(-ry) = c, sin(-ry) = -s
+__device__ __forceinline__ int in_box2d_pre(const BoxPre &b, const P2 &p) {
+    const float MARGIN = 1e-5;
+    const float angle_cos = b.c, angle_sin = -b.s;
+    float rot_x = (p.x - b.cx) * angle_cos + (p.y - b.cy) * angle_sin + b.cx;
+    float rot_y = -(p.x - b.cx) * angle_sin + (p.y - b.cy) * angle_cos + b.cy;
+    return (rot_x > b.x1 - MARGIN && rot_x < b.x2 + MARGIN && rot_y > b.y1 - MARGIN && rot_y < b.y2 + MARGIN);
+}
+
+// rotated-rectangle intersection area from two precomputed boxes.  px / py / pa: scratch for up to 16 polygon vertices
+// (x, y, polar angle), element i at [i * stride] (e.g. a shared-memory column per thread: no local memory)
+__device__ inline float box_overlap_pre(const BoxPre &A, const BoxPre &B, float *px, float *py, float *pa, int stride) {
+    float sum_x = 0.f, sum_y = 0.f;
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            P2 ans;
+            if (seg_intersection(A.k[(i + 1) & 3], A.k[i], B.k[(j + 1) & 3], B.k[j], ans)) {
+                sum_x = sum_x + ans.x; sum_y = sum_y + ans.y;
+                px[cnt * stride] = ans.x; py[cnt * stride] = ans.y;
+                cnt++;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (in_box2d_pre(A, B.k[q])) {
+            sum_x = sum_x + B.k[q].x; sum_y = sum_y + B.k[q].y;
+            px[cnt * stride] = B.k[q].x; py[cnt * stride] = B.k[q].y;
+            cnt++;
+        }
+        if (in_box2d_pre(B, A.k[q])) {
+            sum_x = sum_x + A.k[q].x; sum_y = sum_y + A.k[q].y;
+            px[cnt * stride] = A.k[q].x; py[cnt * stride] = A.k[q].y;
+            cnt++;
+        }
+    }
+    if (cnt < 3) {
+        // fewer than three vertices: the fan below has no triangle (cnt = 0 divides by zero in the reference and then
+        // loops over nothing: area 0 as well)
+        return 0.f;
+    }
+    const float ctr_x = sum_x / cnt, ctr_y = sum_y / cnt;
+    for (int i = 0; i < cnt; ++i) pa[i * stride] = atan2(py[i * stride] - ctr_y, px[i * stride] - ctr_x);
+    // the reference's bubble sort (swap when strictly greater): same comparisons on the same angles
+    for (int j = 0; j < cnt - 1; j++)
+        for (int i = 0; i < cnt - j - 1; i++) {
+            const float a0 = pa[i * stride], a1 = pa[(i + 1) * stride];
+            if (a0 > a1) {
+                pa[i * stride] = a1; pa[(i + 1) * stride] = a0;
+                float t = px[i * stride]; px[i * stride] = px[(i + 1) * stride]; px[(i + 1) * stride] = t;
+                t = py[i * stride]; py[i * stride] = py[(i + 1) * stride]; py[(i + 1) * stride] = t;
+            }
+        }
+    float area = 0;
+    const float x0 = px[0], y0 = py[0];
+    for (int q = 0; q < cnt - 1; q++)
+        area += cross2(mk(px[q * stride] - x0, py[q * stride] - y0), mk(px[(q + 1) * stride] - x0, py[(q + 1) * stride] - y0));
+    return fabs(area) / 2.0;
+}
+
+__device__ __forceinline__ float iou_bev_pre(const BoxPre &A, const BoxPre &B, float *px, float *py, float *pa, int stride) {
+    const float EPS = 1e-8;
+    float sa = (A.x2 - A.x1) * (A.y2 - A.y1);
+    float sb = (B.x2 - B.x1) * (B.y2 - B.y1);
+    float s_overlap = box_overlap_pre(A, B, px, py, pa, stride);
+    return s_overlap / fmaxf(sa + sb - s_overlap, EPS);
+}
+
 }  // namespace prb

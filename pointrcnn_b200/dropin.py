@@ -7,6 +7,7 @@ After this, with the reference tree on sys.path, `lib/net/*.py` and `tools/*.py`
     pointnet2_lib.pointnet2.{pointnet2_utils,pointnet2_modules,pytorch_utils} -> pointrcnn_b200.pointnet2.*
     lib.utils.iou3d.iou3d_utils, lib.utils.roipool3d.roipool3d_utils       -> pointrcnn_b200.{iou3d,roipool3d}.*
     lib.rpn.proposal_layer (ProposalLayer)                                 -> pointrcnn_b200.rpn.proposal_layer
+    lib.rpn.proposal_target_layer (ProposalTargetLayer)                    -> pointrcnn_b200.rpn.proposal_target_layer
 Optionally (compat=True) also provides the tiny stand-ins the 2019-era reference needs on a modern stack:
 `easydict`, `tensorboardX.SummaryWriter` (no-op), `fire`, and a default Loader for `yaml.load`
  -- none of them is on the operator path.
@@ -58,8 +59,10 @@ def activate(compat=False):
         m = types.ModuleType("lib.rpn")
         m.__path__ = []
         _alias("lib.rpn", m)
-    from .rpn import proposal_layer
+    from .rpn import proposal_layer, proposal_target_layer
     _alias("lib.rpn.proposal_layer", proposal_layer)
+    # rank 2: the RCNN target layer (one IoU launch per batch, batched jitter loop); lib/net/rcnn_net.py imports it by name
+    _alias("lib.rpn.proposal_target_layer", proposal_target_layer)
 
 
 def _install_compat():
