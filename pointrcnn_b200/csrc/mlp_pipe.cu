@@ -71,6 +71,17 @@ struct Cursor {
     }
 };
 
+// The four single-role warps (two weight producers, two MMA issuers) run their loops WARP-UNIFORMLY and only the
+// instruction that must come from one thread (bulk copy, tcgen05.mma, tcgen05.commit, expect_tx) sits under elect.sync.
+// Inside `if (lane == 0) { loops }` every descriptor lives in vector registers and ptxas wraps each UTCHMMA / UBLKCP in an
+// ELECT + 6 x R2UR.BROADCAST waterfall loop (~12 instructions per MMA, measured: the single-thread issue rate bounded the
+// wide levels); with uniform control flow the operands stay in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // every wait parks the warp in hardware (try_wait with a suspend hint) instead of spinning in the issue slots
 __device__ __forceinline__ void bwait(uint64_t *bar, uint32_t parity) { mbar_wait_sleepy(s2u(bar), parity); }
 // roles that run AHEAD of their consumer (gather warps, weight producers: a full ring is the normal state) poll rarely:
@@ -217,11 +228,11 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
     const int tile0 = (int)blockIdx.x / nsplit, tstep = (int)gridDim.x / nsplit;
     const int ntiles = p.num_tiles;
     TraceTimer tt;
-    tt.start(p.trace != 0 && blockIdx.x == 0 && lane == 0 && (warp >= W_MISC || warp == W_GATHER || warp == 0));
+    tt.start(p.trace != 0 && blockIdx.x == 0 && (warp >= W_MISC || warp == W_GATHER || warp == 0));   // warp-uniform
 
     if (warp == W_MISC) {
         // ===================================================== weight producer, layer 0
-        if (lane == 0) {
+        {
             RingPos rb = {0, 0};
             const int col0 = sj * p.split_w;
             const int width = L == 1 ? min(p.split_w, p.np[0] - col0) : p.np[0];
@@ -236,15 +247,17 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                     for (int h = 0; h < halves; ++h) {
                         const uint32_t bytes = (uint32_t)min(brows, width - h * brows) * KC * 4;
                         tt.timed(0, [&] { bwait_lazy(&S.b0_empty[rb.stage], rb.phase ^ 1); });
-                        mbar_expect_tx(s2u(&S.b0_full[rb.stage]), bytes);
-                        bulk_g2s(s2u(sB0) + rb.stage * stage_bytes, src + (size_t)h * brows * KC, bytes, s2u(&S.b0_full[rb.stage]));
+                        if (elect_one()) {
+                            mbar_expect_tx(s2u(&S.b0_full[rb.stage]), bytes);
+                            bulk_g2s(s2u(sB0) + rb.stage * stage_bytes, src + (size_t)h * brows * KC, bytes, s2u(&S.b0_full[rb.stage]));
+                        }
                         rb.advance(nb);
                     }
             }
         }
     } else if (warp == W_MISC + 1) {
         // ===================================================== weight producer, layers >= 1
-        if (lane == 0 && L > 1) {
+        if (L > 1) {
             RingPos rb = {0, 0};
             const int nb = p.nb1;
             const uint32_t stage_bytes = (uint32_t)p.b1_stage_bytes;
@@ -262,8 +275,10 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                             for (int h = 0; h < halves; ++h) {
                                 const uint32_t bytes = (uint32_t)min(brows, width - h * brows) * KC * 4;
                                 tt.timed(0, [&] { bwait_lazy(&S.b1_empty[rb.stage], rb.phase ^ 1); });
-                                mbar_expect_tx(s2u(&S.b1_full[rb.stage]), bytes);
-                                bulk_g2s(s2u(sB1) + rb.stage * stage_bytes, src + (size_t)h * brows * KC, bytes, s2u(&S.b1_full[rb.stage]));
+                                if (elect_one()) {
+                                    mbar_expect_tx(s2u(&S.b1_full[rb.stage]), bytes);
+                                    bulk_g2s(s2u(sB1) + rb.stage * stage_bytes, src + (size_t)h * brows * KC, bytes, s2u(&S.b1_full[rb.stage]));
+                                }
                                 rb.advance(nb);
                             }
                     }
@@ -272,7 +287,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
         }
     } else if (warp == W_MISC + 2) {
         // ===================================================== MMA issuer A: layer 0 (A operand from the shared-memory ring)
-        if (lane == 0) {
+        {
             RingPos ra = {0, 0}, rb = {0, 0};
             const int width = L == 1 ? min(p.split_w, p.np[0] - sj * p.split_w) : p.np[0];
             const int halves = (width + brows - 1) / brows;
@@ -304,20 +319,22 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                         const uint64_t bdesc = make_desc(b_base + rb.stage * b_bytes);
                         const uint32_t idesc = make_idesc(rows);
                         const uint32_t d = tmem + dcol + (uint32_t)(h * brows);
-                        for (int ks = 0; ks < ksteps; ++ks)  // +32 bytes (= 2 x 16 B) per K=8 step inside the swizzle row
-                            umma_tf32(d, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-                        umma_commit(s2u(&S.b0_empty[rb.stage]));
+                        if (elect_one()) {
+                            for (int ks = 0; ks < ksteps; ++ks)  // +32 bytes (= 2 x 16 B) per K=8 step inside the swizzle row
+                                umma_tf32(d, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                            umma_commit(s2u(&S.b0_empty[rb.stage]));
+                            if (h == halves - 1) umma_commit(s2u(&S.a_empty[ra.stage]));
+                            if (h == halves - 1 && kc == nch - 1) umma_commit(L > 1 ? s2u(&S.r_full[0]) : s2u(&S.z_full[buf]));
+                        }
                         rb.advance(nb);
                     }
-                    umma_commit(s2u(&S.a_empty[ra.stage]));
                     ra.advance(na);
                 }
-                umma_commit(L > 1 ? s2u(&S.r_full[0]) : s2u(&S.z_full[buf]));
             }
         }
     } else if (warp == W_MISC + 3) {
         // ===================================================== MMA issuer B: layers >= 1 (A operand from tensor memory)
-        if (lane == 0 && L > 1) {
+        if (L > 1) {
             RingPos rb = {0, 0};
             const int nb = p.nb1;
             const uint32_t b_base = s2u(sB1), b_bytes = (uint32_t)p.b1_stage_bytes;
@@ -352,16 +369,21 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                                 const uint64_t bdesc = make_desc(b_base + rb.stage * b_bytes);
                                 const uint32_t idesc = make_idesc(rows);
                                 const uint32_t d = tmem + dcol + (uint32_t)(h * brows);
+                                if (elect_one()) {
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks)
-                                    umma_tf32_ts(d, a_t + (uint32_t)(8 * ks), bdesc + (uint64_t)(2 * ks), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-                                umma_commit(s2u(&S.b1_empty[rb.stage]));
+                                    for (int ks = 0; ks < 4; ++ks)
+                                        umma_tf32_ts(d, a_t + (uint32_t)(8 * ks), bdesc + (uint64_t)(2 * ks), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                                    umma_commit(s2u(&S.b1_empty[rb.stage]));
+                                    if (h == halves - 1 && kc == nch - 1) {
+                                        umma_commit(last ? s2u(&S.z_full[buf]) : s2u(&S.r_full[l]));
+                                        // region 0 may take the next item's layer 0 once layer 1 (all its slices) has read it
+                                        if (l == 1 && s + 1 == nsl) umma_commit(s2u(&S.x_free));
+                                    }
+                                }
                                 rb.advance(nb);
                             }
                         }
-                        umma_commit(last ? s2u(&S.z_full[buf]) : s2u(&S.r_full[l]));
                     }
-                    if (l == 1) umma_commit(s2u(&S.x_free));      // region 0 may take the next item's layer 0
                 }
             }
         }
@@ -810,7 +832,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
         }
     }
 
-    if (tt.on) {
+    if (tt.on && lane == 0) {
         if (warp == W_MISC + 2) tt.finish(0, 3);
         else if (warp == W_MISC + 3) tt.finish(1, 3);
         else if (warp == W_MISC) tt.finish(2, 1);
