@@ -637,6 +637,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
         else if (MOUT == OUT_FP) cur.init(tile0 * TM, tstep * TM, p.n);
         else cur.init(0, 0, 1);
         uint32_t it = 0, u = 0;
+        int pool_par = 0;
         if (skew && tile0 < ntiles) mid_epilogue(0, 0u);
         for (int tile = tile0; tile < ntiles; tile += tstep, ++it, cur.advance()) {
             const int R = tile * TM + r;
@@ -653,7 +654,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
             bool ok = valid;
             if (MOUT == OUT_SA_MAX) {
                 // 16 / 32 samples: the centre of my own row; other sample counts: the centre of my 16-row segment
-                const int rowc = (ns == 16 || ns == 32) ? r : (r & ~15);
+                const int rowc = (ns >= 16) ? r : (r & ~15);
                 int scn, pp;
                 cur.at(rowc >> p.log_ns, scn, pp);
                 ok = tile * TM + rowc < rows;
@@ -674,7 +675,54 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                 tt.timed(1, [&] { bwait(&S.z_full[buf], (nbuf == 2 ? (u >> 1) : u) & 1); });
                 tc_fence_after();
                 const uint32_t zc = trow + (uint32_t)p.zcol[buf];
-                if (MOUT == OUT_SA_MAX && (ns == 32 || ns == 16)) {
+                if (MOUT == OUT_SA_MAX && (ns == 64 || ns == 128)) {
+                    // ---- 64 / 128 samples (RCNN stage): a centre spans 2 / 4 warps.  Every warp pools its 32 rows with the
+                    // warp-wide reduction, the partial maxima of a centre's warps meet in a tiny double-buffered shared tile
+                    // (one named barrier per batch instead of a 128 x 16 staging tile and three barriers)
+                    const int wpc = ns >> 5;                          // warps per centre
+                    const bool head = (wq & (wpc - 1)) == 0;
+                    const int ch = lane & 15;
+                    const int c_first = s_lo + grp * 16;
+                    float *ocm = p.out + off_cm + (size_t)(c_first + ch) * p.npoint;
+                    float *opm = p.out_pm ? p.out_pm + off_pm + c_first + ch : nullptr;
+                    const size_t cm_step = (size_t)(16 * NE) * p.npoint;
+                    const float *shp = sh + c_first + ch;
+                    uint32_t taddr = zc + (uint32_t)(c_first - s_lo);
+                    const int n_ok = Cl - ch;
+                    // pool_par toggles with EVERY batch of the kernel's lifetime (not per slice): a warp that runs ahead into the
+                    // next slice must not overwrite the buffer its centre's head warp is still reading
+                    for (int c0 = c_first; c0 < s_hi; c0 += 16 * NE, ocm += cm_step, shp += 16 * NE, taddr += 16 * NE, opm += (opm ? 16 * NE : 0), pool_par ^= 1) {
+                        uint32_t acc[16];
+                        tmem_ld16(taddr, acc);
+                        float v[16];
+                        if (pool_raw) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(acc[q]);
+                        } else {
+                            const float4 *sh4 = reinterpret_cast<const float4 *>(sh + c0), *sc4 = reinterpret_cast<const float4 *>(sc + c0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 a = sc4[j], b = sh4[j];
+                                v[4 * j + 0] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 0]), a.x, b.x), lo);
+                                v[4 * j + 1] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 1]), a.y, b.y), lo);
+                                v[4 * j + 2] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 2]), a.z, b.z), lo);
+                                v[4 * j + 3] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 3]), a.w, b.w), lo);
+                            }
+                        }
+                        float x = pool_batch<32, 0>(v, lane);                  // max over my warp's 32 rows, channel lane & 15
+                        float *tile2 = pool2 + pool_par * 64;                   // [4 warps][16 channels]
+                        if (lane < 16) tile2[wq * 16 + ch] = x;
+                        bar_named(2 + grp, 128);
+                        if (head) {
+                            for (int w2 = 1; w2 < wpc; ++w2) x = fmaxf(x, tile2[(wq + w2) * 16 + ch]);
+                            if (pool_raw) x = fmaxf(x + *shp, lo);
+                            if (ok && lane < 16 && c0 < n_ok) {
+                                *ocm = x;
+                                if (opm) *opm = x;
+                            }
+                        }
+                    }
+                } else if (MOUT == OUT_SA_MAX && (ns == 32 || ns == 16)) {
                     // ---- fast path: dispatched ONCE per slice on (nsample, pooling kind); everything that does not depend on
                     // the 16-column batch is computed before the batch loop
                     auto slice_loop = [&](auto ns_c, auto pool_c) {
