@@ -86,9 +86,12 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void bwait(uint64_t *bar, uint32_t parity) { mbar_wait_sleepy(s2u(bar), parity); }
 // roles that run AHEAD of their consumer (gather warps, weight producers: a full ring is the normal state) poll rarely:
 // a try_wait wakes on every barrier event of the CTA, ~100 polls per tile and warp were 23 % of all issued instructions
-__device__ __forceinline__ void bwait_lazy(uint64_t *bar, uint32_t parity) {
+// ... but only where the ring has slack (narrow chains, two CTAs per SM): on the wide chains the weight ring IS the critical
+// resource and a 400 ns poll interval on 41 stage refills per tile cost 10 % (SA3 0.131 -> 0.144 ms)
+__device__ __forceinline__ void bwait_lazy(uint64_t *bar, uint32_t parity, bool lazy) {
     const uint32_t b = s2u(bar);
-    while (!mbar_test(b, parity)) __nanosleep(400);
+    if (lazy) { while (!mbar_test(b, parity)) __nanosleep(400); }
+    else mbar_wait_sleepy(b, parity);
 }
 
 // SA max-pool of one 16-column batch when the nsample rows of a centre are lanes of ONE warp (NS = 16 / 32).
@@ -227,6 +230,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
     const int sj = (int)blockIdx.x % nsplit;
     const int tile0 = (int)blockIdx.x / nsplit, tstep = (int)gridDim.x / nsplit;
     const int ntiles = p.num_tiles;
+    const bool lazy = NE == 1;           // the two-CTA build runs the narrow chains: rings with slack
     TraceTimer tt;
     tt.start(p.trace != 0 && blockIdx.x == 0 && (warp >= W_MISC || warp == W_GATHER || warp == 0));   // warp-uniform
 
@@ -246,7 +250,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                 for (int kc = 0; kc < nch; ++kc, src += chunk_stride)
                     for (int h = 0; h < halves; ++h) {
                         const uint32_t bytes = (uint32_t)min(brows, width - h * brows) * KC * 4;
-                        tt.timed(0, [&] { bwait_lazy(&S.b0_empty[rb.stage], rb.phase ^ 1); });
+                        tt.timed(0, [&] { bwait_lazy(&S.b0_empty[rb.stage], rb.phase ^ 1, lazy); });
                         if (elect_one()) {
                             mbar_expect_tx(s2u(&S.b0_full[rb.stage]), bytes);
                             bulk_g2s(s2u(sB0) + rb.stage * stage_bytes, src + (size_t)h * brows * KC, bytes, s2u(&S.b0_full[rb.stage]));
@@ -274,7 +278,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                         for (int kc = 0; kc < nch; ++kc, src += chunk_stride)
                             for (int h = 0; h < halves; ++h) {
                                 const uint32_t bytes = (uint32_t)min(brows, width - h * brows) * KC * 4;
-                                tt.timed(0, [&] { bwait_lazy(&S.b1_empty[rb.stage], rb.phase ^ 1); });
+                                tt.timed(0, [&] { bwait_lazy(&S.b1_empty[rb.stage], rb.phase ^ 1, lazy); });
                                 if (elect_one()) {
                                     mbar_expect_tx(s2u(&S.b1_full[rb.stage]), bytes);
                                     bulk_g2s(s2u(sB1) + rb.stage * stage_bytes, src + (size_t)h * brows * KC, bytes, s2u(&S.b1_full[rb.stage]));
@@ -492,7 +496,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                                     }
                                 }
                             }
-                            if (half == 0) tt.timed(0, [&] { bwait_lazy(empty_bar, empty_par); });
+                            if (half == 0) tt.timed(0, [&] { bwait_lazy(empty_bar, empty_par, lazy); });
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const int rr = wq * 32 + rsub + 4 * (half * 4 + i);
@@ -524,7 +528,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                                 }
                             }
                         }
-                        tt.timed(0, [&] { bwait_lazy(empty_bar, empty_par); });
+                        tt.timed(0, [&] { bwait_lazy(empty_bar, empty_par, lazy); });
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int rr = wq * 32 + rsub + 4 * i;
@@ -551,7 +555,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                             if (cf > 4) v2.w = to_tf32(__ldg(f + 4));
                         }
                     }
-                    tt.timed(0, [&] { bwait_lazy(empty_bar, empty_par); });
+                    tt.timed(0, [&] { bwait_lazy(empty_bar, empty_par, lazy); });
                     *reinterpret_cast<float4 *>(A + swz(r, 0)) = v;
                     *reinterpret_cast<float4 *>(A + swz(r, 1)) = v2;
                 } else if (MIN == IN_FP) {
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                         const int ch = k0 + q;
                         o[q] = (valid && ch < width) ? __ldg(bsrc + (size_t)ch * p.n) : 0.f;
                     }
-                    tt.timed(0, [&] { bwait_lazy(empty_bar, empty_par); });
+                    tt.timed(0, [&] { bwait_lazy(empty_bar, empty_par, lazy); });
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<float4 *>(A + swz(r, j)) =
