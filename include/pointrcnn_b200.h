@@ -187,6 +187,15 @@ PRB_API int prb_fp_interp_mlp_ws(int b, int n, int m, int c_known, int c_skip, c
  * replaces a pt_utils.SharedMLP applied to (B,C,N,1) tensors (lib/net/rcnn_net.py:58-66 xyz_up_layer / merge_down_layer) */
 PRB_API int prb_mlp_rows(long rows, int c_in, const float *x_rows, const prb_mlp_desc *mlp, float *out_rows,
                          int out_pitch, void *workspace, size_t workspace_bytes, void *stream);
+/* the same with strided inputs and an optional second K segment: layer 0 reads [a_rows[:, :c_a] | b_rows[:, :c_b]] (row
+ * pitches in floats, any alignment; 128-bit loads when base and pitch are 16-byte aligned).  With c_b > 0 the weights are
+ * packed with prb_mlp_pack_weights_ex(kind 1, split c_a), else kind 2.  This is merge_down_layer on cat(xyz_feature,
+ * rpn_feature) (lib/net/rcnn_net.py:171-175) without materialising the concatenation, and xyz_up_layer on a column
+ * slice of the pooled rows. */
+PRB_API size_t prb_rows2_workspace_bytes(long rows, int c_a, int c_b, int num_layers, const int *c_out);
+PRB_API int prb_mlp_rows2(long rows, int c_a, const float *a_rows, int a_pitch, int c_b, const float *b_rows, int b_pitch,
+                          const prb_mlp_desc *mlp, float *out_rows, int out_pitch, void *workspace, size_t workspace_bytes,
+                          void *stream);
 
 /* ------------------------------------------------------------------ RPN proposal path (next to the hot path) -----
  * prb_decode_rpn_proposals replaces decode_bbox_target as called by the proposal layer (lib/utils/bbox_transform.py:
@@ -209,8 +218,9 @@ PRB_API int prb_rpn_proposals(int b, int n, const float *boxes, const float *sco
 /* diagnostics (PRB_MLP_TRACE=1): clock64 stamps of CTA 0 at the phase boundaries of its first 32 tiles (32 x 16) */
 PRB_API int prb_debug_mlp_trace(long long *dst);
 /* pipelined kernel (prb_options.mlp_trace): cycles CTA 0's roles spent in each class of barrier wait during the last traced
- * launch, 8 x 4 int64: rows = issuer A {x/z_free, a_full, b0_full, total}, issuer B {z_free, ready, b1_full, total}, weight
- * producer 0 {b0_empty, -, -, total}, producer 1 {b1_empty, ...}, gather warp 0 {a_empty, ...}, epilogue warp 0 {r_full, z_full, -, total} */
+ * launch, 8 x 8 int64 (slot 7 of a row = total cycles of the role's loop): issuer A {x/z_free, a_full, b0_full}, issuer B
+ * {z_free, ready, b1_full, fence, mma issue, commit}, weight producer 0 {b0_empty}, producer 1 {b1_empty}, gather warp 0
+ * {a_empty}, epilogue warp 0 {r_full, z_full} */
 PRB_API int prb_debug_pipe_trace(long long *dst);
 
 /* --- uniform-grid neighbour search: same results, bit for bit, as prb_ball_query(_msg2) / prb_three_nn

@@ -52,6 +52,8 @@ struct ChainParams {
     // DIRECT
     const float *x_rows;
     int x_pitch;
+    const float *x2_rows;   // IN_DIRECT, second K segment (nullptr: one segment)
+    int x2_pitch;
     // output
     float *out;
     float *out_pm;       // optional second copy of the final output in point-major layout (rows x out_stride_c)

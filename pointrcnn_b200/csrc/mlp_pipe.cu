@@ -169,11 +169,15 @@ __device__ __forceinline__ float pool_batch(float (&v)[16], int lane) {
 // and the total cycles of its item loop; read back with prb_debug_pipe_trace.  Slots: 0 issuer A {x_free|z_free, a_full,
 // b0_full, total}, 1 issuer B {z_free, ready, b1_full, total}, 2 producer 0 {b0_empty, total}, 3 producer 1 {b1_empty,
 // total}, 4 gather warp 0 {a_empty, total}, 5 epilogue warp 0 {r_full, z_full, total}
-__device__ long long g_pipe_trace[8][4];
+__device__ long long g_pipe_trace[8][8];
 struct TraceTimer {
     bool on;
-    long long acc[3], t0;
-    __device__ __forceinline__ void start(bool enable) { on = enable; acc[0] = acc[1] = acc[2] = 0; t0 = on ? clock64() : 0; }
+    long long acc[7], t0;
+    __device__ __forceinline__ void start(bool enable) {
+        on = enable;
+        for (int k = 0; k < 7; ++k) acc[k] = 0;
+        t0 = on ? clock64() : 0;
+    }
     template <class F>
     __device__ __forceinline__ void timed(int k, F &&f) {
         if (on) { const long long t = clock64(); f(); acc[k] += clock64() - t; } else f();
@@ -181,7 +185,7 @@ struct TraceTimer {
     __device__ __forceinline__ void finish(int slot, int nclass) {
         if (!on) return;
         for (int k = 0; k < nclass; ++k) g_pipe_trace[slot][k] = acc[k];
-        g_pipe_trace[slot][3] = clock64() - t0;
+        g_pipe_trace[slot][7] = clock64() - t0;
     }
 };
 
@@ -369,21 +373,27 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                             for (int h = 0; h < halves; ++h) {
                                 const int rows = min(brows, width - h * brows);
                                 tt.timed(2, [&] { bwait(&S.b1_full[rb.stage], rb.phase); });
-                                tc_fence_after();
+                                tt.timed(3, [&] { tc_fence_after(); });
                                 const uint64_t bdesc = make_desc(b_base + rb.stage * b_bytes);
                                 const uint32_t idesc = make_idesc(rows);
                                 const uint32_t d = tmem + dcol + (uint32_t)(h * brows);
-                                if (elect_one()) {
+                                tt.timed(4, [&] {
+                                    if (elect_one()) {
 #pragma unroll
-                                    for (int ks = 0; ks < 4; ++ks)
-                                        umma_tf32_ts(d, a_t + (uint32_t)(8 * ks), bdesc + (uint64_t)(2 * ks), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-                                    umma_commit(s2u(&S.b1_empty[rb.stage]));
-                                    if (h == halves - 1 && kc == nch - 1) {
-                                        umma_commit(last ? s2u(&S.z_full[buf]) : s2u(&S.r_full[l]));
-                                        // region 0 may take the next item's layer 0 once layer 1 (all its slices) has read it
-                                        if (l == 1 && s + 1 == nsl) umma_commit(s2u(&S.x_free));
+                                        for (int ks = 0; ks < 4; ++ks)
+                                            umma_tf32_ts(d, a_t + (uint32_t)(8 * ks), bdesc + (uint64_t)(2 * ks), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
                                     }
-                                }
+                                });
+                                tt.timed(5, [&] {
+                                    if (elect_one()) {
+                                        umma_commit(s2u(&S.b1_empty[rb.stage]));
+                                        if (h == halves - 1 && kc == nch - 1) {
+                                            umma_commit(last ? s2u(&S.z_full[buf]) : s2u(&S.r_full[l]));
+                                            // region 0 may take the next item's layer 0 once layer 1 (all its slices) has read it
+                                            if (l == 1 && s + 1 == nsl) umma_commit(s2u(&S.x_free));
+                                        }
+                                    }
+                                });
                                 rb.advance(nb);
                             }
                         }
@@ -510,15 +520,17 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                             }
                         }
                     } else {
-                        const int pitch = MIN == IN_DIRECT ? p.x_pitch : p.c_feat;
-                        const float *srcbase = MIN == IN_DIRECT ? p.x_rows : p.feats_pm;
+                        const int pitch = MIN == IN_DIRECT ? (seg ? p.x2_pitch : p.x_pitch) : p.c_feat;
+                        const float *srcbase = MIN == IN_DIRECT ? (seg ? p.x2_rows : p.x_rows) : p.feats_pm;
+                        // 128-bit loads need 16-byte aligned rows (a column slice of wider rows is not)
+                        const bool vec = ((pitch & 3) | (int)(reinterpret_cast<uintptr_t>(srcbase) & 15)) == 0;
                         float4 t[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (s8[i] >= 0 && kk < width) {
                                 const float *sp = srcbase + (size_t)s8[i] * pitch + kk;
-                                if ((pitch & 3) == 0) {
+                                if (vec) {
                                     t[i] = __ldg((const float4 *)sp);
                                 } else {
                                     float o[4];
@@ -679,7 +691,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                 tt.timed(1, [&] { bwait(&S.z_full[buf], (nbuf == 2 ? (u >> 1) : u) & 1); });
                 tc_fence_after();
                 const uint32_t zc = trow + (uint32_t)p.zcol[buf];
-                if (MOUT == OUT_SA_MAX && (ns == 64 || ns == 128)) {
+                if (MOUT == OUT_SA_MAX && (ns == 64 || ns == 128) && p.pool_mode != 2) {
                     // ---- 64 / 128 samples (RCNN stage): a centre spans 2 / 4 warps.  Every warp pools its 32 rows with the
                     // warp-wide reduction, the partial maxima of a centre's warps meet in a tiny double-buffered shared tile
                     // (one named barrier per batch instead of a 128 x 16 staging tile and three barriers)
@@ -886,7 +898,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
 
     if (tt.on && lane == 0) {
         if (warp == W_MISC + 2) tt.finish(0, 3);
-        else if (warp == W_MISC + 3) tt.finish(1, 3);
+        else if (warp == W_MISC + 3) tt.finish(1, 6);
         else if (warp == W_MISC) tt.finish(2, 1);
         else if (warp == W_MISC + 1) tt.finish(3, 1);
         else if (warp == W_GATHER) tt.finish(4, 1);
@@ -1047,12 +1059,11 @@ int launch_chain_pipe(ChainParams &p, cudaStream_t st) {
 
 }  // namespace prb
 
-// wait-time trace of the last traced pipelined launch: 8 roles x {3 wait classes, total cycles} (see g_pipe_trace); also
-// reports the plan of that launch in plan[0..7] = {ne, ngw, occ, zs, nbuf, na, nb, tmem columns}
+// wait-time trace of the last traced pipelined launch: 8 roles x {up to 7 classes, total cycles in slot 7} (see g_pipe_trace)
 extern "C" int prb_debug_pipe_trace(long long *dst) {
     PRB_CUDA(cudaDeviceSynchronize());
-    PRB_CUDA(cudaMemcpyFromSymbol(dst, prb::g_pipe_trace, sizeof(long long) * 32));
-    static long long zeros[32];
+    PRB_CUDA(cudaMemcpyFromSymbol(dst, prb::g_pipe_trace, sizeof(long long) * 64));
+    static long long zeros[64];
     PRB_CUDA(cudaMemcpyToSymbol(prb::g_pipe_trace, zeros, sizeof(zeros)));
     return 0;
 }

@@ -925,6 +925,7 @@ static int run_chain(const ChainIO &io, const prb_mlp_desc *mlp, void *workspace
             p.mode_in = IN_DIRECT;
             p.x_rows = cur_rows;
             p.x_pitch = cur_pitch;
+            p.x2_rows = nullptr;
             p.nseg = 1; p.seg_chunks[0] = g[l0].k_chunks; p.seg_width[0] = cur_pitch;
         } else {
             p.nseg = ps.nseg;
@@ -1032,6 +1033,31 @@ PRB_API int prb_mlp_rows(long rows, int c_in, const float *x_rows, const prb_mlp
     io.rows = rows;
     io.base.mode_in = IN_DIRECT; io.base.mode_out = OUT_ROWS;
     io.base.x_rows = x_rows; io.base.x_pitch = c_in;
+    io.base.out = out_rows; io.base.out_pitch = out_pitch;
+    return run_chain(io, mlp, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+PRB_API size_t prb_rows2_workspace_bytes(long rows, int c_a, int c_b, int num_layers, const int *c_out) {
+    return chain_workspace_bytes(rows, num_layers, c_b > 0 ? 1 : 2, c_a + c_b, c_b > 0 ? c_a : 0, c_out);
+}
+
+PRB_API int prb_mlp_rows2(long rows, int c_a, const float *a_rows, int a_pitch, int c_b, const float *b_rows, int b_pitch,
+                          const prb_mlp_desc *mlp, float *out_rows, int out_pitch, void *workspace, size_t workspace_bytes,
+                          void *stream) {
+    PRB_REQUIRE(rows >= 0 && c_a > 0 && a_rows && a_pitch >= c_a && mlp && out_rows, "mlp_rows2: bad arguments");
+    PRB_REQUIRE(c_b >= 0 && (c_b == 0 || (b_rows && b_pitch >= c_b)), "mlp_rows2: bad second segment");
+    PRB_REQUIRE(mlp->c_in == c_a + c_b, "mlp_rows2: c_in %d != %d + %d", mlp->c_in, c_a, c_b);
+    PRB_REQUIRE(c_b == 0 || use_pipe(), "mlp_rows2: two input segments need the pipelined kernel (mlp_pipeline = 1, mlp_gather = 0)");
+    const int np_last = (mlp->c_out[mlp->num_layers - 1] + 31) / 32 * 32;
+    PRB_REQUIRE(out_pitch >= np_last && (out_pitch & 3) == 0, "mlp_rows2: out_pitch %d must be >= %d and a multiple of 4", out_pitch, np_last);
+    if (rows == 0) return 0;
+    ChainIO io;
+    memset(&io, 0, sizeof(io));
+    io.kind = c_b > 0 ? 1 : 2; io.split = c_b > 0 ? c_a : 0;      // weights packed with prb_mlp_pack_weights_ex(kind, split, ...)
+    io.rows = rows;
+    io.base.mode_in = IN_DIRECT; io.base.mode_out = OUT_ROWS;
+    io.base.x_rows = a_rows; io.base.x_pitch = a_pitch;
+    io.base.x2_rows = c_b > 0 ? b_rows : nullptr; io.base.x2_pitch = b_pitch;
     io.base.out = out_rows; io.base.out_pitch = out_pitch;
     return run_chain(io, mlp, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -155,6 +155,31 @@ def _point_major(t):
     return pointnet2_utils.transpose_bcn_to_bnc(t.contiguous())
 
 
+def rows_mlp(fused: "_FusedMLP", mlp: nn.Sequential, a: torch.Tensor, b: torch.Tensor = None, tag="rows_mlp"):
+    """SharedMLP over point rows on the tensor-core chain: `a` (rows, c_a) and optionally `b` (rows, c_b) are 2-D views with
+    unit column stride and any row pitch (e.g. column slices of the pooled RoI rows); layer 0 reads [a | b] without the
+    concatenation ever existing in memory.  Returns (rows, c_out) row-major.  Replaces pt_utils.SharedMLP on (B,C,N,1)
+    tensors (lib/net/rcnn_net.py:58-66,171-175)."""
+    lib = C.lib()
+    dev = a.device
+    rows, c_a = a.shape
+    c_b = 0 if b is None else b.size(1)
+    assert a.stride(1) == 1 and (b is None or (b.stride(1) == 1 and b.size(0) == rows))
+    desc = fused.get(mlp, 1 if c_b else 2, c_a if c_b else 0, dev)
+    c_out = fused.c_out
+    pitch = _round_up(c_out[-1], 32)
+    out = torch.empty((rows, pitch), dtype=torch.float32, device=dev)
+    co_arr = (ctypes.c_int * 3)(*(c_out + [0] * (3 - len(c_out))))
+    with torch.cuda.device(dev):
+        wsb = lib.prb_rows2_workspace_bytes(C.c_long(rows), c_a, c_b, desc.num_layers, co_arr)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        with prof.region(tag, "%d [%d+%d]+%s" % (rows, c_a, c_b, c_out)):
+            C.check(lib.prb_mlp_rows2(C.c_long(rows), c_a, C.ptr(a), a.stride(0), c_b, C.ptr(b) if c_b else None,
+                                      b.stride(0) if c_b else 0, ctypes.byref(desc), C.ptr(out), pitch, C.ptr(ws), C.c_size_t(wsb),
+                                      C.stream()), "mlp_rows2")
+    return out if pitch == c_out[-1] else out[:, :c_out[-1]]
+
+
 def _fold_scale():
     """config.fold_scale=False keeps the BN scale as a separate epilogue multiply (y = relu(s * (W x) + t))"""
     return config.get("fold_scale")

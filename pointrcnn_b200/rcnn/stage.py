@@ -11,6 +11,8 @@ the same natives; this class exists so benches and GPU tests run on the box, whe
 import torch
 import torch.nn as nn
 
+from .. import config
+from ..pointnet2 import pointnet2_modules as pn2
 from ..pointnet2 import pytorch_utils as pt_utils
 from ..pointnet2.pointnet2_modules import PointnetSAModule
 from ..roipool3d import roipool3d_utils
@@ -31,6 +33,7 @@ class RCNNStage(nn.Module):
         super().__init__()
         c = dict(RCNN_DEFAULT, **(cfg or {}))
         self.cfg = c
+        self._fused_rows = None
         self.SA_modules = nn.ModuleList()
         channel_in = input_channels
         if c["USE_RPN_FEATURES"]:
@@ -69,6 +72,17 @@ class RCNNStage(nn.Module):
             layers.insert(1, nn.Dropout(c["DP_RATIO"]))
         return nn.Sequential(*layers)
 
+    def _apply(self, fn, *args, **kwargs):
+        self._fused_rows = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def _rows_fusable(self, pts_input):
+        if config.get("disable_fused") or not pts_input.is_cuda or pts_input.dtype != torch.float32 or not pts_input.is_contiguous():
+            return False
+        if torch.is_grad_enabled() and (pts_input.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return False
+        return pn2._FusedMLP.supported(self.xyz_up_layer) and pn2._FusedMLP.supported(self.merge_down_layer)
+
     def pool(self, rpn_xyz, rpn_features, seg_mask, pts_depth, roi_boxes3d, rpn_intensity=None):
         """rcnn_net.py:127-152: pts_feature = [intensity?, seg_mask, depth/70-0.5, rpn features]; roipool3d; canonical
         transform (fused into the pooling kernel).  -> pts_input (B*M, NUM_POINTS, 3 + extra + C), empty flags (B,M)"""
@@ -84,7 +98,18 @@ class RCNNStage(nn.Module):
     def forward_pts(self, pts_input):
         """rcnn_net.py:165-190 on pooled, canonical points (R, NUM_POINTS, 3 + extra + C) -> rcnn_cls (R, cls), rcnn_reg (R, reg)"""
         xyz = pts_input[..., 0:3].contiguous()
-        if self.cfg["USE_RPN_FEATURES"]:
+        if self.cfg["USE_RPN_FEATURES"] and self._rows_fusable(pts_input):
+            # tensor-core row chains straight on the pooled rows: xyz_up reads the first columns of every row, merge reads
+            # [xyz feature | the row's RPN feature columns]; the result is already the point-major layout SA 1 gathers from
+            R, P, W = pts_input.shape
+            rows = pts_input.view(R * P, W)
+            ci = self.rcnn_input_channel
+            if self._fused_rows is None:
+                self._fused_rows = (pn2._FusedMLP(), pn2._FusedMLP())
+            up = pn2.rows_mlp(self._fused_rows[0], self.xyz_up_layer, rows[:, :ci], tag="rcnn_rows_mlp")
+            merged = pn2.rows_mlp(self._fused_rows[1], self.merge_down_layer, up, rows[:, ci:], tag="rcnn_rows_mlp").view(R, P, -1)
+            l_xyz, l_features = [xyz], [pn2._attach_pm(merged.transpose(1, 2), merged)]
+        elif self.cfg["USE_RPN_FEATURES"]:
             xyz_input = pts_input[..., 0:self.rcnn_input_channel].transpose(1, 2).unsqueeze(dim=3)
             xyz_feature = self.xyz_up_layer(xyz_input)
             rpn_feature = pts_input[..., self.rcnn_input_channel:].transpose(1, 2).unsqueeze(dim=3)

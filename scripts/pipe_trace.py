@@ -13,7 +13,7 @@ opts = {k: (float(v) if "." in v else int(v)) for k, v in (a.split("=") for a in
 dev = torch.device("cuda", 0)
 net = bench.build_model(dev)
 pc = torch.from_numpy(bench.make_scenes(0, bench.BATCH)).to(dev)
-ROLES = [("issuerA", ["x/z_free", "a_full", "b0_full"]), ("issuerB", ["z_free", "ready", "b1_full"]), ("prod0", ["b0_empty"]),
+ROLES = [("issuerA", ["x/z_free", "a_full", "b0_full"]), ("issuerB", ["z_free", "ready", "b1_full", "fence", "mma", "commit"]), ("prod0", ["b0_empty"]),
          ("prod1", ["b1_empty"]), ("gather0", ["a_empty"]), ("epi0", ["r_full", "z_full"])]
 lib = C.lib()
 orig_sa, orig_fp = lib.prb_sa_group_mlp_max_ws, lib.prb_fp_interp_mlp_ws
@@ -21,12 +21,12 @@ rows = []
 
 
 def report(tag, ms):
-    buf = (ctypes.c_longlong * 32)()
+    buf = (ctypes.c_longlong * 64)()
     lib.prb_debug_pipe_trace(buf)
-    t = np.array(buf[:], dtype=np.int64).reshape(8, 4)
+    t = np.array(buf[:], dtype=np.int64).reshape(8, 8)
     d = {"launch": tag, "ms": round(ms, 4)}
     for i, (name, classes) in enumerate(ROLES):
-        tot = max(1, int(t[i, 3]))
+        tot = max(1, int(t[i, 7]))
         d[name] = {c: round(float(t[i, k]) / tot, 3) for k, c in enumerate(classes)}
         d[name]["kcycles"] = int(tot // 1000)
     rows.append(d)
@@ -45,7 +45,7 @@ with torch.no_grad(), C.options(mlp_trace=1, **opts):
     def region(name, detail=None):
         if name in ("sa_mlp", "fp_mlp") and detail is not None:
             torch.cuda.synchronize()
-            buf = (ctypes.c_longlong * 32)(); lib.prb_debug_pipe_trace(buf)      # clear
+            buf = (ctypes.c_longlong * 64)(); lib.prb_debug_pipe_trace(buf)      # clear
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             yield

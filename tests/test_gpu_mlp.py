@@ -125,6 +125,44 @@ ROW_CASES = [
 ]
 
 
+@pytest.mark.parametrize("rows,c_a,c_b,off_a,off_b,width,dims", [
+    (4096, 5, 0, 0, 0, 133, [128, 128]),          # xyz_up_layer on the first 5 columns of the pooled rows (pitch 133: scalar loads)
+    (4096, 128, 128, 0, 5, 133, [128]),           # merge_down_layer: [up rows (own tensor) | columns 5.. of the pooled rows]
+    (1000, 40, 24, 4, 48, 80, [64, 32]),          # both segments slices of one 16-byte aligned tensor, tail tile
+    (300, 33, 7, 1, 35, 45, [48]),                # misaligned slices, widths that are not multiples of 4
+])
+def test_mlp_rows2_strided_segments(cuda, rows, c_a, c_b, off_a, off_b, width, dims):
+    """prb_mlp_rows2: layer 0 reads [a | b] from strided row views -- cat(xyz_feature, rpn_feature) of rcnn_net.py:171-175 is
+    never materialised"""
+    rng = np.random.default_rng(rows + c_a)
+    layers = _rand_layers(rng, [c_a + c_b] + dims)
+    wide = rng.standard_normal((rows, width)).astype(np.float32)
+    own = rng.standard_normal((rows, c_a)).astype(np.float32)
+    wt, ot = torch.from_numpy(wide).to(cuda), torch.from_numpy(own).to(cuda)
+    if c_b and off_a == 0 and c_a == 128:          # the merge case: segment a is its own contiguous tensor
+        a_t, a_np = ot, own
+    else:
+        a_t, a_np = wt[:, off_a:off_a + c_a], wide[:, off_a:off_a + c_a]
+    b_t = wt[:, off_b:off_b + c_b] if c_b else None
+    x = np.concatenate([a_np] + ([wide[:, off_b:off_b + c_b]] if c_b else []), axis=1)
+    d, keep, co = _desc(layers, 1 if c_b else 2, c_a if c_b else 0, cuda, False)
+    lib = C.lib()
+    np_last = (dims[-1] + 31) // 32 * 32
+    out = torch.full((rows, np_last), float("nan"), device=cuda)
+    wsb = lib.prb_rows2_workspace_bytes(C.c_long(rows), c_a, c_b, len(layers), co)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=cuda)
+    C.check(lib.prb_mlp_rows2(C.c_long(rows), c_a, C.ptr(a_t), a_t.stride(0), c_b, C.ptr(b_t) if c_b else None,
+                              b_t.stride(0) if c_b else 0, ctypes.byref(d), C.ptr(out), np_last, C.ptr(ws), C.c_size_t(wsb),
+                              C.stream()), "mlp_rows2")
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()[:, :dims[-1]]
+    tight = mlp_tf32_ref(x, layers)
+    err = np.abs(got - tight)
+    assert (err <= 5e-3 * (1 + np.abs(tight))).all() and (err <= 2e-4 * (1 + np.abs(tight))).mean() >= 0.97, err.max()
+    loose = O.shared_mlp(x, layers)
+    assert np.abs(got - loose).max() <= TOL * np.abs(loose).max()
+
+
 @pytest.mark.parametrize("folded", [False, True])
 @pytest.mark.parametrize("rows,dims", ROW_CASES)
 def test_mlp_rows_tcgen05(cuda, rows, dims, folded):
