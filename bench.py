@@ -252,6 +252,21 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def tuned_plans():
+    """measured build choice per chain shape (prb_debug_tuned_plans): CTAs per SM of the faster build"""
+    import ctypes
+    from pointrcnn_b200 import _cabi
+    buf = (ctypes.c_int * (10 * 64))()
+    n = _cabi.lib().prb_debug_tuned_plans(buf, 64)
+    kinds_in, kinds_out = ("sa", "fp", "rows"), ("rows", "sa_max", "fp")
+    out = []
+    for i in range(n):
+        r = buf[10 * i:10 * i + 10]
+        out.append({"in": kinds_in[r[0]], "out": kinds_out[r[1]], "nsample": r[3], "k_chunks": r[4], "tiles": r[5],
+                    "np": [x for x in r[6:6 + r[2]]], "build": {2: "2 CTAs x (4 epilogue + 4 gather warps)", 1: "1 CTA x (8 + 8)", 3: "1 CTA x (8 + 12)"}.get(r[9], r[9])})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -395,6 +410,26 @@ def main():
         prof.disable()
         fam = prof.collect()
         ms_seq = sum(a.elapsed_time(b_) for a, b_ in ev) / KS
+        # the same single batch with the geometry chain (4 FPS levels, ball queries, 3-NN: coordinates only) on side
+        # streams, overlapping the feature MLPs of the previous level (backbone._forward_planned): per-batch latency when
+        # there is no second batch to overlap with
+        from pointrcnn_b200 import config as prb_config
+        ms_plan = None
+        try:
+            with prb_config.override(enable_plan=True):
+                for i in range(2):
+                    net(dev_pool[i % P])
+                torch.cuda.synchronize()
+                evp = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KS)]
+                for i, (a, b_) in enumerate(evp):
+                    flush.fill_(1.0)
+                    a.record()
+                    net(dev_pool[i % P])
+                    b_.record()
+                torch.cuda.synchronize()
+                ms_plan = sum(a.elapsed_time(b_) for a, b_ in evp) / KS
+        except Exception as e:
+            ms_plan = None
     # ---------------- BASELINE configs[2]: RPN training step, data parallel over the ranks (16 scenes per GPU), gradient
     # all-reduce bucketed and overlapped with backward (parallel_utils.GradBucketReducer over NCCL)
     train = None
@@ -429,7 +464,7 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         try:
             import bench_rcnn_stage
-            rcnn = bench_rcnn_stage.measure(dev, steps=min(K, 10), warm=3)
+            rcnn = bench_rcnn_stage.measure(dev, steps=min(K, 10), warm=5)
         except Exception as e:
             rcnn = {"unavailable": "%s: %s" % (type(e).__name__, e)}
         torch.cuda.empty_cache()
@@ -554,7 +589,7 @@ def main():
             "pipeline": {"batches_in_flight": F, "cuda_graphs": G,
                          "l2": "inputs rotate through %d distinct batches (%.0f MB > 126 MB L2)" % (P, P * BATCH * POINTS * CHANNELS * 4 / 1e6)},
             "repeats": summary(ms_list),
-            "single_batch": {"ms_per_step": ms_seq, "value": single_val, "unit": "scenes/s",
+            "single_batch": {"ms_per_step": ms_seq, "value": single_val, "unit": "scenes/s", "ms_per_step_planned": ms_plan,
                              "note": "one batch at a time on one stream (eager launches), 256 MB L2 flush write between steps"},
             "e2e": {"value": scenes / (ms_e2e * 1e-3), "unit": "scenes/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": host_pool[0].numel() * 4, "d2h_bytes_per_step": d2h_bytes,
@@ -565,7 +600,7 @@ def main():
                              "h2d_bytes_per_step": host_pool[0].numel() * 4, "d2h_bytes_per_step": BATCH * 128 * POINTS * 4,
                              "what": "backbone only, full (B,128,16384) features copied to pinned host memory every step (PCIe bound)",
                              "repeats": summary(feat_list)},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+            "gpu_launches": launches, "chain_plans": tuned_plans(), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
             "ref_cuda": ref_cuda, "vs_ref_cuda": vs_ref, "strong_scaling": strong, "train_step": train, "rcnn_stage": rcnn}
     if args.profile_out:
         json.dump(line, open(args.profile_out, "w"), indent=1)

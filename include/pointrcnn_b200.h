@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PRB_ABI_VERSION 3   /* 3: prb_options (per-thread tuning block; no per-call environment reads) */
+#define PRB_ABI_VERSION 4   /* 3: prb_options (per-thread tuning block; no per-call environment reads); 4: mlp_tune, prb_mlp_rows2 */
 #if defined(__GNUC__)
 #define PRB_API __attribute__((visibility("default")))
 #else
@@ -58,10 +58,13 @@ typedef struct prb_options {
     int mlp_sleepy;    /* bit 0: MMA issuer waits with a suspend hint, bit 1: weight producer does */
     int mlp_trace;     /* 1: record the phase trace read by prb_debug_mlp_trace */
     int mlp_pipeline;  /* 1: role-specialised pipelined chain kernel (gather of tile i+1 overlaps tile i); 0: legacy */
-    int mlp_ne, mlp_ngw;   /* pipelined kernel: epilogue / gather warp groups per CTA (1 or 2); 0 = plan rule */
+    int mlp_ne, mlp_ngw;   /* pipelined kernel: epilogue (1, 2) / gather (1, 2, 3) warp groups per CTA; 0 = plan rule */
     int mlp_zs, mlp_nbuf;  /* pipelined kernel: last-layer slice width (multiple of 32) / slice buffers (1 or 2); 0 = plan rule */
     int mlp_brows;     /* pipelined kernel: rows per weight stage / MMA N (32..256); 0 = 64 */
     int mlp_pool;      /* SA max-pool over 16/32 samples: 0 = CREDUX (warp-wide max per channel), 1 = shuffle butterfly */
+    int mlp_tune;      /* 1 (default): the first eager launch of a chain shape times the two-CTA and the one-CTA build and
+                        * caches the faster one per device and shape; 0: rule-based plan only */
+    int roipool_exhaustive;  /* 1: roipool3d pass A tests every point against every box (no x-z binning) */
     int grid_debug;    /* 1: print (and synchronise for) the 3-NN grid's fallback counts */
     float nn_cell;     /* 3-NN grid cell edge in units of the mean point spacing (default 1.6) */
 } prb_options;
@@ -222,6 +225,9 @@ PRB_API int prb_debug_mlp_trace(long long *dst);
  * {z_free, ready, b1_full, fence, mma issue, commit}, weight producer 0 {b0_empty}, producer 1 {b1_empty}, gather warp 0
  * {a_empty}, epilogue warp 0 {r_full, z_full} */
 PRB_API int prb_debug_pipe_trace(long long *dst);
+/* measured plan choices so far: up to max_entries rows of 10 ints {mode_in, mode_out, layers, nsample, K chunks of layer 0,
+ * tiles, np0, np1, np2, winning build: 2 = two CTAs per SM (4 epilogue + 4 gather warps), 1 = one CTA 8 + 8, 3 = one CTA 8 + 12}; returns the number of rows */
+PRB_API int prb_debug_tuned_plans(int *dst, int max_entries);
 
 /* --- uniform-grid neighbour search: same results, bit for bit, as prb_ball_query(_msg2) / prb_three_nn
  * (first-nsample-in-index-order and lexicographic (d2, idx) rules kept; queries the grid cannot answer
@@ -246,7 +252,7 @@ PRB_API int prb_roipool3d(int B, int N, int M, int C, int S, const float *xyz, c
  * per-box index lists into caller scratch (prb_roipool3d_workspace_bytes), pass B streams the pooled rows with
  * 128-bit stores.  zero_fill_empty != 0: the kernel zeroes the rows of empty boxes itself, so `pooled` may be
  * uninitialised (saves the caller's 558 MB memset at C4); 0: untouched, as the reference leaves them. */
-PRB_API size_t prb_roipool3d_workspace_bytes(int B, int M, int S);
+PRB_API size_t prb_roipool3d_workspace_bytes(int B, int N, int M, int S);
 PRB_API int prb_roipool3d_ws(int B, int N, int M, int C, int S, const float *xyz, const float *boxes3d,
                      const float *pts_feature, float *pooled, int *empty_flag, const float *rois_canonical,
                      int zero_fill_empty, void *workspace, size_t workspace_bytes, void *stream);

@@ -8,6 +8,7 @@ environment variables ONCE at import; at run time they are changed with `overrid
     enable_plan     side-stream plan of the backbone forward (measured slower at batch 16, opt-in)
     prof_detail     per-shape lines in prof.collect()
     fp_project      FP modules: project the known points through layer 0 before interpolating (linearity), default on
+    fp_project_min_rows   ... for FP levels with at least this many unknown points in the batch (B * n)
 """
 import contextlib
 import os
@@ -20,6 +21,7 @@ _DEFAULTS = dict(
     enable_plan=os.environ.get("PRB_ENABLE_PLAN", "0") == "1",
     prof_detail=os.environ.get("PRB_PROF_DETAIL", "0") == "1",
     fp_project=os.environ.get("PRB_FP_PROJECT", "1") != "0",
+    fp_project_min_rows=int(os.environ.get("PRB_FP_PROJECT_MIN_ROWS", "131072")),
 )
 _local = threading.local()
 

@@ -23,6 +23,9 @@
 // z_full (commit) / z_free (epilogue arrive) barriers.
 #include <type_traits>
 
+#include <map>
+#include <mutex>
+
 #include "mlp_dev.cuh"
 
 namespace prb {
@@ -43,9 +46,10 @@ struct PipeSmem {
     int row_valid[2][TM];
 };
 
-__host__ __device__ inline size_t pipe_smem_bytes(int ne, int na, int nb0, int b0_bytes, int nb1, int b1_bytes, int np_total) {
+// `pool`: the max-pool staging tiles exist only for SA outputs (the last region of the layout: other modes never touch it)
+__host__ __device__ inline size_t pipe_smem_bytes(int ne, int na, int nb0, int b0_bytes, int nb1, int b1_bytes, int np_total, bool pool) {
     return 1024 /*alignment slack*/ + (size_t)na * A_STAGE_BYTES + (size_t)nb0 * b0_bytes + (size_t)nb1 * b1_bytes +
-           (size_t)2 * np_total * sizeof(float) + (size_t)ne * (TM * POOL_STRIDE + 8 * 16) * sizeof(float) + 64;
+           (size_t)2 * np_total * sizeof(float) + (pool ? (size_t)ne * (TM * POOL_STRIDE + 8 * 16) * sizeof(float) : 0) + 64;
 }
 
 __device__ __forceinline__ void bar_named(int id, int nthreads) {
@@ -170,24 +174,43 @@ __device__ __forceinline__ float pool_batch(float (&v)[16], int lane) {
 // b0_full, total}, 1 issuer B {z_free, ready, b1_full, total}, 2 producer 0 {b0_empty, total}, 3 producer 1 {b1_empty,
 // total}, 4 gather warp 0 {a_empty, total}, 5 epilogue warp 0 {r_full, z_full, total}
 __device__ long long g_pipe_trace[8][8];
+__shared__ unsigned int s_trace_acc[8][8];             // [slot][class]: cycles, accumulated by lane 0 of the traced warps of CTA 0
 struct TraceTimer {
-    bool on;
-    long long acc[7], t0;
-    __device__ __forceinline__ void start(bool enable) {
-        on = enable;
-        for (int k = 0; k < 7; ++k) acc[k] = 0;
-        t0 = on ? clock64() : 0;
+    int slot;                                           // -1: not traced (one register; the sums live in shared memory)
+    long long t0;
+    __device__ __forceinline__ void start(bool enable, int slot_) {
+        slot = enable ? slot_ : -1;
+        t0 = enable ? clock64() : 0;
+        if (enable && (threadIdx.x & 31) == 0)
+            for (int k = 0; k < 8; ++k) s_trace_acc[slot_][k] = 0u;
     }
     template <class F>
     __device__ __forceinline__ void timed(int k, F &&f) {
-        if (on) { const long long t = clock64(); f(); acc[k] += clock64() - t; } else f();
+        if (slot >= 0) {
+            const long long t = clock64();
+            f();
+            if ((threadIdx.x & 31) == 0) s_trace_acc[slot][k] += (unsigned int)(clock64() - t);
+        } else f();
     }
-    __device__ __forceinline__ void finish(int slot, int nclass) {
-        if (!on) return;
-        for (int k = 0; k < nclass; ++k) g_pipe_trace[slot][k] = acc[k];
+    __device__ __forceinline__ void finish() {
+        if (slot < 0 || (threadIdx.x & 31) != 0) return;
+        for (int k = 0; k < 7; ++k) g_pipe_trace[slot][k] = (long long)s_trace_acc[slot][k];
         g_pipe_trace[slot][7] = clock64() - t0;
     }
 };
+
+// registers per thread of each role.  Launch allocation = 65536 / (threads x CTAs per SM) rounded down to 8 (what
+// __launch_bounds__ makes ptxas assume); the misc warpgroup releases down to MISC, the others raise to EPI / GATHER:
+//   128 * (MISC + NE * EPI + NGW * GATHER) <= 65536 / MINB
+template <int NE, int NGW, int MINB> struct RegPlan;
+template <> struct RegPlan<1, 1, 2> { static constexpr int MISC = 56, EPI = 96, GATHER = 88; };     // 384 x 2: base 80
+template <> struct RegPlan<2, 2, 1> { static constexpr int MISC = 56, EPI = 112, GATHER = 96; };    // 640: base 96
+template <> struct RegPlan<2, 3, 1> { static constexpr int MISC = 56, EPI = 80, GATHER = 88; };     // 768: base 80
+template <bool INC, int N>
+__device__ __forceinline__ void reg_set() {
+    if (INC) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 
 template <int NE, int NGW, int MINB, int MIN, int MOUT>
 __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(const __grid_constant__ ChainParams p) {
@@ -197,8 +220,10 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
     __shared__ PipeSmem S;
     uint8_t *base = smem_raw + ((1024u - (s2u(smem_raw) & 1023u)) & 1023u);
     const int L = p.num_layers;
-    int np_total = 0, sc_off[MAX_LAYERS];
-    for (int l = 0; l < L; ++l) { sc_off[l] = np_total; np_total += p.np[l]; }
+    // offset of layer l's scale / shift inside the shared copies (no dynamically indexed local array: it would live on the stack)
+    auto sc_off = [&](int l) { return l == 0 ? 0 : (l == 1 ? p.np[0] : p.np[0] + p.np[1]); };
+    static_assert(MAX_LAYERS == 3, "sc_off assumes at most three layers");
+    const int np_total = sc_off(L - 1) + p.np[L - 1];
     uint8_t *sA = base;
     uint8_t *sB0 = sA + (size_t)p.na * A_STAGE_BYTES;
     uint8_t *sB1 = sB0 + (size_t)p.nb0 * p.b0_stage_bytes;
@@ -223,7 +248,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
     }
     if (warp == W_MISC + 2) tmem_alloc(s2u(&S.tmem_base), (uint32_t)p.tmem_cols);
     for (int l = 0; l < L; ++l)
-        for (int i = tid; i < p.np[l]; i += NTHREADS) { s_scale[sc_off[l] + i] = p.unit_scale ? 1.f : p.scale[l][i]; s_shift[sc_off[l] + i] = p.shift[l][i]; }
+        for (int i = tid; i < p.np[l]; i += NTHREADS) { s_scale[sc_off(l) + i] = p.unit_scale ? 1.f : p.scale[l][i]; s_shift[sc_off(l) + i] = p.shift[l][i]; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -236,8 +261,15 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
     const int ntiles = p.num_tiles;
     const bool lazy = NE == 1;           // the two-CTA build runs the narrow chains: rings with slack
     TraceTimer tt;
-    tt.start(p.trace != 0 && blockIdx.x == 0 && (warp >= W_MISC || warp == W_GATHER || warp == 0));   // warp-uniform
+    // traced warps of CTA 0 (warp-uniform): issuer A -> slot 0, issuer B 1, producers 2 / 3, gather warp 0 -> 4, epilogue warp 0 -> 5
+    tt.start(p.trace != 0 && blockIdx.x == 0 && (warp >= W_MISC || warp == W_GATHER || warp == 0),
+             warp == W_MISC + 2 ? 0 : warp == W_MISC + 3 ? 1 : warp == W_MISC ? 2 : warp == W_MISC + 1 ? 3 : warp == W_GATHER ? 4 : 5);
 
+    // Register budget per role (setmaxnreg, warpgroup granularity): the four single-thread roles give most of theirs
+    // back, the epilogue and gather warps -- which hold 32-column accumulator chunks / 12 gathered float4 per lane --
+    // take it (RegPlan).  Without this every thread of the CTA is allocated the same count and the row warps spill.
+    if (warp >= W_MISC) {
+    reg_set<false, RegPlan<NE, NGW, MINB>::MISC>();
     if (warp == W_MISC) {
         // ===================================================== weight producer, layer 0
         {
@@ -401,7 +433,9 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                 }
             }
         }
+    }
     } else if (warp >= W_GATHER) {
+        reg_set<true, RegPlan<NE, NGW, MINB>::GATHER>();
         // ===================================================== gather warps: layer-0 A chunks, running ahead of the MMAs
         const int gw = warp - W_GATHER;
         const int wq = gw & 3, grp = gw >> 2;
@@ -590,6 +624,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
             }
         }
     } else {
+        reg_set<true, RegPlan<NE, NGW, MINB>::EPI>();
         // ===================================================== epilogue warps (warps 0 .. 4*NE-1)
         const int wq = warp & 3, grp = warp >> 2;
         const int r = wq * 32 + lane;       // my row inside the tile / my TMEM lane
@@ -598,7 +633,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
         float *pool2 = pool + TM * POOL_STRIDE;   // 8 x 16 partial maxima (nsample > 32)
         const int Cl = p.c_last;
         const int rows = p.rows32;
-        const float *sc = s_scale + sc_off[L - 1], *sh = s_shift + sc_off[L - 1];
+        const float *sc = s_scale + sc_off(L - 1), *sh = s_shift + sc_off(L - 1);
         const bool unit = p.unit_scale != 0;
         const bool pool_raw = unit && MOUT == OUT_SA_MAX;
         const float lo = p.linear_last ? -CUDART_INF_F : 0.f;    // ReLU = max(., 0); a linear last layer keeps the sign
@@ -615,7 +650,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
             for (int kc = grp; kc < nch; kc += NE) {
                 uint32_t acc[32];
                 tmem_ld32(col0 + (uint32_t)(kc * KC), acc);
-                const float4 *sh4 = reinterpret_cast<const float4 *>(s_shift + sc_off[l] + kc * KC);
+                const float4 *sh4 = reinterpret_cast<const float4 *>(s_shift + sc_off(l) + kc * KC);
                 if (unit) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -626,7 +661,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                         acc[4 * j + 3] = __float_as_uint(relu_to_tf32(__uint_as_float(acc[4 * j + 3]) + b.w));
                     }
                 } else {
-                    const float4 *sc4 = reinterpret_cast<const float4 *>(s_scale + sc_off[l] + kc * KC);
+                    const float4 *sc4 = reinterpret_cast<const float4 *>(s_scale + sc_off(l) + kc * KC);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 a = sc4[j], b = sh4[j];
@@ -896,14 +931,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
         }
     }
 
-    if (tt.on && lane == 0) {
-        if (warp == W_MISC + 2) tt.finish(0, 3);
-        else if (warp == W_MISC + 3) tt.finish(1, 6);
-        else if (warp == W_MISC) tt.finish(2, 1);
-        else if (warp == W_MISC + 1) tt.finish(3, 1);
-        else if (warp == W_GATHER) tt.finish(4, 1);
-        else if (warp == 0) tt.finish(5, 2);
-    }
+    tt.finish();
     tc_fence_before();
     __syncthreads();
     if (warp == W_MISC + 2) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
@@ -922,7 +950,7 @@ struct PipePlan {
 //    (two CTAs per SM), then double buffering, then wide slices;
 //  * <= 256 columns: two CTAs of 4 epilogue + 4 gather warps (384 threads, 85 registers);
 //    otherwise one CTA with 8 epilogue warps and 8 (layer 0 has >= 2 K chunks) or 4 gather warps.
-static bool pipe_plan(const ChainParams &p, int max_optin, PipePlan *out) {
+static bool pipe_plan(const ChainParams &p, int max_optin, PipePlan *out, int force_occ = 0, int force_ngw = 0) {
     const int L = p.num_layers;
     const int np_last = p.np[L - 1];
     int np_total = 0, mid = 0;
@@ -963,10 +991,12 @@ static bool pipe_plan(const ChainParams &p, int max_optin, PipePlan *out) {
             PipePlan pl;
             pl.zs = z; pl.nbuf = nbuf; pl.nslice = nslice; pl.cols = cols; pl.nsplit = nsplit; pl.split_w = split_w;
             pl.occ = cols <= 256 ? 2 : 1;
-            if (o.mlp_occ == 1) pl.occ = 1;
+            if (o.mlp_occ == 1 || force_occ == 1) pl.occ = 1;
+            if (force_occ == 2 && pl.occ != 2) continue;
             pl.ne = pl.ngw = pl.occ == 2 ? 1 : 2;         // two builds: 4+4 row warps x 2 CTAs, or 8+8 row warps x 1 CTA
             if (o.mlp_ne == 1) pl.ne = pl.ngw = 1;
             if (o.mlp_ne == 2) { pl.ne = pl.ngw = 2; pl.occ = 1; }
+            if (pl.ne == 2 && (o.mlp_ngw == 3 || force_ngw == 3)) pl.ngw = 3;     // third build: 8 epilogue + 12 gather warps
             // weight stages: up to BROWS rows (output channels) of one 32-column K chunk.  Measured (profiles/r2_notes.md): 64-row
             // stages with 8-12 deep rings are SLOWER than 256-row stages 3 deep (SA3 0.178 vs 0.131 ms, FP1 0.242 vs 0.158):
             // every stage costs two single-thread barrier round trips and an N=64 MMA per K step, which outweighs the
@@ -983,7 +1013,7 @@ static bool pipe_plan(const ChainParams &p, int max_optin, PipePlan *out) {
             // weight rings 3 deep (2 if tight); the A ring as deep as fits, up to one whole item + 2
             for (int nb = 3; nb >= 2 && !ok; --nb)
                 for (int na = (k0 + 2 < PIPE_MAX_A ? (k0 + 2 > 3 ? k0 + 2 : 3) : PIPE_MAX_A); na >= 2 && !ok; --na) {
-                    const size_t smem = pipe_smem_bytes(pl.ne, na, nb, pl.b0_bytes, L > 1 ? nb : 0, pl.b1_bytes, np_total);
+                    const size_t smem = pipe_smem_bytes(pl.ne, na, nb, pl.b0_bytes, L > 1 ? nb : 0, pl.b1_bytes, np_total, p.mode_out == OUT_SA_MAX);
                     if (smem <= budget && smem <= (size_t)max_optin && (nb == 2 || na >= (k0 < 4 ? k0 : 4))) {
                         pl.na = na; pl.nb0 = nb; pl.nb1 = L > 1 ? nb : 0; pl.smem = smem; ok = true;
                     }
@@ -998,19 +1028,9 @@ static bool pipe_plan(const ChainParams &p, int max_optin, PipePlan *out) {
     return true;
 }
 
-// launch one fused segment on the pipelined kernel; returns -2 when the segment is not supported (caller falls back)
-int launch_chain_pipe(ChainParams &p, cudaStream_t st) {
-    int max_optin = 0;
-    {
-        int dev = 0;
-        PRB_CUDA(cudaGetDevice(&dev));
-        PRB_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    }
-    p.num_tiles = (int)((p.total_rows + TM - 1) / TM);
-    if (p.num_tiles == 0) return 0;
+// apply a plan to the launch parameters and launch
+static int launch_with_plan(ChainParams &p, const PipePlan &pl, cudaStream_t st) {
     const int L = p.num_layers;
-    PipePlan pl;
-    PRB_REQUIRE(pipe_plan(p, max_optin, &pl), "mlp: no tensor-memory / shared-memory plan for this chain segment");
     int col = 0;
     for (int l = 0; l + 1 < L; ++l) { p.rcol[l] = col; col += p.np[l]; }
     p.zcol[0] = col; p.zcol[1] = col + pl.zs;
@@ -1051,15 +1071,115 @@ int launch_chain_pipe(ChainParams &p, cudaStream_t st) {
         }                                                                                                  \
     } while (0)
     if (pl.ne == 1 && pl.ngw == 1) PRB_LAUNCH_PIPE_IO(1, 1, 2);      // launch bounds only cap the registers; occ 1 runs the same build
+    else if (pl.ngw == 3) PRB_LAUNCH_PIPE_IO(2, 3, 1);
     else PRB_LAUNCH_PIPE_IO(2, 2, 1);
 #undef PRB_LAUNCH_PIPE_IO
 #undef PRB_LAUNCH_PIPE
     return check_launch("mlp_pipe_kernel");
 }
 
+// Which build runs a given chain shape -- two CTAs per SM of 4 epilogue + 4 gather warps, one CTA of 8 + 8 with twice the
+// tensor memory (double-buffered last layer), or one CTA of 8 + 12 for gather-bound shapes -- is MEASURED, not guessed: the
+// first eager launch of a shape times them
+// (CUDA events on the launching stream, best of 2 after a warm-up; the launches are idempotent and every plan computes
+// bit-identical results, K order and per-element arithmetic do not depend on the plan) and the winner is cached per
+// device and shape.  Launches inside a stream capture, traced launches and launches with any plan option forced through
+// prb_options use the rule-based plan (prefer two CTAs per SM).  profiles/r2_notes.md: SA2 scale 1 0.152 -> 0.139 ms,
+// FP0 0.150 -> 0.125, FP3 0.122 -> 0.085 on the wide build; SA1 0.207 -> 0.266 the other way.
+struct TuneKey {
+    int dev, mode_in, mode_out, L, ns, k0, tiles, np[3];
+    bool operator<(const TuneKey &o) const { return memcmp(this, &o, sizeof(TuneKey)) < 0; }
+};
+static std::mutex g_tune_mu;
+static std::map<TuneKey, int> g_tune;      // -> winning build: 2 = two CTAs per SM (4+4 row warps), 1 = one CTA 8+8, 3 = one CTA 8+12
+
+static bool tuning_allowed(cudaStream_t st) {
+    const prb_options &o = opts();
+    if (!o.mlp_tune || o.mlp_trace || o.mlp_occ || o.mlp_ne || o.mlp_ngw || o.mlp_zs || o.mlp_nbuf || o.mlp_sms) return false;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+    return cs == cudaStreamCaptureStatusNone;
+}
+
+// launch one fused segment on the pipelined kernel
+int launch_chain_pipe(ChainParams &p, cudaStream_t st) {
+    int max_optin = 0, dev = 0;
+    PRB_CUDA(cudaGetDevice(&dev));
+    PRB_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    p.num_tiles = (int)((p.total_rows + TM - 1) / TM);
+    if (p.num_tiles == 0) return 0;
+    PipePlan pl;
+    PRB_REQUIRE(pipe_plan(p, max_optin, &pl), "mlp: no tensor-memory / shared-memory plan for this chain segment");
+    // candidates: the rule-based plan first, then the one-CTA builds it did not pick (8 + 8 and 8 + 12 row warps)
+    PipePlan cand[3];
+    int code[3], nc = 0;
+    cand[nc] = pl; code[nc++] = pl.occ == 2 ? 2 : (pl.ngw == 3 ? 3 : 1);
+    if (pl.occ == 2 && pipe_plan(p, max_optin, &cand[nc], 1, 0)) code[nc++] = 1;
+    if (pl.ngw != 3 && pipe_plan(p, max_optin, &cand[nc], 1, 3) && cand[nc].ngw == 3) code[nc++] = 3;
+    if (nc > 1) {
+        TuneKey key;
+        memset(&key, 0, sizeof(key));
+        key.dev = dev; key.mode_in = p.mode_in; key.mode_out = p.mode_out; key.L = p.num_layers; key.ns = p.ns;
+        key.k0 = p.nchunks[0]; key.tiles = p.num_tiles;
+        for (int l = 0; l < p.num_layers; ++l) key.np[l] = p.np[l];
+        int choice = 0;
+        {
+            std::lock_guard<std::mutex> g(g_tune_mu);
+            auto it = g_tune.find(key);
+            if (it != g_tune.end()) choice = it->second;
+        }
+        if (choice == 0 && tuning_allowed(st)) {
+            cudaEvent_t e0, e1;
+            PRB_CUDA(cudaEventCreate(&e0));
+            PRB_CUDA(cudaEventCreate(&e1));
+            float best[3] = {1e30f, 1e30f, 1e30f};
+            int rc = 0;
+            for (int c = 0; c < nc && !rc; ++c)
+                for (int rep = 0; rep < 3 && !rc; ++rep) {
+                    ChainParams q = p;
+                    cudaEventRecord(e0, st);
+                    rc = launch_with_plan(q, cand[c], st);
+                    cudaEventRecord(e1, st);
+                    if (cudaEventSynchronize(e1) != cudaSuccess) rc = rc ? rc : -1;
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    if (rep > 0 && ms < best[c]) best[c] = ms;
+                }
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            if (rc) return rc;
+            int win = 0;
+            for (int c = 1; c < nc; ++c)
+                if (best[c] < 0.97f * best[win]) win = c;       // a later candidate has to win by a margin
+            choice = code[win];
+            std::lock_guard<std::mutex> g(g_tune_mu);
+            g_tune[key] = choice;
+        }
+        for (int c = 0; c < nc; ++c)
+            if (code[c] == choice) pl = cand[c];
+    }
+    return launch_with_plan(p, pl, st);
+}
+
+// tuned plans so far: n entries of {mode_in, mode_out, layers, nsample, k chunks, tiles, np0, np1, np2, occupancy}
+int pipe_tuned_plans(int *dst, int max_entries) {
+    std::lock_guard<std::mutex> g(g_tune_mu);
+    int n = 0;
+    for (const auto &kv : g_tune) {
+        if (n >= max_entries) break;
+        const TuneKey &k = kv.first;
+        int *d = dst + 10 * n++;
+        d[0] = k.mode_in; d[1] = k.mode_out; d[2] = k.L; d[3] = k.ns; d[4] = k.k0; d[5] = k.tiles; d[6] = k.np[0]; d[7] = k.np[1]; d[8] = k.np[2];
+        d[9] = kv.second;
+    }
+    return n;
+}
+
 }  // namespace prb
 
 // wait-time trace of the last traced pipelined launch: 8 roles x {up to 7 classes, total cycles in slot 7} (see g_pipe_trace)
+extern "C" int prb_debug_tuned_plans(int *dst, int max_entries) { return prb::pipe_tuned_plans(dst, max_entries); }
+
 extern "C" int prb_debug_pipe_trace(long long *dst) {
     PRB_CUDA(cudaDeviceSynchronize());
     PRB_CUDA(cudaMemcpyFromSymbol(dst, prb::g_pipe_trace, sizeof(long long) * 64));

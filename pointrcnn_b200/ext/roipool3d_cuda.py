@@ -28,7 +28,7 @@ def forward(xyz, boxes3d, pts_feature, pooled_features, pooled_empty_flag, rois_
         raise RuntimeError("roipool3d: inconsistent tensor shapes")
     lib = C.lib()
     with torch.cuda.device(xyz.device):
-        wsb = lib.prb_roipool3d_workspace_bytes(B, M, S)
+        wsb = lib.prb_roipool3d_workspace_bytes(B, N, M, S)
         ws = torch.empty(wsb, dtype=torch.uint8, device=xyz.device)
         C.check(lib.prb_roipool3d_ws(B, N, M, Cf, S, C.ptr(xyz), C.ptr(boxes3d), C.ptr(pts_feature), C.ptr(pooled_features),
                                      C.ptr(pooled_empty_flag), C.ptr(rois_canonical), int(bool(zero_fill_empty)), C.ptr(ws),

@@ -393,7 +393,8 @@ class PointnetFPModule(nn.Module):
         # c_known floats for each of the 3 neighbours of every one of the n >= m unknown points
         # measured (profiles/r2_notes.md): pays at the finest level (262144 rows: 0.267 -> 0.231 ms incl. the projection launch),
         # not at the coarse ones, where the extra launch costs more than the narrower gather saves
-        project = self.project_known and config.get("fp_project") and _fold_scale() and c1 < c_known and n >= m and B * n >= 131072
+        project = (self.project_known and config.get("fp_project") and _fold_scale() and c1 < c_known and n >= m
+                   and B * n >= config.get("fp_project_min_rows"))
         desc = self._fused.get(self.mlp, 1, c_known, dev, project_known=project)
         c_out = self._fused.c_out
         if project:

@@ -269,6 +269,50 @@ def test_roipool3d_vs_reference_and_oracle(cuda, B, N, M, C, S):
         assert mg.min() < 1e-4, "non-borderline roipool3d mismatch at scene %d box %d" % (b, m)
 
 
+@pytest.mark.parametrize("case", ["duplicates", "degenerate_line", "nan_inf", "huge_boxes", "tiny", "odd_n", "far_coordinates"])
+def test_roipool3d_binned_equals_exhaustive(cuda, case):
+    """the x-z binned assign pass (default) must select exactly the rows of the exhaustive scan: same predicate, the
+    footprint only prunes cells that cannot hold an inside point.  Degenerate clouds and boxes included."""
+    from pointrcnn_b200 import _cabi as C
+    rng = np.random.default_rng(len(case))
+    B, N, M, Cf, S = 2, 5000, 40, 7, 64
+    xyz, boxes, feat = _roi_scene(B, N, M, Cf, 300 + len(case))
+    if case == "duplicates":
+        xyz[:, N // 2:] = xyz[:, :N - N // 2]                      # every point twice: ties in every cell
+    elif case == "degenerate_line":
+        xyz[0, :, 0] = 3.0                                         # zero x extent: one grid column
+        xyz[1, :, :] = xyz[1, 0, :]                                # a single location
+        boxes[:, :10, 0:3] = xyz[:, :10, :] + np.float32(0.3)
+    elif case == "nan_inf":
+        xyz[0, ::7, 0] = np.nan; xyz[0, 3::11, 2] = np.inf; xyz[1, 5::13, 1] = -np.inf
+        boxes[0, 0, 0] = np.nan; boxes[0, 1, 6] = np.inf; boxes[1, 2, 5] = np.nan
+    elif case == "huge_boxes":
+        boxes[:, :8, 3:6] = 500.0                                  # the |dx|, |dz| <= 10 m rule of pt_in_box3d caps them
+        boxes[:, 8:12, 3:6] = -1.0                                 # negative sizes: nothing inside
+    elif case == "tiny":
+        N = 1
+        xyz, feat = xyz[:, :1].copy(), feat[:, :1].copy()
+        boxes[:, 0, 0:3] = xyz[:, 0, :] + np.array([0, 0.5, 0], dtype=np.float32)
+    elif case == "odd_n":
+        N = 4099
+        xyz, feat = xyz[:, :N].copy(), feat[:, :N].copy()
+    elif case == "far_coordinates":
+        xyz += np.float32(30000.0); boxes[:, :, 0:3] += np.float32(30000.0)     # coarse fp32 spacing around the boxes
+    x, bx, f = T(xyz, cuda), T(boxes, cuda), T(feat, cuda)
+    out = []
+    for exhaustive in (0, 1):
+        pooled = torch.zeros((B, M, S, 3 + Cf), device=cuda)
+        empty = torch.zeros((B, M), dtype=torch.int32, device=cuda)
+        with C.options(roipool_exhaustive=exhaustive):
+            roipool3d_cuda.forward(x, bx, f, pooled, empty)
+        torch.cuda.synchronize()
+        out.append((pooled.cpu().numpy(), empty.cpu().numpy()))
+    assert np.array_equal(out[0][1], out[1][1]), "empty flags differ"
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32)), "pooled rows differ (bitwise)"
+    if case in ("duplicates", "huge_boxes", "odd_n", "far_coordinates"):
+        assert (out[0][1] == 0).sum() > 0, "case should have non-empty boxes"
+
+
 def test_roipool3d_utils_and_canonical(cuda):
     xyz, boxes, feat = _roi_scene(2, 8192, 48, 6, 77)
     x, bx, f = T(xyz, cuda), T(boxes, cuda), T(feat, cuda)
