@@ -61,10 +61,12 @@ typedef struct prb_options {
     int mlp_ne, mlp_ngw;   /* pipelined kernel: epilogue (1, 2) / gather (1, 2, 3) warp groups per CTA; 0 = plan rule */
     int mlp_zs, mlp_nbuf;  /* pipelined kernel: last-layer slice width (multiple of 32) / slice buffers (1 or 2); 0 = plan rule */
     int mlp_brows;     /* pipelined kernel: rows per weight stage / MMA N (32..256); 0 = 64 */
-    int mlp_pool;      /* SA max-pool over 16/32 samples: 0 = CREDUX (warp-wide max per channel), 1 = shuffle butterfly */
+    int mlp_pool;      /* SA max-pool over 16..128 samples: 0 = quad tensor-memory layout (2 rows x 4 columns per thread, 3 exchange
+                        * stages), 1 = shuffle butterfly, 2 = CREDUX (warp-wide max per channel), 3 = staged tile for 64/128 samples */
     int mlp_tune;      /* 1 (default): the first eager launch of a chain shape times the two-CTA and the one-CTA build and
                         * caches the faster one per device and shape; 0: rule-based plan only */
     int roipool_exhaustive;  /* 1: roipool3d pass A tests every point against every box (no x-z binning) */
+    int grid_csr;      /* 1: hash grid as CSR runs (counting sort per scene) instead of linked lists; slower at the RPN shapes */
     int grid_debug;    /* 1: print (and synchronise for) the 3-NN grid's fallback counts */
     float nn_cell;     /* 3-NN grid cell edge in units of the mean point spacing (default 1.6) */
 } prb_options;

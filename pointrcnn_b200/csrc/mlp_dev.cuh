@@ -184,6 +184,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// 16 lanes x 16 consecutive fp32 columns in the "quad" register layout (measured, scripts/micro/tmem_layout.cu): thread t gets
+//   r0,r1 = row t/4,     columns 2(t%4), +1      r2,r3 = row t/4 + 8, same columns
+//   r4,r5 = row t/4,     columns 8 + 2(t%4), +1  r6,r7 = row t/4 + 8, same columns
+// i.e. a thread holds 2 rows x 4 columns instead of 1 row x 8 columns: a reduction over ROWS (max-pool over the samples of a
+// centre) needs 3 cross-lane stages instead of 5.  No wait inside: issue both halves of a warp's 32 lanes, then tmem_ld_wait.
+__device__ __forceinline__ void tmem_ld_quad16(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // 32 lanes x 32 consecutive 32-bit columns in one instruction each way
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(

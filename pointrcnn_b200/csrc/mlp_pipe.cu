@@ -169,6 +169,52 @@ __device__ __forceinline__ float pool_batch(float (&v)[16], int lane) {
     return fmaxf(b0 ? w2[1] : w2[0], __shfl_xor_sync(0xffffffffu, b0 ? w2[0] : w2[1], 1));   // channel bit-reversed-ish, see caller
 }
 
+// Max-pool of 16 accumulator columns straight from tensor memory in the quad layout (tmem_ld_quad16): the warp's 32 rows are
+// read as two 16-lane halves A (rows 0-15) and B (rows 16-31), a thread then owns rows {g, g+8} of each half (g = lane / 4)
+// for the 4 columns col(k) = 2 (lane % 4) + (k & 1) + 8 (k >> 1).  `act(x, col)` is applied to every element first (identity
+// when the activation commutes with the max and is applied after pooling).
+//   NS == 32: one centre per warp -> 12 in-thread maxima, then 3 halving exchange stages over lane bits 4, 3, 2 (4 shuffles);
+//             lanes with bit 2 clear own column  2 (lane % 4) + bit3 + 8 bit4
+//   NS == 16: half A is centre 0, half B centre 1 -> 8 in-thread maxima, 7 shuffles; lane owns centre bit4, column
+//             2 (lane % 4) + bit2 + 8 bit3
+// ~30 / ~40 instructions per 16-column batch against ~80 for the one-row-per-thread layout (16 CREDUX + 16 UR->R + 15 selects).
+template <int NS, class Act>
+__device__ __forceinline__ float pool_quad(uint32_t taddr, int lane, Act &&act) {
+    uint32_t A[8], B[8];
+    tmem_ld_quad16(taddr, A);
+    tmem_ld_quad16(taddr + (16u << 16), B);
+    tmem_ld_wait();
+    const int cb = 2 * (lane & 3);
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    if (NS == 32) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int q = (k & 1) + 4 * (k >> 1), col = cb + (k & 1) + 8 * (k >> 1);
+            v[k] = fmaxf(fmaxf(act(__uint_as_float(A[q]), col), act(__uint_as_float(A[q + 2]), col)),
+                         fmaxf(act(__uint_as_float(B[q]), col), act(__uint_as_float(B[q + 2]), col)));
+        }
+        float k0 = b4 ? v[2] : v[0], k1 = b4 ? v[3] : v[1];
+        k0 = fmaxf(k0, __shfl_xor_sync(0xffffffffu, b4 ? v[0] : v[2], 16));
+        k1 = fmaxf(k1, __shfl_xor_sync(0xffffffffu, b4 ? v[1] : v[3], 16));
+        float x = fmaxf(b3 ? k1 : k0, __shfl_xor_sync(0xffffffffu, b3 ? k0 : k1, 8));
+        return fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 4));
+    } else {
+        float a[4], b[4], w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int q = (k & 1) + 4 * (k >> 1), col = cb + (k & 1) + 8 * (k >> 1);
+            a[k] = fmaxf(act(__uint_as_float(A[q]), col), act(__uint_as_float(A[q + 2]), col));
+            b[k] = fmaxf(act(__uint_as_float(B[q]), col), act(__uint_as_float(B[q + 2]), col));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = fmaxf(b4 ? b[k] : a[k], __shfl_xor_sync(0xffffffffu, b4 ? a[k] : b[k], 16));
+        const float u0 = fmaxf(b3 ? w[2] : w[0], __shfl_xor_sync(0xffffffffu, b3 ? w[0] : w[2], 8));
+        const float u1 = fmaxf(b3 ? w[3] : w[1], __shfl_xor_sync(0xffffffffu, b3 ? w[1] : w[3], 8));
+        return fmaxf(b2 ? u1 : u0, __shfl_xor_sync(0xffffffffu, b2 ? u0 : u1, 4));
+    }
+}
+
 // optional wait-time trace (prb_options.mlp_trace): CTA 0 accumulates the cycles each role spends in each class of wait
 // and the total cycles of its item loop; read back with prb_debug_pipe_trace.  Slots: 0 issuer A {x_free|z_free, a_full,
 // b0_full, total}, 1 issuer B {z_free, ready, b1_full, total}, 2 producer 0 {b0_empty, total}, 3 producer 1 {b1_empty,
@@ -726,13 +772,16 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                 tt.timed(1, [&] { bwait(&S.z_full[buf], (nbuf == 2 ? (u >> 1) : u) & 1); });
                 tc_fence_after();
                 const uint32_t zc = trow + (uint32_t)p.zcol[buf];
-                if (MOUT == OUT_SA_MAX && (ns == 64 || ns == 128) && p.pool_mode != 2) {
-                    // ---- 64 / 128 samples (RCNN stage): a centre spans 2 / 4 warps.  Every warp pools its 32 rows with the
-                    // warp-wide reduction, the partial maxima of a centre's warps meet in a tiny double-buffered shared tile
-                    // (one named barrier per batch instead of a 128 x 16 staging tile and three barriers)
+                if (MOUT == OUT_SA_MAX && (ns == 64 || ns == 128) && p.pool_mode != 3) {
+                    // ---- 64 / 128 samples (RCNN stage): a centre spans 2 / 4 warps.  Every warp pools its 32 rows (quad layout,
+                    // or the warp-wide reduction with pool_mode 2), the partial maxima of a centre's warps meet in a tiny
+                    // double-buffered shared tile (one named barrier per batch instead of a 128 x 16 staging tile and three barriers)
                     const int wpc = ns >> 5;                          // warps per centre
                     const bool head = (wq & (wpc - 1)) == 0;
-                    const int ch = lane & 15;
+                    const bool quad = p.pool_mode == 0;
+                    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+                    const int ch = quad ? 2 * (lane & 3) + (b3 ? 1 : 0) + (b4 ? 8 : 0) : (lane & 15);
+                    const bool own = quad ? !b2 : lane < 16;          // lanes that hold a distinct column of the batch
                     const int c_first = s_lo + grp * 16;
                     float *ocm = p.out + off_cm + (size_t)(c_first + ch) * p.npoint;
                     float *opm = p.out_pm ? p.out_pm + off_pm + c_first + ch : nullptr;
@@ -743,31 +792,41 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                     // pool_par toggles with EVERY batch of the kernel's lifetime (not per slice): a warp that runs ahead into the
                     // next slice must not overwrite the buffer its centre's head warp is still reading
                     for (int c0 = c_first; c0 < s_hi; c0 += 16 * NE, ocm += cm_step, shp += 16 * NE, taddr += 16 * NE, opm += (opm ? 16 * NE : 0), pool_par ^= 1) {
-                        uint32_t acc[16];
-                        tmem_ld16(taddr, acc);
-                        float v[16];
-                        if (pool_raw) {
-#pragma unroll
-                            for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(acc[q]);
-                        } else {
-                            const float4 *sh4 = reinterpret_cast<const float4 *>(sh + c0), *sc4 = reinterpret_cast<const float4 *>(sc + c0);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float4 a = sc4[j], b = sh4[j];
-                                v[4 * j + 0] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 0]), a.x, b.x), lo);
-                                v[4 * j + 1] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 1]), a.y, b.y), lo);
-                                v[4 * j + 2] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 2]), a.z, b.z), lo);
-                                v[4 * j + 3] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 3]), a.w, b.w), lo);
+                        float x;
+                        if (quad) {
+                            if (pool_raw) {
+                                x = pool_quad<32>(taddr, lane, [](float v, int) { return v; });
+                            } else {
+                                const float *sc0 = sc + c0, *sh0 = sh + c0;
+                                x = pool_quad<32>(taddr, lane, [&](float v, int col) { return fmaxf(fmaf(v, sc0[col], sh0[col]), lo); });
                             }
+                        } else {
+                            uint32_t acc[16];
+                            tmem_ld16(taddr, acc);
+                            float v[16];
+                            if (pool_raw) {
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(acc[q]);
+                            } else {
+                                const float4 *sh4 = reinterpret_cast<const float4 *>(sh + c0), *sc4 = reinterpret_cast<const float4 *>(sc + c0);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float4 a = sc4[j], b = sh4[j];
+                                    v[4 * j + 0] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 0]), a.x, b.x), lo);
+                                    v[4 * j + 1] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 1]), a.y, b.y), lo);
+                                    v[4 * j + 2] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 2]), a.z, b.z), lo);
+                                    v[4 * j + 3] = fmaxf(fmaf(__uint_as_float(acc[4 * j + 3]), a.w, b.w), lo);
+                                }
+                            }
+                            x = pool_batch<32, 0>(v, lane);                    // max over my warp's 32 rows, channel lane & 15
                         }
-                        float x = pool_batch<32, 0>(v, lane);                  // max over my warp's 32 rows, channel lane & 15
                         float *tile2 = pool2 + pool_par * 64;                   // [4 warps][16 channels]
-                        if (lane < 16) tile2[wq * 16 + ch] = x;
+                        if (own) tile2[wq * 16 + ch] = x;
                         bar_named(2 + grp, 128);
                         if (head) {
                             for (int w2 = 1; w2 < wpc; ++w2) x = fmaxf(x, tile2[(wq + w2) * 16 + ch]);
                             if (pool_raw) x = fmaxf(x + *shp, lo);
-                            if (ok && lane < 16 && c0 < n_ok) {
+                            if (ok && own && c0 < n_ok) {
                                 *ocm = x;
                                 if (opm) *opm = x;
                             }
@@ -776,6 +835,33 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                 } else if (MOUT == OUT_SA_MAX && (ns == 32 || ns == 16)) {
                     // ---- fast path: dispatched ONCE per slice on (nsample, pooling kind); everything that does not depend on
                     // the 16-column batch is computed before the batch loop
+                    auto quad_loop = [&](auto ns_c) {
+                        constexpr int NSC = decltype(ns_c)::value;
+                        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+                        const int ch = 2 * (lane & 3) + (NSC == 32 ? (b3 ? 1 : 0) + (b4 ? 8 : 0) : (b2 ? 1 : 0) + (b3 ? 8 : 0));
+                        const bool st_lane = ok && (NSC == 16 || !b2);
+                        const int c_first = s_lo + grp * 16;
+                        float *ocm = p.out + off_cm + (size_t)(c_first + ch) * p.npoint;
+                        float *opm = p.out_pm ? p.out_pm + off_pm + c_first + ch : nullptr;
+                        const size_t cm_step = (size_t)(16 * NE) * p.npoint;
+                        const float *shp = sh + c_first + ch;
+                        uint32_t taddr = zc + (uint32_t)(c_first - s_lo);
+                        const int n_ok = Cl - ch;
+                        for (int c0 = c_first; c0 < s_hi; c0 += 16 * NE, ocm += cm_step, shp += 16 * NE, taddr += 16 * NE, opm += (opm ? 16 * NE : 0)) {
+                            float x;
+                            if (pool_raw) {
+                                x = pool_quad<NSC>(taddr, lane, [](float v, int) { return v; });
+                                x = fmaxf(x + *shp, lo);
+                            } else {
+                                const float *sc0 = sc + c0, *sh0 = sh + c0;
+                                x = pool_quad<NSC>(taddr, lane, [&](float v, int col) { return fmaxf(fmaf(v, sc0[col], sh0[col]), lo); });
+                            }
+                            if (st_lane && c0 < n_ok) {
+                                *ocm = x;
+                                if (opm) *opm = x;
+                            }
+                        }
+                    };
                     auto slice_loop = [&](auto ns_c, auto pool_c) {
                         constexpr int NSC = decltype(ns_c)::value, POOLC = decltype(pool_c)::value;
                         const int ch = POOLC == 0 ? (lane & 15)
@@ -820,8 +906,8 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                     using I32 = std::integral_constant<int, 32>;
                     using P0 = std::integral_constant<int, 0>;
                     using P1 = std::integral_constant<int, 1>;
-                    if (ns == 32) { if (p.pool_mode == 0) slice_loop(I32{}, P0{}); else slice_loop(I32{}, P1{}); }
-                    else { if (p.pool_mode == 0) slice_loop(I16{}, P0{}); else slice_loop(I16{}, P1{}); }
+                    if (ns == 32) { if (p.pool_mode == 0) quad_loop(I32{}); else if (p.pool_mode == 2) slice_loop(I32{}, P0{}); else slice_loop(I32{}, P1{}); }
+                    else { if (p.pool_mode == 0) quad_loop(I16{}); else if (p.pool_mode == 2) slice_loop(I16{}, P0{}); else slice_loop(I16{}, P1{}); }
                 } else
                 for (int c0 = s_lo + grp * 16; c0 < s_hi; c0 += 16 * NE) {
                     uint32_t acc[16];

@@ -57,6 +57,7 @@ static prb_options make_defaults() {
     o.mlp_pool = env_int("PRB_MLP_POOL", 0);
     o.mlp_tune = env_int("PRB_MLP_TUNE", 1);
     o.roipool_exhaustive = env_int("PRB_ROIPOOL_EXHAUSTIVE", 0);
+    o.grid_csr = env_int("PRB_GRID_CSR", 0);
     o.grid_debug = env_int("PRB_GRID_DEBUG", 0);
     o.nn_cell = 1.6f;
     if (const char *e = getenv("PRB_NN_CELL")) { float v = (float)atof(e); if (v > 0.2f && v < 50.f) o.nn_cell = v; }

@@ -301,6 +301,29 @@ def test_sa_module_scale_fold_modes_agree(cuda, ns):
     assert (outs["0"] - outs["1"]).abs().max().item() <= TOL * scale
 
 
+@pytest.mark.parametrize("fold", [True, False])
+@pytest.mark.parametrize("ns,widths", [(16, [24, 32, 48]), (32, [64, 96, 128]), (64, [32, 32, 80]), (128, [32, 64]), (32, [16, 200])])
+def test_sa_pooling_layouts_bit_identical(cuda, ns, widths, fold):
+    """max-pool epilogues of the chain kernel (prb_options.mlp_pool): 0 quad tensor-memory layout (default), 1 shuffle
+    butterfly, 2 warp-wide CREDUX, 3 staged tile (64 / 128 samples) -- a max is exact, so every layout must give the same bits
+    (channel counts that are not multiples of 16, both scale modes)"""
+    from pointrcnn_b200 import _cabi as C, config
+    torch.manual_seed(ns)
+    mod = pm.PointnetSAModuleMSG(npoint=150, radii=[0.3], nsamples=[ns], mlps=[[20] + widths], bn=True).to(cuda).eval()
+    _randomise_bn(mod, 5)
+    x = torch.from_numpy(synth.u_cube(2, 2500, 31)).to(cuda)
+    f = torch.randn(2, 20, 2500, device=cuda)
+    outs = []
+    for mode in (0, 1, 2, 3):
+        with torch.no_grad(), config.override(fold_scale=fold), C.options(mlp_pool=mode):
+            outs.append(mod(x, f)[1].clone())
+    for mode in (1, 2, 3):
+        assert torch.equal(outs[0], outs[mode]), "pooling layout %d differs from the quad layout" % mode
+    with torch.no_grad():
+        ref = _unfused(lambda: mod(x, f))[1]
+    assert (outs[0] - ref).abs().max().item() <= TOL * ref.abs().max().item()
+
+
 def test_sa_module_group_all_and_no_bn(cuda):
     torch.manual_seed(1)
     B, N, c_feat = 6, 32, 256

@@ -406,7 +406,9 @@ def test_iou3d_utils_api(cuda):
     ("cube", 300, 40, (0.2,), (16,)),                # tiny set through the grid, single radius
     ("kitti", 5000, 777, (2.0, 4.0), (16, 32)),      # n not a power of two, big balls
 ])
-def test_ball_query_grid_path_exact(cuda, kind, N, M, radii, nss):
+@pytest.mark.parametrize("csr", [0, 1])                # linked lists (default) / CSR runs
+def test_ball_query_grid_path_exact(cuda, kind, N, M, radii, nss, csr):
+    from pointrcnn_b200 import _cabi
     xyz = _cloud(kind, 2, N, 51 + N)
     fidx = O.fps(xyz, M)
     new_xyz = np.stack([xyz[b][fidx[b]] for b in range(2)])
@@ -414,10 +416,11 @@ def test_ball_query_grid_path_exact(cuda, kind, N, M, radii, nss):
     old = pu.GRID_MIN_POINTS_BQ
     pu.GRID_MIN_POINTS_BQ = 1
     try:
-        if len(radii) == 2:
-            got = pu.ball_query_msg2(radii, nss, x, c)
-        else:
-            got = [pu.ball_query(radii[0], nss[0], x, c)]
+        with _cabi.options(grid_csr=csr):
+            if len(radii) == 2:
+                got = pu.ball_query_msg2(radii, nss, x, c)
+            else:
+                got = [pu.ball_query(radii[0], nss[0], x, c)]
     finally:
         pu.GRID_MIN_POINTS_BQ = old
     for g, r, ns in zip(got, radii, nss):
@@ -427,7 +430,8 @@ def test_ball_query_grid_path_exact(cuda, kind, N, M, radii, nss):
 @pytest.mark.parametrize("cell", [None, 0.5, 4.0])     # default edge; tiny cells (most queries go to the exhaustive scan); big cells
 @pytest.mark.parametrize("kind,n,m", [("kitti", 8192, 2048), ("cube", 2000, 500), ("dup", 1024, 256), ("cube", 100, 5),
                                       ("kitti", 300, 3), ("dup", 4096, 64)])
-def test_three_nn_grid_path_exact(cuda, kind, n, m, cell):
+@pytest.mark.parametrize("csr", [0, 1])
+def test_three_nn_grid_path_exact(cuda, kind, n, m, cell, csr):
     unknown = _cloud(kind, 2, n, 61 + n)
     known = np.ascontiguousarray(unknown[:, ::max(1, n // m)][:, :m])
     if kind == "kitti":
@@ -437,7 +441,7 @@ def test_three_nn_grid_path_exact(cuda, kind, n, m, cell):
     old = pu.GRID_MIN_POINTS_NN
     pu.GRID_MIN_POINTS_NN = 1
     try:
-        with _cabi.options(**({} if cell is None else {"nn_cell": cell})):
+        with _cabi.options(grid_csr=csr, **({} if cell is None else {"nn_cell": cell})):
             got_d2, got_idx, w = pu.three_nn_weights(T(unknown, cuda), T(known, cuda))
     finally:
         pu.GRID_MIN_POINTS_NN = old
