@@ -66,6 +66,8 @@ typedef struct prb_options {
     int mlp_tune;      /* 1 (default): the first eager launch of a chain shape times the two-CTA and the one-CTA build and
                         * caches the faster one per device and shape; 0: rule-based plan only */
     int roipool_exhaustive;  /* 1: roipool3d pass A tests every point against every box (no x-z binning) */
+    int roipool_parts;     /* roipool3d pass B: CTAs per box (1..8); 0 = 1 */
+    int roipool_stage_kb;  /* roipool3d pass B: shared staging area per CTA in KB (8..160); 0 = 24 */
     int grid_csr;      /* 1: hash grid as CSR runs (counting sort per scene) instead of linked lists; slower at the RPN shapes */
     int grid_debug;    /* 1: print (and synchronise for) the 3-NN grid's fallback counts */
     float nn_cell;     /* 3-NN grid cell edge in units of the mean point spacing (default 1.6) */

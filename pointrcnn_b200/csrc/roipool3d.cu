@@ -367,15 +367,15 @@ __global__ void __launch_bounds__(RGA_THREADS) roipool3d_assign_grid_kernel(int 
 // flat, the output IS the cnt x (3+C) source block repeated -- out[e] = block[e mod (cnt*(3+C))].  The block is staged in
 // shared memory once (coalesced row reads, canonical transform applied there) and streamed out with 128-bit stores;
 // boxes with more points than the staging area holds take the direct path (sources through L1).
-constexpr int RB_STAGE_FLOATS = 12 * 1024;   // 48 KB: 92 rows of 133 floats
+constexpr int RB_STAGE_FLOATS = 6 * 1024;    // 24 KB: 46 rows of 133 floats (more resident CTAs than with 48 KB; fuller boxes take the direct path)
 
 __global__ void __launch_bounds__(RP_THREADS) roipool3d_copy_kernel(int N, int M, int C, int S, const float *__restrict__ xyz,
                                                                     const float *__restrict__ pts_feature,
                                                                     const int *__restrict__ idx_in, const int *__restrict__ cnt_in,
                                                                     float *__restrict__ pooled, int *__restrict__ empty_flag,
-                                                                    const float *__restrict__ rois, int zero_fill) {
-    extern __shared__ float s_blk[];          // RB_STAGE_FLOATS floats, then S ints (direct path)
-    int *s_idx = reinterpret_cast<int *>(s_blk + RB_STAGE_FLOATS);
+                                                                    const float *__restrict__ rois, int zero_fill, int stage_floats) {
+    extern __shared__ float s_blk[];          // stage_floats floats, then S ints (direct path)
+    int *s_idx = reinterpret_cast<int *>(s_blk + stage_floats);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int box = blockIdx.x, scene = blockIdx.y;
     const size_t bi = (size_t)scene * M + box;
@@ -384,6 +384,10 @@ __global__ void __launch_bounds__(RP_THREADS) roipool3d_copy_kernel(int N, int M
     const long total = (long)S * W;
     float *dst = pooled + bi * (size_t)total;
     const bool vec = (total & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    // a box's output is dealt to gridDim.z CTAs (contiguous ranges of the flat row stream): twice the CTAs, half the tail
+    const int part = blockIdx.z, nparts = gridDim.z;
+    const long e_lo = vec ? 4 * ((total / 4) * part / nparts) : total * part / nparts;
+    const long e_hi = vec ? 4 * ((total / 4) * (part + 1) / nparts) : total * (part + 1) / nparts;
     // canonical transform constants (rcnn_net.py:146-152): xyz -= roi centre, rotate (x,z) by roi ry
     float rcx = 0.f, rcy = 0.f, rcz = 0.f, rcos = 1.f, rsin = 0.f;
     if (rois) {
@@ -397,23 +401,23 @@ __global__ void __launch_bounds__(RP_THREADS) roipool3d_copy_kernel(int N, int M
         return col == 0 ? __fmaf_rn(x, rcos, -__fmul_rn(z, rsin)) : (col == 1 ? y : __fmaf_rn(x, rsin, __fmul_rn(z, rcos)));
     };
     if (cnt == 0) {
-        if (tid == 0) empty_flag[bi] = 1;
+        if (tid == 0 && part == 0) empty_flag[bi] = 1;
         // The reference leaves the rows of an empty box zero -- and then applies the canonical transform to those zeros too
         // (rcnn_net.py:146-152 runs over every RoI).  With the transform fused, an empty box's xyz columns get the
         // transformed origin; without it the rows are zero-filled on request or left to the caller's memset.
         if (rois) {
             const float ex = canon(0.f, 0.f, 0.f, 0), ey = canon(0.f, 0.f, 0.f, 1), ez = canon(0.f, 0.f, 0.f, 2);
-            for (long e = tid; e < total; e += RP_THREADS) { const int c = (int)(e % W); dst[e] = c == 0 ? ex : (c == 1 ? ey : (c == 2 ? ez : 0.f)); }
+            for (long e = e_lo + tid; e < e_hi; e += RP_THREADS) { const int c = (int)(e % W); dst[e] = c == 0 ? ex : (c == 1 ? ey : (c == 2 ? ez : 0.f)); }
         } else if (zero_fill) {
-            if (vec) for (long e = 4L * tid; e < total; e += 4L * RP_THREADS) *reinterpret_cast<float4 *>(dst + e) = make_float4(0.f, 0.f, 0.f, 0.f);
-            else for (long e = tid; e < total; e += RP_THREADS) dst[e] = 0.f;
+            if (vec) for (long e = e_lo + 4L * tid; e < e_hi; e += 4L * RP_THREADS) *reinterpret_cast<float4 *>(dst + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+            else for (long e = e_lo + tid; e < e_hi; e += RP_THREADS) dst[e] = 0.f;
         }
         return;
     }
     const float *pts = xyz + (size_t)scene * N * 3;
     const float *feat = pts_feature + (size_t)scene * N * C;
     const int *idx = idx_in + bi * S;
-    if ((long)cnt * W <= RB_STAGE_FLOATS && vec) {
+    if ((long)cnt * W <= stage_floats && vec) {
         // ---- stage the cnt distinct rows (warp per row, lanes along the row), then stream the block cyclically
         for (int j = warp; j < cnt; j += RP_WARPS) {
             const int k = idx[j];
@@ -428,8 +432,8 @@ __global__ void __launch_bounds__(RP_THREADS) roipool3d_copy_kernel(int N, int M
         __syncthreads();
         const int P = cnt * W;                       // period of the output, in floats
         const int step = (4 * RP_THREADS) % P;
-        int m = (4 * tid) % P;
-        for (long e = 4L * tid; e < total; e += 4L * RP_THREADS) {
+        int m = (int)((e_lo + 4 * tid) % P);
+        for (long e = e_lo + 4L * tid; e < e_hi; e += 4L * RP_THREADS) {
             float4 v;
             if (m + 3 < P) {
                 v = make_float4(s_blk[m], s_blk[m + 1], s_blk[m + 2], s_blk[m + 3]);
@@ -458,8 +462,8 @@ __global__ void __launch_bounds__(RP_THREADS) roipool3d_copy_kernel(int N, int M
         // thread t owns float4 units t, t + T, ...: (row, col) of the unit's first float advance by a constant stride
         const int step = 4 * RP_THREADS;
         const int d_row = step / W, d_col = step % W;
-        int row = (4 * tid) / W, col = (4 * tid) % W;
-        for (long e = 4L * tid; e < total; e += step) {
+        int row = (int)((e_lo + 4 * tid) / W), col = (int)((e_lo + 4 * tid) % W);
+        for (long e = e_lo + 4L * tid; e < e_hi; e += step) {
             float v[4];
             int r = row, c = col;
 #pragma unroll
@@ -472,7 +476,7 @@ __global__ void __launch_bounds__(RP_THREADS) roipool3d_copy_kernel(int N, int M
             if (col >= W) { col -= W; ++row; }
         }
     } else {
-        for (long e = tid; e < total; e += RP_THREADS) dst[e] = value((int)(e / W), (int)(e % W));
+        for (long e = e_lo + tid; e < e_hi; e += RP_THREADS) dst[e] = value((int)(e / W), (int)(e % W));
     }
 }
 
@@ -496,7 +500,13 @@ extern "C" int prb_roipool3d_ws(int B, int N, int M, int C, int S, const float *
     PRB_REQUIRE(workspace && workspace_bytes >= prb_roipool3d_workspace_bytes(B, N, M, S), "roipool3d: workspace too small");
     const bool small_idx = N <= 65536;
     const size_t smem_a = (size_t)RA_BOXES * RA_WARPS * S * (small_idx ? sizeof(unsigned short) : sizeof(int));
-    const size_t smem_b = (size_t)RB_STAGE_FLOATS * sizeof(float) + (size_t)S * sizeof(int);
+    // staging area of pass B: boxes whose distinct rows do not fit take the direct path; a smaller area = more resident CTAs
+    int stage_kb = opts().roipool_stage_kb;
+    if (stage_kb < 8 || stage_kb > 160) stage_kb = RB_STAGE_FLOATS * 4 / 1024;     // measured at C4 (profiles/r2_notes.md): 16 KB 0.130 ms, 24 KB 0.132, 48 KB 0.136, 64 KB 0.144
+    const int stage_floats = stage_kb * 256;
+    int parts = opts().roipool_parts;
+    if (parts < 1 || parts > 8) parts = 1;                                           // 2-4 CTAs per box: 0.134-0.140 ms (no gain)
+    const size_t smem_b = (size_t)stage_floats * sizeof(float) + (size_t)S * sizeof(int);
     PRB_REQUIRE(smem_a <= 200 * 1024 && smem_b <= 200 * 1024, "roipool3d: sampled_pts_num %d too large", S);
     int *idx = reinterpret_cast<int *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     int *cnt = idx + (size_t)B * M * S;
@@ -522,8 +532,8 @@ extern "C" int prb_roipool3d_ws(int B, int N, int M, int C, int S, const float *
     if (int rc = check_launch("roipool3d_assign_kernel")) return rc;   // (no launch since the last check on the binned path: returns 0)
     if (smem_b > 48 * 1024)
         PRB_CUDA(cudaFuncSetAttribute(roipool3d_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-    roipool3d_copy_kernel<<<dim3(M, B), RP_THREADS, smem_b, st>>>(N, M, C, S, xyz, pts_feature, idx, cnt, pooled, empty_flag,
-                                                                 rois_canonical, zero_fill_empty);
+    roipool3d_copy_kernel<<<dim3(M, B, parts), RP_THREADS, smem_b, st>>>(N, M, C, S, xyz, pts_feature, idx, cnt, pooled, empty_flag,
+                                                                        rois_canonical, zero_fill_empty, stage_floats);
     return check_launch("roipool3d_copy_kernel");
 }
 

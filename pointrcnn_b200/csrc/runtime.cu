@@ -57,6 +57,8 @@ static prb_options make_defaults() {
     o.mlp_pool = env_int("PRB_MLP_POOL", 0);
     o.mlp_tune = env_int("PRB_MLP_TUNE", 1);
     o.roipool_exhaustive = env_int("PRB_ROIPOOL_EXHAUSTIVE", 0);
+    o.roipool_parts = env_int("PRB_ROIPOOL_PARTS", 0);
+    o.roipool_stage_kb = env_int("PRB_ROIPOOL_STAGE_KB", 0);
     o.grid_csr = env_int("PRB_GRID_CSR", 0);
     o.grid_debug = env_int("PRB_GRID_DEBUG", 0);
     o.nn_cell = 1.6f;
