@@ -490,9 +490,12 @@ __device__ __forceinline__ float redux_min_f32(float v) {
         if (lane == (J)) { gval = mx; gpay = mp; }                                                           \
     } break;
 
-template <int NS>
-__global__ void __launch_bounds__(512, 1) fps_pruned_kernel(const FpsParams p, const FpsSorted s) {
-    constexpr int W = 16;
+// W warps x NS slots per lane cover the W * NS groups of a scene: <32,16> is the default for 16384 points.  <16,32> (1024
+// threads, prb_options.fps_threads = 1024: fewer touched slots on the busiest warp but a wider CTA arg-max and twice the
+// instruction issue per round) measured SLOWER: 543 vs 490 ns per round at 16 x 16384 -> 4096, 499 vs 425 at 8192 -> 2048
+// (profiles/r2_notes.md): the round is bound by the fixed arg-max / barrier chain, not by the slot updates.
+template <int NS, int W>
+__global__ void __launch_bounds__(32 * W, 1) fps_pruned_kernel(const FpsParams p, const FpsSorted s) {
     constexpr int NP = W * NS * 32;
     extern __shared__ __align__(16) float s_pl[];       // three planes of NP floats
     __shared__ uint2 s_w[2][W];                         // per-warp winner {temp bits, (0x3fff - rank) << 14 | position}
@@ -507,7 +510,7 @@ __global__ void __launch_bounds__(512, 1) fps_pruned_kernel(const FpsParams p, c
         const float4 *gx = reinterpret_cast<const float4 *>(s.sx + (size_t)scene * NP);
         const float4 *gy = reinterpret_cast<const float4 *>(s.sy + (size_t)scene * NP);
         const float4 *gz = reinterpret_cast<const float4 *>(s.sz + (size_t)scene * NP);
-        for (int i = tid; i < NP / 4; i += 512) {
+        for (int i = tid; i < NP / 4; i += 32 * W) {
             reinterpret_cast<float4 *>(px)[i] = gx[i];
             reinterpret_cast<float4 *>(py)[i] = gy[i];
             reinterpret_cast<float4 *>(pz)[i] = gz[i];
@@ -586,7 +589,7 @@ __global__ void __launch_bounds__(512, 1) fps_pruned_kernel(const FpsParams p, c
         }
     }
     __syncthreads();
-    for (int j = tid; j < m; j += 512) idx[j] = rank_to_k(idx[j], p.S, p.logS, p.Q);
+    for (int j = tid; j < m; j += 32 * W) idx[j] = rank_to_k(idx[j], p.S, p.logS, p.Q);
 }
 #undef PRB_FPS_SLOT
 
@@ -604,14 +607,14 @@ static int pruned_slots(int n) {
     return 0;
 }
 
-template <int NS>
+template <int NS, int W>
 static int launch_pruned(const FpsParams &p, const FpsSorted &s, cudaStream_t st) {
-    const size_t smem = (size_t)3 * 16 * NS * 32 * sizeof(float);
+    const size_t smem = (size_t)3 * W * NS * 32 * sizeof(float);
     if (smem + 1024 > 48 * 1024)
-        PRB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PRB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<NS, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fps_sort_kernel<<<p.b, 1024, 0, st>>>(p, s);
     if (int rc = check_launch("fps_sort_kernel")) return rc;
-    fps_pruned_kernel<NS><<<p.b, 512, smem, st>>>(p, s);
+    fps_pruned_kernel<NS, W><<<p.b, 32 * W, smem, st>>>(p, s);
     return check_launch("fps_pruned_kernel");
 }
 
@@ -647,10 +650,11 @@ extern "C" int prb_furthest_point_sampling_ws(int b, int n, int m, const float *
         s.sx = w; s.sy = w + b * np; s.sz = w + 2 * b * np; s.st = w + 3 * b * np;
         s.srank = reinterpret_cast<int *>(w + 4 * b * np);
         s.np = (int)np;
+        const int thr = opts().fps_threads;            // 0 / 512: 16 warps (default); 1024: 32 warps x half the slots
         switch (ns) {
-            case 8: return launch_pruned<8>(p, s, st);
-            case 16: return launch_pruned<16>(p, s, st);
-            default: return launch_pruned<32>(p, s, st);
+            case 8: return thr == 1024 ? launch_pruned<4, 32>(p, s, st) : launch_pruned<8, 16>(p, s, st);
+            case 16: return thr == 1024 ? launch_pruned<8, 32>(p, s, st) : launch_pruned<16, 16>(p, s, st);
+            default: return thr == 1024 ? launch_pruned<16, 32>(p, s, st) : launch_pruned<32, 16>(p, s, st);
         }
     }
 

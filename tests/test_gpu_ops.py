@@ -71,7 +71,8 @@ def test_fps_index_exact(cuda, B, N, M, kind):
 
 
 @pytest.mark.parametrize("opt", [{"fps_cluster": 1}, {"fps_cluster": 2}, {"fps_cluster": 4}, {"fps_cluster": 8},
-                                 {"fps_generic": 1}, {"fps_cluster": 1, "fps_threads": 1024}, {"fps_prune": 1}])
+                                 {"fps_generic": 1}, {"fps_cluster": 1, "fps_threads": 1024}, {"fps_prune": 1},
+                                 {"fps_prune": 2, "fps_threads": 1024}])     # pruned kernel, 32 warps x half the slots
 def test_fps_all_kernel_variants_agree(cuda, opt):
     from pointrcnn_b200 import _cabi
     xyz = synth.dup_cloud(2, 8192, 5, unique=3000)
