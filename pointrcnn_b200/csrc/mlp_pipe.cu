@@ -1058,7 +1058,7 @@ static bool pipe_plan(const ChainParams &p, int max_optin, PipePlan *out, int fo
                 // fraction of the GPU with one long K loop per CTA)
                 nsplit = (np_last + 255) / 256;
                 const int want = (num_sms() + p.num_tiles - 1) / p.num_tiles;
-                if (want > nsplit) nsplit = want;
+                if (want > nsplit && o.mlp_fill) nsplit = want;
                 if (nsplit > np_last / 64) nsplit = np_last / 64 > 0 ? np_last / 64 : 1;
                 if (nsplit < (np_last + 255) / 256) nsplit = (np_last + 255) / 256;
                 if (o.mlp_zs >= 32 && o.mlp_zs < np_last) nsplit = (np_last + o.mlp_zs - 1) / o.mlp_zs;

@@ -55,6 +55,7 @@ static prb_options make_defaults() {
     o.mlp_nbuf = env_int("PRB_MLP_NBUF", 0);
     o.mlp_brows = env_int("PRB_MLP_BROWS", 0);
     o.mlp_pool = env_int("PRB_MLP_POOL", 0);
+    o.mlp_fill = env_int("PRB_MLP_FILL", 1);
     o.mlp_tune = env_int("PRB_MLP_TUNE", 1);
     o.roipool_exhaustive = env_int("PRB_ROIPOOL_EXHAUSTIVE", 0);
     o.roipool_parts = env_int("PRB_ROIPOOL_PARTS", 0);

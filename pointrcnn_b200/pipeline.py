@@ -46,7 +46,17 @@ class BatchPipeline:
 
     # ------------------------------------------------------------------ one batch on one slot
     def _forward(self, slot, x):
-        """run fn on x (already on the slot's stream); returns the output tuple"""
+        """run fn on x (already on the slot's stream); returns the output tuple.
+        With several batches in flight the library runs in THROUGHPUT mode (`prb_options.mlp_fill = 0`): small single-layer
+        chain launches are not dealt to extra column groups just to fill idle SMs -- those SMs belong to the other batches
+        (+1.2 % at 16 scenes per batch, profiles/r2_notes.md; baked into the graph at capture)."""
+        from . import _cabi
+        if len(self.slots) > 1 and _cabi.lib() is not None:
+            with _cabi.options(mlp_fill=0):
+                return self._forward_impl(slot, x)
+        return self._forward_impl(slot, x)
+
+    def _forward_impl(self, slot, x):
         if not self.graphs:
             out = self.fn(x)
             return out if isinstance(out, (tuple, list)) else (out,)
