@@ -225,6 +225,30 @@ __global__ void __launch_bounds__(GR_THREADS) ball_query_grid_kernel(const GridB
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         int *out = p.idx[r] + ((size_t)scene * p.m + centre) * p.ns[r];
+        if (cnt <= 32) {
+            // the common case (ncu: one 32-candidate chunk per centre, where the all-pairs ranking below costs ~245
+            // instructions per radius): a 15-stage bitonic sort of the hit indices across the warp; lane k then HOLDS rank k
+            int v = 0x7fffffff;
+            if (lane < cnt) {
+                const int k = s_cand[warp][lane];
+                const float d2 = dist2_ref(cx - xyz[(size_t)k * 3], cy - xyz[(size_t)k * 3 + 1], cz - xyz[(size_t)k * 3 + 2]);
+                if (d2 < p.r2[r]) v = k;
+            }
+#pragma unroll
+            for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    const int o = __shfl_xor_sync(0xffffffffu, v, j);
+                    const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
+                    v = keep_min ? min(v, o) : max(v, o);
+                }
+            const int nh = __popc(__ballot_sync(0xffffffffu, v != 0x7fffffff));
+            const int first = __shfl_sync(0xffffffffu, v, 0);
+            if (lane < nh && lane < p.ns[r]) out[lane] = v;
+            if (nh > 0)
+                for (int sl = nh + lane; sl < p.ns[r]; sl += 32) out[sl] = first;
+            continue;
+        }
         int nh = 0, first = 0x7fffffff;
         for (int c0 = 0; c0 < cnt; c0 += 32) {
             const int c = c0 + lane;
@@ -394,6 +418,7 @@ struct GridNnParams {
     GridView g;
     const float *h;     // (b) cell edge
     int *overflow;      // [0] = count, [1..] = scene*n + unknown index
+    const float4 *qnodes;   // optional: the queries grouped by hash bucket, {x, y, z, query index} (see prb_three_nn_grid)
 };
 
 __device__ __forceinline__ void nn_insert(float d, int k, float &b1, float &b2, float &b3, int &i1, int &i2, int &i3) {
@@ -422,10 +447,17 @@ __device__ __forceinline__ void nn_store(const GridNnParams &p, size_t o, float 
 
 __global__ void __launch_bounds__(GR_THREADS) three_nn_grid_kernel(const GridNnParams p) {
     const int scene = blockIdx.y;
-    const int u = blockIdx.x * GR_THREADS + threadIdx.x;
-    if (u >= p.n) return;
-    const float *q = p.unknown + ((size_t)scene * p.n + u) * 3;
-    const float ux = q[0], uy = q[1], uz = q[2];
+    const int t_ = blockIdx.x * GR_THREADS + threadIdx.x;
+    if (t_ >= p.n) return;
+    int u = t_;
+    float ux, uy, uz;
+    if (p.qnodes) {          // queries in cell order: the lanes of a warp walk the same few buckets (L1 hits instead of L2 sectors)
+        const float4 qn = __ldg(p.qnodes + (size_t)scene * p.n + t_);
+        ux = qn.x; uy = qn.y; uz = qn.z; u = __float_as_int(qn.w);
+    } else {
+        const float *q = p.unknown + ((size_t)scene * p.n + u) * 3;
+        ux = q[0]; uy = q[1]; uz = q[2];
+    }
     const float4 *nodes = p.g.nodes + (size_t)scene * p.m;
     const int *heads = p.g.heads + (size_t)scene * p.g.table_size;
     const double ih = p.g.inv_h[scene];
@@ -468,6 +500,90 @@ __global__ void __launch_bounds__(GR_THREADS) three_nn_grid_kernel(const GridNnP
             if (++walked > 2048) over = true;
         }
     }
+    const float hb = p.h[scene] * 0.9999f;
+    if (over || !(b3 < hb * hb)) {   // something outside the 3x3x3 block could be closer (or tie): brute force decides
+        p.overflow[1 + atomicAdd(p.overflow, 1)] = scene * p.n + u;
+        return;
+    }
+    nn_store(p, ((size_t)scene * p.n + u) * 3, b1, b2, b3, i1, i2, i3);
+}
+
+// The same search as ONE convergent loop per lane (prb_options.nn_walk = 1; MEASURED SLOWER, see the end of this comment).
+// ncu on the kernel above at the
+// finest RPN level (262144 queries): issue slots 78 % busy with 7 of 32 lanes active per instruction -- 27 unrolled cell
+// bodies, each with its own list walk, so lanes that skip a cell or walk a shorter list idle through everybody else's code.
+// Here a lane keeps a cursor (next cell in centre-out order, current node): every iteration either advances the cursor to
+// the next cell that can still hold a better neighbour, or processes one node; all lanes run the same short body.  Bucket
+// heads live in shared memory ([cell][thread], conflict free), the visiting order in a 27-entry shared table.  Same cells,
+// same order per query, same pruning and certification: identical results.
+// Result (profiles/r2_notes.md): 3-NN family 0.474 ms against 0.260 ms for the unrolled kernel.  The divergence of the
+// unrolled form is not waste: with independent thread scheduling the diverged lane groups of a warp cover each other's
+// dependent L2 loads like extra warps would; the convergent loop waits for every load with all 32 lanes.
+__global__ void __launch_bounds__(GR_THREADS) three_nn_walk_kernel(const GridNnParams p) {
+    __shared__ int s_hd[27][GR_THREADS];
+    __shared__ int s_order[27];
+    const int scene = blockIdx.y, tid = threadIdx.x;
+    const int t_ = blockIdx.x * GR_THREADS + tid;
+    if (tid < 27) {
+        constexpr int kOrder[27] = {13, 12, 14, 10, 16, 4, 22, 9, 11, 15, 17, 3, 5, 21, 23, 1, 7, 19, 25, 0, 2, 6, 8, 18, 20, 24, 26};
+        int v = 0;
+#pragma unroll
+        for (int i = 0; i < 27; ++i) v = tid == i ? kOrder[i] : v;
+        s_order[tid] = v;
+    }
+    const bool live = t_ < p.n;
+    int u = live ? t_ : 0;
+    float ux = 0.f, uy = 0.f, uz = 0.f;
+    if (live) {
+        if (p.qnodes) {
+            const float4 qn = __ldg(p.qnodes + (size_t)scene * p.n + t_);
+            ux = qn.x; uy = qn.y; uz = qn.z; u = __float_as_int(qn.w);
+        } else {
+            const float *q = p.unknown + ((size_t)scene * p.n + u) * 3;
+            ux = q[0]; uy = q[1]; uz = q[2];
+        }
+    }
+    const float4 *nodes = p.g.nodes + (size_t)scene * p.m;
+    const int *heads = p.g.heads + (size_t)scene * p.g.table_size;
+    const double ih = p.g.inv_h[scene];
+    const int cx = cell_coord(ux, ih), cy = cell_coord(uy, ih), cz = cell_coord(uz, ih);
+#pragma unroll
+    for (int c = 0; c < 27; ++c)
+        s_hd[c][tid] = live ? __ldg(heads + cell_hash(cx + c % 3 - 1, cy + (c / 3) % 3 - 1, cz + c / 9 - 1, p.g.table_size - 1)) : -1;
+    float glo[3], ghi[3];         // squared gaps to the low / high faces of my cell (0 for the middle slab)
+    {
+        const double hd_ = 1.0 / ih;
+        const double f[3] = {(double)ux - (double)cx * hd_, (double)uy - (double)cy * hd_, (double)uz - (double)cz * hd_};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float lo = (float)fmax(f[a] - 1e-9, 0.0) * 0.999f, hi = (float)fmax(hd_ - f[a] - 1e-9, 0.0) * 0.999f;
+            glo[a] = lo * lo; ghi[a] = hi * hi;
+        }
+    }
+    __syncthreads();
+    float b1 = CUDART_INF_F, b2 = CUDART_INF_F, b3 = CUDART_INF_F;
+    int i1 = -1, i2 = -1, i3 = -1;
+    int walked = 0, t = 0, j = -1;
+    bool over = false, done = !live;
+    while (!done) {
+        if (j < 0) {                         // next cell, centre-out, that can still hold a closer (or tying) point
+            while (t < 27) {
+                const int c = s_order[t++];
+                const int ox = c % 3, oy = (c / 3) % 3, oz = c / 9;
+                const float lb = (ox == 0 ? glo[0] : ox == 2 ? ghi[0] : 0.f) + (oy == 0 ? glo[1] : oy == 2 ? ghi[1] : 0.f) +
+                                 (oz == 0 ? glo[2] : oz == 2 ? ghi[2] : 0.f);
+                if (lb > b3) continue;
+                j = s_hd[c][tid];
+                if (j >= 0) break;
+            }
+            if (j < 0) { done = true; continue; }
+        }
+        const float4 nd = __ldg(nodes + j);
+        nn_insert(dist2_ref(ux - nd.x, uy - nd.y, uz - nd.z), j, b1, b2, b3, i1, i2, i3);
+        j = __float_as_int(nd.w);
+        if (++walked > 2048) { over = true; done = true; }
+    }
+    if (!live) return;
     const float hb = p.h[scene] * 0.9999f;
     if (over || !(b3 < hb * hb)) {   // something outside the 3x3x3 block could be closer (or tie): brute force decides
         p.overflow[1 + atomicAdd(p.overflow, 1)] = scene * p.n + u;
@@ -604,13 +720,16 @@ struct GridWs {
     int table;
     int *heads, *overflow;
     float4 *nodes;
+    float4 *qnodes;     // (b, n_queries)
+    int2 *qrange;       // (b, table)
     double *inv_h;
     float *h;
 };
 
 static size_t grid_ws_bytes(int b, int n_points, int n_queries) {
     const size_t t = (size_t)table_size_for(n_points);
-    return (size_t)b * t * 8 + (size_t)b * n_points * 16 + ((size_t)b * n_queries + 64) * 4 + (size_t)b * 16 + 2048;   // t * 8: CSR ranges
+    // t * 8: CSR ranges (or list heads); second t * 8 + n_queries * 16: the queries grouped by bucket (three_nn)
+    return (size_t)b * t * 16 + (size_t)b * n_points * 16 + (size_t)b * n_queries * 16 + ((size_t)b * n_queries + 64) * 4 + (size_t)b * 16 + 4096;
 }
 
 static GridWs carve(void *ws, int b, int n_points, int n_queries) {
@@ -621,6 +740,8 @@ static GridWs carve(void *ws, int b, int n_points, int n_queries) {
     g.h = (float *)c; c += (((size_t)b * 4 + 255) & ~(size_t)255);
     g.nodes = (float4 *)c; c += (size_t)b * n_points * 16;
     g.heads = (int *)c; c += (size_t)b * g.table * 8;     // linked-list heads (int) or CSR ranges (int2) live here
+    g.qnodes = (float4 *)c; c += (size_t)b * n_queries * 16;
+    g.qrange = (int2 *)c; c += (size_t)b * g.table * 8;
     g.overflow = (int *)c;
     (void)n_queries;
     return g;
@@ -722,7 +843,19 @@ PRB_API int prb_three_nn_grid(int b, int n, int m, const float *unknown, const f
     GridNnParams p;
     p.b = b; p.n = n; p.m = m; p.unknown = unknown; p.known = known; p.dist2 = dist2; p.weight = weight; p.idx = idx;
     p.g = view_of(w, csr); p.h = w.h; p.overflow = w.overflow;
+    p.qnodes = nullptr;
+    if (!csr && w.table <= GB_MAX_TABLE && opts().nn_sort_queries) {
+        // group the QUERIES by hash bucket of the same grid (counting sort, one CTA per scene): a warp then holds queries of one
+        // or two cells and its 27 head loads / node walks hit L1 instead of pulling one L2 sector per lane
+        const size_t smem = (size_t)w.table * sizeof(int);
+        if (smem > 48 * 1024)
+            PRB_CUDA(cudaFuncSetAttribute(grid_build_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        grid_build_csr_kernel<<<b, GB_THREADS, smem, st>>>(n, w.table, unknown, w.inv_h, w.qrange, w.qnodes);
+        if (int rc = check_launch("grid_build_csr_kernel(queries)")) return rc;
+        p.qnodes = w.qnodes;
+    }
     if (csr) three_nn_csr_kernel<<<dim3(ceil_div(n, GR_THREADS), b), GR_THREADS, 0, st>>>(p);
+    else if (opts().nn_walk == 1) three_nn_walk_kernel<<<dim3(ceil_div(n, GR_THREADS), b), GR_THREADS, 0, st>>>(p);
     else three_nn_grid_kernel<<<dim3(ceil_div(n, GR_THREADS), b), GR_THREADS, 0, st>>>(p);
     if (int rc = check_launch("three_nn_grid_kernel")) return rc;
     three_nn_overflow_kernel<<<4 * num_sms(), GR_THREADS, 0, st>>>(p);

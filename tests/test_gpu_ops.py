@@ -431,8 +431,9 @@ def test_ball_query_grid_path_exact(cuda, kind, N, M, radii, nss, csr):
 @pytest.mark.parametrize("cell", [None, 0.5, 4.0])     # default edge; tiny cells (most queries go to the exhaustive scan); big cells
 @pytest.mark.parametrize("kind,n,m", [("kitti", 8192, 2048), ("cube", 2000, 500), ("dup", 1024, 256), ("cube", 100, 5),
                                       ("kitti", 300, 3), ("dup", 4096, 64)])
-@pytest.mark.parametrize("csr", [0, 1])
-def test_three_nn_grid_path_exact(cuda, kind, n, m, cell, csr):
+@pytest.mark.parametrize("mode", ["sorted_queries", "plain", "cursor_loop", "csr"])     # queries grouped by cell; default; convergent cursor loop; CSR
+def test_three_nn_grid_path_exact(cuda, kind, n, m, cell, mode):
+    grid_opts = {"sorted_queries": {"nn_sort_queries": 1}, "plain": {}, "cursor_loop": {"nn_walk": 1}, "csr": {"grid_csr": 1}}[mode]
     unknown = _cloud(kind, 2, n, 61 + n)
     known = np.ascontiguousarray(unknown[:, ::max(1, n // m)][:, :m])
     if kind == "kitti":
@@ -442,7 +443,7 @@ def test_three_nn_grid_path_exact(cuda, kind, n, m, cell, csr):
     old = pu.GRID_MIN_POINTS_NN
     pu.GRID_MIN_POINTS_NN = 1
     try:
-        with _cabi.options(grid_csr=csr, **({} if cell is None else {"nn_cell": cell})):
+        with _cabi.options(**grid_opts, **({} if cell is None else {"nn_cell": cell})):
             got_d2, got_idx, w = pu.three_nn_weights(T(unknown, cuda), T(known, cuda))
     finally:
         pu.GRID_MIN_POINTS_NN = old
