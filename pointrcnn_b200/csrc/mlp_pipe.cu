@@ -1181,7 +1181,7 @@ static std::map<TuneKey, int> g_tune;      // -> winning build: 2 = two CTAs per
 
 static bool tuning_allowed(cudaStream_t st) {
     const prb_options &o = opts();
-    if (!o.mlp_tune || o.mlp_trace || o.mlp_occ || o.mlp_ne || o.mlp_ngw || o.mlp_zs || o.mlp_nbuf || o.mlp_sms) return false;
+    if (!o.mlp_tune || o.mlp_trace || o.mlp_occ || o.mlp_ne || o.mlp_ngw || o.mlp_zs || o.mlp_nbuf) return false;
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
     return cs == cudaStreamCaptureStatusNone;
