@@ -69,7 +69,8 @@ typedef struct prb_options {
                         * caches the faster one per device and shape; 0: rule-based plan only */
     int roipool_exhaustive;  /* 1: roipool3d pass A tests every point against every box (no x-z binning) */
     int roipool_parts;     /* roipool3d pass B: CTAs per box (1..8); 0 = 1 */
-    int roipool_stage_kb;  /* roipool3d pass B: shared staging area per CTA in KB (8..160); 0 = 24 */
+    int roipool_stage_kb;  /* roipool3d pass B: shared staging area per CTA in KB (8..160); 0 = 48 */
+    int roipool_direct;    /* 1: roipool3d pass B takes boxes with many rows through scalar L1 gathers (first version) instead of chunked staging */
     int nn_walk;           /* three_nn on the grid: 0 = 27 unrolled cell walks (default), 1 = one convergent cursor loop per lane (slower) */
     int nn_sort_queries;   /* 1: three_nn groups the queries by grid cell before the search; measured: the sort costs what the locality saves */
     int grid_csr;      /* 1: hash grid as CSR runs (counting sort per scene) instead of linked lists; slower at the RPN shapes */

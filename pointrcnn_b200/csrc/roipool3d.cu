@@ -367,13 +367,14 @@ __global__ void __launch_bounds__(RGA_THREADS) roipool3d_assign_grid_kernel(int 
 // flat, the output IS the cnt x (3+C) source block repeated -- out[e] = block[e mod (cnt*(3+C))].  The block is staged in
 // shared memory once (coalesced row reads, canonical transform applied there) and streamed out with 128-bit stores;
 // boxes with more points than the staging area holds take the direct path (sources through L1).
-constexpr int RB_STAGE_FLOATS = 6 * 1024;    // 24 KB: 46 rows of 133 floats (more resident CTAs than with 48 KB; fuller boxes take the direct path)
+constexpr int RB_STAGE_FLOATS = 12 * 1024;   // 48 KB: 92 rows of 133 floats.  Data dependent (profiles/r2_notes.md): 24 KB is 3 % faster when boxes
+                                             // hold a few points, 48 KB 20 % faster with ~60 points per enlarged RoI (the RCNN stage's regime)
 
 __global__ void __launch_bounds__(RP_THREADS) roipool3d_copy_kernel(int N, int M, int C, int S, const float *__restrict__ xyz,
                                                                     const float *__restrict__ pts_feature,
                                                                     const int *__restrict__ idx_in, const int *__restrict__ cnt_in,
                                                                     float *__restrict__ pooled, int *__restrict__ empty_flag,
-                                                                    const float *__restrict__ rois, int zero_fill, int stage_floats) {
+                                                                    const float *__restrict__ rois, int zero_fill, int stage_floats, int opts_chunked) {
     extern __shared__ float s_blk[];          // stage_floats floats, then S ints (direct path)
     int *s_idx = reinterpret_cast<int *>(s_blk + stage_floats);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -458,7 +459,34 @@ __global__ void __launch_bounds__(RP_THREADS) roipool3d_copy_kernel(int N, int M
         if (!rois) return __ldg(pts + (size_t)k * 3 + col);
         return canon(__ldg(pts + (size_t)k * 3), __ldg(pts + (size_t)k * 3 + 1), __ldg(pts + (size_t)k * 3 + 2), col);
     };
-    if (vec) {
+    if (vec && W <= stage_floats / 2 && opts_chunked) {
+        // ---- chunked staging (boxes with more distinct rows than the staging area holds: the regime of real RoIs, ~60 and
+        // more points per enlarged box): the output is produced in pieces of CH rows -- gather the piece's rows into shared
+        // memory (warp per row, coalesced), stream the piece out with 128-bit stores -- instead of assembling every float4
+        // from four scalar loads through L1.  Pieces are cut at multiples of 4 floats, so a piece needs one row more than
+        // its length.
+        const int CH = stage_floats / W - 1;                    // whole rows per piece (>= 1)
+        const long piece = ((long)CH * W) & ~3L;
+        for (long f0 = e_lo; f0 < e_hi; f0 += piece) {
+            const long f1 = f0 + piece < e_hi ? f0 + piece : e_hi;
+            const int r0 = (int)(f0 / W), r1 = (int)((f1 - 1) / W);
+            __syncthreads();                                     // the previous piece has been streamed out
+            for (int j = r0 + warp; j <= r1; j += RP_WARPS) {
+                const int k = s_idx[j];
+                float *row = s_blk + (size_t)(j - r0) * W;
+                if (lane < 3) {
+                    const float px = __ldg(pts + (size_t)k * 3), py = __ldg(pts + (size_t)k * 3 + 1), pz = __ldg(pts + (size_t)k * 3 + 2);
+                    row[lane] = rois ? canon(px, py, pz, lane) : (lane == 0 ? px : (lane == 1 ? py : pz));
+                }
+                const float *f = feat + (size_t)k * C;
+                for (int c = lane; c < C; c += 32) row[3 + c] = __ldg(f + c);
+            }
+            __syncthreads();
+            const float *src = s_blk - (size_t)r0 * W;           // src[e] is output element e of this box
+            for (long e = f0 + 4L * tid; e < f1; e += 4L * RP_THREADS)
+                *reinterpret_cast<float4 *>(dst + e) = make_float4(src[e], src[e + 1], src[e + 2], src[e + 3]);
+        }
+    } else if (vec) {
         // thread t owns float4 units t, t + T, ...: (row, col) of the unit's first float advance by a constant stride
         const int step = 4 * RP_THREADS;
         const int d_row = step / W, d_col = step % W;
@@ -502,7 +530,7 @@ extern "C" int prb_roipool3d_ws(int B, int N, int M, int C, int S, const float *
     const size_t smem_a = (size_t)RA_BOXES * RA_WARPS * S * (small_idx ? sizeof(unsigned short) : sizeof(int));
     // staging area of pass B: boxes whose distinct rows do not fit take the direct path; a smaller area = more resident CTAs
     int stage_kb = opts().roipool_stage_kb;
-    if (stage_kb < 8 || stage_kb > 160) stage_kb = RB_STAGE_FLOATS * 4 / 1024;     // measured at C4 (profiles/r2_notes.md): 16 KB 0.130 ms, 24 KB 0.132, 48 KB 0.136, 64 KB 0.144
+    if (stage_kb < 8 || stage_kb > 160) stage_kb = RB_STAGE_FLOATS * 4 / 1024;
     const int stage_floats = stage_kb * 256;
     int parts = opts().roipool_parts;
     if (parts < 1 || parts > 8) parts = 1;                                           // 2-4 CTAs per box: 0.134-0.140 ms (no gain)
@@ -533,7 +561,7 @@ extern "C" int prb_roipool3d_ws(int B, int N, int M, int C, int S, const float *
     if (smem_b > 48 * 1024)
         PRB_CUDA(cudaFuncSetAttribute(roipool3d_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     roipool3d_copy_kernel<<<dim3(M, B, parts), RP_THREADS, smem_b, st>>>(N, M, C, S, xyz, pts_feature, idx, cnt, pooled, empty_flag,
-                                                                        rois_canonical, zero_fill_empty, stage_floats);
+                                                                        rois_canonical, zero_fill_empty, stage_floats, opts().roipool_direct ? 0 : 1);
     return check_launch("roipool3d_copy_kernel");
 }
 

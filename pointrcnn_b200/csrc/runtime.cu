@@ -60,6 +60,7 @@ static prb_options make_defaults() {
     o.roipool_exhaustive = env_int("PRB_ROIPOOL_EXHAUSTIVE", 0);
     o.roipool_parts = env_int("PRB_ROIPOOL_PARTS", 0);
     o.roipool_stage_kb = env_int("PRB_ROIPOOL_STAGE_KB", 0);
+    o.roipool_direct = env_int("PRB_ROIPOOL_DIRECT", 0);
     o.nn_walk = env_int("PRB_NN_WALK", 0);
     o.nn_sort_queries = env_int("PRB_NN_SORT_QUERIES", 0);
     o.grid_csr = env_int("PRB_GRID_CSR", 0);

@@ -255,6 +255,12 @@ def test_roipool3d_vs_reference_and_oracle(cuda, B, N, M, C, S):
     pooled = torch.zeros((B, M, S, 3 + C), device=cuda)
     empty = torch.zeros((B, M), dtype=torch.int32, device=cuda)
     roipool3d_cuda.forward(x, bx, f, pooled, empty)
+    from pointrcnn_b200 import _cabi
+    for alt in ({"roipool_direct": 1}, {"roipool_stage_kb": 8}, {"roipool_parts": 3}):   # scalar-gather path; tiny staging area
+        p2 = torch.zeros_like(pooled); e2 = torch.zeros_like(empty)                       # (every box chunked); 3 CTAs per box
+        with _cabi.options(**alt):
+            roipool3d_cuda.forward(x, bx, f, p2, e2)
+        assert torch.equal(p2, pooled) and torch.equal(e2, empty), "pass-B variant %r differs" % alt
     if HAVE_REF and C > 0:
         rp, re = R.roipool3d(x, f, bx, S)
         assert torch.equal(empty, re), "empty flags differ from the reference kernel"
