@@ -256,14 +256,16 @@ def tuned_plans():
     """measured build choice per chain shape (prb_debug_tuned_plans): CTAs per SM of the faster build"""
     import ctypes
     from pointrcnn_b200 import _cabi
-    buf = (ctypes.c_int * (10 * 64))()
+    buf = (ctypes.c_int * (18 * 64))()
     n = _cabi.lib().prb_debug_tuned_plans(buf, 64)
     kinds_in, kinds_out = ("sa", "fp", "rows"), ("rows", "sa_max", "fp")
+    builds = {2: "2 CTAs x (4 epilogue + 4 gather warps)", 1: "1 CTA x (8 + 8)", 3: "1 CTA x (8 + 12)", 4: "3 CTAs x (4 + 4)"}
     out = []
     for i in range(n):
-        r = buf[10 * i:10 * i + 10]
+        r = buf[18 * i:18 * i + 18]
         out.append({"in": kinds_in[r[0]], "out": kinds_out[r[1]], "nsample": r[3], "k_chunks": r[4], "tiles": r[5],
-                    "np": [x for x in r[6:6 + r[2]]], "build": {2: "2 CTAs x (4 epilogue + 4 gather warps)", 1: "1 CTA x (8 + 8)", 3: "1 CTA x (8 + 12)"}.get(r[9], r[9])})
+                    "np": [x for x in r[6:6 + r[2]]], "build": builds.get(r[9], r[9]),
+                    "measured_us": {builds.get(r[10 + 2 * c], r[10 + 2 * c]): r[11 + 2 * c] for c in range(4) if r[10 + 2 * c]}})
     return out
 
 

@@ -52,7 +52,7 @@ typedef struct prb_options {
     int fps_generic;   /* 1: force the generic (reference-shaped) kernel */
     int mlp_gather;    /* layer-0 row gather of the chain kernel: 0 registers (+tf32 rounding), 1 cp.async.cg, 2 cp.async.ca */
     int mlp_ng;        /* row groups per CTA (legacy kernel); 0 = heuristic */
-    int mlp_occ;       /* cap on CTAs per SM; 0 = none */
+    int mlp_occ;       /* 1: one CTA per SM; 3: the three-CTA build where it applies (narrow SA chains); 0 = plan rule / measured */
     int mlp_sms;       /* size the persistent grid for this many SMs; 0 = all */
     int mlp_atmem;     /* 1: layers >= 1 take their A operand from tensor memory (legacy kernel) */
     int mlp_sleepy;    /* bit 0: MMA issuer waits with a suspend hint, bit 1: weight producer does */
@@ -234,8 +234,9 @@ PRB_API int prb_debug_mlp_trace(long long *dst);
  * {z_free, ready, b1_full, fence, mma issue, commit}, weight producer 0 {b0_empty}, producer 1 {b1_empty}, gather warp 0
  * {a_empty}, epilogue warp 0 {r_full, z_full} */
 PRB_API int prb_debug_pipe_trace(long long *dst);
-/* measured plan choices so far: up to max_entries rows of 10 ints {mode_in, mode_out, layers, nsample, K chunks of layer 0,
- * tiles, np0, np1, np2, winning build: 2 = two CTAs per SM (4 epilogue + 4 gather warps), 1 = one CTA 8 + 8, 3 = one CTA 8 + 12}; returns the number of rows */
+/* measured plan choices so far: up to max_entries rows of 18 ints {mode_in, mode_out, layers, nsample, K chunks of layer 0,
+ * tiles, np0, np1, np2, winning build, then 4 x (candidate build, measured microseconds; 0 = no candidate)}; builds: 2 = two
+ * CTAs per SM (4 epilogue + 4 gather warps), 1 = one CTA 8 + 8, 3 = one CTA 8 + 12, 4 = three CTAs 4 + 4; returns the rows */
 PRB_API int prb_debug_tuned_plans(int *dst, int max_entries);
 
 /* --- uniform-grid neighbour search: same results, bit for bit, as prb_ball_query(_msg2) / prb_three_nn

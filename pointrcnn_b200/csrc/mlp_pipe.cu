@@ -251,16 +251,21 @@ struct TraceTimer {
 template <int NE, int NGW, int MINB> struct RegPlan;
 template <> struct RegPlan<1, 1, 2> { static constexpr int MISC = 56, EPI = 96, GATHER = 88; };     // 384 x 2: base 80
 template <> struct RegPlan<2, 2, 1> { static constexpr int MISC = 56, EPI = 112, GATHER = 96; };    // 640: base 96
+template <> struct RegPlan<1, 1, 3> { static constexpr int MISC = 40, EPI = 80, GATHER = 48; };     // 384 x 3: base 56 (narrow SA levels)
 template <> struct RegPlan<2, 3, 1> { static constexpr int MISC = 56, EPI = 80, GATHER = 88; };     // 768: base 80
-template <bool INC, int N>
+// BASE = the launch allocation (what ptxas pins the kernel at when setmaxnreg is present): raise or release relative to it
+template <int BASE, int N>
 __device__ __forceinline__ void reg_set() {
-    if (INC) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+    if (N > BASE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+    else if (N < BASE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 template <int NE, int NGW, int MINB, int MIN, int MOUT>
 __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(const __grid_constant__ ChainParams p) {
     constexpr int NTHREADS = (NE + NGW + 1) * 128;
+    constexpr int REG_BASE = (65536 / (NTHREADS * MINB)) / 8 * 8 > 255 ? 255 : (65536 / (NTHREADS * MINB)) / 8 * 8;
+    static_assert(128 * (RegPlan<NE, NGW, MINB>::MISC + NE * RegPlan<NE, NGW, MINB>::EPI + NGW * RegPlan<NE, NGW, MINB>::GATHER) <= NTHREADS * REG_BASE,
+                  "register plan exceeds the CTA's launch allocation");
     constexpr int W_GATHER = 4 * NE, W_MISC = 4 * (NE + NGW);
     extern __shared__ uint8_t smem_raw[];
     __shared__ PipeSmem S;
@@ -315,7 +320,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
     // back, the epilogue and gather warps -- which hold 32-column accumulator chunks / 12 gathered float4 per lane --
     // take it (RegPlan).  Without this every thread of the CTA is allocated the same count and the row warps spill.
     if (warp >= W_MISC) {
-    reg_set<false, RegPlan<NE, NGW, MINB>::MISC>();
+    reg_set<REG_BASE, RegPlan<NE, NGW, MINB>::MISC>();
     if (warp == W_MISC) {
         // ===================================================== weight producer, layer 0
         {
@@ -481,7 +486,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
         }
     }
     } else if (warp >= W_GATHER) {
-        reg_set<true, RegPlan<NE, NGW, MINB>::GATHER>();
+        reg_set<REG_BASE, RegPlan<NE, NGW, MINB>::GATHER>();
         // ===================================================== gather warps: layer-0 A chunks, running ahead of the MMAs
         const int gw = warp - W_GATHER;
         const int wq = gw & 3, grp = gw >> 2;
@@ -670,7 +675,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
             }
         }
     } else {
-        reg_set<true, RegPlan<NE, NGW, MINB>::EPI>();
+        reg_set<REG_BASE, RegPlan<NE, NGW, MINB>::EPI>();
         // ===================================================== epilogue warps (warps 0 .. 4*NE-1)
         const int wq = warp & 3, grp = warp >> 2;
         const int r = wq * 32 + lane;       // my row inside the tile / my TMEM lane
@@ -1079,7 +1084,11 @@ static bool pipe_plan(const ChainParams &p, int max_optin, PipePlan *out, int fo
             pl.occ = cols <= 256 ? 2 : 1;
             if (o.mlp_occ == 1 || force_occ == 1) pl.occ = 1;
             if (force_occ == 2 && pl.occ != 2) continue;
-            pl.ne = pl.ngw = pl.occ == 2 ? 1 : 2;         // two builds: 4+4 row warps x 2 CTAs, or 8+8 row warps x 1 CTA
+            if (force_occ == 3) {                          // three CTAs per SM: <= 128 columns each, SA gather without row segments
+                if (cols > 128 || p.mode_in != IN_SA || p.mode_out != OUT_SA_MAX || p.c_feat > 5 || !(p.ns == 16 || p.ns == 32)) continue;
+                pl.occ = 3;
+            }
+            pl.ne = pl.ngw = pl.occ >= 2 ? 1 : 2;         // builds: 4+4 row warps x 2 (or 3) CTAs, or 8+8 row warps x 1 CTA
             if (o.mlp_ne == 1) pl.ne = pl.ngw = 1;
             if (o.mlp_ne == 2) { pl.ne = pl.ngw = 2; pl.occ = 1; }
             if (pl.ne == 2 && (o.mlp_ngw == 3 || force_ngw == 3)) pl.ngw = 3;     // third build: 8 epilogue + 12 gather warps
@@ -1099,7 +1108,8 @@ static bool pipe_plan(const ChainParams &p, int max_optin, PipePlan *out, int fo
             // weight rings 3 deep (2 if tight); the A ring as deep as fits, up to one whole item + 2
             for (int nb = 3; nb >= 2 && !ok; --nb)
                 for (int na = (k0 + 2 < PIPE_MAX_A ? (k0 + 2 > 3 ? k0 + 2 : 3) : PIPE_MAX_A); na >= 2 && !ok; --na) {
-                    const size_t smem = pipe_smem_bytes(pl.ne, na, nb, pl.b0_bytes, L > 1 ? nb : 0, pl.b1_bytes, np_total, p.mode_out == OUT_SA_MAX);
+                    const size_t smem = pipe_smem_bytes(pl.ne, na, nb, pl.b0_bytes, L > 1 ? nb : 0, pl.b1_bytes, np_total,
+                                                        p.mode_out == OUT_SA_MAX && !(p.ns == 16 || p.ns == 32));   // 16 / 32 samples pool in registers
                     if (smem <= budget && smem <= (size_t)max_optin && (nb == 2 || na >= (k0 < 4 ? k0 : 4))) {
                         pl.na = na; pl.nb0 = nb; pl.nb1 = L > 1 ? nb : 0; pl.smem = smem; ok = true;
                     }
@@ -1156,7 +1166,8 @@ static int launch_with_plan(ChainParams &p, const PipePlan &pl, cudaStream_t st)
             default: set_error("mlp: unsupported input / output mode pair %d / %d", p.mode_in, p.mode_out); return -1; \
         }                                                                                                  \
     } while (0)
-    if (pl.ne == 1 && pl.ngw == 1) PRB_LAUNCH_PIPE_IO(1, 1, 2);      // launch bounds only cap the registers; occ 1 runs the same build
+    if (pl.occ == 3) PRB_LAUNCH_PIPE(1, 1, 3, IN_SA, OUT_SA_MAX);
+    else if (pl.ne == 1 && pl.ngw == 1) PRB_LAUNCH_PIPE_IO(1, 1, 2);      // launch bounds only cap the registers; occ 1 runs the same build
     else if (pl.ngw == 3) PRB_LAUNCH_PIPE_IO(2, 3, 1);
     else PRB_LAUNCH_PIPE_IO(2, 2, 1);
 #undef PRB_LAUNCH_PIPE_IO
@@ -1177,7 +1188,8 @@ struct TuneKey {
     bool operator<(const TuneKey &o) const { return memcmp(this, &o, sizeof(TuneKey)) < 0; }
 };
 static std::mutex g_tune_mu;
-static std::map<TuneKey, int> g_tune;      // -> winning build: 2 = two CTAs per SM (4+4 row warps), 1 = one CTA 8+8, 3 = one CTA 8+12
+struct TuneVal { int choice; int nc; int code[4]; float ms[4]; };
+static std::map<TuneKey, TuneVal> g_tune;      // -> winning build: 2 = two CTAs per SM (4+4 row warps), 1 = one CTA 8+8, 3 = one CTA 8+12, 4 = three CTAs
 
 static bool tuning_allowed(cudaStream_t st) {
     const prb_options &o = opts();
@@ -1195,11 +1207,13 @@ int launch_chain_pipe(ChainParams &p, cudaStream_t st) {
     p.num_tiles = (int)((p.total_rows + TM - 1) / TM);
     if (p.num_tiles == 0) return 0;
     PipePlan pl;
-    PRB_REQUIRE(pipe_plan(p, max_optin, &pl), "mlp: no tensor-memory / shared-memory plan for this chain segment");
+    if (!(opts().mlp_occ == 3 && pipe_plan(p, max_optin, &pl, 3, 0)))       // mlp_occ = 3 forces the three-CTA build where it applies
+        PRB_REQUIRE(pipe_plan(p, max_optin, &pl), "mlp: no tensor-memory / shared-memory plan for this chain segment");
     // candidates: the rule-based plan first, then the one-CTA builds it did not pick (8 + 8 and 8 + 12 row warps)
-    PipePlan cand[3];
-    int code[3], nc = 0;
+    PipePlan cand[4];
+    int code[4], nc = 0;
     cand[nc] = pl; code[nc++] = pl.occ == 2 ? 2 : (pl.ngw == 3 ? 3 : 1);
+    if (pl.occ == 2 && opts().mlp_occ != 2 && pipe_plan(p, max_optin, &cand[nc], 3, 0)) code[nc++] = 4;      // three CTAs per SM
     if (pl.occ == 2 && pipe_plan(p, max_optin, &cand[nc], 1, 0)) code[nc++] = 1;
     if (pl.ngw != 3 && pipe_plan(p, max_optin, &cand[nc], 1, 3) && cand[nc].ngw == 3) code[nc++] = 3;
     if (nc > 1) {
@@ -1212,13 +1226,13 @@ int launch_chain_pipe(ChainParams &p, cudaStream_t st) {
         {
             std::lock_guard<std::mutex> g(g_tune_mu);
             auto it = g_tune.find(key);
-            if (it != g_tune.end()) choice = it->second;
+            if (it != g_tune.end()) choice = it->second.choice;
         }
         if (choice == 0 && tuning_allowed(st)) {
             cudaEvent_t e0, e1;
             PRB_CUDA(cudaEventCreate(&e0));
             PRB_CUDA(cudaEventCreate(&e1));
-            float best[3] = {1e30f, 1e30f, 1e30f};
+            float best[4] = {1e30f, 1e30f, 1e30f, 1e30f};
             int rc = 0;
             for (int c = 0; c < nc && !rc; ++c)
                 for (int rep = 0; rep < 3 && !rc; ++rep) {
@@ -1238,8 +1252,12 @@ int launch_chain_pipe(ChainParams &p, cudaStream_t st) {
             for (int c = 1; c < nc; ++c)
                 if (best[c] < 0.97f * best[win]) win = c;       // a later candidate has to win by a margin
             choice = code[win];
+            TuneVal tv;
+            memset(&tv, 0, sizeof(tv));
+            tv.choice = choice; tv.nc = nc;
+            for (int c = 0; c < nc; ++c) { tv.code[c] = code[c]; tv.ms[c] = best[c]; }
             std::lock_guard<std::mutex> g(g_tune_mu);
-            g_tune[key] = choice;
+            g_tune[key] = tv;
         }
         for (int c = 0; c < nc; ++c)
             if (code[c] == choice) pl = cand[c];
@@ -1247,16 +1265,21 @@ int launch_chain_pipe(ChainParams &p, cudaStream_t st) {
     return launch_with_plan(p, pl, st);
 }
 
-// tuned plans so far: n entries of {mode_in, mode_out, layers, nsample, k chunks, tiles, np0, np1, np2, occupancy}
+// tuned plans so far: n entries of 18 ints {mode_in, mode_out, layers, nsample, k chunks, tiles, np0, np1, np2, winner,
+// 4 x (candidate build, measured microseconds)}
 int pipe_tuned_plans(int *dst, int max_entries) {
     std::lock_guard<std::mutex> g(g_tune_mu);
     int n = 0;
     for (const auto &kv : g_tune) {
         if (n >= max_entries) break;
         const TuneKey &k = kv.first;
-        int *d = dst + 10 * n++;
+        int *d = dst + 18 * n++;
         d[0] = k.mode_in; d[1] = k.mode_out; d[2] = k.L; d[3] = k.ns; d[4] = k.k0; d[5] = k.tiles; d[6] = k.np[0]; d[7] = k.np[1]; d[8] = k.np[2];
-        d[9] = kv.second;
+        d[9] = kv.second.choice;
+        for (int c = 0; c < 4; ++c) {       // candidates: build code (0 = none) and measured microseconds
+            d[10 + 2 * c] = c < kv.second.nc ? kv.second.code[c] : 0;
+            d[11 + 2 * c] = c < kv.second.nc ? (int)(kv.second.ms[c] * 1000.f + 0.5f) : 0;
+        }
     }
     return n;
 }

@@ -324,6 +324,28 @@ def test_sa_pooling_layouts_bit_identical(cuda, ns, widths, fold):
     assert (outs[0] - ref).abs().max().item() <= TOL * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("ns,widths", [(16, [16, 16, 32]), (32, [32, 32, 64])])
+def test_sa_builds_bit_identical(cuda, ns, widths):
+    """the builds of the chain kernel (CTAs per SM x row warps; prb_options.mlp_occ / mlp_ne / mlp_ngw) compute the same bits: K
+    order and per-element arithmetic do not depend on the plan -- the premise of the measured build choice.  SA1-shaped chains
+    (xyz + 1 feature channel), which is where the three-CTA build applies."""
+    from pointrcnn_b200 import _cabi as C
+    torch.manual_seed(3 + ns)
+    mod = pm.PointnetSAModuleMSG(npoint=700, radii=[0.3], nsamples=[ns], mlps=[[1] + widths], bn=True).to(cuda).eval()
+    _randomise_bn(mod, 9)
+    x = torch.from_numpy(synth.u_cube(3, 4000, 13)).to(cuda)
+    f = torch.randn(3, 1, 4000, device=cuda)
+    outs = []
+    for opt in ({"mlp_tune": 0}, {"mlp_occ": 3}, {"mlp_occ": 1}, {"mlp_occ": 1, "mlp_ne": 2, "mlp_ngw": 3}):
+        with torch.no_grad(), C.options(**opt):
+            outs.append(mod(x, f)[1].clone())
+    for k in range(1, len(outs)):
+        assert torch.equal(outs[0], outs[k]), "build %d differs" % k
+    with torch.no_grad():
+        ref = _unfused(lambda: mod(x, f))[1]
+    assert (outs[0] - ref).abs().max().item() <= TOL * ref.abs().max().item()
+
+
 def test_sa_module_group_all_and_no_bn(cuda):
     torch.manual_seed(1)
     B, N, c_feat = 6, 32, 256
