@@ -63,6 +63,8 @@ typedef struct prb_options {
     int mlp_brows;     /* pipelined kernel: rows per weight stage / MMA N (32..256); 0 = 64 */
     int mlp_pool;      /* SA max-pool over 16..128 samples: 0 = quad tensor-memory layout (2 rows x 4 columns per thread, 3 exchange
                         * stages), 1 = shuffle butterfly, 2 = CREDUX (warp-wide max per channel), 3 = staged tile for 64/128 samples */
+    int mlp_resident;  /* 1 (default): chains whose weight stages all fit in shared memory load them once per CTA instead of per tile */
+    int mlp_lazy_ns;   /* poll interval (ns) of the run-ahead roles (gather warps, weight producers) in the narrow builds; 0 = 400 */
     int mlp_fill;      /* 1 (default): single-layer launches with fewer tiles than SMs are dealt to more column groups until every
                         * SM has one (lower latency, each group re-gathers its rows); 0: only as many groups as tensor memory needs */
     int mlp_tune;      /* 1 (default): the first eager launch of a chain shape times the two-CTA and the one-CTA build and

@@ -25,6 +25,8 @@ struct ChainParams {
     int dcol[MAX_LAYERS];      // TMEM column of the accumulator
     const float *w[MAX_LAYERS];      // packed weight images
     const float *scale[MAX_LAYERS];  // np floats (zero padded); unused when unit_scale
+    int w_resident;                  // 1: the weight rings hold a whole tile's stages, filled once (no recycling)
+    int sleepy_ns;                   // poll interval of the run-ahead roles in the narrow builds (ns)
     int sleepy;                      // bit 0: MMA issuer waits with a suspend hint, bit 1: weight producer does
     int a_tmem;                      // layers >= 1 take their A operand from tensor memory: the epilogue rewrites the
                                      // previous accumulator IN PLACE (relu(x + t) -> tf32), no shared-memory stage, no proxy fence

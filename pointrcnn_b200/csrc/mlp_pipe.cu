@@ -92,9 +92,9 @@ __device__ __forceinline__ void bwait(uint64_t *bar, uint32_t parity) { mbar_wai
 // a try_wait wakes on every barrier event of the CTA, ~100 polls per tile and warp were 23 % of all issued instructions
 // ... but only where the ring has slack (narrow chains, two CTAs per SM): on the wide chains the weight ring IS the critical
 // resource and a 400 ns poll interval on 41 stage refills per tile cost 10 % (SA3 0.131 -> 0.144 ms)
-__device__ __forceinline__ void bwait_lazy(uint64_t *bar, uint32_t parity, bool lazy) {
+__device__ __forceinline__ void bwait_lazy(uint64_t *bar, uint32_t parity, int lazy_ns) {
     const uint32_t b = s2u(bar);
-    if (lazy) { while (!mbar_test(b, parity)) __nanosleep(400); }
+    if (lazy_ns > 0) { while (!mbar_test(b, parity)) __nanosleep((unsigned)lazy_ns); }
     else mbar_wait_sleepy(b, parity);
 }
 
@@ -310,7 +310,8 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
     const int sj = (int)blockIdx.x % nsplit;
     const int tile0 = (int)blockIdx.x / nsplit, tstep = (int)gridDim.x / nsplit;
     const int ntiles = p.num_tiles;
-    const bool lazy = NE == 1;           // the two-CTA build runs the narrow chains: rings with slack
+    const bool resident = p.w_resident != 0;   // all weight stages of a tile fit the rings: loaded once, never recycled (narrow chains)
+    const int lazy = NE == 1 ? p.sleepy_ns : 0;   // the two-/three-CTA builds run the narrow chains: rings with slack -> poll interval in ns
     TraceTimer tt;
     // traced warps of CTA 0 (warp-uniform): issuer A -> slot 0, issuer B 1, producers 2 / 3, gather warp 0 -> 4, epilogue warp 0 -> 5
     tt.start(p.trace != 0 && blockIdx.x == 0 && (warp >= W_MISC || warp == W_GATHER || warp == 0),
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
             const float *w0 = p.w[0] + (size_t)col0 * KC;
             const size_t chunk_stride = (size_t)p.np[0] * KC;
             for (int tile = tile0; tile < ntiles; tile += tstep) {
+                if (p.w_resident && tile != tile0) break;      // every stage was filled once and is never recycled
                 const float *src = w0;
                 for (int kc = 0; kc < nch; ++kc, src += chunk_stride)
                     for (int h = 0; h < halves; ++h) {
@@ -353,6 +355,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
             const int nb = p.nb1;
             const uint32_t stage_bytes = (uint32_t)p.b1_stage_bytes;
             for (int tile = tile0; tile < ntiles; tile += tstep) {
+                if (p.w_resident && tile != tile0) break;
                 for (int l = 1; l < L; ++l) {
                     const bool last = l == L - 1;
                     const int nsl = last ? p.nslice : 1;
@@ -405,7 +408,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                     const uint64_t adesc = make_desc(a_base + ra.stage * A_STAGE_BYTES);
                     for (int h = 0; h < halves; ++h) {
                         const int rows = min(brows, width - h * brows);
-                        tt.timed(2, [&] { bwait(&S.b0_full[rb.stage], rb.phase); });
+                        if (!(resident && it > 0)) tt.timed(2, [&] { bwait(&S.b0_full[rb.stage], rb.phase); });
                         tc_fence_after();
                         const uint64_t bdesc = make_desc(b_base + rb.stage * b_bytes);
                         const uint32_t idesc = make_idesc(rows);
@@ -413,7 +416,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                         if (elect_one()) {
                             for (int ks = 0; ks < ksteps; ++ks)  // +32 bytes (= 2 x 16 B) per K=8 step inside the swizzle row
                                 umma_tf32(d, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-                            umma_commit(s2u(&S.b0_empty[rb.stage]));
+                            if (!resident) umma_commit(s2u(&S.b0_empty[rb.stage]));
                             if (h == halves - 1) umma_commit(s2u(&S.a_empty[ra.stage]));
                             if (h == halves - 1 && kc == nch - 1) umma_commit(L > 1 ? s2u(&S.r_full[0]) : s2u(&S.z_full[buf]));
                         }
@@ -455,7 +458,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                             const uint32_t a_t = a_col + (uint32_t)(kc * KC);
                             for (int h = 0; h < halves; ++h) {
                                 const int rows = min(brows, width - h * brows);
-                                tt.timed(2, [&] { bwait(&S.b1_full[rb.stage], rb.phase); });
+                                if (!(resident && it > 0)) tt.timed(2, [&] { bwait(&S.b1_full[rb.stage], rb.phase); });
                                 tt.timed(3, [&] { tc_fence_after(); });
                                 const uint64_t bdesc = make_desc(b_base + rb.stage * b_bytes);
                                 const uint32_t idesc = make_idesc(rows);
@@ -469,7 +472,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
                                 });
                                 tt.timed(5, [&] {
                                     if (elect_one()) {
-                                        umma_commit(s2u(&S.b1_empty[rb.stage]));
+                                        if (!resident) umma_commit(s2u(&S.b1_empty[rb.stage]));
                                         if (h == halves - 1 && kc == nch - 1) {
                                             umma_commit(last ? s2u(&S.z_full[buf]) : s2u(&S.r_full[l]));
                                             // region 0 may take the next item's layer 0 once layer 1 (all its slices) has read it
@@ -1032,7 +1035,7 @@ __global__ void __launch_bounds__((NE + NGW + 1) * 128, MINB) mlp_pipe_kernel(co
 // Can this chain segment run on the pipelined kernel, and with which tensor-memory plan?  Fills the plan fields of p.
 // Returns the CTAs per SM the plan allows (0 = not supported: the caller falls back to the legacy kernel).
 struct PipePlan {
-    int ne, ngw, occ, zs, nbuf, nslice, cols, na, nb0, nb1, b0_bytes, b1_bytes, nsplit, split_w, brows;
+    int ne, ngw, occ, zs, nbuf, nslice, cols, na, nb0, nb1, b0_bytes, b1_bytes, nsplit, split_w, brows, resident;
     size_t smem;
 };
 
@@ -1105,6 +1108,27 @@ static bool pipe_plan(const ChainParams &p, int max_optin, PipePlan *out, int fo
             pl.b0_bytes = b0_rows * KC * 4; pl.b1_bytes = L > 1 ? b1_rows * KC * 4 : 0;
             const size_t budget = (size_t)(227 * 1024) / pl.occ - 1024 - sizeof(PipeSmem) - 512;
             bool ok = false;
+            pl.resident = 0;
+            // resident weights: when every weight stage a tile needs fits next to a useful A ring, the rings are as deep as
+            // one tile, filled once and never recycled -- no weight traffic, no stage barriers, no empty commits per tile
+            if (o.mlp_resident) {
+                const int halves0 = ((L == 1 ? z : p.np[0]) + brows - 1) / brows;
+                int st0 = p.nchunks[0] * halves0, st1 = 0;
+                for (int l = 1; l < L; ++l) {
+                    const int w = (l == L - 1) ? z : p.np[l];
+                    st1 += (l == L - 1 ? nslice : 1) * p.nchunks[l] * ((w + brows - 1) / brows);
+                }
+                if (st0 <= PIPE_MAX_B && st1 <= PIPE_MAX_B) {
+                    const int na_min = k0 + 1 < PIPE_MAX_A ? (k0 + 1 > 3 ? k0 + 1 : 3) : PIPE_MAX_A;
+                    for (int na = (k0 + 2 < PIPE_MAX_A ? (k0 + 2 > 3 ? k0 + 2 : 3) : PIPE_MAX_A); na >= na_min && !ok; --na) {
+                        const size_t smem = pipe_smem_bytes(pl.ne, na, st0, pl.b0_bytes, st1, pl.b1_bytes, np_total,
+                                                            p.mode_out == OUT_SA_MAX && !(p.ns == 16 || p.ns == 32));
+                        if (smem <= budget && smem <= (size_t)max_optin) {
+                            pl.na = na; pl.nb0 = st0; pl.nb1 = st1; pl.smem = smem; pl.resident = 1; ok = true;
+                        }
+                    }
+                }
+            }
             // weight rings 3 deep (2 if tight); the A ring as deep as fits, up to one whole item + 2
             for (int nb = 3; nb >= 2 && !ok; --nb)
                 for (int na = (k0 + 2 < PIPE_MAX_A ? (k0 + 2 > 3 ? k0 + 2 : 3) : PIPE_MAX_A); na >= 2 && !ok; --na) {
@@ -1136,6 +1160,7 @@ static int launch_with_plan(ChainParams &p, const PipePlan &pl, cudaStream_t st)
     p.b0_stage_bytes = pl.b0_bytes; p.b1_stage_bytes = pl.b1_bytes;
     p.nsplit = pl.nsplit; p.split_w = pl.split_w;
     p.b_rows = pl.brows;
+    p.w_resident = pl.resident;
     p.num_items = p.num_tiles * pl.nsplit;
     int sms = num_sms();
     if (const int v = opts().mlp_sms; v >= 1 && v < sms) sms = v;
@@ -1146,6 +1171,7 @@ static int launch_with_plan(ChainParams &p, const PipePlan &pl, cudaStream_t st)
     p.trace = opts().mlp_trace ? 1 : 0;
     p.rows32 = (int)p.total_rows;
     p.pool_mode = opts().mlp_pool;
+    p.sleepy_ns = opts().mlp_lazy_ns > 0 ? opts().mlp_lazy_ns : 400;
     const size_t smem = pl.smem;
 #define PRB_LAUNCH_PIPE(NE, NGW, MB, MI, MO)                                                                                   \
     do {                                                                                                                       \

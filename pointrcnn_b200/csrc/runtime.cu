@@ -55,6 +55,8 @@ static prb_options make_defaults() {
     o.mlp_nbuf = env_int("PRB_MLP_NBUF", 0);
     o.mlp_brows = env_int("PRB_MLP_BROWS", 0);
     o.mlp_pool = env_int("PRB_MLP_POOL", 0);
+    o.mlp_resident = env_int("PRB_MLP_RESIDENT", 1);
+    o.mlp_lazy_ns = env_int("PRB_MLP_LAZY_NS", 0);
     o.mlp_fill = env_int("PRB_MLP_FILL", 1);
     o.mlp_tune = env_int("PRB_MLP_TUNE", 1);
     o.roipool_exhaustive = env_int("PRB_ROIPOOL_EXHAUSTIVE", 0);
