@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PRB_ABI_VERSION 4   /* 3: prb_options (per-thread tuning block; no per-call environment reads); 4: mlp_tune, prb_mlp_rows2 */
+#define PRB_ABI_VERSION 5   /* 3: prb_options (per-thread tuning block; no per-call environment reads); 4: mlp_tune, prb_mlp_rows2; 5: ordered FPS */
 #if defined(__GNUC__)
 #define PRB_API __attribute__((visibility("default")))
 #else
@@ -98,6 +98,17 @@ PRB_API int prb_furthest_point_sampling(int b, int n, int m, const float *xyz, f
 PRB_API size_t prb_fps_workspace_bytes(int b, int n);
 PRB_API int prb_furthest_point_sampling_ws(int b, int n, int m, const float *xyz, float *temp, int *idx,
                                    float *new_xyz, void *workspace, size_t workspace_bytes, void *stream);
+/* same result, for inputs that are LIKELY already in sampling order (the output of a previous
+ * furthest_point_sampling from point 0: SA level l+1 samples level l's output, pointnet2_msg.py:57-61, where the
+ * answer is 0..m-1 unless two points tie for a maximum).  Per scene the library PROVES idx = (0..m-1) with n*m
+ * independent distance evaluations (every pick a strict, unique maximum; nothing is assumed about the input) and
+ * writes idx / new_xyz / temp exactly as the sampling kernels would; scenes where the proof fails (ties, duplicates,
+ * NaN, unordered input) are sampled by the ordinary kernels in the same call.  No host synchronisation.
+ * todo_out (b) int32, optional: 0 = scene answered by the proof, 1 = sampled.  Scratch: prb_fps_ordered_workspace_bytes. */
+PRB_API size_t prb_fps_ordered_workspace_bytes(int b, int n, int m);
+PRB_API int prb_furthest_point_sampling_ordered_ws(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                           float *new_xyz, int *todo_out, void *workspace, size_t workspace_bytes,
+                                           void *stream);
 
 /* gather_points_wrapper_fast / gather_points_grad_wrapper_fast, sampling.cpp:11-33 */
 PRB_API int prb_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx,

@@ -9,6 +9,8 @@ environment variables ONCE at import; at run time they are changed with `overrid
     prof_detail     per-shape lines in prof.collect()
     fp_project      FP modules: project the known points through layer 0 before interpolating (linearity), default on
     fp_project_min_rows   ... for FP levels with at least this many unknown points in the batch (B * n)
+    fps_ordered     SA modules whose input coordinates are the output of a previous sampling (nested encoder levels) take
+                    the proven-prefix shortcut of prb_furthest_point_sampling_ordered_ws (same indices), default on
 """
 import contextlib
 import os
@@ -22,6 +24,7 @@ _DEFAULTS = dict(
     prof_detail=os.environ.get("PRB_PROF_DETAIL", "0") == "1",
     fp_project=os.environ.get("PRB_FP_PROJECT", "1") != "0",
     fp_project_min_rows=int(os.environ.get("PRB_FP_PROJECT_MIN_ROWS", "131072")),
+    fps_ordered=os.environ.get("PRB_FPS_ORDERED", "1") != "0",
 )
 _local = threading.local()
 

@@ -91,17 +91,47 @@ class FurthestPointSampling(Function):
 furthest_point_sample = FurthestPointSampling.apply
 
 
-def furthest_point_sample_xyz(xyz: torch.Tensor, npoint: int):
-    """FPS that also emits the sampled coordinates: (idx (B,npoint) int32, new_xyz (B,npoint,3)); no grad"""
+def mark_sampling_order(t: torch.Tensor) -> torch.Tensor:
+    """tag coordinates as "listed in furthest-point-sampling order from point 0" (a hint, never trusted: see
+    furthest_point_sample_xyz)"""
+    t._prb_sampling_order = True
+    return t
+
+
+def in_sampling_order(t: torch.Tensor) -> bool:
+    return bool(getattr(t, "_prb_sampling_order", False))
+
+
+def furthest_point_sample_xyz(xyz: torch.Tensor, npoint: int, ordered: bool = None, return_todo: bool = False):
+    """FPS that also emits the sampled coordinates: (idx (B,npoint) int32, new_xyz (B,npoint,3)); no grad.
+    The returned new_xyz is tagged as being in sampling order.  `ordered` (default: the tag of `xyz`): the input is
+    probably the output of an earlier sampling, so try to PROVE idx = 0..npoint-1 per scene first
+    (prb_furthest_point_sampling_ordered_ws; scenes where the proof fails are sampled as usual, results identical).
+    return_todo: also return the (B,) int32 per-scene flags (1 = sampled by the kernels, 0 = answered by the proof)."""
     assert xyz.is_contiguous()
     C.require_cuda(xyz)
     B, N, _ = xyz.size()
+    if ordered is None:
+        ordered = in_sampling_order(xyz) and config.get("fps_ordered")
     idx = _cuda_empty((B, npoint), torch.int32, xyz)
     new_xyz = _cuda_empty((B, npoint, 3), torch.float32, xyz)
     temp = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device)
+    todo = None
     with torch.cuda.device(xyz.device), prof.region("fps"):
-        _fps_native(B, N, npoint, xyz, temp, idx, new_xyz)
-    return idx, new_xyz
+        if ordered and 2 <= npoint <= N:
+            lib = C.lib()
+            wsb = lib.prb_fps_ordered_workspace_bytes(B, N, int(npoint))
+            ws = torch.empty(wsb, dtype=torch.uint8, device=xyz.device)
+            todo = torch.empty(B, dtype=torch.int32, device=xyz.device) if return_todo else None
+            C.check(lib.prb_furthest_point_sampling_ordered_ws(B, N, int(npoint), C.ptr(xyz), C.ptr(temp), C.ptr(idx), C.ptr(new_xyz),
+                                                               C.ptr(todo), C.ptr(ws), C.c_size_t(wsb), C.stream()),
+                    "furthest_point_sampling_ordered")
+        else:
+            _fps_native(B, N, npoint, xyz, temp, idx, new_xyz)
+            if return_todo:
+                todo = torch.ones(B, dtype=torch.int32, device=xyz.device)
+    mark_sampling_order(new_xyz)
+    return (idx, new_xyz, todo) if return_todo else (idx, new_xyz)
 
 
 class GatherOperation(Function):

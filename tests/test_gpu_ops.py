@@ -83,6 +83,93 @@ def test_fps_all_kernel_variants_agree(cuda, opt):
     assert np.array_equal(got.cpu().numpy(), want)
 
 
+ORDERED_CASES = [
+    # (B, N0, levels, cloud): nested sampling levels as the encoder runs them (pointnet2_msg.py:57-61)
+    (3, 16384, [4096, 1024, 256, 64], "kitti"),   # the RPN encoder
+    (2, 8192, [2048, 512, 100], "cube"),
+    (2, 4096, [1024, 1024, 300], "kitti"),        # m == n at the second level
+    (4, 2048, [512, 128], "dup"),                  # duplicates: picks with distance 0 -> the proof fails, kernels sample
+]
+
+
+@pytest.mark.parametrize("B,N0,levels,kind", ORDERED_CASES)
+def test_fps_ordered_levels_identical_to_sampling(cuda, B, N0, levels, kind):
+    """the proven-prefix shortcut returns exactly what the sampling kernels (and the oracle) return at every nested level"""
+    from pointrcnn_b200.ext import pointnet2_cuda
+    from pointrcnn_b200 import _cabi as C
+    xyz = _cloud(kind, B, N0, 23 + N0)
+    x = T(xyz, cuda)
+    proven = []
+    for li, m in enumerate(levels):
+        n = x.size(1)
+        idx_o, nx_o, todo = pu.furthest_point_sample_xyz(x, m, ordered=True, return_todo=True)
+        idx_p, nx_p = pu.furthest_point_sample_xyz(x, m, ordered=False)
+        assert torch.equal(idx_o, idx_p), "level %d: ordered path differs from the sampling kernels" % li
+        assert torch.equal(nx_o, nx_p)
+        want, want_temp = O.fps(x.cpu().numpy(), m, return_temp=True)
+        assert np.array_equal(idx_o.cpu().numpy(), want), "level %d: differs from the oracle" % li
+        # temp written by the proof == temp written by the kernels == the oracle's
+        lib = C.lib()
+        wsb = lib.prb_fps_ordered_workspace_bytes(B, n, m)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=cuda)
+        temp = torch.full((B, n), 1e10, device=cuda)
+        idx2 = torch.empty((B, m), dtype=torch.int32, device=cuda)
+        C.check(lib.prb_furthest_point_sampling_ordered_ws(B, n, m, C.ptr(x), C.ptr(temp), C.ptr(idx2), None, None, C.ptr(ws),
+                                                           C.c_size_t(wsb), C.stream()), "fps_ordered")
+        assert np.array_equal(temp.cpu().numpy(), want_temp), "level %d: temp differs from the oracle" % li
+        assert torch.equal(idx2, idx_p)
+        proven.append(int((todo == 0).sum()))
+        x = nx_o
+    if kind in ("kitti", "cube"):
+        assert proven[0] == 0, "raw clouds are not in sampling order"
+        assert all(p == B for p in proven[1:]), "nested levels of a tie-free cloud must be answered by the proof: %s" % proven
+    else:
+        assert proven[-1] < B, "duplicate-heavy levels cannot be proven"
+
+
+def test_fps_ordered_mixed_batch_and_caller_temp(cuda):
+    """per-scene decision: scene 0 in sampling order, scene 1 shuffled, scene 2 ordered but with one exact tie;
+    plus a caller-initialised temp (in/out contract) -- all identical to the plain entry"""
+    from pointrcnn_b200 import _cabi as C
+    base = synth.u_kitti(3, 4096, 77)
+    order = O.fps(base, 1024)
+    lvl = np.stack([base[b][order[b]] for b in range(3)])          # (3,1024,3) in sampling order
+    rng = np.random.default_rng(3)
+    lvl[1] = lvl[1][rng.permutation(1024)]
+    lvl[2][200] = lvl[2][100]                                       # duplicate of an early pick: v_200 == 0
+    x = T(lvl, cuda)
+    for t0 in (None, (rng.random((3, 1024)) * 50.0 + 1.0).astype(np.float32)):
+        lib = C.lib()
+        m = 256
+        wsb = lib.prb_fps_ordered_workspace_bytes(3, 1024, m)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=cuda)
+        temp = torch.full((3, 1024), 1e10, device=cuda) if t0 is None else T(t0.copy(), cuda)
+        idx = torch.empty((3, m), dtype=torch.int32, device=cuda)
+        nx = torch.empty((3, m, 3), device=cuda)
+        todo = torch.empty(3, dtype=torch.int32, device=cuda)
+        C.check(lib.prb_furthest_point_sampling_ordered_ws(3, 1024, m, C.ptr(x), C.ptr(temp), C.ptr(idx), C.ptr(nx), C.ptr(todo),
+                                                           C.ptr(ws), C.c_size_t(wsb), C.stream()), "fps_ordered")
+        want, want_temp = O.fps(lvl, m, return_temp=True, temp0=t0)
+        assert np.array_equal(idx.cpu().numpy(), want)
+        assert np.array_equal(temp.cpu().numpy(), want_temp)
+        assert np.array_equal(nx.cpu().numpy(), np.stack([lvl[b][want[b]] for b in range(3)]))
+        if t0 is None:
+            assert todo.tolist() == [0, 1, 1]
+
+
+def test_backbone_takes_the_ordered_shortcut(cuda):
+    """SA levels 2..4 of the fused encoder receive tagged coordinates; switching the shortcut off changes nothing"""
+    from pointrcnn_b200 import backbone, config
+    torch.manual_seed(0)
+    net = backbone.get_model(input_channels=0).to(cuda).eval()
+    pc = T(synth.u_kitti(2, 16384, 5), cuda)
+    with torch.no_grad():
+        xyz_a, f_a = net(pc)
+        with config.override(fps_ordered=False):
+            xyz_b, f_b = net(pc)
+    assert torch.equal(f_a, f_b) and torch.equal(xyz_a, xyz_b)
+
+
 def test_options_are_thread_local(cuda):
     """natives are re-entered from nn.DataParallel worker threads; one thread's prb_options must not leak"""
     import threading
