@@ -309,6 +309,47 @@ PRB_API int prb_nms_host(const float *boxes, int n, float thresh, int normal, lo
 PRB_API int prb_nms_mask(const float *boxes, int n, float thresh, int normal, unsigned long long *mask,
                  void *stream);
 
+/* ------------------------------------------------------------------ input pipeline / KITTI output ------
+ * lib/datasets/kitti_rcnn_dataset.py:246-394 (get_rpn_sample, generate_rpn_training_labels)
+ * and tools/eval_rcnn.py:69-94 (save_kitti_format), batched on the device.  A batch of raw scans is RAGGED:
+ * lidar (total, stride>=3[,intensity]) holds the scenes back to back, offsets (b+1) int32 (device) delimits them. */
+
+/* calib (b,32) per scene: M[12] (4x3 row-major, rect = [x y z 1].M with M = V2C^T.R0^T, calibration.py:51-59),
+ * P2[12] (3x4 row-major), image height, image width, range box x0,x1,y0,y1,z0,z1 (PC_AREA_SCOPE; read if use_range).
+ * rect (total,3): rectified coordinates of EVERY point; flags (total) uint8: bit 0 = valid (projects into the image,
+ * depth >= 0, inside the range box: get_valid_flag, kitti_rcnn_dataset.py:198-219), bit 1 = near (rect z < 40 m);
+ * counts (b,2) int32 or NULL: valid points, valid far points per scene. */
+PRB_API int prb_kitti_prepare_points(int b, int total, const int *offsets, const float *lidar, int stride, const float *calib,
+                             int use_range, float *rect, unsigned char *flags, int *counts, void *stream);
+/* the npoints draw of kitti_rcnn_dataset.py:285-303 per scene, on the device: every valid far point + a random subset
+ * (without replacement) of the valid near points, or every valid point + random extra copies when there are fewer
+ * than npoints, in random order.  choice (b,npoints) int32 indexes the scene's RAW points.  Counter-based hashes of
+ * (seed, scene, point) replace np.random: same distribution, not the same stream.  cand_scratch (total) int32.
+ * status (b) int32 or NULL: 1 = scene without a valid point (rows zero).  npoints <= 16384. */
+PRB_API int prb_kitti_draw_points(int b, int total, const int *offsets, const unsigned char *flags, int npoints, unsigned seed,
+                          int *cand_scratch, int *choice, int *status, void *stream);
+/* rows of the network input: rect[choice] (+ intensity - 0.5 when channels == 4), with the scene's augmentation
+ * (aug (b,4) DOUBLE: cos, sin of the y rotation, scale, flip 0/1, applied in the order of data_augmentation,
+ * kitti_rcnn_dataset.py:526-568; NULL = none); rows of scenes with status != 0 are zero.  Any of pts_input (b,npoints,channels), pts_rect (b,npoints,3),
+ * intensity (b,npoints) may be NULL. */
+PRB_API int prb_kitti_gather_points(int b, int npoints, const int *offsets, const float *rect, const float *lidar, int stride,
+                            const int *choice, const double *aug, const int *status, int channels, float *pts_input,
+                            float *pts_rect, float *intensity, void *stream);
+/* generate_rpn_training_labels (kitti_rcnn_dataset.py:355-391) for a batch: pts_rect (b,n,3), gt_boxes3d (b,g,7),
+ * gt_count (b) or NULL (then all-zero rows of a padded batch are skipped) -> cls_label (b,n) int32 in {1,0,-1},
+ * reg_label (b,n,7) [dx,dy,dz,h,w,l,ry].  Boxes are visited in order and later boxes overwrite, as in the reference;
+ * the inside test is exact box geometry instead of a Delaunay triangulation of the corners.  g <= 128. */
+PRB_API int prb_rpn_training_labels(int b, int n, int g, const float *pts_rect, const float *gt_boxes3d, const int *gt_count,
+                            float extra_width, int *cls_label, float *reg_label, void *stream);
+/* save_kitti_format's arithmetic (eval_rcnn.py:69-82, calibration.py:106-124): boxes3d (n,7) -> img_boxes (n,4) clipped
+ * to the image, alpha (n), valid (n) int32 (box narrower / lower than 0.8 of the image). */
+PRB_API int prb_kitti_image_boxes(int n, const float *boxes3d, const float *P2, float img_h, float img_w, float *img_boxes,
+                          float *alpha, int *valid, void *stream);
+/* HOST function: the text of one KITTI result file (eval_rcnn.py:85-94) from host arrays; returns the bytes needed
+ * (without terminator), writes at most cap bytes. */
+PRB_API size_t prb_kitti_format_detections(const char *cls_name, int n, const float *boxes3d, const float *img_boxes,
+                                   const float *alpha, const float *scores, const int *valid, char *buf, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

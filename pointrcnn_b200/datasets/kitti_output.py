@@ -1,0 +1,60 @@
+"""KITTI-format result files: mirror of tools/eval_rcnn.py:69-94 (save_kitti_format) -- SURVEY.md 8(f) rank 4.
+
+The box arithmetic (8 corners, projection through P2, clipping, the 0.8-of-the-image validity rule, alpha) is one launch
+over the scene's detections (`prb_kitti_image_boxes`); the text is formatted by the library's host function
+(`prb_kitti_format_detections`, one snprintf per line instead of a Python `print` per box).
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from .. import _cabi as C
+from .kitti_rcnn_dataset import Calibration
+
+
+def kitti_image_boxes(bbox3d, P2, img_shape):
+    """bbox3d (N,7) CUDA float32 -> (img_boxes (N,4) float32, alpha (N) float32, valid (N) int32), all CUDA"""
+    C.require_cuda(bbox3d)
+    b = bbox3d.contiguous().float()
+    n = b.size(0)
+    dev = b.device
+    img_boxes = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    alpha = torch.empty(n, dtype=torch.float32, device=dev)
+    valid = torch.empty(n, dtype=torch.int32, device=dev)
+    p2 = torch.as_tensor(np.asarray(P2, dtype=np.float32).reshape(-1)).to(dev)
+    with torch.cuda.device(dev):
+        C.check(C.lib().prb_kitti_image_boxes(n, C.ptr(b), C.ptr(p2), ctypes.c_float(float(img_shape[0])), ctypes.c_float(float(img_shape[1])),
+                                              C.ptr(img_boxes), C.ptr(alpha), C.ptr(valid), C.stream()), "kitti_image_boxes")
+    return img_boxes, alpha, valid
+
+
+def format_kitti_lines(bbox3d, img_boxes, alpha, scores, valid, classes="Car"):
+    """host arrays -> the file's text (str)"""
+    b = np.ascontiguousarray(bbox3d, dtype=np.float32)
+    ib = np.ascontiguousarray(img_boxes, dtype=np.float32)
+    al = np.ascontiguousarray(alpha, dtype=np.float32)
+    sc = np.ascontiguousarray(scores, dtype=np.float32).reshape(-1)
+    va = np.ascontiguousarray(valid, dtype=np.int32)
+    n = b.shape[0]
+    lib = C.lib()
+    P = ctypes.c_void_p
+    args = (classes.encode(), n, P(b.ctypes.data), P(ib.ctypes.data), P(al.ctypes.data), P(sc.ctypes.data), P(va.ctypes.data))
+    need = lib.prb_kitti_format_detections(*args, None, ctypes.c_size_t(0))
+    buf = ctypes.create_string_buffer(need + 1)
+    lib.prb_kitti_format_detections(*args, buf, ctypes.c_size_t(need + 1))
+    return buf.value.decode()
+
+
+def save_kitti_format(sample_id, calib, bbox3d, kitti_output_dir, scores, img_shape, classes="Car"):
+    """same arguments as the reference; bbox3d / scores may be CUDA tensors (no per-box host work) or numpy arrays"""
+    calib = Calibration(calib)
+    dev_boxes = bbox3d if torch.is_tensor(bbox3d) else torch.from_numpy(np.ascontiguousarray(bbox3d, dtype=np.float32)).cuda()
+    img_boxes, alpha, valid = kitti_image_boxes(dev_boxes, calib.P2, img_shape)
+    sc = scores.detach().cpu().numpy() if torch.is_tensor(scores) else np.asarray(scores)
+    text = format_kitti_lines(dev_boxes.detach().cpu().numpy(), img_boxes.cpu().numpy(), alpha.cpu().numpy(), sc, valid.cpu().numpy(), classes)
+    path = os.path.join(kitti_output_dir, "%06d.txt" % sample_id)
+    with open(path, "w") as f:
+        f.write(text)
+    return path

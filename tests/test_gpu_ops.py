@@ -88,7 +88,7 @@ ORDERED_CASES = [
     (3, 16384, [4096, 1024, 256, 64], "kitti"),   # the RPN encoder
     (2, 8192, [2048, 512, 100], "cube"),
     (2, 4096, [1024, 1024, 300], "kitti"),        # m == n at the second level
-    (4, 2048, [512, 128], "dup"),                  # duplicates: picks with distance 0 -> the proof fails, kernels sample
+    (4, 2048, [1024, 600], "dup"),                 # 512 distinct points: picks beyond them have distance 0 -> no proof, kernels sample
 ]
 
 
@@ -124,7 +124,7 @@ def test_fps_ordered_levels_identical_to_sampling(cuda, B, N0, levels, kind):
         assert proven[0] == 0, "raw clouds are not in sampling order"
         assert all(p == B for p in proven[1:]), "nested levels of a tie-free cloud must be answered by the proof: %s" % proven
     else:
-        assert proven[-1] < B, "duplicate-heavy levels cannot be proven"
+        assert proven[-1] == 0, "a level that runs out of distinct points cannot be proven"
 
 
 def test_fps_ordered_mixed_batch_and_caller_temp(cuda):
