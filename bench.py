@@ -24,6 +24,8 @@ a barrier + synchronize on both sides (CUDA events, max over ranks) and is REPEA
   strong_scaling  (N > 1) global batch 16: 16/N scenes per GPU per step, same pipeline.
   train_step    BASELINE configs[2]: RPN training step, 16 scenes per GPU, NCCL gradient all-reduce overlapped with backward.
   rcnn_stage    BASELINE configs[3]: roipool3d on 4 x 512 RoIs x 512 points + the RCNN PointNet++ stack (rank 0).
+  eval_e2e      BASELINE configs[4]: raw scans -> input pipeline -> RPN -> RCNN -> rotated NMS -> KITTI result text, global
+                batch 8 sharded over the ranks (8 / N scenes per GPU).
   cpu_baseline  oracle port on the host cores over a bounded sample of the same workload.
 """
 import argparse
@@ -280,6 +282,7 @@ def main():
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-CUDA comparator leg")
     ap.add_argument("--no-train", action="store_true", help="skip the RPN training-step leg (BASELINE configs[2])")
     ap.add_argument("--no-rcnn", action="store_true", help="skip the RCNN stage-2 leg (BASELINE configs[3])")
+    ap.add_argument("--no-eval", action="store_true", help="skip the end-to-end two-stage evaluation leg (BASELINE configs[4])")
     ap.add_argument("--inflight", type=int, default=6, help="independent batches in flight (CUDA streams); 1 = sequential")
     ap.add_argument("--graphs", type=int, default=1, help="1: one CUDA graph per pipeline slot (default), 0: eager launches")
     ap.add_argument("--min-seconds", type=float, default=1.0, help="each leg repeats its K-step region until this much is timed (>= 3 repeats)")
@@ -482,6 +485,19 @@ def main():
         except Exception as e:
             rcnn = {"unavailable": "%s: %s" % (type(e).__name__, e)}
         torch.cuda.empty_cache()
+    # ---------------- BASELINE configs[4]: end-to-end two-stage evaluation, global batch 8 sharded over the ranks
+    eval_e2e = None
+    if not args.no_eval:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        try:
+            import bench_eval_e2e
+            eval_e2e = bench_eval_e2e.measure(dev, rank=rank, world=world, steps=min(K, 10), warm=3, barrier=barrier,
+                                              max_over_ranks=max_over_ranks)
+        except Exception as e:
+            if world > 1:
+                raise          # a rank that drops out of the barriers would hang the others
+            eval_e2e = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+        torch.cuda.empty_cache()
     clocks = sampler.stop() if sampler else None
 
     # ---------------- the reference's CUDA-extension build (oracle/_ref kernels + cuDNN MLP), same process, same inputs
@@ -616,7 +632,7 @@ def main():
                              "what": "backbone only, full (B,128,16384) features copied to pinned host memory every step (PCIe bound)",
                              "repeats": summary(feat_list)},
             "gpu_launches": launches, "chain_plans": tuned_plans(), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
-            "ref_cuda": ref_cuda, "vs_ref_cuda": vs_ref, "strong_scaling": strong, "train_step": train, "rcnn_stage": rcnn}
+            "ref_cuda": ref_cuda, "vs_ref_cuda": vs_ref, "strong_scaling": strong, "train_step": train, "rcnn_stage": rcnn, "eval_e2e": eval_e2e}
     if args.profile_out:
         json.dump(line, open(args.profile_out, "w"), indent=1)
     print(json.dumps(line))

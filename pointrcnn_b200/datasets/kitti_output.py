@@ -47,13 +47,22 @@ def format_kitti_lines(bbox3d, img_boxes, alpha, scores, valid, classes="Car"):
     return buf.value.decode()
 
 
+def detections_to_host(bbox3d, scores, P2, img_shape):
+    """device work + ONE device-to-host copy for a scene's detections: -> (bbox3d, img_boxes, alpha, scores, valid) numpy"""
+    n = bbox3d.size(0)
+    img_boxes, alpha, valid = kitti_image_boxes(bbox3d, P2, img_shape)
+    packed = torch.cat((bbox3d.float(), img_boxes, alpha.unsqueeze(1), scores.float().view(n, 1), valid.float().unsqueeze(1)), dim=1)
+    h = packed.cpu().numpy()
+    return h[:, 0:7], h[:, 7:11], h[:, 11], h[:, 12], h[:, 13].astype(np.int32)
+
+
 def save_kitti_format(sample_id, calib, bbox3d, kitti_output_dir, scores, img_shape, classes="Car"):
     """same arguments as the reference; bbox3d / scores may be CUDA tensors (no per-box host work) or numpy arrays"""
     calib = Calibration(calib)
     dev_boxes = bbox3d if torch.is_tensor(bbox3d) else torch.from_numpy(np.ascontiguousarray(bbox3d, dtype=np.float32)).cuda()
-    img_boxes, alpha, valid = kitti_image_boxes(dev_boxes, calib.P2, img_shape)
-    sc = scores.detach().cpu().numpy() if torch.is_tensor(scores) else np.asarray(scores)
-    text = format_kitti_lines(dev_boxes.detach().cpu().numpy(), img_boxes.cpu().numpy(), alpha.cpu().numpy(), sc, valid.cpu().numpy(), classes)
+    dev_scores = scores if torch.is_tensor(scores) else torch.from_numpy(np.ascontiguousarray(scores, dtype=np.float32))
+    host = detections_to_host(dev_boxes.contiguous(), dev_scores.to(dev_boxes.device), calib.P2, img_shape)
+    text = format_kitti_lines(*host, classes=classes)
     path = os.path.join(kitti_output_dir, "%06d.txt" % sample_id)
     with open(path, "w") as f:
         f.write(text)

@@ -10,7 +10,8 @@ of raw scans goes through four launches (csrc/kitti_io.cu) and comes out as the 
     batch = pipe.prepare_batch(scans, seed=step)          # dict of CUDA tensors, same keys as collate_batch
 
 File IO (KITTI .bin / calib / label readers, the GT-paste database) stays with the caller: a scan is
-`dict(lidar=(n,4) float32, calib=Calibration|dict, img_shape=(H,W[,3]), gt_boxes3d=(g,7), gt_alpha=(g,))`.
+`dict(lidar=(n,4) float32 numpy array or (pinned) torch tensor, calib=Calibration|dict, img_shape=(H,W[,3]),
+gt_boxes3d=(g,7), gt_alpha=(g,))`.
 
 Two ways to draw the npoints sample:
   draw="device" (default)  counter-based hashes on the device, no host round trip; same distribution as the reference
@@ -196,14 +197,15 @@ class RPNInputPipeline(object):
         offsets[1:] = np.cumsum(counts)
         total = int(offsets[-1])
         stride = int(scans[0]["lidar"].shape[1])
-        host = torch.empty((max(total, 1), stride), dtype=torch.float32, pin_memory=True)
-        for s, o in zip(scans, offsets[:-1]):
-            n = s["lidar"].shape[0]
-            if n:
-                host[o:o + n] = torch.from_numpy(np.ascontiguousarray(s["lidar"], dtype=np.float32))
-        calib = np.stack([Calibration(s["calib"]).pack(s["img_shape"], self.scope if self.reduce_by_range else None) for s in scans])
         dev = self.device
-        lidar = host.to(dev, non_blocking=True)
+        lidar = torch.empty((max(total, 1), stride), dtype=torch.float32, device=dev)
+        for s, o in zip(scans, offsets[:-1]):      # one DMA per scan, straight from the caller's (ideally pinned) memory
+            src = s["lidar"]
+            n = int(src.shape[0])
+            if n:
+                src = src if torch.is_tensor(src) else torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32))
+                lidar[o:o + n].copy_(src, non_blocking=True)
+        calib = np.stack([Calibration(s["calib"]).pack(s["img_shape"], self.scope if self.reduce_by_range else None) for s in scans])
         return (B, total, stride, torch.from_numpy(offsets).to(dev, non_blocking=True), lidar,
                 torch.from_numpy(calib).to(dev, non_blocking=True), offsets)
 

@@ -15,7 +15,7 @@ B, RAW, NPOINTS = 16, 120000, 16384
 scans = []
 for i in range(B):
     lidar, gt, alpha = KO.synth_scan(500 + i, RAW, 8)
-    scans.append(dict(lidar=lidar, calib=KO.CALIB, img_shape=KO.IMG_SHAPE, gt_boxes3d=gt, gt_alpha=alpha))
+    scans.append(dict(lidar=torch.from_numpy(lidar).pin_memory(), calib=KO.CALIB, img_shape=KO.IMG_SHAPE, gt_boxes3d=gt, gt_alpha=alpha))
 res = {"batch": B, "raw_points_per_scan": int(scans[0]["lidar"].shape[0]), "npoints": NPOINTS}
 pipe = RPNInputPipeline(npoints=NPOINTS, mode="TRAIN", draw="device", device=dev)
 for _ in range(3):
@@ -41,7 +41,7 @@ res["launches_per_batch"] = C.launch_count() - lc0
 rng = np.random.RandomState(0)
 t0 = time.perf_counter()
 for s in scans[:4]:
-    KO.rpn_sample(s["lidar"], KO.CALIB, KO.IMG_SHAPE, s["gt_boxes3d"], s["gt_alpha"], NPOINTS, rng, train=True)
+    KO.rpn_sample(s["lidar"].numpy(), KO.CALIB, KO.IMG_SHAPE, s["gt_boxes3d"], s["gt_alpha"], NPOINTS, rng, train=True)
 host = (time.perf_counter() - t0) / 4
 res["numpy_ms_per_scene"] = 1e3 * host
 res["numpy_scenes_per_s"] = 1.0 / host

@@ -175,16 +175,18 @@ def test_device_draw_has_the_reference_distribution_rules(cuda):
             assert len(uniq) >= nv - 2 and cnt.max() == 2 and (cnt == 2).sum() == NPOINTS - len(uniq)
         # shuffled: the far points are not bunched at either end, indices are not sorted
         assert np.abs(np.corrcoef(np.arange(NPOINTS), ch)[0, 1]) < 0.1
-    # a near-uniform draw: over several seeds every near point is drawn with about the same frequency
+    # a uniform draw: every seed takes exactly `need` of the near points, each with the same probability
     rect = KO.lidar_to_rect(scans[0]["lidar"], KO.CALIB)
+    uv, depth = KO.rect_to_img(rect, KO.CALIB)
+    ok = KO.get_valid_flag(rect, uv, depth, KO.IMG_SHAPE)
+    near = ok & (rect[:, 2] < 40.0)
+    q = (NPOINTS - int((ok & ~near).sum())) / float(near.sum())
     hits = np.zeros(len(rect))
     for seed in range(24):
         ch = pipe.prepare_batch(scans[:1], seed=100 + seed)["choice"][0].cpu().numpy()
         hits[ch] += 1
-    uv, depth = KO.rect_to_img(rect, KO.CALIB)
-    near = KO.get_valid_flag(rect, uv, depth, KO.IMG_SHAPE) & (rect[:, 2] < 40.0)
     p = hits[near] / 24.0
-    assert 0.3 < p.mean() < 1.0 and p.std() < 2.0 * np.sqrt(p.mean() * (1 - p.mean()) / 24.0)
+    assert abs(p.mean() - q) < 2e-3 and p.std() < 1.5 * np.sqrt(q * (1 - q) / 24.0), (p.mean(), q, p.std())
 
 
 @pytest.mark.gpu
