@@ -345,6 +345,9 @@ PRB_API int prb_rpn_training_labels(int b, int n, int g, const float *pts_rect, 
  * to the image, alpha (n), valid (n) int32 (box narrower / lower than 0.8 of the image). */
 PRB_API int prb_kitti_image_boxes(int n, const float *boxes3d, const float *P2, float img_h, float img_w, float *img_boxes,
                           float *alpha, int *valid, void *stream);
+/* the same for a batch: boxes3d (b,m,7), scene k with its own P2 (b,12) and image size img_hw (b,2) [height, width] */
+PRB_API int prb_kitti_image_boxes_batch(int b, int m, const float *boxes3d, const float *P2, const float *img_hw, float *img_boxes,
+                                float *alpha, int *valid, void *stream);
 /* HOST function: the text of one KITTI result file (eval_rcnn.py:85-94) from host arrays; returns the bytes needed
  * (without terminator), writes at most cap bytes. */
 PRB_API size_t prb_kitti_format_detections(const char *cls_name, int n, const float *boxes3d, const float *img_boxes,

@@ -345,12 +345,17 @@ __global__ void __launch_bounds__(256) rpn_labels_kernel(int n, int g, const flo
 // ---------------------------------------------------------------------------------------------------- output
 // save_kitti_format (eval_rcnn.py:69-94): corners in fp32 (kitti_utils.py:66-101), projection in fp64 like the
 // reference's np.matmul of a float64 homogeneous array (calibration.py:106-124)
+// per_scene > 0: box i belongs to scene i / per_scene with its own P2 (12 floats) and image size hw (2 floats)
 __global__ void __launch_bounds__(128) kitti_image_boxes_kernel(int n, const float *__restrict__ boxes,
-                                                                 const float *__restrict__ P2, float img_h, float img_w,
+                                                                 const float *__restrict__ P2_all, int per_scene,
+                                                                 const float *__restrict__ hw_all, float img_h, float img_w,
                                                                  float *__restrict__ img_boxes, float *__restrict__ alpha,
                                                                  int *__restrict__ valid) {
     const int i = blockIdx.x * 128 + threadIdx.x;
     if (i >= n) return;
+    const int scene = per_scene > 0 ? i / per_scene : 0;
+    const float *P2 = P2_all + (size_t)scene * 12;
+    if (hw_all) { img_h = hw_all[scene * 2]; img_w = hw_all[scene * 2 + 1]; }
     const float *q = boxes + (size_t)i * 7;
     const float x = q[0], y = q[1], z = q[2], h = q[3], w = q[4], l = q[5], ry = q[6];
     const float cs = cosf(ry), sn = sinf(ry);
@@ -434,7 +439,17 @@ extern "C" int prb_kitti_image_boxes(int n, const float *boxes3d, const float *P
                                      float *alpha, int *valid, void *stream) {
     PRB_REQUIRE(n >= 0 && P2 && (n == 0 || (boxes3d && img_boxes && alpha && valid)), "kitti_image_boxes: bad arguments");
     if (n == 0) return 0;
-    kitti_image_boxes_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(n, boxes3d, P2, img_h, img_w, img_boxes, alpha, valid);
+    kitti_image_boxes_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(n, boxes3d, P2, 0, nullptr, img_h, img_w, img_boxes, alpha,
+                                                                               valid);
+    return check_launch("kitti_image_boxes_kernel");
+}
+
+extern "C" int prb_kitti_image_boxes_batch(int b, int m, const float *boxes3d, const float *P2, const float *img_hw, float *img_boxes,
+                                           float *alpha, int *valid, void *stream) {
+    PRB_REQUIRE(b >= 0 && m >= 0 && P2 && img_hw && (b * m == 0 || (boxes3d && img_boxes && alpha && valid)), "kitti_image_boxes_batch: bad arguments");
+    if (b * m == 0) return 0;
+    kitti_image_boxes_kernel<<<ceil_div(b * m, 128), 128, 0, (cudaStream_t)stream>>>(b * m, boxes3d, P2, m, img_hw, 0.f, 0.f, img_boxes, alpha,
+                                                                                   valid);
     return check_launch("kitti_image_boxes_kernel");
 }
 

@@ -67,3 +67,31 @@ def save_kitti_format(sample_id, calib, bbox3d, kitti_output_dir, scores, img_sh
     with open(path, "w") as f:
         f.write(text)
     return path
+
+
+def write_kitti_batch(sample_ids, calibs, img_shapes, boxes3d, scores, select, kitti_output_dir=None, classes="Car"):
+    """A batch of scenes with ONE launch and ONE device-to-host copy: boxes3d (B,M,7), scores (B,M) CUDA tensors,
+    select (B,M) bool/0-1 CUDA tensor marking the rows that are detections (e.g. the NMS survivors), rows are written in
+    their order.  Returns the list of texts; also writes <dir>/<sample_id>.txt when kitti_output_dir is given."""
+    C.require_cuda(boxes3d, scores, select)
+    B, M = boxes3d.shape[0], boxes3d.shape[1]
+    dev = boxes3d.device
+    b = boxes3d.contiguous().float()
+    p2 = torch.from_numpy(np.stack([Calibration(c).P2.reshape(-1) for c in calibs]).astype(np.float32)).to(dev, non_blocking=True)
+    hw = torch.tensor([[float(s[0]), float(s[1])] for s in img_shapes], dtype=torch.float32).to(dev, non_blocking=True)
+    img_boxes = torch.empty((B, M, 4), dtype=torch.float32, device=dev)
+    alpha = torch.empty((B, M), dtype=torch.float32, device=dev)
+    valid = torch.empty((B, M), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        C.check(C.lib().prb_kitti_image_boxes_batch(B, M, C.ptr(b), C.ptr(p2), C.ptr(hw), C.ptr(img_boxes), C.ptr(alpha), C.ptr(valid), C.stream()),
+                "kitti_image_boxes_batch")
+    keep = valid.float() * select.float()
+    h = torch.cat((b, img_boxes, alpha.unsqueeze(2), scores.float().unsqueeze(2), keep.unsqueeze(2)), dim=2).cpu().numpy()   # the one sync
+    texts = []
+    for k in range(B):
+        r = h[k]
+        texts.append(format_kitti_lines(r[:, 0:7], r[:, 7:11], r[:, 11], r[:, 12], r[:, 13].astype(np.int32), classes))
+        if kitti_output_dir is not None:
+            with open(os.path.join(kitti_output_dir, "%06d.txt" % int(sample_ids[k])), "w") as f:
+                f.write(texts[-1])
+    return texts

@@ -59,3 +59,35 @@ class PointRCNNInference(nn.Module):
             keep = iou3d_utils.nms_gpu(kitti_utils.boxes3d_to_bev_torch(boxes_k), raw_k, self.rcnn_nms_thresh).view(-1)
             res.append((boxes_k[keep], raw_k[keep]))
         return res, pred
+
+    def detections_device(self, out):
+        """detections() without a host round trip: the same decode / score threshold / rotated NMS, batched, results left
+        on the device: (boxes (B,M,7) in descending raw-score order, raw scores (B,M), select (B,M) bool = the detections).
+        Boxes under the score threshold are ordered LAST (score -inf) instead of being compacted away: greedy NMS visits
+        boxes in order, so they cannot change which of the boxes above the threshold survive, and they are masked out
+        afterwards -- the selected rows equal detections()'s per-scene lists, in the same order."""
+        from .ext import iou3d_cuda
+        rois = out["rois"]
+        B, M = rois.shape[0], rois.shape[1]
+        c = self.rcnn_net.cfg
+        rcnn_cls = out["rcnn_cls"].view(B, M, -1)
+        rcnn_reg = out["rcnn_reg"].view(B, M, -1)
+        pred = decode_bbox_target(rois.reshape(-1, 7), rcnn_reg.reshape(-1, rcnn_reg.shape[-1]), anchor_size=self.mean_size,
+                                  loc_scope=c["LOC_SCOPE"], loc_bin_size=c["LOC_BIN_SIZE"], num_head_bin=c["NUM_HEAD_BIN"],
+                                  get_xz_fine=True, get_y_by_bin=c["LOC_Y_BY_BIN"], loc_y_scope=c["LOC_Y_SCOPE"],
+                                  loc_y_bin_size=c["LOC_Y_BIN_SIZE"], get_ry_fine=True).view(B, M, 7)
+        raw = rcnn_cls[:, :, 0]
+        above = torch.sigmoid(raw) > self.rcnn_score_thresh
+        order = torch.where(above, raw, torch.full_like(raw, float("-inf"))).sort(dim=1, descending=True)[1]
+        boxes = torch.gather(pred, 1, order.unsqueeze(2).expand(B, M, 7)).contiguous()
+        raw_s = torch.gather(raw, 1, order)
+        n_above = above.sum(dim=1, keepdim=True)
+        bev = kitti_utils.boxes3d_to_bev_torch(boxes.view(-1, 7)).view(B, M, 5).contiguous()
+        select = torch.zeros((B, M), dtype=torch.bool, device=rois.device)
+        pos = torch.arange(M, device=rois.device)
+        for k in range(B):                                   # launches only; nothing comes back to the host
+            keep, num = iou3d_cuda.nms_device(bev[k], self.rcnn_nms_thresh, 0)
+            kept = (pos < num.to(torch.int64)).float()       # keep[:num] are the surviving positions; the tail of keep is undefined
+            select[k] = torch.zeros(M, device=rois.device).scatter_add_(0, keep.clamp(0, M - 1), kept) > 0
+        select &= pos.unsqueeze(0) < n_above
+        return boxes, raw_s, select

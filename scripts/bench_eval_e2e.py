@@ -67,11 +67,10 @@ def measure(dev, rank=0, world=1, steps=10, warm=3, barrier=lambda: None, max_ov
         scans = pool[i % len(pool)]
         batch = pipe.prepare_batch(scans, seed=i)
         out = model(batch["pts_input"])
-        dets, _ = model.detections(out)
-        for k, (boxes, raw) in enumerate(dets):
-            host = kitti_output.detections_to_host(boxes, raw, P2, IMG_SHAPE)       # one D2H per scene
-            text = kitti_output.format_kitti_lines(*host)
-            stats["detections"] += int(boxes.shape[0]); stats["text_bytes"] += len(text); stats["d2h"] += sum(h.nbytes for h in host)
+        boxes, raw, select = model.detections_device(out)          # no host round trip up to here
+        texts = kitti_output.write_kitti_batch(range(len(scans)), [CALIB] * len(scans), [IMG_SHAPE] * len(scans), boxes, raw, select)
+        stats["detections"] += sum(t.count("\n") for t in texts); stats["text_bytes"] += sum(len(t) for t in texts)
+        stats["d2h"] += boxes.shape[0] * boxes.shape[1] * 14 * 4
 
     with torch.no_grad():
         for i in range(warm):

@@ -155,3 +155,25 @@ def test_final_detections_against_reference_nms(cuda, chain):
         assert torch.equal(dets[k][0], boxes_k[want]) and torch.equal(dets[k][1], raw_k[want]), "scene %d: kept detections differ" % k
         total += want.numel()
     assert total > 0, "no detections at all: the final NMS was not exercised"
+
+
+def test_batched_detections_and_kitti_writer_equal_the_per_scene_path(cuda, chain, tmp_path):
+    """detections_device (no host round trip) selects exactly detections()'s boxes in the same order; write_kitti_batch writes
+    what save_kitti_format writes scene by scene"""
+    from pointrcnn_b200.datasets import kitti_output
+    from oracle import kitti_io as KO
+    model, pc, out, dets, _ = chain
+    with torch.no_grad():
+        boxes, raw, select = model.detections_device(out)
+    B = boxes.shape[0]
+    assert sum(int(d[0].shape[0]) for d in dets) > 0, "the fixture must produce detections"
+    for k in range(B):
+        sel = select[k]
+        assert torch.equal(boxes[k][sel], dets[k][0]), "scene %d: batched detections differ" % k
+        assert torch.equal(raw[k][sel], dets[k][1])
+    texts = kitti_output.write_kitti_batch(range(B), [KO.CALIB] * B, [KO.IMG_SHAPE] * B, boxes, raw, select, str(tmp_path))
+    for k in range(B):
+        single = tmp_path / "single"
+        single.mkdir(exist_ok=True)
+        path = kitti_output.save_kitti_format(k, KO.CALIB, dets[k][0], str(single), dets[k][1], KO.IMG_SHAPE)
+        assert open(path).read() == texts[k] == open(tmp_path / ("%06d.txt" % k)).read()
