@@ -69,10 +69,10 @@ def save_kitti_format(sample_id, calib, bbox3d, kitti_output_dir, scores, img_sh
     return path
 
 
-def write_kitti_batch(sample_ids, calibs, img_shapes, boxes3d, scores, select, kitti_output_dir=None, classes="Car"):
-    """A batch of scenes with ONE launch and ONE device-to-host copy: boxes3d (B,M,7), scores (B,M) CUDA tensors,
-    select (B,M) bool/0-1 CUDA tensor marking the rows that are detections (e.g. the NMS survivors), rows are written in
-    their order.  Returns the list of texts; also writes <dir>/<sample_id>.txt when kitti_output_dir is given."""
+def submit_kitti_batch(calibs, img_shapes, boxes3d, scores, select):
+    """device half of write_kitti_batch on the CURRENT stream: one launch, one packed (B,M,14) tensor, one asynchronous copy
+    into pinned host memory.  Returns (pinned host tensor, event); nothing waits for the GPU here, so several batches can be
+    in flight on different streams."""
     C.require_cuda(boxes3d, scores, select)
     B, M = boxes3d.shape[0], boxes3d.shape[1]
     dev = boxes3d.device
@@ -85,13 +85,33 @@ def write_kitti_batch(sample_ids, calibs, img_shapes, boxes3d, scores, select, k
     with torch.cuda.device(dev):
         C.check(C.lib().prb_kitti_image_boxes_batch(B, M, C.ptr(b), C.ptr(p2), C.ptr(hw), C.ptr(img_boxes), C.ptr(alpha), C.ptr(valid), C.stream()),
                 "kitti_image_boxes_batch")
-    keep = valid.float() * select.float()
-    h = torch.cat((b, img_boxes, alpha.unsqueeze(2), scores.float().unsqueeze(2), keep.unsqueeze(2)), dim=2).cpu().numpy()   # the one sync
+        keep = valid.float() * select.float()
+        packed = torch.cat((b, img_boxes, alpha.unsqueeze(2), scores.float().unsqueeze(2), keep.unsqueeze(2)), dim=2)
+        host = torch.empty(packed.shape, dtype=torch.float32, pin_memory=True)
+        host.copy_(packed, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        packed.record_stream(torch.cuda.current_stream())
+    return host, ev
+
+
+def collect_kitti_batch(handle, sample_ids=None, kitti_output_dir=None, classes="Car"):
+    """host half: wait for the batch's copy, format every scene's text (and write <dir>/<sample_id>.txt when asked)"""
+    host, ev = handle
+    ev.synchronize()
+    h = host.numpy()
     texts = []
-    for k in range(B):
+    for k in range(h.shape[0]):
         r = h[k]
         texts.append(format_kitti_lines(r[:, 0:7], r[:, 7:11], r[:, 11], r[:, 12], r[:, 13].astype(np.int32), classes))
         if kitti_output_dir is not None:
             with open(os.path.join(kitti_output_dir, "%06d.txt" % int(sample_ids[k])), "w") as f:
                 f.write(texts[-1])
     return texts
+
+
+def write_kitti_batch(sample_ids, calibs, img_shapes, boxes3d, scores, select, kitti_output_dir=None, classes="Car"):
+    """A batch of scenes with ONE launch and ONE device-to-host copy: boxes3d (B,M,7), scores (B,M) CUDA tensors,
+    select (B,M) bool/0-1 CUDA tensor marking the rows that are detections (e.g. the NMS survivors), rows are written in
+    their order.  Returns the list of texts; also writes <dir>/<sample_id>.txt when kitti_output_dir is given."""
+    return collect_kitti_batch(submit_kitti_batch(calibs, img_shapes, boxes3d, scores, select), sample_ids, kitti_output_dir, classes)
