@@ -25,7 +25,7 @@ class Options(ctypes.Structure):
     """struct prb_options (per-thread tuning block)"""
     _fields_ = [(k, c_int) for k in ("fps_cluster", "fps_prune", "fps_threads", "fps_generic", "mlp_gather", "mlp_ng", "mlp_occ",
                                      "mlp_sms", "mlp_atmem", "mlp_sleepy", "mlp_trace", "mlp_pipeline", "mlp_ne", "mlp_ngw", "mlp_zs",
-                                     "mlp_nbuf", "mlp_brows", "mlp_pool", "mlp_resident", "mlp_lazy_ns", "mlp_fill", "mlp_tune", "roipool_exhaustive", "roipool_parts", "roipool_stage_kb", "roipool_direct", "nn_walk", "nn_sort_queries", "grid_csr", "grid_debug")] + [("nn_cell", c_float)]
+                                     "mlp_nbuf", "mlp_brows", "mlp_pool", "mlp_resident", "mlp_lazy_ns", "mlp_fill", "mlp_tune", "roipool_exhaustive", "roipool_parts", "roipool_stage_kb", "roipool_direct", "nn_walk", "nn_sort_queries", "grid_csr", "grid_debug")] + [("nn_cell", c_float), ("roipool_fused", c_int)]
 
 
 @contextlib.contextmanager

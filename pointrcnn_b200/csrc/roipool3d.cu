@@ -303,21 +303,16 @@ __global__ void __launch_bounds__(RG_THREADS) roipool3d_bin_kernel(int N, const 
     }
 }
 
-constexpr int RGA_THREADS = 128;
-__global__ void __launch_bounds__(RGA_THREADS) roipool3d_assign_grid_kernel(int N, int M, int S, const float *__restrict__ xyz,
-                                                                           const float *__restrict__ boxes3d,
-                                                                           const int *__restrict__ sorted_idx,
-                                                                           const int *__restrict__ cell_start,
-                                                                           const SceneGrid *__restrict__ grids,
-                                                                           int *__restrict__ idx_out, int *__restrict__ cnt_out) {
-    extern __shared__ unsigned int s_bits[];          // ceil(N / 32) words
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int box = blockIdx.x, scene = blockIdx.y;
+// The binned assign pass of one box, by all threads of the CTA: set the bit of every inside point in s_bits (N bits, shared),
+// then warp 0 walks the bitmap and writes the first S set bits -- "the first S inside points in point-index order" -- to
+// list[] (global or shared).  Returns min(count, S) to every thread of warp 0 (other warps: undefined).  Ends with no barrier.
+__device__ __forceinline__ int assign_grid_box(int N, int S, const float *__restrict__ pts, const float *__restrict__ bx,
+                                               const int *__restrict__ sorted, const int *__restrict__ cstart, const SceneGrid g,
+                                               unsigned int *s_bits, int *list) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
     const int nwords = (N + 31) >> 5;
-    for (int i = tid; i < nwords; i += RGA_THREADS) s_bits[i] = 0u;
-    const float *bx = boxes3d + ((size_t)scene * M + box) * 7;
+    for (int i = tid; i < nwords; i += nthreads) s_bits[i] = 0u;
     const BoxConst bc = make_box(bx);
-    const SceneGrid g = grids[scene];
     // conservative x-z footprint of the predicate (see above); NaN / Inf boxes degrade to "every cell" or "cell 0", both safe
     const float hl = (float)bc.half_l, hw = (float)bc.half_w, ac = fabsf(bc.cosa), as = fabsf(bc.sina);
     float ex = fminf(__fmaf_rn(ac, hl, as * hw), 10.f), ez = fminf(__fmaf_rn(as, hl, ac * hw), 10.f);
@@ -328,12 +323,9 @@ __global__ void __launch_bounds__(RGA_THREADS) roipool3d_assign_grid_kernel(int 
     if (!(ex == ex) || !(ez == ez) || !(bc.cx == bc.cx) || !(bc.cz == bc.cz)) { xc0 = zc0 = 0; xc1 = zc1 = RG - 1; }
     if (xc0 > xc1) { const int t = xc0; xc0 = xc1; xc1 = t; }
     if (zc0 > zc1) { const int t = zc0; zc0 = zc1; zc1 = t; }
-    const float *pts = xyz + (size_t)scene * N * 3;
-    const int *sorted = sorted_idx + (size_t)scene * N;
-    const int *cstart = cell_start + (size_t)scene * (RG_CELLS + 1);
     __syncthreads();
     // a z-row of the footprint is one contiguous span of the permutation
-    for (int zc = zc0 + warp; zc <= zc1; zc += RGA_THREADS / 32) {
+    for (int zc = zc0 + warp; zc <= zc1; zc += nthreads / 32) {
         const int lo = cstart[zc * RG + xc0], hi = cstart[zc * RG + xc1 + 1];
         for (int e = lo + lane; e < hi; e += 32) {
             const int k = sorted[e];
@@ -342,8 +334,7 @@ __global__ void __launch_bounds__(RGA_THREADS) roipool3d_assign_grid_kernel(int 
         }
     }
     __syncthreads();
-    if (warp != 0) return;
-    int *dst = idx_out + ((size_t)scene * M + box) * S;
+    if (warp != 0) return 0;
     int run = 0;
     for (int w0 = 0; w0 < nwords && run < S; w0 += 32) {
         unsigned word = w0 + lane < nwords ? s_bits[w0 + lane] : 0u;
@@ -356,12 +347,29 @@ __global__ void __launch_bounds__(RGA_THREADS) roipool3d_assign_grid_kernel(int 
         while (word && pos < S) {
             const int b = __ffs(word) - 1;
             word &= word - 1;
-            dst[pos++] = base + b;
+            list[pos++] = base + b;
         }
         run += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (lane == 0) cnt_out[(size_t)scene * M + box] = min(run, S);
+    return min(run, S);
 }
+
+constexpr int RGA_THREADS = 128;
+__global__ void __launch_bounds__(RGA_THREADS) roipool3d_assign_grid_kernel(int N, int M, int S, const float *__restrict__ xyz,
+                                                                           const float *__restrict__ boxes3d,
+                                                                           const int *__restrict__ sorted_idx,
+                                                                           const int *__restrict__ cell_start,
+                                                                           const SceneGrid *__restrict__ grids,
+                                                                           int *__restrict__ idx_out, int *__restrict__ cnt_out) {
+    extern __shared__ unsigned int s_bits[];          // ceil(N / 32) words
+    const int box = blockIdx.x, scene = blockIdx.y;
+    const int n = assign_grid_box(N, S, xyz + (size_t)scene * N * 3, boxes3d + ((size_t)scene * M + box) * 7,
+                                  sorted_idx + (size_t)scene * N, cell_start + (size_t)scene * (RG_CELLS + 1), grids[scene], s_bits,
+                                  idx_out + ((size_t)scene * M + box) * S);
+    if (threadIdx.x == 0) cnt_out[(size_t)scene * M + box] = n;
+}
+
+struct FusedAssign { const int *sorted_idx, *cell_start; const SceneGrid *grids; const float *boxes3d; };   // sorted_idx == nullptr: two-kernel form
 
 // Pass B.  A box usually holds far fewer than S points, so its S output rows are `cnt` distinct rows repeated cyclically:
 // flat, the output IS the cnt x (3+C) source block repeated -- out[e] = block[e mod (cnt*(3+C))].  The block is staged in
@@ -374,13 +382,25 @@ __global__ void __launch_bounds__(RP_THREADS) roipool3d_copy_kernel(int N, int M
                                                                     const float *__restrict__ pts_feature,
                                                                     const int *__restrict__ idx_in, const int *__restrict__ cnt_in,
                                                                     float *__restrict__ pooled, int *__restrict__ empty_flag,
-                                                                    const float *__restrict__ rois, int zero_fill, int stage_floats, int opts_chunked) {
-    extern __shared__ float s_blk[];          // stage_floats floats, then S ints (direct path)
+                                                                    const float *__restrict__ rois, int zero_fill, int stage_floats, int opts_chunked,
+                                                                    const FusedAssign fa) {
+    extern __shared__ float s_blk[];          // stage_floats floats, then S ints (direct path / fused index list), then the fused pass's bitmap
     int *s_idx = reinterpret_cast<int *>(s_blk + stage_floats);
+    __shared__ int s_cnt;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int box = blockIdx.x, scene = blockIdx.y;
     const size_t bi = (size_t)scene * M + box;
-    const int cnt = cnt_in[bi];
+    // Fused form (default): this CTA first runs the binned assign pass of ITS box -- bitmap and index list stay in shared
+    // memory -- and copies straight away: one launch less, no index list in HBM, and the dependent loads of the assign pass
+    // (cell offsets -> permutation -> coordinates) hide behind the row streams of the SM's other CTAs.
+    if (fa.sorted_idx) {
+        const int n = assign_grid_box(N, S, xyz + (size_t)scene * N * 3, fa.boxes3d + bi * 7, fa.sorted_idx + (size_t)scene * N,
+                                      fa.cell_start + (size_t)scene * (RG_CELLS + 1), fa.grids[scene],
+                                      reinterpret_cast<unsigned int *>(s_idx + S), s_idx);
+        if (tid == 0) s_cnt = n;
+        __syncthreads();
+    }
+    const int cnt = fa.sorted_idx ? s_cnt : cnt_in[bi];
     const int W = 3 + C;
     const long total = (long)S * W;
     float *dst = pooled + bi * (size_t)total;
@@ -417,7 +437,7 @@ __global__ void __launch_bounds__(RP_THREADS) roipool3d_copy_kernel(int N, int M
     }
     const float *pts = xyz + (size_t)scene * N * 3;
     const float *feat = pts_feature + (size_t)scene * N * C;
-    const int *idx = idx_in + bi * S;
+    const int *idx = fa.sorted_idx ? s_idx : idx_in + bi * S;
     if ((long)cnt * W <= stage_floats && vec) {
         // ---- stage the cnt distinct rows (warp per row, lanes along the row), then stream the block cyclically
         for (int j = warp; j < cnt; j += RP_WARPS) {
@@ -451,7 +471,11 @@ __global__ void __launch_bounds__(RP_THREADS) roipool3d_copy_kernel(int N, int M
         return;
     }
     // ---- direct path: many points in the box (or an unaligned output): sources through L1
-    for (int j = tid; j < S; j += RP_THREADS) s_idx[j] = idx[j < cnt ? j : j % cnt];
+    if (fa.sorted_idx) {      // the list already sits in s_idx[0 .. cnt): extend it cyclically in place
+        for (int j = cnt + tid; j < S; j += RP_THREADS) s_idx[j] = s_idx[j % cnt];
+    } else {
+        for (int j = tid; j < S; j += RP_THREADS) s_idx[j] = idx[j < cnt ? j : j % cnt];
+    }
     __syncthreads();
     auto value = [&](int row, int col) -> float {
         const int k = s_idx[row];
@@ -534,7 +558,8 @@ extern "C" int prb_roipool3d_ws(int B, int N, int M, int C, int S, const float *
     const int stage_floats = stage_kb * 256;
     int parts = opts().roipool_parts;
     if (parts < 1 || parts > 8) parts = 1;                                           // 2-4 CTAs per box: 0.134-0.140 ms (no gain)
-    const size_t smem_b = (size_t)stage_floats * sizeof(float) + (size_t)S * sizeof(int);
+    size_t smem_b = (size_t)stage_floats * sizeof(float) + (size_t)S * sizeof(int);
+    FusedAssign fa = {nullptr, nullptr, nullptr, nullptr};
     PRB_REQUIRE(smem_a <= 200 * 1024 && smem_b <= 200 * 1024, "roipool3d: sampled_pts_num %d too large", S);
     int *idx = reinterpret_cast<int *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     int *cnt = idx + (size_t)B * M * S;
@@ -546,8 +571,13 @@ extern "C" int prb_roipool3d_ws(int B, int N, int M, int C, int S, const float *
         SceneGrid *grids = reinterpret_cast<SceneGrid *>(((uintptr_t)(cstart + (size_t)B * (RG_CELLS + 1)) + 15) & ~(uintptr_t)15);
         roipool3d_bin_kernel<<<B, RG_THREADS, 0, st>>>(N, xyz, sorted, cstart, grids);
         if (int rc = check_launch("roipool3d_bin_kernel")) return rc;
-        roipool3d_assign_grid_kernel<<<dim3(M, B), RGA_THREADS, smem_bits, st>>>(N, M, S, xyz, boxes3d, sorted, cstart, grids, idx, cnt);
-        if (int rc = check_launch("roipool3d_assign_grid_kernel")) return rc;
+        if (opts().roipool_fused != 0 && parts == 1 && smem_b + smem_bits <= 200 * 1024) {
+            fa.sorted_idx = sorted; fa.cell_start = cstart; fa.grids = grids; fa.boxes3d = boxes3d;
+            smem_b += smem_bits;
+        } else {
+            roipool3d_assign_grid_kernel<<<dim3(M, B), RGA_THREADS, smem_bits, st>>>(N, M, S, xyz, boxes3d, sorted, cstart, grids, idx, cnt);
+            if (int rc = check_launch("roipool3d_assign_grid_kernel")) return rc;
+        }
     } else if (small_idx) {
         if (smem_a > 48 * 1024)
             PRB_CUDA(cudaFuncSetAttribute(roipool3d_assign_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
@@ -561,7 +591,7 @@ extern "C" int prb_roipool3d_ws(int B, int N, int M, int C, int S, const float *
     if (smem_b > 48 * 1024)
         PRB_CUDA(cudaFuncSetAttribute(roipool3d_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     roipool3d_copy_kernel<<<dim3(M, B, parts), RP_THREADS, smem_b, st>>>(N, M, C, S, xyz, pts_feature, idx, cnt, pooled, empty_flag,
-                                                                        rois_canonical, zero_fill_empty, stage_floats, opts().roipool_direct ? 0 : 1);
+                                                                        rois_canonical, zero_fill_empty, stage_floats, opts().roipool_direct ? 0 : 1, fa);
     return check_launch("roipool3d_copy_kernel");
 }
 
