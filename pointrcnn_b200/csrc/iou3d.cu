@@ -44,35 +44,39 @@ __global__ void __launch_bounds__(PM_T * PM_T) pair_matrix_kernel(int num_a, con
 }
 
 // ---------------------------------------------------------------- NMS mask (upper-triangle tiles)
-// One CTA of 8 warps per 64 x 64 tile.  Warp w takes rows w, w+8, ...; lane l tests columns l and l+32 of the row and two
-// ballots assemble the 64-bit mask word (the reference and the round-1 kernel: one thread per row, 64 pairs in sequence).
-// Rotated: the 128 boxes of the tile are precomputed once; axis-aligned: plain extents.
+// One CTA of 8 warps per RT x 64 tile (RT rows, one 64-column mask word per row).  Warp w takes rows w, w+8, ...; lane l tests
+// columns l and l+32 of the row and two ballots assemble the 64-bit mask word (the reference and the round-1 kernel: one
+// thread per row, 64 pairs in sequence).  Rotated: the boxes of the tile are precomputed once; axis-aligned: plain extents.
+// RT = 64 for the cheap axis-aligned test.  RT = 8 for the rotated test (one row per warp, two polygon clippings per
+// thread): with 64-row tiles a thread clipped 16 polygons in sequence and N = 1000 gave only 136 busy CTAs -- 176 us at
+// 8.7 % SM utilisation (profiles/r2_ncu_ops_summary.csv); short tiles trade 72 box precomputations per 512 pairs for 8x the CTAs.
 constexpr int NM_THREADS = 256;
-template <bool NORMAL>
+template <bool NORMAL, int RT>
 __global__ void __launch_bounds__(NM_THREADS) nms_mask_kernel(int n, float thresh, const float *__restrict__ boxes,
                                                               unsigned long long *__restrict__ mask) {
     extern __shared__ float s_poly[];                     // rotated only: 3 x POLY_SLOTS x 256 floats
-    __shared__ BoxPre cpre[NORMAL ? 1 : 64], rpre[NORMAL ? 1 : 64];
-    __shared__ float cbx[NORMAL ? 64 * 5 : 1], rbx[NORMAL ? 64 * 5 : 1];
-    const int row_blk = blockIdx.y, col_blk = blockIdx.x;
+    __shared__ BoxPre cpre[NORMAL ? 1 : 64], rpre[NORMAL ? 1 : RT];
+    __shared__ float cbx[NORMAL ? 64 * 5 : 1], rbx[NORMAL ? RT * 5 : 1];
+    const int col_blk = blockIdx.x;
+    const int row0 = blockIdx.y * RT, col0 = col_blk * 64;
     const int col_blocks = ceil_div(n, 64);
-    const int row_size = min(n - row_blk * 64, 64), col_size = min(n - col_blk * 64, 64);
+    const int row_size = min(n - row0, RT), col_size = min(n - col0, 64);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (row_blk > col_blk) {  // never read by the scan; keep the buffer defined
-        if (tid < row_size) mask[(size_t)(row_blk * 64 + tid) * col_blocks + col_blk] = 0ull;
+    if (row0 >= col0 + 64) {  // every row lies behind every column: never read by the scan; keep the buffer defined
+        if (tid < row_size) mask[(size_t)(row0 + tid) * col_blocks + col_blk] = 0ull;
         return;
     }
     if (NORMAL) {
-        for (int i = tid; i < col_size * 5; i += NM_THREADS) cbx[i] = boxes[(size_t)col_blk * 64 * 5 + i];
-        for (int i = tid; i < row_size * 5; i += NM_THREADS) rbx[i] = boxes[(size_t)row_blk * 64 * 5 + i];
+        for (int i = tid; i < col_size * 5; i += NM_THREADS) cbx[i] = boxes[(size_t)col0 * 5 + i];
+        for (int i = tid; i < row_size * 5; i += NM_THREADS) rbx[i] = boxes[(size_t)row0 * 5 + i];
     } else {
-        if (tid < col_size) box_pre(boxes + (size_t)(col_blk * 64 + tid) * 5, cpre[tid]);
-        else if (tid >= 64 && tid - 64 < row_size) box_pre(boxes + (size_t)(row_blk * 64 + tid - 64) * 5, rpre[tid - 64]);
+        if (tid < col_size) box_pre(boxes + (size_t)(col0 + tid) * 5, cpre[tid]);
+        else if (tid >= 64 && tid - 64 < row_size) box_pre(boxes + (size_t)(row0 + tid - 64) * 5, rpre[tid - 64]);
     }
     __syncthreads();
     float *px = s_poly + tid, *py = px + POLY_SLOTS * NM_THREADS, *pa = py + POLY_SLOTS * NM_THREADS;
     for (int r = warp; r < row_size; r += NM_THREADS / 32) {
-        const int start = (row_blk == col_blk) ? r + 1 : 0;        // inside a diagonal tile only columns behind the row
+        const int start = row0 + r + 1 - col0;                      // only columns behind the row (<= 0 above the diagonal)
         bool hit[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -84,7 +88,7 @@ __global__ void __launch_bounds__(NM_THREADS) nms_mask_kernel(int n, float thres
             }
         }
         const unsigned lo = __ballot_sync(0xffffffffu, hit[0]), hi = __ballot_sync(0xffffffffu, hit[1]);
-        if (lane == 0) mask[(size_t)(row_blk * 64 + r) * col_blocks + col_blk] = ((unsigned long long)hi << 32) | lo;
+        if (lane == 0) mask[(size_t)(row0 + r) * col_blocks + col_blk] = ((unsigned long long)hi << 32) | lo;
     }
 }
 
@@ -130,14 +134,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(int n, const uns
         const unsigned long long *tile = s_tile[buf];
         const int lim = min(64, n - bi * 64);
         if (tid == 0) {
+            // one step per KEPT box (not per box): jump to the next box that is still alive with a find-first-set
             unsigned long long cur = s_remv[bi], kept = 0ull;
+            const unsigned long long valid = lim == 64 ? ~0ull : ((1ull << lim) - 1ull);
+            unsigned long long alive = ~cur & valid;
             int num = s_num;
-            for (int t = 0; t < lim; ++t) {
-                if (!((cur >> t) & 1ull)) {
-                    kept |= 1ull << t;
-                    keep[num++] = (long long)bi * 64 + t;
-                    cur |= tile[(size_t)t * cb + bi];
-                }
+            while (alive) {
+                const int t = __ffsll((long long)alive) - 1;
+                kept |= 1ull << t;
+                keep[num++] = (long long)bi * 64 + t;
+                cur |= tile[(size_t)t * cb + bi];
+                alive = ~cur & valid & ~((2ull << t) - 1ull);       // boxes behind t only
             }
             s_num = num;
             s_kept = kept;
@@ -146,9 +153,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(int n, const uns
         const unsigned long long kept = s_kept;
         for (int j = bi + 1 + tid; j < cb; j += SCAN_THREADS) {
             unsigned long long acc = s_remv[j];
-#pragma unroll 8
-            for (int t = 0; t < 64; ++t)
-                if ((kept >> t) & 1ull) acc |= tile[(size_t)t * cb + j];
+            for (unsigned long long k = kept; k; k &= k - 1ull)          // kept rows only
+                acc |= tile[(size_t)(__ffsll((long long)k) - 1) * cb + j];
             s_remv[j] = acc;
         }
         __syncthreads();   // tile[buf] is overwritten by the prefetch of block bi+2
@@ -175,9 +181,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_global_kernel(int n, co
         if (tid == 0) {
             unsigned long long cur = s_remv[bi], kept = 0ull;
             const int lim = min(64, n - bi * 64);
+            const unsigned long long valid = lim == 64 ? ~0ull : ((1ull << lim) - 1ull);
+            unsigned long long alive = ~cur & valid;
             int num = s_num;
-            for (int t = 0; t < lim; ++t)
-                if (!((cur >> t) & 1ull)) { kept |= 1ull << t; keep[num++] = (long long)bi * 64 + t; cur |= s_diag[t]; }
+            while (alive) {
+                const int t = __ffsll((long long)alive) - 1;
+                kept |= 1ull << t;
+                keep[num++] = (long long)bi * 64 + t;
+                cur |= s_diag[t];
+                alive = ~cur & valid & ~((2ull << t) - 1ull);
+            }
             s_num = num;
             s_kept = kept;
         }
@@ -288,13 +301,13 @@ extern "C" int prb_nms_mask(const float *boxes, int n, float thresh, int normal,
     PRB_REQUIRE(n >= 0 && boxes && mask, "nms_mask: bad arguments");
     if (n == 0) return 0;
     const int cb = ceil_div(n, 64);
-    dim3 grid(cb, cb);
     if (normal) {
-        nms_mask_kernel<true><<<grid, NM_THREADS, 0, (cudaStream_t)stream>>>(n, thresh, boxes, mask);
+        nms_mask_kernel<true, 64><<<dim3(cb, cb), NM_THREADS, 0, (cudaStream_t)stream>>>(n, thresh, boxes, mask);
     } else {
+        constexpr int RT = 8;
         const size_t smem = (size_t)3 * POLY_SLOTS * NM_THREADS * sizeof(float);    // 48 KB of polygon scratch
-        PRB_CUDA(cudaFuncSetAttribute(nms_mask_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nms_mask_kernel<false><<<grid, NM_THREADS, smem, (cudaStream_t)stream>>>(n, thresh, boxes, mask);
+        PRB_CUDA(cudaFuncSetAttribute(nms_mask_kernel<false, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_mask_kernel<false, RT><<<dim3(cb, ceil_div(n, RT)), NM_THREADS, smem, (cudaStream_t)stream>>>(n, thresh, boxes, mask);
     }
     return check_launch("nms_mask_kernel");
 }

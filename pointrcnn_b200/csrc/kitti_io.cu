@@ -37,29 +37,39 @@ __global__ void __launch_bounds__(256) kitti_prepare_kernel(int b, int total, co
                                                              float *__restrict__ rect, unsigned char *__restrict__ flags,
                                                              int *__restrict__ counts) {
     const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= total) return;
-    const int s = scene_of(offsets, b, i);
-    const float *c = calib + (size_t)s * kCalibFloats;
-    const float x = lidar[(size_t)i * stride], y = lidar[(size_t)i * stride + 1], z = lidar[(size_t)i * stride + 2];
-    float r[3];
+    const bool inb = i < total;
+    const int s = inb ? scene_of(offsets, b, i) : -1;
+    bool ok = false, near = true;
+    if (inb) {
+        const float *c = calib + (size_t)s * kCalibFloats;
+        const float x = lidar[(size_t)i * stride], y = lidar[(size_t)i * stride + 1], z = lidar[(size_t)i * stride + 2];
+        float r[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) r[k] = __fmaf_rn(z, c[6 + k], __fmaf_rn(y, c[3 + k], __fmul_rn(x, c[k]))) + c[9 + k];
-    const float *P = c + 12;
-    float h[3];
+        for (int k = 0; k < 3; ++k) r[k] = __fmaf_rn(z, c[6 + k], __fmaf_rn(y, c[3 + k], __fmul_rn(x, c[k]))) + c[9 + k];
+        const float *P = c + 12;
+        float h[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k)
-        h[k] = __fmaf_rn(r[2], P[k * 4 + 2], __fmaf_rn(r[1], P[k * 4 + 1], __fmul_rn(r[0], P[k * 4]))) + P[k * 4 + 3];
-    const float u = __fdiv_rn(h[0], r[2]), v = __fdiv_rn(h[1], r[2]);     // the reference divides by the rect depth
-    const float depth = h[2] - P[11];
-    const float H = c[24], W = c[25];
-    bool ok = u >= 0.f && u < W && v >= 0.f && v < H && depth >= 0.f;
-    if (use_range) ok = ok && r[0] >= c[26] && r[0] <= c[27] && r[1] >= c[28] && r[1] <= c[29] && r[2] >= c[30] && r[2] <= c[31];
-    const bool near = r[2] < 40.0f;
-    rect[(size_t)i * 3] = r[0]; rect[(size_t)i * 3 + 1] = r[1]; rect[(size_t)i * 3 + 2] = r[2];
-    flags[i] = (unsigned char)((ok ? 1 : 0) | (near ? 2 : 0));
-    if (counts && ok) {
-        atomicAdd(&counts[s * 2], 1);
-        if (!near) atomicAdd(&counts[s * 2 + 1], 1);
+        for (int k = 0; k < 3; ++k)
+            h[k] = __fmaf_rn(r[2], P[k * 4 + 2], __fmaf_rn(r[1], P[k * 4 + 1], __fmul_rn(r[0], P[k * 4]))) + P[k * 4 + 3];
+        const float u = __fdiv_rn(h[0], r[2]), v = __fdiv_rn(h[1], r[2]);     // the reference divides by the rect depth
+        const float depth = h[2] - P[11];
+        const float H = c[24], W = c[25];
+        ok = u >= 0.f && u < W && v >= 0.f && v < H && depth >= 0.f;
+        if (use_range) ok = ok && r[0] >= c[26] && r[0] <= c[27] && r[1] >= c[28] && r[1] <= c[29] && r[2] >= c[30] && r[2] <= c[31];
+        near = r[2] < 40.0f;
+        rect[(size_t)i * 3] = r[0]; rect[(size_t)i * 3 + 1] = r[1]; rect[(size_t)i * 3 + 2] = r[2];
+        flags[i] = (unsigned char)((ok ? 1 : 0) | (near ? 2 : 0));
+    }
+    if (counts) {
+        // one atomic per warp and scene (a warp nearly always lies inside one scene): per-point atomics on the 2*b counters
+        // serialised the whole kernel (665 us for 960 k points, profiles/r2_ncu_ops_summary.csv)
+        const unsigned grp = __match_any_sync(0xffffffffu, s);
+        const unsigned okm = __ballot_sync(0xffffffffu, ok) & grp;
+        const unsigned farm = __ballot_sync(0xffffffffu, ok && !near) & grp;
+        if (inb && (threadIdx.x & 31) == __ffs(grp) - 1) {
+            if (okm) atomicAdd(&counts[s * 2], __popc(okm));
+            if (farm) atomicAdd(&counts[s * 2 + 1], __popc(farm));
+        }
     }
 }
 
@@ -123,21 +133,27 @@ __global__ void __launch_bounds__(1024) kitti_draw_kernel(int b, const int *__re
     const unsigned char *f = flags + beg;
     int *cnd = cand + beg;      // compacted raw indices of the valid points, in index order
 
-    // 1. compact the valid points; count the far ones
-    int nv = 0, nfar = 0;
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + tid;
-        const int fl = i < n ? f[i] : 0;
-        const int ok = fl & 1;
+    // 1. compact the valid points (4 consecutive points per thread and scan step); count the far ones
+    int nv = 0, far_mine = 0;
+    for (int base = 0; base < n; base += 4096) {
+        const int i0 = base + tid * 4;
+        int okq[4], c = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int fl = i0 + q < n ? f[i0 + q] : 0;
+            okq[q] = fl & 1;
+            c += okq[q];
+            far_mine += (fl & 1) && !(fl & 2);
+        }
         int tot;
-        const int pos = block_excl_scan(ok, s_warp, &tot);
-        if (ok) cnd[nv + pos] = i;
+        int pos = nv + block_excl_scan(c, s_warp, &tot);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (okq[q]) cnd[pos++] = i0 + q;
         nv += tot;
-        const int far = ok && !(fl & 2);
-        const int pf = block_excl_scan(far, s_warp, &tot);
-        (void)pf;
-        nfar += tot;
     }
+    int nfar;
+    (void)block_excl_scan(far_mine, s_warp, &nfar);
     __syncthreads();
     int *ch = choice + (size_t)scene * npoints;
     if (nv == 0) {
@@ -188,35 +204,46 @@ __global__ void __launch_bounds__(1024) kitti_draw_kernel(int b, const int *__re
     }
     // keys < prefix are taken, keys == prefix: the first `remaining` in index order
 
-    // 3. emit base + chosen (+ whole extra copies) into the sort buffers
+    // 3. emit base + chosen (+ whole extra copies) into the sort buffers, 4 consecutive candidates per thread and scan step
     int out = 0, eq_seen = 0;
-    for (int base = 0; base < nv; base += 1024) {
-        const int e = base + tid;
-        int i = 0, take = 0, eq = 0;
-        if (e < nv) {
-            i = cnd[e];
-            const bool pool = in_pool(i);
-            const bool isbase = sub ? (far_base && !pool) : true;
-            take = isbase ? 1 : 0;
-            if (pool && need > 0) {
-                const uint32_t k = draw_key(seed, scene, i, 0x51ed27u);
-                if (k < prefix) take += 1;
-                else if (k == prefix) eq = 1;
+    for (int base = 0; base < nv; base += 4096) {
+        const int e0 = base + tid * 4;
+        int iq[4], takeq[4], eqq[4], eqs = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            iq[q] = 0; takeq[q] = 0; eqq[q] = 0;
+            if (e0 + q < nv) {
+                const int i = cnd[e0 + q];
+                iq[q] = i;
+                const bool pool = in_pool(i);
+                const bool isbase = sub ? (far_base && !pool) : true;
+                takeq[q] = isbase ? 1 : 0;
+                if (pool && need > 0) {
+                    const uint32_t k = draw_key(seed, scene, i, 0x51ed27u);
+                    if (k < prefix) takeq[q] += 1;
+                    else if (k == prefix) eqq[q] = 1;
+                }
+                if (pool) takeq[q] += cycles;
             }
-            if (pool) take += cycles;
+            eqs += eqq[q];
         }
         int tot;
-        const int eqpos = block_excl_scan(eq, s_warp, &tot);
-        if (eq && eq_seen + eqpos < remaining) take += 1;
+        int eqpos = eq_seen + block_excl_scan(eqs, s_warp, &tot);
         eq_seen += tot;
-        const int pos = block_excl_scan(take, s_warp, &tot);
-        for (int t = 0; t < take; ++t) {
-            const int o = out + pos + t;
-            if (o < npoints) {
-                s_key[o] = draw_key(seed, scene, i, 0xa511e9b3u + (uint32_t)t);
-                s_idx[o] = i;
-            }
+        int ts = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (eqq[q] && eqpos++ < remaining) takeq[q] += 1;
+            ts += takeq[q];
         }
+        int o = out + block_excl_scan(ts, s_warp, &tot);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            for (int t = 0; t < takeq[q]; ++t, ++o)
+                if (o < npoints) {
+                    s_key[o] = draw_key(seed, scene, iq[q], 0xa511e9b3u + (uint32_t)t);
+                    s_idx[o] = iq[q];
+                }
         out += tot;
     }
     __syncthreads();
