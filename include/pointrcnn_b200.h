@@ -78,7 +78,8 @@ typedef struct prb_options {
     int grid_csr;      /* 1: hash grid as CSR runs (counting sort per scene) instead of linked lists; slower at the RPN shapes */
     int grid_debug;    /* 1: print (and synchronise for) the 3-NN grid's fallback counts */
     float nn_cell;     /* 3-NN grid cell edge in units of the mean point spacing (default 1.6) */
-    int roipool_fused;     /* 1 (default): the binned assign pass of a box runs inside the copy kernel's CTA (no index list in HBM); 0: two kernels */
+    int roipool_fused;     /* 1: the binned assign pass of a box runs inside the copy kernel's CTA (no index list in HBM); 0 (default): two kernels --
+                            * measured: fused 0.167 ms, two kernels 0.156 ms at the configs[3] shape */
 } prb_options;
 PRB_API void prb_options_init(prb_options *o);                 /* library defaults */
 PRB_API int prb_set_thread_options(const prb_options *o);      /* NULL: back to the defaults */

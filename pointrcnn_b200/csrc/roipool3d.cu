@@ -390,7 +390,8 @@ __global__ void __launch_bounds__(RP_THREADS) roipool3d_copy_kernel(int N, int M
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int box = blockIdx.x, scene = blockIdx.y;
     const size_t bi = (size_t)scene * M + box;
-    // Fused form (default): this CTA first runs the binned assign pass of ITS box -- bitmap and index list stay in shared
+    // Fused form (prb_options.roipool_fused; measured SLOWER than two kernels, 0.167 vs 0.156 ms at the configs[3] shape -- the
+    // assign phase holds the CTA's 50 KB of shared memory idle while it chases pointers): this CTA first runs the binned assign pass of ITS box -- bitmap and index list stay in shared
     // memory -- and copies straight away: one launch less, no index list in HBM, and the dependent loads of the assign pass
     // (cell offsets -> permutation -> coordinates) hide behind the row streams of the SM's other CTAs.
     if (fa.sorted_idx) {

@@ -67,7 +67,7 @@ static prb_options make_defaults() {
     o.nn_sort_queries = env_int("PRB_NN_SORT_QUERIES", 0);
     o.grid_csr = env_int("PRB_GRID_CSR", 0);
     o.grid_debug = env_int("PRB_GRID_DEBUG", 0);
-    o.roipool_fused = env_int("PRB_ROIPOOL_FUSED", 1);
+    o.roipool_fused = env_int("PRB_ROIPOOL_FUSED", 0);
     o.nn_cell = 1.6f;
     if (const char *e = getenv("PRB_NN_CELL")) { float v = (float)atof(e); if (v > 0.2f && v < 50.f) o.nn_cell = v; }
     return o;

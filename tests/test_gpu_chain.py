@@ -177,3 +177,18 @@ def test_batched_detections_and_kitti_writer_equal_the_per_scene_path(cuda, chai
         single.mkdir(exist_ok=True)
         path = kitti_output.save_kitti_format(k, KO.CALIB, dets[k][0], str(single), dets[k][1], KO.IMG_SHAPE)
         assert open(path).read() == texts[k] == open(tmp_path / ("%06d.txt" % k)).read()
+
+
+def test_batched_detections_with_nothing_above_the_threshold(cuda, chain):
+    from pointrcnn_b200.datasets import kitti_output
+    from oracle import kitti_io as KO
+    model, pc, out, _, _ = chain
+    out2 = dict(out)
+    out2["rcnn_cls"] = torch.full_like(out["rcnn_cls"], -20.0)          # sigmoid ~ 0: every box is under the score threshold
+    with torch.no_grad():
+        boxes, raw, select = model.detections_device(out2)
+        dets, _ = model.detections(out2)
+    assert int(select.sum()) == 0 and all(d[0].shape[0] == 0 for d in dets)
+    B = boxes.shape[0]
+    texts = kitti_output.write_kitti_batch(range(B), [KO.CALIB] * B, [KO.IMG_SHAPE] * B, boxes, raw, select)
+    assert texts == [""] * B

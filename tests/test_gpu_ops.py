@@ -394,8 +394,8 @@ def test_roipool3d_binned_equals_exhaustive(cuda, case):
         xyz += np.float32(30000.0); boxes[:, :, 0:3] += np.float32(30000.0)     # coarse fp32 spacing around the boxes
     x, bx, f = T(xyz, cuda), T(boxes, cuda), T(feat, cuda)
     out = []
-    # binned + assign fused into the copy kernel (default), binned as two kernels, exhaustive
-    for opt in (dict(roipool_exhaustive=0, roipool_fused=1), dict(roipool_exhaustive=1), dict(roipool_exhaustive=0, roipool_fused=0)):
+    # binned as two kernels (default), exhaustive, binned with the assign pass fused into the copy kernel
+    for opt in (dict(roipool_exhaustive=0, roipool_fused=0), dict(roipool_exhaustive=1), dict(roipool_exhaustive=0, roipool_fused=1)):
         pooled = torch.zeros((B, M, S, 3 + Cf), device=cuda)
         empty = torch.zeros((B, M), dtype=torch.int32, device=cuda)
         with C.options(**opt):
@@ -404,7 +404,7 @@ def test_roipool3d_binned_equals_exhaustive(cuda, case):
         out.append((pooled.cpu().numpy(), empty.cpu().numpy()))
     assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[2][1], out[1][1]), "empty flags differ"
     assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32)), "pooled rows differ (bitwise)"
-    assert np.array_equal(out[2][0].view(np.uint32), out[1][0].view(np.uint32)), "pooled rows differ (bitwise, two-kernel form)"
+    assert np.array_equal(out[2][0].view(np.uint32), out[1][0].view(np.uint32)), "pooled rows differ (bitwise, fused form)"
     if case in ("duplicates", "huge_boxes", "odd_n", "far_coordinates"):
         assert (out[0][1] == 0).sum() > 0, "case should have non-empty boxes"
 
