@@ -133,21 +133,29 @@ __global__ void __launch_bounds__(SCAN_THREADS) nms_scan_kernel(int n, const uns
         __syncthreads();
         const unsigned long long *tile = s_tile[buf];
         const int lim = min(64, n - bi * 64);
-        if (tid == 0) {
-            // one step per KEPT box (not per box): jump to the next box that is still alive with a find-first-set
-            unsigned long long cur = s_remv[bi], kept = 0ull;
+        if (tid < 32) {
+            // The block's 64 boxes are resolved by ONE WARP as a fixed point instead of a 64-step serial walk: with d_t = row t's
+            // diagonal word (bits > t only), the greedy answer is the unique K with  K = alive & ~OR_{t in K} d_t.  Iterating
+            // K <- alive & ~OR_{t in K} d_t from K = alive fixes bit b after at most b rounds (bit b depends on bits < b only),
+            // i.e. after (longest suppression chain + 1) rounds -- 2 to 4 for real box sets -- of two selects and two REDUX.OR.
+            const int lane = tid;
             const unsigned long long valid = lim == 64 ? ~0ull : ((1ull << lim) - 1ull);
-            unsigned long long alive = ~cur & valid;
-            int num = s_num;
-            while (alive) {
-                const int t = __ffsll((long long)alive) - 1;
-                kept |= 1ull << t;
-                keep[num++] = (long long)bi * 64 + t;
-                cur |= tile[(size_t)t * cb + bi];
-                alive = ~cur & valid & ~((2ull << t) - 1ull);       // boxes behind t only
-            }
-            s_num = num;
-            s_kept = kept;
+            const unsigned long long dlo = lane < lim ? tile[(size_t)lane * cb + bi] : 0ull;
+            const unsigned long long dhi = lane + 32 < lim ? tile[(size_t)(lane + 32) * cb + bi] : 0ull;
+            const unsigned long long alive = ~s_remv[bi] & valid;
+            unsigned long long kept = alive, prev;
+            do {
+                prev = kept;
+                const unsigned long long x = (((kept >> lane) & 1ull) ? dlo : 0ull) | (((kept >> (lane + 32)) & 1ull) ? dhi : 0ull);
+                const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)x);
+                const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(x >> 32));
+                kept = alive & ~(((unsigned long long)hi << 32) | lo);
+            } while (kept != prev);
+            const int num = s_num;
+            if ((kept >> lane) & 1ull) keep[num + __popcll(kept & ((1ull << lane) - 1ull))] = (long long)bi * 64 + lane;
+            if ((kept >> (lane + 32)) & 1ull) keep[num + __popcll(kept & ((1ull << (lane + 32)) - 1ull))] = (long long)bi * 64 + lane + 32;
+            __syncwarp();
+            if (lane == 0) { s_num = num + __popcll(kept); s_kept = kept; }
         }
         __syncthreads();
         const unsigned long long kept = s_kept;
