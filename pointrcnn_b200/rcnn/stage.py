@@ -125,6 +125,24 @@ class RCNNStage(nn.Module):
         rcnn_reg = self.reg_layer(l_features[-1]).transpose(1, 2).contiguous().squeeze(dim=1)
         return rcnn_cls, rcnn_reg
 
+    def forward_train(self, input_data, target_layer=None):
+        """training branch of RCNNNet.forward with cfg.RCNN.ROI_SAMPLE_JIT (rcnn_net.py:119-126, :165-190): the target layer
+        (RoI sampling, pooling, augmentation, canonical transform, labels -- no grad) then the network on the sampled RoIs.
+        input_data: the eval keys + gt_boxes3d (B,G,7).  -> the reference's ret_dict: rcnn_cls, rcnn_reg + the target dict
+        (cls_label, reg_valid_mask, gt_of_rois, roi_boxes3d, pts_input, ...)."""
+        if target_layer is None:
+            if getattr(self, "proposal_target_layer", None) is None:
+                from ..rpn.proposal_target_layer import ProposalTargetLayer
+                self.proposal_target_layer = ProposalTargetLayer()
+            target_layer = self.proposal_target_layer
+        with torch.no_grad():
+            target = target_layer(input_data)
+            target["pts_input"] = torch.cat((target["sampled_pts"], target["pts_feature"]), dim=2)
+        rcnn_cls, rcnn_reg = self.forward_pts(target["pts_input"])
+        ret = {"rcnn_cls": rcnn_cls, "rcnn_reg": rcnn_reg}
+        ret.update(target)
+        return ret
+
     def forward(self, input_data):
         """eval branch of RCNNNet.forward with cfg.RCNN.ROI_SAMPLE_JIT: input dict keys rpn_xyz (B,N,3), rpn_features (B,N,C),
         seg_mask (B,N), pts_depth (B,N), roi_boxes3d (B,M,7) [, rpn_intensity] -> {'rcnn_cls', 'rcnn_reg'}"""

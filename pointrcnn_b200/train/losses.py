@@ -146,3 +146,48 @@ def rpn_loss(rpn_cls, rpn_reg, rpn_cls_label, rpn_reg_label, mean_size, loss_cls
     total = loss_c * loss_weight[0] + loss_r * loss_weight[1]
     terms.update(rpn_loss_cls=loss_c, rpn_loss_reg=loss_r, rpn_loss=total)
     return total, terms
+
+
+def rcnn_loss(rcnn_cls, rcnn_reg, cls_label, reg_valid_mask, roi_boxes3d, gt_of_rois, mean_size, loss_cls="BinaryCrossEntropy",
+              focal_alpha=0.25, focal_gamma=2.0, size_res_on_roi=False, loc_scope=1.5, loc_bin_size=0.5, num_head_bin=9,
+              loc_y_by_bin=False, loc_y_scope=0.5, loc_y_bin_size=0.25, ce_weight=None):
+    """get_rcnn_loss (train_functions.py:121-209).  rcnn_cls (R,1|K), rcnn_reg (R,C), cls_label (R) in {-1,0,1},
+    reg_valid_mask (R), roi_boxes3d (R,7), gt_of_rois (R,7) canonical -> total loss, dict of device tensors (no .item())."""
+    R = rcnn_reg.shape[0]
+    label = cls_label.float().view(-1)
+    terms = {}
+    if loss_cls == "SigmoidFocalLoss":
+        flat = rcnn_cls.view(-1)
+        pos, neg = (label > 0).float(), (label == 0).float()
+        w = (pos + neg) / torch.clamp(pos.sum(), min=1.0)
+        per = SigmoidFocalClassificationLoss(alpha=focal_alpha, gamma=focal_gamma)(flat, pos, w)
+        terms["rpn_loss_cls_pos"], terms["rpn_loss_cls_neg"] = (per * pos).sum(), (per * neg).sum()     # the reference's key names
+        loss_c = per.sum()
+    elif loss_cls == "BinaryCrossEntropy":
+        flat = rcnn_cls.view(-1)
+        # the reference passes the -1 ("ignore") labels straight into F.binary_cross_entropy and masks the rows afterwards; current
+        # torch rejects targets outside [0,1], so the ignored rows get a dummy target here (they are masked out all the same)
+        bl = F.binary_cross_entropy(torch.sigmoid(flat), label.clamp(min=0.0), reduction="none")
+        valid = (label >= 0).float()
+        loss_c = (bl * valid).sum() / torch.clamp(valid.sum(), min=1.0)
+    elif loss_cls == "CrossEntropy":
+        logits = rcnn_cls.view(R, -1)
+        valid = (label >= 0).float()
+        bl = F.cross_entropy(logits, label.long(), weight=ce_weight, ignore_index=-1, reduction="none")
+        loss_c = (bl * valid).sum() / torch.clamp(valid.sum(), min=1.0)      # (the reference's .mean(dim=1) of a 1-D loss is a no-op for K classes)
+    else:
+        raise NotImplementedError(loss_cls)
+    fg = reg_valid_mask.view(-1) > 0
+    reg_fg = rcnn_reg.view(R, -1)[fg]
+    if reg_fg.shape[0] != 0:
+        anchor = roi_boxes3d.view(R, 7)[:, 3:6][fg] if size_res_on_roi else mean_size
+        loc, ang, size, reg_terms = get_reg_loss(reg_fg, gt_of_rois.view(R, 7)[fg], loc_scope=loc_scope, loc_bin_size=loc_bin_size,
+                                                 num_head_bin=num_head_bin, anchor_size=anchor, get_xz_fine=True, get_y_by_bin=loc_y_by_bin,
+                                                 loc_y_scope=loc_y_scope, loc_y_bin_size=loc_y_bin_size, get_ry_fine=True)
+        terms.update(reg_terms)
+        loss_r = loc + ang + 3 * size              # "consistent with old codes" (train_functions.py:193)
+    else:
+        loss_r = loss_c * 0
+    total = loss_c + loss_r
+    terms.update(rcnn_loss_cls=loss_c, rcnn_loss_reg=loss_r, rcnn_loss=total)
+    return total, terms

@@ -14,7 +14,7 @@ import torch
 
 from ..parallel_utils import GradBucketReducer
 from ..rpn.stage import CLS_MEAN_SIZE, RPNStage
-from .losses import rpn_loss
+from .losses import rcnn_loss, rpn_loss
 
 
 class RPNTrainer:
@@ -58,3 +58,48 @@ def synthetic_labels(pts_input, seed=0):
     reg[..., 3:6] = torch.from_numpy(CLS_MEAN_SIZE[0]) * (1 + 0.1 * torch.randn(B, N, 3, generator=g))
     reg[..., 6] = (torch.rand(B, N, generator=g) * 2 - 1) * float(np.pi)
     return cls.to(pts_input.device), reg.to(pts_input.device)
+
+
+class RCNNTrainer:
+    """One RCNN training step with the RPN fixed (the reference's second training phase: tools/train_rcnn.py --train_mode rcnn,
+    cfg.RPN.FIXED): the RPN stage runs in eval mode without grad on the fused path and hands (rois, point features, mask,
+    depth) to the RCNN stage, whose target layer samples 64 RoIs per scene; forward / backward of the RCNN network on the
+    op-by-op path, get_rcnn_loss, bucketed gradient all-reduce, optimizer step."""
+
+    def __init__(self, input_channels=1, device="cuda", world=1, lr=0.002, weight_decay=0.001, bucket_mb=4.0, seed=0, rpn_score_thresh=0.3):
+        from ..rcnn.stage import RCNNStage
+        torch.manual_seed(seed)
+        self.device = torch.device(device)
+        self.rpn = RPNStage(input_channels=input_channels, mode="TRAIN").to(self.device).eval()     # TRAIN quotas: 512 RoIs per scene
+        for p in self.rpn.parameters():
+            p.requires_grad_(False)
+        self.model = RCNNStage(num_classes=2, input_channels=128).to(self.device).train()
+        self.params = [p for p in self.model.parameters() if p.requires_grad]
+        self.reducer = GradBucketReducer(self.params, world=world, bucket_mb=bucket_mb)
+        self.opt = torch.optim.Adam(self.params, lr=lr, weight_decay=weight_decay, **({"fused": True} if self.device.type == "cuda" else {}))
+        self.mean_size = torch.from_numpy(CLS_MEAN_SIZE[0]).to(self.device)
+        self.rpn_score_thresh = rpn_score_thresh
+
+    @torch.no_grad()
+    def rpn_outputs(self, pts_input, gt_boxes3d):
+        rois, _, rpn_cls, _, xyz, feats = self.rpn(pts_input, with_features=True)       # point_rcnn.py:36-55
+        seg_mask = (torch.sigmoid(rpn_cls[:, :, 0]) > self.rpn_score_thresh).float()
+        return {"rpn_xyz": xyz, "rpn_features": feats.permute(0, 2, 1).contiguous(), "seg_mask": seg_mask, "roi_boxes3d": rois,
+                "pts_depth": torch.norm(xyz, p=2, dim=2), "gt_boxes3d": gt_boxes3d}
+
+    def forward_loss(self, pts_input, gt_boxes3d):
+        ret = self.model.forward_train(self.rpn_outputs(pts_input, gt_boxes3d))
+        c = self.model.cfg
+        return rcnn_loss(ret["rcnn_cls"], ret["rcnn_reg"], ret["cls_label"], ret["reg_valid_mask"], ret["roi_boxes3d"], ret["gt_of_rois"],
+                         self.mean_size, loc_scope=c["LOC_SCOPE"], loc_bin_size=c["LOC_BIN_SIZE"], num_head_bin=c["NUM_HEAD_BIN"],
+                         loc_y_by_bin=c["LOC_Y_BY_BIN"], loc_y_scope=c["LOC_Y_SCOPE"], loc_y_bin_size=c["LOC_Y_BIN_SIZE"])
+
+    def step(self, pts_input, gt_boxes3d, grad_norm_clip=None):
+        self.reducer.reset()
+        loss, terms = self.forward_loss(pts_input, gt_boxes3d)
+        loss.backward()
+        self.reducer.finish()
+        if grad_norm_clip:
+            torch.nn.utils.clip_grad_norm_(self.params, grad_norm_clip)
+        self.opt.step()
+        return loss.detach(), terms

@@ -146,3 +146,37 @@ def test_decode_and_losses_match_the_reference_python():
     logits, tgt, w = G.cls_inputs()
     assert np.array_equal(L.SigmoidFocalClassificationLoss(2.0, 0.25)(logits, tgt, w).numpy(), g["focal"])
     np.testing.assert_allclose(float(L.DiceLoss()(logits, tgt)), g["dice"][0], rtol=1e-6)
+
+
+def test_stage_losses_match_the_reference_functions():
+    """train.losses.rpn_loss / rcnn_loss against get_rpn_loss / get_rcnn_loss of lib/net/train_functions.py:55-209 (their own
+    source, run by oracle/make_golden_stage_losses.py with tools/cfgs/default.yaml)"""
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import make_golden_stage_losses as G
+    from pointrcnn_b200.rpn.stage import CLS_MEAN_SIZE
+    from pointrcnn_b200.train import losses as L
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stage_losses.npz"))
+    mean = torch.from_numpy(CLS_MEAN_SIZE[0])
+    cls, reg, lab, rl = G.rpn_inputs()
+    for name in ("SigmoidFocalLoss", "DiceLoss", "BinaryCrossEntropy"):
+        total, t = L.rpn_loss(cls, reg, lab, rl, mean, loss_cls=name)
+        got = [float(total), float(t["rpn_loss_cls"]), float(t["rpn_loss_reg"]), float(t["loss_loc"]), float(t["loss_angle"]), 3 * float(t["loss_size"])]
+        np.testing.assert_allclose(got, g["rpn_%s" % name], rtol=3e-6, atol=1e-6, err_msg=name)
+    rc, rr, rlab, valid, roi, gt = G.rcnn_inputs()
+    for name in ("BinaryCrossEntropy", "SigmoidFocalLoss"):
+        for on_roi in (False, True):
+            lab_in = rlab.clamp(min=0) if name == "BinaryCrossEntropy" else rlab      # see the generator: {0,1} labels for this variant
+            total, t = L.rcnn_loss(rc, rr, lab_in, valid, roi, gt, mean, loss_cls=name, size_res_on_roi=on_roi)
+            want = g["rcnn_%s_%d" % (name, int(on_roi))]
+            np.testing.assert_allclose([float(total), float(t["rcnn_loss_cls"]), float(t["rcnn_loss_reg"])], want[:3], rtol=3e-6, atol=1e-6,
+                                       err_msg="%s %s" % (name, on_roi))
+            assert int((valid > 0).sum()) == int(want[3])
+    # ignore labels (-1) in the cross-entropy variant: the same loss as on the valid rows alone
+    total, t = L.rcnn_loss(rc, rr, rlab, valid, roi, gt, mean, loss_cls="BinaryCrossEntropy")
+    keep = rlab >= 0
+    ref = torch.nn.functional.binary_cross_entropy(torch.sigmoid(rc.view(-1)[keep]), rlab[keep].float())
+    np.testing.assert_allclose(float(t["rcnn_loss_cls"]), float(ref), rtol=1e-6)
+    # no foreground row at all: the regression term is an exact zero that still carries the graph
+    total0, t0 = L.rcnn_loss(rc.requires_grad_(True), rr, rlab, torch.zeros_like(valid), roi, gt, mean)
+    assert float(t0["rcnn_loss_reg"]) == 0.0 and total0.requires_grad

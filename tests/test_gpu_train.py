@@ -101,3 +101,29 @@ def test_rpn_training_step_runs_and_learns(cuda):
         b = tr.reducer.buckets[tr.reducer._owner[p]]["flat"]
         assert b.data_ptr() <= p.grad.data_ptr() < b.data_ptr() + b.numel() * 4
     assert {"rpn_loss_cls", "rpn_loss_reg", "loss_x_bin", "loss_ry_res", "loss_size"} <= set(terms)
+
+
+def test_rcnn_training_step_runs_and_learns(cuda):
+    """RCNN phase with the RPN fixed: RPN stage (fused, no grad) -> target layer (64 RoIs per scene) -> RCNN network in training
+    mode -> get_rcnn_loss mirror -> backward -> optimizer; GT boxes sit on proposals so that foreground RoIs exist"""
+    from pointrcnn_b200.train.step import RCNNTrainer
+    tr = RCNNTrainer(input_channels=1, device=cuda, world=1, lr=0.002, seed=5)
+    with torch.no_grad():
+        tr.rpn.rpn_reg_layer[-1].conv.weight.mul_(0.2)            # usable box sizes on random weights (as in the chain test)
+    pc = torch.from_numpy(synth.u_kitti(2, 16384, 321, channels=4)).to(cuda)
+    rois = tr.rpn_outputs(pc, None)["roi_boxes3d"]
+    gt = torch.zeros((2, 12, 7), device=cuda)
+    gt[:, :8] = rois[:, ::40][:, :8]                               # 8 GT boxes per scene = 8 of the proposals; 4 padding rows
+    assert (gt[:, :8, 3:6] > 0).all(), "degenerate proposals"
+    w0 = tr.model.cls_layer[0].conv.weight.detach().clone()
+    losses = []
+    for _ in range(5):
+        loss, terms = tr.step(pc, gt, grad_norm_clip=1.0)
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)), losses
+    assert not torch.equal(tr.model.cls_layer[0].conv.weight, w0), "the optimizer did not move the RCNN parameters"
+    assert all(p.grad is None for p in tr.rpn.parameters()), "the fixed RPN must not receive gradients"
+    assert {"rcnn_loss_cls", "rcnn_loss_reg", "rcnn_loss"} <= set(terms)
+    ret = tr.model.forward_train(tr.rpn_outputs(pc, gt))
+    assert ret["rcnn_cls"].shape[0] == 2 * 64 and ret["pts_input"].shape[1:] == (512, 133)
+    assert int((ret["reg_valid_mask"] > 0).sum()) > 0, "no foreground RoI: the regression branch is not exercised"
