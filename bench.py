@@ -474,6 +474,39 @@ def main():
         tr.reducer.remove()
         del tr
         torch.cuda.empty_cache()
+        # second training phase (tools/train_rcnn.py --train_mode rcnn, RPN fixed): 4 scenes per GPU, 64 sampled RoIs per scene
+        try:
+            from pointrcnn_b200.train.step import RCNNTrainer
+            rt = RCNNTrainer(input_channels=CHANNELS - 3, device=dev, world=world)
+            with torch.no_grad():
+                rt.rpn.rpn_reg_layer[-1].conv.weight.mul_(0.2)
+            pcs = [dev_pool[i][:4].contiguous() for i in range(2)]
+            gts = []
+            for pc4 in pcs:                      # GT boxes = 8 of the scene's own proposals (foreground RoIs exist), 4 padding rows
+                g4 = torch.zeros((4, 12, 7), device=dev)
+                g4[:, :8] = rt.rpn_outputs(pc4, None)["roi_boxes3d"][:, ::60][:, :8]
+                gts.append(g4)
+            for i in range(2):
+                rt.step(pcs[i % 2], gts[i % 2], grad_norm_clip=1.0)
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier(); torch.cuda.synchronize()
+            t0.record()
+            for i in range(KT):
+                loss_r, _ = rt.step(pcs[i % 2], gts[i % 2], grad_norm_clip=1.0)
+            t1.record()
+            torch.cuda.synchronize(); barrier()
+            ms_r = max_over_ranks(t0.elapsed_time(t1) / KT, device=dev)
+            train["rcnn_phase"] = {"what": "RCNN training step with the RPN fixed: fused RPN stage (no grad) -> target layer (64 RoIs per scene) -> RCNN "
+                                           "network forward / backward -> get_rcnn_loss -> bucketed all-reduce -> fused Adam; 4 scenes per GPU",
+                                   "ms_per_step": ms_r, "value": 4 * world / (ms_r * 1e-3), "unit": "scenes/s", "steps": KT,
+                                   "allreduce_bytes_per_step": rt.reducer.bytes_per_step if world > 1 else 0, "final_loss": float(loss_r)}
+            rt.reducer.remove()
+            del rt
+        except Exception as e:
+            if world > 1:
+                raise
+            train["rcnn_phase"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+        torch.cuda.empty_cache()
 
     # ---------------- BASELINE configs[3]: RCNN stage 2 (roipool3d of 4 x 512 RoIs x 512 points + RCNN PointNet++), rank 0 only
     rcnn = None
