@@ -157,6 +157,36 @@ def test_fps_ordered_mixed_batch_and_caller_temp(cuda):
             assert todo.tolist() == [0, 1, 1]
 
 
+@pytest.mark.parametrize("case", ["nan", "inf", "tiny", "all_equal", "single_scene"])
+def test_fps_ordered_degenerate_inputs_equal_the_plain_entry(cuda, case):
+    """whatever the input, the ordered entry returns what the sampling kernels return (the proof simply fails)"""
+    base = synth.u_kitti(3, 1024, 91)
+    order = O.fps(base, 256)
+    lvl = np.stack([base[b][order[b]] for b in range(3)])
+    m = 64
+    if case == "nan":
+        lvl[0, 100, 1] = np.nan
+        lvl[1, 10, :] = np.nan
+    elif case == "inf":
+        lvl[0, 7, 0] = np.inf
+        lvl[2, 200, 2] = -np.inf
+    elif case == "tiny":
+        lvl, m = lvl[:, :2].copy(), 2
+    elif case == "all_equal":
+        lvl[1] = lvl[1, 0]
+    elif case == "single_scene":
+        lvl = lvl[:1].copy()
+    x = T(lvl, cuda)
+    idx_o, nx_o, todo = pu.furthest_point_sample_xyz(x, m, ordered=True, return_todo=True)
+    idx_p, nx_p = pu.furthest_point_sample_xyz(x, m, ordered=False)
+    assert torch.equal(idx_o, idx_p)
+    assert np.array_equal(nx_o.cpu().numpy(), nx_p.cpu().numpy(), equal_nan=True)
+    if case == "all_equal":
+        assert todo[1].item() == 1
+    if case in ("tiny", "single_scene"):
+        assert int(todo.sum()) == 0
+
+
 def test_backbone_takes_the_ordered_shortcut(cuda):
     """SA levels 2..4 of the fused encoder receive tagged coordinates; switching the shortcut off changes nothing"""
     from pointrcnn_b200 import backbone, config
