@@ -93,7 +93,7 @@ def generate_rpn_training_labels(pts_rect, gt_boxes3d, extra_width=0.2, gt_count
     return cls, reg
 
 
-def draw_augmentation(n_gt_alpha_unused=None, rng=np.random, aug_list=("rotation", "scaling", "flip"),
+def draw_augmentation(rng=np.random, aug_list=("rotation", "scaling", "flip"),
                       aug_prob=(0.5, 0.5, 0.5), rot_range=18, mustaug=False):
     """the random draws of data_augmentation (kitti_rcnn_dataset.py:520-568) in the reference's order:
     -> (angle or None, scale or None, flip bool, aug_method list)"""
@@ -211,7 +211,7 @@ class RPNInputPipeline(object):
 
     def prepare_batch(self, scans, seed=0, rng=np.random):
         """-> dict of CUDA tensors with collate_batch's keys: pts_input (B,npoints,3|4), pts_rect (B,npoints,3),
-        pts_features (B,npoints,1), gt_boxes3d (B,max_g,7) zero padded, and in TRAIN mode rpn_cls_label (B,npoints) int32,
+        pts_features (B,npoints,1), and unless mode == 'TEST' gt_boxes3d (B,max_g,7) zero padded, rpn_cls_label (B,npoints) int32,
         rpn_reg_label (B,npoints,7); plus `choice` (B,npoints) int32 raw-point indices and `aug_method` per scene."""
         lib = C.lib()
         dev = self.device
@@ -275,8 +275,8 @@ class RPNInputPipeline(object):
                 gt_t = torch.from_numpy(gpad).to(dev, non_blocking=True)
                 gcnt = torch.tensor([len(g) for g in gts], dtype=torch.int32).to(dev, non_blocking=True)
                 out["gt_boxes3d"] = gt_t
-                if self.mode == "TRAIN":
-                    out["rpn_cls_label"], out["rpn_reg_label"] = generate_rpn_training_labels(pts_rect, gt_t, gt_count=gcnt)
+                # like get_rpn_sample, every mode but TEST carries the per-point labels (kitti_rcnn_dataset.py:343-352)
+                out["rpn_cls_label"], out["rpn_reg_label"] = generate_rpn_training_labels(pts_rect, gt_t, gt_count=gcnt)
             if self.aug_data:
                 out["aug_method"] = aug_methods
         return out

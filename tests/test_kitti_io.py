@@ -119,7 +119,12 @@ def test_pipeline_with_the_reference_stream_matches_the_reference(cuda, gold):
     np.random.seed(7)
     out = ev.prepare_batch([scans[0]], rng=np.random)
     np.testing.assert_allclose(out["pts_input"][0].cpu().numpy(), gold["eval0_pts_input"], rtol=0, atol=2e-5)
-    assert "rpn_cls_label" not in out and "aug_method" not in out
+    assert "aug_method" not in out
+    _label_agreement(out["rpn_cls_label"][0].cpu().numpy(), out["rpn_reg_label"][0].cpu().numpy(), gold["eval0_rpn_cls_label"],
+                     gold["eval0_rpn_reg_label"], 2e-3)
+    np.testing.assert_allclose(out["gt_boxes3d"][0].cpu().numpy(), gold["eval0_gt_boxes3d"], rtol=0, atol=1e-6)
+    test = RPNInputPipeline(npoints=NPOINTS, mode="TEST", draw="device", device=cuda).prepare_batch(scans)
+    assert "rpn_cls_label" not in test and "gt_boxes3d" not in test
 
 
 @pytest.mark.gpu
