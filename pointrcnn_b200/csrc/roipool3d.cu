@@ -229,30 +229,14 @@ __device__ __forceinline__ int grid_cell(float v, float v0, float inv) {
     return (int)fminf(fmaxf((v - v0) * inv, 0.f), (float)(RG - 1));
 }
 
-// `staged` != 0: the scene's coordinates are first copied into shared memory with coalesced 128-bit loads (3 N floats of dynamic
-// shared memory; N <= 16384) and the three passes (bounds, histogram, scatter) read them there instead of paying three rounds
-// of strided global loads: one CTA per scene is a latency chain (20 us at B = 4 x 16384 points before).
 __global__ void __launch_bounds__(RG_THREADS) roipool3d_bin_kernel(int N, const float *__restrict__ xyz, int *__restrict__ sorted_idx,
-                                                                  int *__restrict__ cell_start, SceneGrid *__restrict__ grids, int staged) {
-    extern __shared__ __align__(16) float s_stage[];
+                                                                  int *__restrict__ cell_start, SceneGrid *__restrict__ grids) {
     __shared__ int s_hist[RG_CELLS];
     __shared__ float s_red[4][RG_THREADS / 32];
     __shared__ int s_wsum[RG_THREADS / 32];
     __shared__ SceneGrid s_g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, scene = blockIdx.x;
     const float *pts = xyz + (size_t)scene * N * 3;
-    if (staged) {
-        const int nf = N * 3;
-        if ((reinterpret_cast<uintptr_t>(pts) & 15) == 0) {
-            const float4 *src = reinterpret_cast<const float4 *>(pts);
-            for (int i = tid; i < nf / 4; i += RG_THREADS) reinterpret_cast<float4 *>(s_stage)[i] = __ldg(src + i);
-            for (int i = (nf & ~3) + tid; i < nf; i += RG_THREADS) s_stage[i] = pts[i];
-        } else {
-            for (int i = tid; i < nf; i += RG_THREADS) s_stage[i] = pts[i];
-        }
-        __syncthreads();
-        pts = s_stage;
-    }
     int *sorted = sorted_idx + (size_t)scene * N;
     int *cstart = cell_start + (size_t)scene * (RG_CELLS + 1);
     // bounds of the finite x / z coordinates
@@ -586,11 +570,7 @@ extern "C" int prb_roipool3d_ws(int B, int N, int M, int C, int S, const float *
         int *sorted = cnt + (size_t)B * M;
         int *cstart = sorted + (size_t)B * N;
         SceneGrid *grids = reinterpret_cast<SceneGrid *>(((uintptr_t)(cstart + (size_t)B * (RG_CELLS + 1)) + 15) & ~(uintptr_t)15);
-        const size_t smem_stage = (size_t)N * 3 * sizeof(float);
-        const int staged = smem_stage <= 200 * 1024 ? 1 : 0;
-        if (staged && smem_stage > 24 * 1024)
-            PRB_CUDA(cudaFuncSetAttribute(roipool3d_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stage));
-        roipool3d_bin_kernel<<<B, RG_THREADS, staged ? smem_stage : 0, st>>>(N, xyz, sorted, cstart, grids, staged);
+        roipool3d_bin_kernel<<<B, RG_THREADS, 0, st>>>(N, xyz, sorted, cstart, grids);
         if (int rc = check_launch("roipool3d_bin_kernel")) return rc;
         if (opts().roipool_fused != 0 && parts == 1 && smem_b + smem_bits <= 200 * 1024) {
             fa.sorted_idx = sorted; fa.cell_start = cstart; fa.grids = grids; fa.boxes3d = boxes3d;
