@@ -1,6 +1,6 @@
 """the per-GPU shapes of the sharded evaluation leg (8 / N scenes per GPU) on ONE GPU: 1, 2 and 4 scenes per step"""
 import json, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import torch
 import bench_eval_e2e as E

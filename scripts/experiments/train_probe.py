@@ -1,6 +1,6 @@
 """RPN training step (BASELINE configs[2]) under library settings: cuDNN autotuning, channels-last weights; per-family device time"""
 import json, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import bench
