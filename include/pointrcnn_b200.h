@@ -103,7 +103,7 @@ PRB_API int prb_furthest_point_sampling_ws(int b, int n, int m, const float *xyz
 /* same result, for inputs that are LIKELY already in sampling order (the output of a previous
  * furthest_point_sampling from point 0: SA level l+1 samples level l's output, pointnet2_msg.py:57-61, where the
  * answer is 0..m-1 unless two points tie for a maximum).  Per scene the library PROVES idx = (0..m-1) with n*m
- * independent distance evaluations (every pick a strict, unique maximum; nothing is assumed about the input) and
+ * independent distance evaluations (every pick the maximum, exact ties settled by the reference's rank rule; nothing is assumed about the input) and
  * writes idx / new_xyz / temp exactly as the sampling kernels would; scenes where the proof fails (ties, duplicates,
  * NaN, unordered input) are sampled by the ordinary kernels in the same call.  No host synchronisation.
  * todo_out (b) int32, optional: 0 = scene answered by the proof, 1 = sampled.  Scratch: prb_fps_ordered_workspace_bytes. */

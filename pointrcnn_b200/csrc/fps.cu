@@ -735,8 +735,8 @@ static int fps_run(int b, int n, int m, const float *xyz, float *temp, int *idx,
 // Nothing is assumed about where xyz came from.  The shortcut is taken per scene only after it is PROVEN for that
 // scene: with r_j(k) = min(temp0[j], min_{i<k} |p_j - p_i|^2) (the reference's running distance of point j when
 // pick k is chosen if the picks so far were 0..k-1) and v_k = r_k(k),
-//      FPS(xyz, m) = iota(m)   <=   for all k in [1, m), for all j != k:  r_j(k) < v_k      (a STRICT, unique maximum)
-// by induction over k; the tie rule never gets a say.  The check is n*m distance evaluations with no serial
+//      FPS(xyz, m) = iota(m)   <=   for all k in [1, m), for all j != k:  r_j(k) < v_k,  or  r_j(k) == v_k and rank(k) < rank(j)
+// by induction over k (rank = the reference's tie rule, which the sampling kernels implement: equal maxima go to the smaller rank).  The check is n*m distance evaluations with no serial
 // dependence between points (one thread per j, a running minimum over k) instead of m dependent arg-max rounds:
 // 16 x (4096 -> 1024) takes ~20 us against ~400 us.  Scenes that fail the check (ties, duplicates, NaN, or simply an
 // input that is not in FPS order) keep todo[scene] = 1 and are sampled by the ordinary kernels, launched right after
@@ -778,11 +778,14 @@ __global__ void __launch_bounds__(128) fps_prefix_v_kernel(int n, int m, const f
     if (k < m && sub == 0) v_all[(size_t)scene * m + k] = r;
 }
 
-// thread j walks k = 1 .. m-1 with its running minimum and compares it with v_k
+// thread j walks k = 1 .. m-1 with its running minimum and compares it with v_k.  r_j(k) < v_k is the common case; an exact
+// tie (r_j(k) == v_k: ~2 % of uniform 4096-point levels hold one, always between consecutive picks) is settled the way the
+// sampling kernels settle it -- the smaller reference rank wins -- so pick k stands iff rank(k) < rank(j); anything else
+// (r_j(k) > v_k, NaN, a lost tie) leaves the scene to the kernels.
 __global__ void __launch_bounds__(256) fps_prefix_check_kernel(int n, int m, const float *__restrict__ xyz_all,
                                                                 const float *__restrict__ temp_all,
                                                                 const float *__restrict__ v_all, float *__restrict__ rtemp_all,
-                                                                int *__restrict__ todo) {
+                                                                int *__restrict__ todo, int S, int logS, int Q) {
     __shared__ float4 s_c[256];                          // (x, y, z of pick k-1, v_k)
     const int scene = blockIdx.y, tid = threadIdx.x;
     const float *xyz = xyz_all + (size_t)scene * n * 3;
@@ -793,7 +796,6 @@ __global__ void __launch_bounds__(256) fps_prefix_check_kernel(int n, int m, con
         px = xyz[j * 3]; py = xyz[j * 3 + 1]; pz = xyz[j * 3 + 2];
         r = temp_all[(size_t)scene * n + j];
     }
-    const bool plain = (blockIdx.x * 256 + (tid & ~31)) >= m;   // no lane of this warp is one of the picks
     bool bad = false;
     for (int base = 1; base < m; base += 256) {
         __syncthreads();
@@ -803,19 +805,13 @@ __global__ void __launch_bounds__(256) fps_prefix_check_kernel(int n, int m, con
         }
         __syncthreads();
         const int cnt = min(256, m - base);
-        if (plain) {
 #pragma unroll 8
-            for (int e = 0; e < cnt; ++e) {
-                const float4 c = s_c[e];
-                r = fminf(r, dist2_ref(px - c.x, py - c.y, pz - c.z));
-                bad |= !(r < c.w);
-            }
-        } else {
-#pragma unroll 4
-            for (int e = 0; e < cnt; ++e) {
-                const float4 c = s_c[e];
-                r = fminf(r, dist2_ref(px - c.x, py - c.y, pz - c.z));
-                bad |= !(r < c.w) && (base + e != j);
+        for (int e = 0; e < cnt; ++e) {
+            const float4 c = s_c[e];
+            r = fminf(r, dist2_ref(px - c.x, py - c.y, pz - c.z));
+            if (!(r < c.w)) {                            // rare: my own round (k == j), a tie, or a failed proof
+                const int k = base + e;
+                if (k != j && (!(r <= c.w) || k_to_rank(j, S, logS, Q) < k_to_rank(k, S, logS, Q))) bad = true;
             }
         }
     }
@@ -872,7 +868,9 @@ extern "C" int prb_furthest_point_sampling_ordered_ws(int b, int n, int m, const
     cudaStream_t st = (cudaStream_t)stream;
     fps_prefix_v_kernel<<<dim3(ceil_div(m, 32), b), 128, 0, st>>>(n, m, xyz, temp, v, todo);
     if (int rc = check_launch("fps_prefix_v_kernel")) return rc;
-    fps_prefix_check_kernel<<<dim3(ceil_div(n, 256), b), 256, 0, st>>>(n, m, xyz, temp, v, rtemp, todo);
+    int logS = 0;
+    while ((2 << logS) <= n && logS < 10) ++logS;       // the sampling kernels' tie rule: reference rank of a point (fps_run)
+    fps_prefix_check_kernel<<<dim3(ceil_div(n, 256), b), 256, 0, st>>>(n, m, xyz, temp, v, rtemp, todo, 1 << logS, logS, ceil_div(n, 1 << logS));
     if (int rc = check_launch("fps_prefix_check_kernel")) return rc;
     fps_prefix_emit_kernel<<<dim3(ceil_div(n, 256), b), 256, 0, st>>>(n, m, xyz, rtemp, todo, temp, idx, new_xyz);
     if (int rc = check_launch("fps_prefix_emit_kernel")) return rc;

@@ -187,6 +187,28 @@ def test_fps_ordered_degenerate_inputs_equal_the_plain_entry(cuda, case):
         assert int(todo.sum()) == 0
 
 
+def test_fps_ordered_settles_exact_ties_with_the_reference_rank_rule(cuda):
+    """~2 % of uniform 4096-point levels hold an exact fp32 tie between two consecutive picks k, k+1.  The proof applies the
+    sampling kernels' tie rule (smaller reference rank wins): scene A (tie at even k = 718: rank(k) < rank(k+1)) is proven,
+    scene B (tie at odd k = 679: pick k+1 wins the tie) goes to the kernels; both equal the plain entry and the oracle."""
+    import bench
+    scenes = []
+    for first, s in ((32, 1), (96, 7)):                  # bench pool scenes found by replaying the proof on the CPU
+        pc = bench.make_scenes(first, 16)[s:s + 1, :, :3].copy()
+        idx = O.fps(np.ascontiguousarray(pc), 4096)
+        scenes.append(pc[0][idx[0]])
+    lvl = np.stack(scenes)
+    x = T(lvl, cuda)
+    idx_o, nx_o, todo = pu.furthest_point_sample_xyz(x, 1024, ordered=True, return_todo=True)
+    idx_p, nx_p = pu.furthest_point_sample_xyz(x, 1024, ordered=False)
+    want = O.fps(lvl, 1024)
+    assert torch.equal(idx_o, idx_p) and torch.equal(nx_o, nx_p)
+    assert np.array_equal(idx_o.cpu().numpy(), want)
+    assert np.array_equal(want[0], np.arange(1024)), "scene A: the tie is won by pick k"
+    assert want[1][679] == 680 and want[1][680] == 679, "scene B: the tie is won by pick k+1 (a transposition)"
+    assert todo.tolist() == [0, 1]
+
+
 def test_backbone_takes_the_ordered_shortcut(cuda):
     """SA levels 2..4 of the fused encoder receive tagged coordinates; switching the shortcut off changes nothing"""
     from pointrcnn_b200 import backbone, config
