@@ -29,7 +29,8 @@
 extern "C" {
 #endif
 
-#define PRB_ABI_VERSION 5   /* 3: prb_options (per-thread tuning block; no per-call environment reads); 4: mlp_tune, prb_mlp_rows2; 5: ordered FPS */
+#define PRB_ABI_VERSION 5   /* 3: prb_options (per-thread tuning block; no per-call environment reads); 4: mlp_tune, prb_mlp_rows2;
+                             * 5: ordered FPS, input pipeline / KITTI output group, prb_options.roipool_fused */
 #if defined(__GNUC__)
 #define PRB_API __attribute__((visibility("default")))
 #else
